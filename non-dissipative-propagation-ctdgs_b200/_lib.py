@@ -1,0 +1,116 @@
+"""ctypes binding of the C-ABI CUDA library `csrc/libctan_sm100.so` (declared in
+`include/ctan_sm100.h`).  There is NO fallback: if the library is missing or a call fails, we raise."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_float, c_int, c_int64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libctan_sm100.so")
+
+P, I, L, F = c_void_p, c_int, c_int64, c_float
+
+# name -> argument types (the trailing cudaStream_t is appended automatically)
+SIGNATURES = {
+    # loader.cu
+    "ctan_nbr_reset": [P, P, P, L, I],
+    "ctan_nbr_insert": [P, P, P, P, P, I, L, P, I, P],
+    "ctan_nbr_lookup": [P, P, L, I, P, I, P, I, P, P, P, P, I, P, I, P, P, I, P],
+    "ctan_nbr_fill": [P, P, I, P, P, P, I, P, P, P, P, P, P],
+    "ctan_mem_update": [P, P, I, P, P, P, I, P, P, P, P],
+    "ctan_mem_reset": [P, P, L, I, L],
+    # edge.cu
+    "ctan_edge_rel": [P, P, P, P, P, I, P, F, F, P],
+    "ctan_gather_rows2": [P, I, P, I, P, I, P, P],
+    "ctan_antisym_prep": [P, F, I, P],
+    "ctan_antisym_bwd": [P, I, P],
+    "ctan_edge_fwd": [P, P, P, P, I, P, I, P, F, P, P, P, P],
+    "ctan_edge_bwd": [P, P, P, P, I, P, I, P, P, P, F, P, P, I, P],
+    "ctan_tanh_bwd": [P, P, I, P, I, P],
+    "ctan_tenc_bwd": [P, P, P, P, I, P, I, P, P],
+    "ctan_csr_from_sorted": [P, I, I, P, P],
+    # dense.cu
+    "ctan_enc_fwd": [P, I, P, I, P, P, I, P, P, P, P],
+    "ctan_eproj_fwd": [P, I, P, P, P, P, I, P, I, P, I, P],
+    "ctan_qkva_fwd": [P, I, P, I, P, P, P, P, P, P, P, P, P],
+    "ctan_readout_fwd": [P, I, P, P, P, I, P, I, I, P, P, P, P, P, P, P, P],
+    "ctan_readout_bwd": [P, P, P, I, P, P, P, I, P, I, I, P, P, P, P, P, P, P, P, P, P, P],
+    "ctan_qkva_bwd": [P, P, P, I, P, I, P, P, P, P, P, P, P, P, P, P, P, P, P],
+    "ctan_enc_bwd": [P, P, I, P, I, I, P, P],
+    "ctan_eproj_bwd": [P, P, I, P, P, P, P, I, P, I, P, I, P, P],
+}
+
+_lib = None
+
+
+class CtanLibraryError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the CDLL.  Raises loudly when the CUDA library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CtanLibraryError(
+            f"{LIB_PATH} not found: build it with `python __graft_entry__.py build` "
+            "(ctan_b200 has no CPU / PyTorch fallback by design)")
+    dll = ctypes.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(dll, name)                    # AttributeError if the symbol is missing
+        fn.argtypes = list(args) + [c_void_p]
+        fn.restype = c_int
+    _optional_signatures(dll)
+    _lib = dll
+    return dll
+
+
+OPTIONAL_SIGNATURES = {}
+
+
+def _optional_signatures(dll):
+    for name, args in OPTIONAL_SIGNATURES.items():
+        fn = getattr(dll, name)
+        fn.argtypes = list(args) + [c_void_p]
+        fn.restype = c_int
+
+
+def exported_symbols():
+    return list(SIGNATURES) + list(OPTIONAL_SIGNATURES)
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t, dtype=None):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise CtanLibraryError("ctan_b200 kernels need CUDA tensors (no CPU path)")
+    if not t.is_contiguous():
+        raise CtanLibraryError("ctan_b200 kernels need contiguous tensors")
+    if dtype is not None and t.dtype != dtype:
+        raise CtanLibraryError(f"expected dtype {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def call(name: str, *args):
+    fn = getattr(lib(), name)
+    rc = fn(*args, stream_ptr())
+    if rc != 0:
+        raise CtanLibraryError(f"{name} failed with code {rc}"
+                               + (f" ({_cuda_err(rc)})" if rc > 0 else " (bad argument / unsupported size)"))
+
+
+def _cuda_err(rc: int) -> str:
+    try:
+        from cuda.bindings import runtime as cudart  # type: ignore
+        return str(cudart.cudaGetErrorString(cudart.cudaError_t(rc))[1])
+    except Exception:
+        return "cudaError"

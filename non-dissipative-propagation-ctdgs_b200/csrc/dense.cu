@@ -1,0 +1,213 @@
+// Dense contractions of the CTAN step (forward and backward), all instances of gemm.cuh with the
+// gathers / concatenations / time encoding fused into the operand loaders.
+//
+// Replaces:
+//   a6/a7  memory gather + enc_x Linear          models/memory_layers.py:155-156, models/gnn_layers.py:96
+//   a7/a8  edge_attr=[msg | cos(w*rel+b)] @ lin_edge   models/gnn_layers.py:97, TGB/modules/time_enc.py:23-24
+//   a9/a10 q,k,v projections and x @ A^T          PyG TransformerConv / AntiSymmetricConv (App. A.5)
+//   a12    Link/TGBLinkPredictor                  models/predictors.py:16-19,31-34
+//   a15    their gradients (autograd in the reference, train_link.py:279)
+#include "gemm.cuh"
+
+using namespace gemm;
+
+// X0[N,D] = [mem[n_id] | xfeat[n_id]] Wenc^T + benc       (gather fused; n_id int64 global ids)
+// If z0 != nullptr the operand is the already-materialised dense [N, D+Fn] matrix instead.
+extern "C" int ctan_enc_fwd(const float* mem, int D, const float* xfeat, int Fn, const int64_t* n_id,
+                            const float* z0, int N, const int* N_dev, const float* Wenc, const float* benc,
+                            float* X0, cudaStream_t stream) {
+    const int K = D + Fn;
+    BWeight B{Wenc, K};
+    EpiStore epi{X0, D, benc, nullptr, nullptr, 0};
+    if (z0) {
+        ARowMajor A{z0, K};
+        return launch(A, B, epi, N, N_dev, D, K, nullptr, 1, stream);
+    }
+    AGather2 A{mem, D, n_id, D, xfeat, Fn, n_id, nullptr};
+    return launch(A, B, epi, N, N_dev, D, K, nullptr, 1, stream);
+}
+
+// EP[E,D] = [msg[row(e)] | cos(tw*rel[e]+tb)] We^T        (row(e) = eidx ? eidx[e] : e)
+extern "C" int ctan_eproj_fwd(const float* msg, int Fe, const int64_t* eidx, const float* rel, const float* tw,
+                              const float* tb, int T, const float* We, int E, const int* E_dev, int D, float* EP,
+                              cudaStream_t stream) {
+    AEdgeAttr A{msg, Fe, eidx, Fe, rel, tw, tb};
+    BWeight B{We, Fe + T};
+    EpiStore epi{EP, D, nullptr, nullptr, nullptr, 0};
+    return launch(A, B, epi, E, E_dev, D, Fe + T, nullptr, 1, stream);
+}
+
+// QKVA[N,4D] = X [Wq;Wk;Wv;A]^T + [bq;bk;bv;b]
+extern "C" int ctan_qkva_fwd(const float* X, int N, const int* N_dev, int D, const float* Wq, const float* Wk,
+                             const float* Wv, const float* A_, const float* bq, const float* bk, const float* bv,
+                             const float* b, float* QKVA, cudaStream_t stream) {
+    ARowMajor A{X, D};
+    BWeightSeg4 B{{Wq, Wk, Wv, A_}, D, D};
+    EpiStoreSeg4 epi{QKVA, 4 * D, {bq, bk, bv, b}, D};
+    return launch(A, B, epi, N, N_dev, 4 * D, D, nullptr, 1, stream);
+}
+
+// ---------------------------------------------------------------------------------------- readout
+// H[P,Hd] = z[row(src)] Wsrc^T + z[row(dst)] Wdst^T + bsrc + bdst   (pre-activation, saved for backward)
+// OUT[P,O] = relu(H) Wfin^T + bfin                                   row(g) = map ? map[g] : g
+__global__ void head_fwd_kernel(const float* __restrict__ H, int P_host, const int* __restrict__ P_dev, int Hd, int O,
+                                const float* __restrict__ Wfin, const float* __restrict__ bfin,
+                                float* __restrict__ OUT) {
+    const int P = P_dev ? *P_dev : P_host;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int p = warp; p < P; p += nw) {
+        for (int o = 0; o < O; ++o) {
+            float s = 0.f;
+            for (int h = lane; h < Hd; h += 32) s = fmaf(fmaxf(H[(size_t)p * Hd + h], 0.f), __ldg(Wfin + (size_t)o * Hd + h), s);
+            s = warp_sum(s);
+            if (lane == 0) OUT[(size_t)p * O + o] = s + __ldg(bfin + o);
+        }
+    }
+}
+
+extern "C" int ctan_readout_fwd(const float* Z, int D, const int64_t* src, const int64_t* dst, const int64_t* map,
+                                int P, const int* P_dev, int Hd, int O, const float* Wsrc, const float* bsrc,
+                                const float* Wdst, const float* bdst, const float* Wfin, const float* bfin, float* H,
+                                float* OUT, cudaStream_t stream) {
+    if (P <= 0) return 0;
+    const int K1 = Wsrc ? D : 0;          // Wsrc == nullptr: SequencePredictor (destination row only)
+    AGather2 A{Z, D, src, K1, Z, D, dst, map};
+    BWeightCat2 B{Wsrc, D, K1, Wdst, D};
+    EpiStore epi{H, Hd, bsrc, bdst, nullptr, 0};
+    int rc = launch(A, B, epi, P, P_dev, Hd, K1 + D, nullptr, 1, stream);
+    if (rc) return rc;
+    head_fwd_kernel<<<ctan_grid((long long)P * 32, 256), 256, 0, stream>>>(H, P, P_dev, Hd, O, Wfin, bfin, OUT);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+// dHid[p,h] = (H>0) * sum_o dOUT[p,o] Wfin[o,h]
+__global__ void head_bwd_kernel(const float* __restrict__ dOUT, const float* __restrict__ H, int P_host,
+                                const int* __restrict__ P_dev, int Hd, int O, const float* __restrict__ Wfin,
+                                float* __restrict__ dHid) {
+    const int P = P_dev ? *P_dev : P_host;
+    const long long n = (long long)P * Hd;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(i / Hd), h = (int)(i % Hd);
+        float s = 0.f;
+        if (H[i] > 0.f)
+            for (int o = 0; o < O; ++o) s = fmaf(dOUT[(size_t)p * O + o], __ldg(Wfin + (size_t)o * Hd + h), s);
+        dHid[i] = s;
+    }
+}
+
+struct EpiAtomicColSeg2 {          // columns split at K1: [C0 | C1] (each row stride D); rowsum added to rs0 and rs1
+    static constexpr bool HAS_ROWSUM = true;
+    float* C0; float* C1; int K1; int D; float* rs0; float* rs1;
+    __device__ __forceinline__ void operator()(int m, int n, float v) const {
+        if (n < K1) atomicAdd(C0 + (size_t)m * D + n, v); else atomicAdd(C1 + (size_t)m * D + (n - K1), v);
+    }
+    __device__ __forceinline__ void rowsum(int m, float v) const {
+        if (rs0) atomicAdd(rs0 + m, v);
+        if (rs1) atomicAdd(rs1 + m, v);
+    }
+};
+
+// Gradients of the readout.  All outputs are ACCUMULATED (+=): zero them first.
+//   dZ[N,D] += scatter(dHid Wsrc -> row(src)) + scatter(dHid Wdst -> row(dst))
+//   dWsrc,dWdst [Hd,D], dbsrc,dbdst [Hd], dWfin [O,Hd], dbfin [O];  dHid [P,Hd] is scratch.
+extern "C" int ctan_readout_bwd(const float* dOUT, const float* H, const float* Z, int D, const int64_t* src,
+                                const int64_t* dst, const int64_t* map, int P, const int* P_dev, int Hd, int O,
+                                const float* Wsrc, const float* Wdst, const float* Wfin, float* dHid, float* dZ,
+                                float* dWsrc, float* dbsrc, float* dWdst, float* dbdst, float* dWfin, float* dbfin,
+                                cudaStream_t stream) {
+    if (P <= 0) return 0;
+    head_bwd_kernel<<<ctan_grid((long long)P * Hd, 256), 256, 0, stream>>>(dOUT, H, P, P_dev, Hd, O, Wfin, dHid);
+    CTAN_CHECK_LAUNCH();
+    int rc;
+    {   // dWfin[O,Hd] += dOUT^T relu(H);  dbfin += colsum(dOUT)
+        AColMajor A{dOUT, O};
+        BRelu B{H, Hd};
+        EpiAtomic epi{dWfin, Hd, dbfin};
+        rc = launch(A, B, epi, O, nullptr, Hd, P, P_dev, pick_splits(O, Hd, P), stream);
+        if (rc) return rc;
+    }
+    {   // [dWsrc | dWdst] += dHid^T [z[src] | z[dst]];  dbsrc,dbdst += colsum(dHid)
+        const int K1 = Wsrc ? D : 0;
+        AColMajor A{dHid, Hd};
+        BGather2 B{Z, D, src, K1, Z, D, dst, map};
+        EpiAtomicColSeg2 epi{dWsrc, dWdst, K1, D, dbsrc, dbdst};
+        rc = launch(A, B, epi, Hd, nullptr, K1 + D, P, P_dev, pick_splits(Hd, K1 + D, P), stream);
+        if (rc) return rc;
+    }
+    {   // dZ[row(src)] += dHid Wsrc ; dZ[row(dst)] += dHid Wdst
+        ARowMajor A{dHid, Hd};
+        if (Wsrc) {
+            BRowMajor B1{Wsrc, D};
+            EpiScatterAtomic e1{dZ, D, src, map};
+            rc = launch(A, B1, e1, P, P_dev, D, Hd, nullptr, 1, stream);
+            if (rc) return rc;
+        }
+        BRowMajor B2{Wdst, D};
+        EpiScatterAtomic e2{dZ, D, dst, map};
+        rc = launch(A, B2, e2, P, P_dev, D, Hd, nullptr, 1, stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------- embed backward
+// One anti-symmetric iteration, given DQKVA[N,4D] (from ctan_edge_bwd) and G = dL/dx_out:
+//   dXin[N,D] = G + DQKVA [Wq;Wk;Wv;A]
+//   dWq,dWk,dWv,dA [D,D] += DQKVA_seg^T X ;  dbq,dbk,dbv,db [D] += colsum(DQKVA_seg)     (accumulated)
+extern "C" int ctan_qkva_bwd(const float* DQKVA, const float* X, const float* G, int N, const int* N_dev, int D,
+                             const float* Wq, const float* Wk, const float* Wv, const float* A_, float* dXin,
+                             float* dWq, float* dWk, float* dWv, float* dA, float* dbq, float* dbk, float* dbv,
+                             float* db, cudaStream_t stream) {
+    if (N <= 0) return 0;
+    int rc;
+    {
+        ARowMajor A{DQKVA, 4 * D};
+        BRowSeg4 B{{Wq, Wk, Wv, A_}, D, D};
+        EpiStore epi{dXin, D, nullptr, nullptr, G, D};
+        rc = launch(A, B, epi, N, N_dev, D, 4 * D, nullptr, 1, stream);
+        if (rc) return rc;
+    }
+    {
+        AColMajor A{DQKVA, 4 * D};
+        BRowMajor B{X, D};
+        EpiAtomicSeg4 epi{{dWq, dWk, dWv, dA}, {dbq, dbk, dbv, db}, D, D};
+        rc = launch(A, B, epi, 4 * D, nullptr, D, N, N_dev, pick_splits(4 * D, D, N), stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// dWenc[D, D+Fn] += dX0^T Z0 ; dbenc[D] += colsum(dX0)          (Z0 = materialised [mem|x] rows)
+extern "C" int ctan_enc_bwd(const float* dX0, const float* Z0, int N, const int* N_dev, int D, int Fn, float* dWenc,
+                            float* dbenc, cudaStream_t stream) {
+    if (N <= 0) return 0;
+    AColMajor A{dX0, D};
+    BRowMajor B{Z0, D + Fn};
+    EpiAtomic epi{dWenc, D + Fn, dbenc};
+    return launch(A, B, epi, D, nullptr, D + Fn, N, N_dev, pick_splits(D, D + Fn, N), stream);
+}
+
+// dWe[D, Fe+T] += dEP^T [msg | cos(.)] ;  dTenc[E,T] = dEP We[:,Fe:]   (scratch for ctan_tenc_bwd)
+extern "C" int ctan_eproj_bwd(const float* dEP, const float* msg, int Fe, const int64_t* eidx, const float* rel,
+                              const float* tw, const float* tb, int T, const float* We, int E, const int* E_dev, int D,
+                              float* dWe, float* dTenc, cudaStream_t stream) {
+    if (E <= 0) return 0;
+    int rc;
+    {
+        AColMajor A{dEP, D};
+        BEdgeAttr B{msg, Fe, eidx, Fe, rel, tw, tb};
+        EpiAtomic epi{dWe, Fe + T, nullptr};
+        rc = launch(A, B, epi, D, nullptr, Fe + T, E, E_dev, pick_splits(D, Fe + T, E), stream);
+        if (rc) return rc;
+    }
+    if (T > 0 && dTenc) {
+        ARowMajor A{dEP, D};
+        BRowMajor B{We + Fe, Fe + T};
+        EpiStore epi{dTenc, T, nullptr, nullptr, nullptr, 0};
+        rc = launch(A, B, epi, E, E_dev, T, D, nullptr, 1, stream);
+        if (rc) return rc;
+    }
+    return 0;
+}

@@ -1,0 +1,373 @@
+// Edge-message path and anti-symmetric update (forward + backward), plus the small element-wise
+// kernels around them.
+//
+// Replaces:
+//   CTANEmbedding.forward delta-t normalisation            models/gnn_layers.py:94-95
+//   PyG TransformerConv.message + utils.softmax + scatter   (call site models/gnn_layers.py:82)
+//   PyG AntiSymmetricConv.forward update                    (call site models/gnn_layers.py:86,98)
+//   final_act                                               models/ctdg_models.py:457-458
+//
+// The edge list arrives CSR-sorted by destination (the loader emits it that way), so one warp owns
+// one destination row: attention logits, the segmented softmax and the weighted aggregation are
+// warp-shuffle reductions over the row's <= S edges -- no atomics, no [E,D] intermediates in HBM --
+// and the tanh update x <- x + eps*tanh(x A^T + phi + b) is applied in the same pass.
+#include "common.cuh"
+
+// rel[e] = ((|last_update[n_id[src_local[e]]] - t_e| - mean) / std) as fp32   (gnn_layers.py:94-95)
+// n_id == nullptr: last_update is already the gathered per-local-node array.
+__global__ void edge_rel_kernel(const int64_t* __restrict__ last_update, const int64_t* __restrict__ n_id,
+                                const int64_t* __restrict__ edge_src, const int64_t* __restrict__ t_tab,
+                                const int64_t* __restrict__ eidx, int E_host, const int* __restrict__ E_dev,
+                                float mean, float stdv, float* __restrict__ rel) {
+    const int E = E_dev ? *E_dev : E_host;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+        const int64_t lu = last_update[n_id ? n_id[edge_src[e]] : edge_src[e]];
+        const int64_t te = t_tab[eidx ? eidx[e] : (int64_t)e];
+        long long d = lu - te;
+        if (d < 0) d = -d;
+        rel[e] = __fdiv_rn(__ll2float_rn(d) - mean, stdv);
+    }
+}
+
+extern "C" int ctan_edge_rel(const int64_t* last_update, const int64_t* n_id, const int64_t* edge_src,
+                             const int64_t* t_tab, const int64_t* eidx, int E, const int* E_dev, float mean,
+                             float stdv, float* rel, cudaStream_t stream) {
+    if (E <= 0) return 0;
+    edge_rel_kernel<<<ctan_grid(E, 256), 256, 0, stream>>>(last_update, n_id, edge_src, t_tab, eidx, E, E_dev, mean,
+                                                          stdv, rel);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+// z0[r] = [ mem[n_id[r]] | xfeat[n_id[r]] ]   (memory_layers.py:155-156, ctdg_models.py:444-453)
+__global__ void gather_rows2_kernel(const float* __restrict__ t1, int K1, const float* __restrict__ t2, int K2,
+                                    const int64_t* __restrict__ idx, int N_host, const int* __restrict__ N_dev,
+                                    float* __restrict__ out) {
+    const int N = N_dev ? *N_dev : N_host;
+    const int ld = K1 + K2;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int r = warp; r < N; r += nw) {
+        const int64_t g = idx[r];
+        for (int d = lane; d < K1; d += 32) out[(size_t)r * ld + d] = __ldg(t1 + (size_t)g * K1 + d);
+        for (int d = lane; d < K2; d += 32) out[(size_t)r * ld + K1 + d] = __ldg(t2 + (size_t)g * K2 + d);
+    }
+}
+
+extern "C" int ctan_gather_rows2(const float* t1, int K1, const float* t2, int K2, const int64_t* idx, int N,
+                                 const int* N_dev, float* out, cudaStream_t stream) {
+    if (N <= 0) return 0;
+    gather_rows2_kernel<<<ctan_grid((long long)N * 32, 256), 256, 0, stream>>>(t1, K1, t2, K2, idx, N, N_dev, out);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+// A = W - W^T - gamma*I   (AntiSymmetricConv.forward, first line)
+__global__ void antisym_prep_kernel(const float* __restrict__ W, float gamma, int D, float* __restrict__ A) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D * D; i += gridDim.x * blockDim.x) {
+        const int a = i / D, b = i % D;
+        A[i] = W[i] - W[b * D + a] - (a == b ? gamma : 0.f);
+    }
+}
+extern "C" int ctan_antisym_prep(const float* W, float gamma, int D, float* A, cudaStream_t stream) {
+    antisym_prep_kernel<<<ctan_grid(D * D, 256), 256, 0, stream>>>(W, gamma, D, A);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+// dW = dA - dA^T
+__global__ void antisym_bwd_kernel(const float* __restrict__ dA, int D, float* __restrict__ dW) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D * D; i += gridDim.x * blockDim.x) {
+        const int a = i / D, b = i % D;
+        dW[i] = dA[i] - dA[b * D + a];
+    }
+}
+extern "C" int ctan_antisym_bwd(const float* dA, int D, float* dW, cudaStream_t stream) {
+    antisym_bwd_kernel<<<ctan_grid(D * D, 256), 256, 0, stream>>>(dA, D, dW);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K4+K5 forward: one warp per destination node.
+//   QKVA [N,4D] = [q | k | v | x A^T + b]   (produced by the projection contraction)
+//   EP   [E,D]  = lin_edge(edge_attr)        (iteration-invariant, computed once)
+//   s_e = q_i.(k_j + EP_e)/sqrt(D);  alpha = softmax_i(s) with +1e-16;  phi_i = sum alpha (v_j + EP_e)
+//   x_out = x_in + eps * tanh(QKVA[:,3D:] + phi)
+// Saves ALPHA [E] (normalised attention) and TH [N,D] (tanh values) for the backward when non-null.
+// ------------------------------------------------------------------------------------------
+template <int MAXV>
+__global__ void edge_fwd_kernel(const float* __restrict__ QKVA, const float* __restrict__ EP,
+                                const int32_t* __restrict__ rowptr, const int64_t* __restrict__ esrc, int N_host,
+                                const int* __restrict__ N_dev, int D, const float* __restrict__ Xin, float eps,
+                                float* __restrict__ Xout, float* __restrict__ TH, float* __restrict__ ALPHA,
+                                float* __restrict__ Zout, float inv_sqrt_d) {
+    const int N = N_dev ? *N_dev : N_host;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const int ld = 4 * D;
+    for (int i = warp; i < N; i += nw) {
+        const int r0 = rowptr[i], r1 = rowptr[i + 1];
+        float phi[MAXV];
+#pragma unroll
+        for (int v = 0; v < MAXV; ++v) phi[v] = 0.f;
+        if (r1 > r0) {
+            float q[MAXV];
+#pragma unroll
+            for (int v = 0; v < MAXV; ++v) {
+                const int d = lane + 32 * v;
+                q[v] = d < D ? QKVA[(size_t)i * ld + d] : 0.f;
+            }
+            float mx = -INFINITY, den = 0.f;
+            for (int c0 = r0; c0 < r1; c0 += 32) {
+                const int cnt = min(32, r1 - c0);
+                float s_keep = -INFINITY;
+                for (int c = 0; c < cnt; ++c) {
+                    const int e = c0 + c;
+                    const int64_t j = esrc[e];
+                    float part = 0.f;
+#pragma unroll
+                    for (int v = 0; v < MAXV; ++v) {
+                        const int d = lane + 32 * v;
+                        if (d < D) part = fmaf(q[v], QKVA[(size_t)j * ld + D + d] + EP[(size_t)e * D + d], part);
+                    }
+                    const float s = warp_sum(part) * inv_sqrt_d;
+                    if (lane == c) s_keep = s;
+                }
+                if (ALPHA && lane < cnt) ALPHA[c0 + lane] = s_keep;       // raw score, normalised below
+                const float nmx = fmaxf(mx, warp_max(s_keep));
+                const float scale = (mx == -INFINITY) ? 0.f : expf(mx - nmx);
+                den *= scale;
+#pragma unroll
+                for (int v = 0; v < MAXV; ++v) phi[v] *= scale;
+                mx = nmx;
+                const float p_keep = lane < cnt ? expf(s_keep - mx) : 0.f;
+                for (int c = 0; c < cnt; ++c) {
+                    const int e = c0 + c;
+                    const int64_t j = esrc[e];
+                    const float p = __shfl_sync(0xffffffffu, p_keep, c);
+                    den += p;
+#pragma unroll
+                    for (int v = 0; v < MAXV; ++v) {
+                        const int d = lane + 32 * v;
+                        if (d < D) phi[v] = fmaf(p, QKVA[(size_t)j * ld + 2 * D + d] + EP[(size_t)e * D + d], phi[v]);
+                    }
+                }
+            }
+            const float inv = 1.f / (den + 1e-16f);
+#pragma unroll
+            for (int v = 0; v < MAXV; ++v) phi[v] *= inv;
+            if (ALPHA) {
+                for (int e = r0 + lane; e < r1; e += 32) ALPHA[e] = expf(ALPHA[e] - mx) * inv;   // own write, own read
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < MAXV; ++v) {
+            const int d = lane + 32 * v;
+            if (d < D) {
+                const float h = QKVA[(size_t)i * ld + 3 * D + d] + phi[v];
+                const float th = tanhf(h);
+                if (TH) TH[(size_t)i * D + d] = th;
+                const float xn = fmaf(eps, th, Xin[(size_t)i * D + d]);
+                Xout[(size_t)i * D + d] = xn;
+                if (Zout) Zout[(size_t)i * D + d] = tanhf(xn);
+            }
+        }
+    }
+}
+
+extern "C" int ctan_edge_fwd(const float* QKVA, const float* EP, const int32_t* rowptr, const int64_t* esrc, int N,
+                             const int* N_dev, int D, const float* Xin, float eps, float* Xout, float* TH,
+                             float* ALPHA, float* Zout, cudaStream_t stream) {
+    if (N <= 0) return 0;
+    if (D > 512) return CTAN_ERR_UNSUPPORTED;
+    const int grid = ctan_grid((long long)N * 32, 256);
+    const float isd = 1.0f / sqrtf((float)D);
+#define LAUNCH(V) edge_fwd_kernel<V><<<grid, 256, 0, stream>>>(QKVA, EP, rowptr, esrc, N, N_dev, D, Xin, eps, Xout, \
+                                                                TH, ALPHA, Zout, isd)
+    if (D <= 32) LAUNCH(1); else if (D <= 64) LAUNCH(2); else if (D <= 128) LAUNCH(4);
+    else if (D <= 256) LAUNCH(8); else LAUNCH(16);
+#undef LAUNCH
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K4+K5 backward: one warp per destination node.  G = dL/dx_out [N,D].
+//   dh = eps*(1-th^2)*G          -> DQKVA[:,3D:4D]   (gradient of x A^T + b, and of phi)
+//   dalpha_e = dh.(v_j+EP_e); ds_e = alpha_e (dalpha_e - sum alpha dalpha)
+//   dq_i = sum ds_e (k_j+EP_e)/sqrt(D)               -> DQKVA[:,0:D]
+//   dk_j += ds_e q_i/sqrt(D); dv_j += alpha_e dh      -> atomics into DQKVA[:,D:3D] (source rows are not sorted)
+//   dEP_e (+)= alpha_e dh + ds_e q_i/sqrt(D)          (edge owned by this warp: no atomics)
+// DQKVA must be zero on entry.  DS [E] is scratch.
+// ------------------------------------------------------------------------------------------
+template <int MAXV>
+__global__ void edge_bwd_kernel(const float* __restrict__ QKVA, const float* __restrict__ EP,
+                                const int32_t* __restrict__ rowptr, const int64_t* __restrict__ esrc, int N_host,
+                                const int* __restrict__ N_dev, int D, const float* __restrict__ G,
+                                const float* __restrict__ TH, const float* __restrict__ ALPHA, float eps,
+                                float* __restrict__ DQKVA, float* __restrict__ DEP, int accumulate_dep,
+                                float* __restrict__ DS, float inv_sqrt_d) {
+    const int N = N_dev ? *N_dev : N_host;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const int ld = 4 * D;
+    for (int i = warp; i < N; i += nw) {
+        float dh[MAXV];
+#pragma unroll
+        for (int v = 0; v < MAXV; ++v) {
+            const int d = lane + 32 * v;
+            dh[v] = 0.f;
+            if (d < D) {
+                const float th = TH[(size_t)i * D + d];
+                dh[v] = eps * (1.f - th * th) * G[(size_t)i * D + d];
+                DQKVA[(size_t)i * ld + 3 * D + d] = dh[v];
+            }
+        }
+        const int r0 = rowptr[i], r1 = rowptr[i + 1];
+        if (r1 <= r0) continue;
+        float q[MAXV], dq[MAXV];
+#pragma unroll
+        for (int v = 0; v < MAXV; ++v) {
+            const int d = lane + 32 * v;
+            q[v] = d < D ? QKVA[(size_t)i * ld + d] : 0.f;
+            dq[v] = 0.f;
+        }
+        float tmp = 0.f;                                  // sum_e alpha_e * dalpha_e
+        for (int c0 = r0; c0 < r1; c0 += 32) {
+            const int cnt = min(32, r1 - c0);
+            float keep = 0.f;
+            for (int c = 0; c < cnt; ++c) {
+                const int e = c0 + c;
+                const int64_t j = esrc[e];
+                float part = 0.f;
+#pragma unroll
+                for (int v = 0; v < MAXV; ++v) {
+                    const int d = lane + 32 * v;
+                    if (d < D) part = fmaf(dh[v], QKVA[(size_t)j * ld + 2 * D + d] + EP[(size_t)e * D + d], part);
+                }
+                const float da = warp_sum(part);
+                if (lane == c) keep = da;
+            }
+            if (lane < cnt) {
+                DS[c0 + lane] = keep;
+                tmp = fmaf(ALPHA[c0 + lane], keep, tmp);
+            }
+        }
+        tmp = warp_sum(tmp);
+        for (int c0 = r0; c0 < r1; c0 += 32) {
+            const int cnt = min(32, r1 - c0);
+            float a_keep = 0.f, ds_keep = 0.f;
+            if (lane < cnt) {
+                a_keep = ALPHA[c0 + lane];
+                ds_keep = a_keep * (DS[c0 + lane] - tmp);  // own write above, own read here
+            }
+            for (int c = 0; c < cnt; ++c) {
+                const int e = c0 + c;
+                const int64_t j = esrc[e];
+                const float a = __shfl_sync(0xffffffffu, a_keep, c);
+                const float kq = __shfl_sync(0xffffffffu, ds_keep, c) * inv_sqrt_d;
+#pragma unroll
+                for (int v = 0; v < MAXV; ++v) {
+                    const int d = lane + 32 * v;
+                    if (d < D) {
+                        const float ep = EP[(size_t)e * D + d];
+                        dq[v] = fmaf(kq, QKVA[(size_t)j * ld + D + d] + ep, dq[v]);
+                        const float gk = kq * q[v];
+                        const float gv = a * dh[v];
+                        atomicAdd(DQKVA + (size_t)j * ld + D + d, gk);
+                        atomicAdd(DQKVA + (size_t)j * ld + 2 * D + d, gv);
+                        const float dep = gk + gv;
+                        float* o = DEP + (size_t)e * D + d;
+                        *o = accumulate_dep ? (*o + dep) : dep;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < MAXV; ++v) {
+            const int d = lane + 32 * v;
+            if (d < D) DQKVA[(size_t)i * ld + d] = dq[v];
+        }
+    }
+}
+
+extern "C" int ctan_edge_bwd(const float* QKVA, const float* EP, const int32_t* rowptr, const int64_t* esrc, int N,
+                             const int* N_dev, int D, const float* G, const float* TH, const float* ALPHA, float eps,
+                             float* DQKVA, float* DEP, int accumulate_dep, float* DS, cudaStream_t stream) {
+    if (N <= 0) return 0;
+    if (D > 512) return CTAN_ERR_UNSUPPORTED;
+    const int grid = ctan_grid((long long)N * 32, 256);
+    const float isd = 1.0f / sqrtf((float)D);
+#define LAUNCH(V) edge_bwd_kernel<V><<<grid, 256, 0, stream>>>(QKVA, EP, rowptr, esrc, N, N_dev, D, G, TH, ALPHA, eps, \
+                                                                DQKVA, DEP, accumulate_dep, DS, isd)
+    if (D <= 32) LAUNCH(1); else if (D <= 64) LAUNCH(2); else if (D <= 128) LAUNCH(4);
+    else if (D <= 256) LAUNCH(8); else LAUNCH(16);
+#undef LAUNCH
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+// dX = dZ * (1 - Z^2)     (final_act = tanh, ctdg_models.py:457-458)
+__global__ void tanh_bwd_kernel(const float* __restrict__ dZ, const float* __restrict__ Z, long long n_host,
+                                const int* __restrict__ rows_dev, int D, float* __restrict__ dX) {
+    const long long n = rows_dev ? (long long)(*rows_dev) * D : n_host;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float z = Z[i];
+        dX[i] = dZ[i] * (1.f - z * z);
+    }
+}
+extern "C" int ctan_tanh_bwd(const float* dZ, const float* Z, int N, const int* N_dev, int D, float* dX,
+                             cudaStream_t stream) {
+    if (N <= 0) return 0;
+    tanh_bwd_kernel<<<ctan_grid((long long)N * D, 256), 256, 0, stream>>>(dZ, Z, (long long)N * D, N_dev, D, dX);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+// Time-encoder parameter gradients from dTenc[E,T] = dEP . We[:,Fe:]:
+//   d/dw_tau = sum_e -sin(w_tau rel_e + b_tau) rel_e dTenc[e,tau];   d/db_tau = sum_e -sin(.) dTenc[e,tau]
+__global__ void tenc_bwd_kernel(const float* __restrict__ dTenc, const float* __restrict__ rel,
+                                const float* __restrict__ tw, const float* __restrict__ tb, int E_host,
+                                const int* __restrict__ E_dev, int T, float* __restrict__ dtw, float* __restrict__ dtb) {
+    const int E = E_dev ? *E_dev : E_host;
+    const int e0 = blockIdx.x * 128, e1 = min(E, e0 + 128);
+    if (e0 >= E) return;
+    for (int tau = threadIdx.x; tau < T; tau += blockDim.x) {
+        const float w = tw[tau], b = tb[tau];
+        float sw = 0.f, sb = 0.f;
+        for (int e = e0; e < e1; ++e) {
+            const float r = rel[e];
+            const float g = -sinf(fmaf(r, w, b)) * dTenc[(size_t)e * T + tau];
+            sw = fmaf(g, r, sw);
+            sb += g;
+        }
+        atomicAdd(dtw + tau, sw);
+        atomicAdd(dtb + tau, sb);
+    }
+}
+extern "C" int ctan_tenc_bwd(const float* dTenc, const float* rel, const float* tw, const float* tb, int E,
+                             const int* E_dev, int T, float* dtw, float* dtb, cudaStream_t stream) {
+    if (E <= 0 || T <= 0) return 0;
+    const int threads = T >= 256 ? 256 : ((T + 31) / 32) * 32;
+    tenc_bwd_kernel<<<ctan_div_up(E, 128), threads, 0, stream>>>(dTenc, rel, tw, tb, E, E_dev, T, dtw, dtb);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+// rowptr from a destination-sorted edge list that did not come from our loader.  flag[0] |= 1 if unsorted.
+__global__ void csr_from_sorted_kernel(const int64_t* __restrict__ edst, int E, int N, int32_t* __restrict__ rowptr,
+                                       int* __restrict__ flag) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e <= E; e += gridDim.x * blockDim.x) {
+        const long long prev = e > 0 ? edst[e - 1] : -1;
+        const long long cur = e < E ? edst[e] : (long long)N;
+        if (cur < prev || cur > N || prev >= N) { *flag = 1; continue; }
+        for (long long r = prev + 1; r <= cur; ++r) rowptr[r] = e;
+    }
+}
+extern "C" int ctan_csr_from_sorted(const int64_t* edst, int E, int N, int32_t* rowptr, int* flag,
+                                    cudaStream_t stream) {
+    if (N < 0 || E < 0) return CTAN_ERR_BAD_ARG;
+    csr_from_sorted_kernel<<<ctan_grid(E + 1, 256), 256, 0, stream>>>(edst, E, N, rowptr, flag);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,134 @@
+"""Parity of the CUDA CTAN modules with the oracle (restated reference) on the same seeded inputs:
+embeddings / logits / loss / parameter gradients within 1e-4 relative (fp32 path, BASELINE.json
+north_star), memory write-back and `last_update` exact.  Calls go through the C-ABI library."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4     # north_star: 1e-4 relative error on the fp32 path
+
+
+def _rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def _make_pair(num_nodes, tgb, K, D, T, Fe, Fn, H, final_act, eps=0.5, gamma=0.1, out=1):
+    from ctan_b200.models import CTAN, CTAN_tgb
+    from oracle import ctan_oracle as O
+    kw = dict(num_nodes=num_nodes, edge_dim=Fe, memory_dim=D, time_dim=T, node_dim=Fn, num_iters=K, epsilon=eps,
+              gamma=gamma, readout_hidden=H, readout_out=out, mean_delta_t=np.float64(1234.5),
+              std_delta_t=np.float64(4567.8), init_time=torch.tensor(0), final_act=final_act)
+    torch.manual_seed(0)
+    om = O.OracleCTAN(**kw, tgb=tgb)
+    torch.manual_seed(0)
+    mm = (CTAN_tgb if tgb else CTAN)(**kw)
+    sd_o, sd_m = om.state_dict(), mm.state_dict()
+    assert set(sd_o) == set(sd_m)
+    for k in sd_o:                                    # same-seed initialisation is identical (App. A.7)
+        if not k.endswith("_assoc"):
+            assert torch.equal(sd_o[k], sd_m[k]), k
+    return om, mm.to("cuda:0")
+
+
+def _run_steps(st, tgb, K, D, T, H, final_act, S, n_steps, B=200, train=True, lr=1e-3, eps=0.5):
+    from ctan_b200.models import LastNeighborLoader
+    from oracle import ctan_oracle as O
+    dev = torch.device("cuda:0")
+    Fe = st["msg"].size(1)
+    om, mm = _make_pair(st["num_nodes"], tgb, K, D, T, Fe, 1, H, final_act, eps=eps)
+    lo_ref = O.TorchNeighborLoader(st["num_nodes"], S)
+    lo_mine = LastNeighborLoader(st["num_nodes"], S, device=dev)
+    h_ref = torch.zeros(st["num_nodes"], dtype=torch.long)
+    h_mine = torch.zeros(st["num_nodes"], dtype=torch.long, device=dev)
+    opt_ref = torch.optim.Adam(om.parameters(), lr=lr)
+    opt_mine = torch.optim.Adam(mm.parameters(), lr=lr)
+    crit = torch.nn.BCEWithLogitsLoss()
+    g = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in st.items()}
+    worst = 0.0
+    for it in range(n_steps):
+        lo, hi = it * B, (it + 1) * B
+        ng = st["neg"][lo:hi]
+        if train:
+            l_ref, p_ref, n_ref = O.train_step_ref(om, lo_ref, h_ref, opt_ref, st, lo, hi, ng)
+        else:
+            p_ref, n_ref = O.infer_step_ref(om, lo_ref, h_ref, st, lo, hi, ng)
+        # ---- same loop body (train_link.py:237-282) on the CUDA modules
+        s, d, t, msg, ngd = g["src"][lo:hi], g["dst"][lo:hi], g["t"][lo:hi], g["msg"][lo:hi], ng.to(dev)
+        if train:
+            opt_mine.zero_grad()
+        n_id = torch.cat([s, d, ngd]).unique()
+        for _ in range(mm.num_gnn_layers):
+            n_id, ei, eid = lo_mine(n_id)
+        h_mine[n_id] = torch.arange(n_id.size(0), device=dev)
+        if tgb:
+            b = O.Batch(src=torch.cat([s, s]), dst=torch.cat([d, ngd]), n_neg=B, x=g["x"])
+        else:
+            b = O.Batch(src=s, dst=d, neg_dst=ngd, x=g["x"])
+        with torch.set_grad_enabled(train):
+            po, no, se, de = mm(b, n_id, g["msg"][eid], g["t"][eid], ei, h_mine)
+            loss = crit(po, torch.ones_like(po)) + crit(no, torch.zeros_like(no))
+        mm.update(s, d, t, msg, se, de)
+        lo_mine.insert(s, d)
+        if train:
+            loss.backward()
+            if it in (0, n_steps - 1):               # gradients of every parameter that receives one
+                go = {k: p.grad for k, p in om.named_parameters() if p.grad is not None}
+                gm = {k: p.grad for k, p in mm.named_parameters() if p.grad is not None}
+                assert set(go) == set(gm), set(go) ^ set(gm)
+                for k in go:
+                    assert gm[k].shape == go[k].shape, k
+                    err = _rel_err(gm[k], go[k])
+                    assert err < 5e-4, (k, err, it)
+            opt_mine.step()
+            mm.detach_memory()
+            assert abs(float(loss) - float(l_ref)) <= RTOL * abs(float(l_ref)) + 1e-6, (it, float(loss), float(l_ref))
+        worst = max(worst, _rel_err(po, p_ref), _rel_err(no, n_ref))
+        assert _rel_err(po, p_ref) < 5 * RTOL and _rel_err(no, n_ref) < 5 * RTOL, (it, worst)
+        assert torch.equal(mm.memory.last_update.cpu(), om.memory.last_update), it
+        assert _rel_err(mm.memory.memory, om.memory.memory) < 5 * RTOL, it
+        written_m = (mm.memory.memory.cpu().abs().sum(1) > 0)
+        written_o = (om.memory.memory.abs().sum(1) > 0)
+        assert torch.equal(written_m, written_o)
+    return worst
+
+
+@pytest.mark.parametrize("tgb,K,final_act", [(False, 1, None), (False, 3, "tanh"), (True, 2, None)])
+def test_training_steps_match_oracle(small_stream, tgb, K, final_act):
+    worst = _run_steps(small_stream, tgb, K, D=32, T=8, H=16, final_act=final_act, S=5, n_steps=8)
+    print("worst logit rel err", worst)
+
+
+def test_inference_steps_match_oracle(small_stream):
+    _run_steps(small_stream, True, 1, D=64, T=16, H=64, final_act="tanh", S=10, n_steps=8, train=False)
+
+
+def test_reference_config_dims(small_stream):
+    """C2 dims of SURVEY.md S8: D=128, T=16, F_e=172, H=64, S=5, K=1."""
+    _run_steps(small_stream, False, 1, D=128, T=16, H=64, final_act=None, S=5, n_steps=4, eps=0.1)
+
+
+def test_odd_dims_sequence_config():
+    """C1-like dims (D=53, T=1, F_e=F_n=2, S=5, K=5) exercise every unaligned tile edge."""
+    from ctan_b200 import synth
+    st = synth.make_stream("wiki", n_events=1200, seed=3, n_nodes_scale=0.02, msg_dim=2)
+    st["neg"] = synth.draw_negatives(st)[:, 0]
+    _run_steps(st, False, 5, D=53, T=1, H=26, final_act="tanh", S=5, n_steps=5, B=64)
+
+
+def test_state_dict_roundtrip_and_cpu_guard():
+    from ctan_b200.models import CTAN
+    from ctan_b200._lib import CtanLibraryError
+    m = CTAN(num_nodes=50, edge_dim=3, memory_dim=8, time_dim=2, node_dim=1)
+    sd = m.state_dict()
+    for k in ("memory.memory", "memory.last_update", "memory._assoc", "gnn.enc_x.weight", "gnn.aconv.W",
+              "gnn.aconv.bias", "gnn.aconv.eye", "gnn.aconv.phi.lin_key.weight", "gnn.aconv.phi.lin_edge.weight",
+              "gnn.aconv.phi.lin_skip.bias", "gnn.time_enc.lin.weight", "readout.lin_src.weight",
+              "readout.lin_final.bias"):
+        assert k in sd, k
+    m2 = CTAN(num_nodes=50, edge_dim=3, memory_dim=8, time_dim=2, node_dim=1)
+    m2.load_state_dict(sd)
+    with pytest.raises(CtanLibraryError):           # no silent CPU fallback
+        m.reset_memory()
