@@ -71,6 +71,14 @@ def lib():
 
 OPTIONAL_SIGNATURES = {}
 
+SIGNATURES.update({
+    # step.cu
+    "ctan_stage_batch": [P, P, P, P, I, I, P, I, P, P, P, P, P, P],
+    "ctan_bce_loss": [P, I, I, P, P, I, P],
+    "ctan_adam_step": [P, P, P, P, I, F, F, F, F, F, L, P],
+    "ctan_mrr": [P, P, I, I, P],
+})
+
 
 def _optional_signatures(dll):
     for name, args in OPTIONAL_SIGNATURES.items():

@@ -1,0 +1,154 @@
+// Glue kernels of the zero-host-sync step (engine.py): batch staging from the device-resident event
+// stream, BCE-with-logits loss + its gradient, Adam, one-vs-many ranking (MRR).
+//
+// Replaces host-side work of the reference's per-batch loops:
+//   batch slicing + cat(src,src)/cat(dst,neg) + seed cat           train_link.py:239-256
+//   criterion(pos,1) + criterion(neg,0) and its backward seed      train_link.py:269-270, 279
+//   torch.optim.Adam step                                          train_link.py:281 (kept semantics)
+//   TGB Evaluator MRR, numpy branch                                TGB/tgb/linkproppred/evaluate.py:109-120
+#include "common.cuh"
+
+// counters (int64 [8], device): [0] next batch start (event index), [1] current batch start,
+// [2] Adam step (1-based, of the current step), [3] number of steps taken so far.
+__global__ void stage_batch_kernel(const int64_t* __restrict__ src_all, const int64_t* __restrict__ dst_all,
+                                   const int64_t* __restrict__ t_all, const int64_t* __restrict__ neg_all,
+                                   int n_neg, int B, int64_t* __restrict__ counters, int use_cursor,
+                                   int64_t* __restrict__ b_src, int64_t* __restrict__ b_dst,
+                                   int64_t* __restrict__ b_t, int64_t* __restrict__ seeds,
+                                   int64_t* __restrict__ pair_src, int64_t* __restrict__ pair_dst) {
+    // single block; negatives are laid out [event][n_neg]
+    __shared__ int64_t s_off;
+    if (threadIdx.x == 0) {
+        const int64_t cur = counters[0];              // event index of this batch's first event
+        counters[0] = cur + B;
+        counters[1] = cur;
+        counters[2] += 1;
+        counters[3] += 1;
+        s_off = use_cursor ? cur : 0;                 // 0: the arrays ARE the batch (host-staged buffers)
+    }
+    __syncthreads();
+    const int64_t off = s_off;
+    const int P = B * (1 + n_neg);
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        const int64_t s = src_all[off + i], d = dst_all[off + i];
+        b_src[i] = s; b_dst[i] = d; b_t[i] = t_all[off + i];
+        seeds[i] = s; seeds[B + i] = d;
+        pair_src[i] = s; pair_dst[i] = d;
+    }
+    for (int i = threadIdx.x; i < B * n_neg; i += blockDim.x) {
+        const int64_t ng = neg_all[off * n_neg + i];
+        const int ev = i / n_neg;
+        seeds[2 * B + i] = ng;
+        // pair order: all positives first, then negatives grouped by event (CTAN_tgb: out[:-n_neg] / out[-n_neg:])
+        pair_src[B + i] = src_all[off + ev];
+        pair_dst[B + i] = ng;
+    }
+    (void)P;
+}
+
+extern "C" int ctan_stage_batch(const int64_t* src_all, const int64_t* dst_all, const int64_t* t_all,
+                                const int64_t* neg_all, int n_neg, int B, int64_t* counters, int use_cursor,
+                                int64_t* b_src, int64_t* b_dst, int64_t* b_t, int64_t* seeds, int64_t* pair_src,
+                                int64_t* pair_dst, cudaStream_t stream) {
+    if (B <= 0 || n_neg < 0) return CTAN_ERR_BAD_ARG;
+    stage_batch_kernel<<<1, 256, 0, stream>>>(src_all, dst_all, t_all, neg_all, n_neg, B, counters, use_cursor, b_src,
+                                              b_dst, b_t, seeds, pair_src, pair_dst);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+// loss = mean_p softplus(-pos_p) + mean_q softplus(neg_q)   (BCEWithLogitsLoss, mean reduction, twice)
+// dOUT = d loss / d logits.  loss is written to loss_hist[counters[3]-1] (or loss_hist[0] if no counters).
+__device__ __forceinline__ float softplus_stable(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+
+__global__ void bce_loss_kernel(const float* __restrict__ OUT, int n_pos, int n_negs, float* __restrict__ dOUT,
+                                float* __restrict__ loss_hist, int hist_cap, const int64_t* __restrict__ counters) {
+    __shared__ float red[32];
+    const int n = n_pos + n_negs;
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float x = OUT[i];
+        if (i < n_pos) {
+            acc += softplus_stable(-x) / (float)n_pos;
+            if (dOUT) dOUT[i] = -1.f / (1.f + expf(x)) / (float)n_pos;
+        } else {
+            acc += softplus_stable(x) / (float)n_negs;
+            if (dOUT) dOUT[i] = 1.f / (1.f + expf(-x)) / (float)n_negs;
+        }
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) {
+            long long slot = counters ? (long long)counters[3] - 1 : 0;
+            if (slot < 0) slot = 0;
+            loss_hist[slot % hist_cap] = v;
+        }
+    }
+}
+
+extern "C" int ctan_bce_loss(const float* OUT, int n_pos, int n_negs, float* dOUT, float* loss_hist, int hist_cap,
+                             const int64_t* counters, cudaStream_t stream) {
+    if (n_pos <= 0 || n_negs <= 0 || hist_cap <= 0) return CTAN_ERR_BAD_ARG;
+    bce_loss_kernel<<<1, 512, 0, stream>>>(OUT, n_pos, n_negs, dOUT, loss_hist, hist_cap, counters);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+// torch.optim.Adam (amsgrad=False, maximize=False) on a flat parameter vector.
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int n, float lr, float beta1, float beta2, float eps, float wd,
+                            int64_t step_host, const int64_t* __restrict__ counters) {
+    const int64_t step = counters ? counters[2] : step_host;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    const float step_size = (float)((double)lr / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float gi = g[i];
+        const float pi = p[i];
+        if (wd != 0.f) gi = fmaf(wd, pi, gi);
+        const float mi = m[i] + (gi - m[i]) * (1.f - beta1);            // exp_avg.lerp_(grad, 1-beta1)
+        const float vi = fmaf(1.f - beta2, gi * gi, v[i] * beta2);       // exp_avg_sq.mul_(b2).addcmul_(g,g,1-b2)
+        m[i] = mi; v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = pi - step_size * (mi / denom);
+    }
+}
+
+extern "C" int ctan_adam_step(float* p, const float* g, float* m, float* v, int n, float lr, float beta1, float beta2,
+                              float eps, float wd, int64_t step, const int64_t* counters, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    adam_kernel<<<ctan_grid(n, 256), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, step, counters);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+// One-vs-many ranking: query q has one positive score pos[q] and n_neg negatives neg[q*n_neg ...].
+// rank = 0.5*(#neg >= pos + #neg > pos) + 1; rr[q] = 1/rank (fp32)   -- TGB evaluate.py:109-120
+__global__ void mrr_kernel(const float* __restrict__ pos, const float* __restrict__ neg, int Q, int n_neg,
+                           float* __restrict__ rr) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int q = warp; q < Q; q += nw) {
+        const float p = pos[q];
+        int ge = 0, gt = 0;
+        for (int i = lane; i < n_neg; i += 32) {
+            const float x = neg[(size_t)q * n_neg + i];
+            ge += x >= p;
+            gt += x > p;
+        }
+        ge = warp_sum_i(ge); gt = warp_sum_i(gt);
+        if (lane == 0) rr[q] = 1.0f / (0.5f * (float)(ge + gt) + 1.0f);
+    }
+}
+
+extern "C" int ctan_mrr(const float* pos, const float* neg, int Q, int n_neg, float* rr, cudaStream_t stream) {
+    if (Q <= 0) return 0;
+    mrr_kernel<<<ctan_grid((long long)Q * 32, 256), 256, 0, stream>>>(pos, neg, Q, n_neg, rr);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,291 @@
+"""Zero-host-sync per-batch engine: the whole step of train_link.py:237-282 (tgb_train / train) or of
+the no-grad loops (eval, tgb_test 'train' split: train_link.py:161-199, 361-405) as ONE stream of our
+kernels -- lookup -> forward -> loss -> memory write-back + insert -> backward -> Adam -- with every
+data-dependent size kept on the device, captured once in a CUDA graph and replayed per batch.
+
+It drives the SAME module objects as the drop-in API (`CTAN`/`CTAN_tgb`, `LastNeighborLoader`): their
+parameters are re-pointed into one flat buffer (so Adam is a single launch) and their state tables are
+updated in place, so a run can switch between the engine and the reference-style Python loop.
+
+Event stream (device resident): src, dst, t [n] int64, msg [n,Fe] fp32, neg [n, n_neg] int64 (negatives
+are an INPUT, drawn by the caller exactly like train_link.py:245-251 / negative_sampler.py do), x
+[num_nodes,Fn] fp32 or None.  Event ids of the loader are stream indices (cur_e_id counts from the
+first event, train_link.py:265), so `msg[e_id]`/`t[e_id]` are gathers from the same tables."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr
+from .modules import CTAN, CTAN_tgb
+from .neighbor_loader import LastNeighborLoader
+
+
+def _param_list(model):
+    g, a, r = model.gnn, model.gnn.aconv, model.readout
+    p = a.phi
+    return [g.enc_x.weight, g.enc_x.bias, p.lin_query.weight, p.lin_query.bias, p.lin_key.weight, p.lin_key.bias,
+            p.lin_value.weight, p.lin_value.bias, p.lin_edge.weight, a.W, a.bias, g.time_enc.lin.weight,
+            g.time_enc.lin.bias, r.lin_src.weight, r.lin_src.bias, r.lin_dst.weight, r.lin_dst.bias,
+            r.lin_final.weight, r.lin_final.bias]
+
+
+class StepEngine:
+    def __init__(self, model: CTAN, loader: LastNeighborLoader, stream: dict, batch_size: int, n_neg: int = 1,
+                 lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                 use_graph: bool = True, hist_cap: int = 1 << 16, host_staged: bool = False):
+        if model.predict_dst:
+            raise NotImplementedError("StepEngine covers the link-prediction heads")
+        dev = model.memory.memory.device
+        if dev.type != "cuda":
+            raise _lib.CtanLibraryError("StepEngine needs the model on a CUDA device")
+        _lib.lib()
+        self.model, self.loader, self.dev = model, loader, dev
+        self.tgb = isinstance(model, CTAN_tgb)
+        self.B, self.n_neg = int(batch_size), int(n_neg)
+        self.lr, self.betas = float(lr), (float(betas[0]), float(betas[1]))
+        self.eps, self.wd = float(eps), float(weight_decay)
+        self.use_graph, self.hist_cap, self.host_staged = use_graph, int(hist_cap), host_staged
+        self.K = model.num_gnn_layers
+        self.D = model.memory.memory_dim
+        self.S = loader.size
+        self.num_nodes = model.num_nodes
+        self.final_tanh = model.final_act == "tanh"
+        st = stream
+        for k in ("src", "dst", "t", "msg"):
+            if not st[k].is_cuda:
+                raise _lib.CtanLibraryError(f"stream['{k}'] must be device resident")
+        self.src, self.dst, self.t = st["src"].contiguous(), st["dst"].contiguous(), st["t"].contiguous()
+        self.msg = st["msg"].float().contiguous()
+        self.neg = st["neg"].contiguous().view(self.src.numel(), -1)
+        assert self.neg.size(1) == self.n_neg
+        self.x = st.get("x")
+        if self.x is not None:
+            self.x = (self.x.squeeze(0) if self.x.dim() == 3 else self.x).to(dev).float().contiguous()
+        self.Fe = self.msg.size(1)
+        self.Fn = self.x.size(1) if self.x is not None else 0
+        self.T = model.gnn.time_enc.lin.bias.numel()
+        self.Hd = model.readout.lin_src.weight.size(0)
+        self.O = model.readout.lin_final.weight.size(0)
+        if self.O != 1:
+            raise NotImplementedError("StepEngine's fused loss is binary (readout_out=1)")
+        self._flatten_params()
+        self._alloc()
+        self._graphs = {}
+
+    # ------------------------------------------------------------------ parameters in one flat buffer
+    def _flatten_params(self):
+        plist = _param_list(self.model)
+        n = sum(p.numel() for p in plist)
+        self.flat_p = torch.empty(n, device=self.dev)
+        self.flat_g = torch.zeros(n, device=self.dev)
+        self.adam_m = torch.zeros(n, device=self.dev)
+        self.adam_v = torch.zeros(n, device=self.dev)
+        self.p, self.g = [], []
+        o = 0
+        for p in plist:
+            k = p.numel()
+            self.flat_p[o:o + k].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[o:o + k].view(p.shape)
+            p.grad = self.flat_g[o:o + k].view(p.shape)
+            self.p.append(p.data)
+            self.g.append(p.grad)
+            o += k
+        self.n_params = n
+
+    # ------------------------------------------------------------------ workspaces (upper bounds)
+    def _alloc(self):
+        dev, B, S, K, D = self.dev, self.B, self.S, self.K, self.D
+        f32 = dict(device=dev, dtype=torch.float32)
+        i64 = dict(device=dev, dtype=torch.long)
+        self.P = B * (1 + self.n_neg)
+        n_seeds = B * (2 + self.n_neg)
+        self.n_seeds = n_seeds
+        self.n_cap = min(self.num_nodes, n_seeds * (S + 1) ** K)
+        c_cap = min(self.num_nodes, n_seeds * (S + 1) ** (K - 1))
+        self.e_cap = max(c_cap * S, 1)
+        N, E, P = self.n_cap, self.e_cap, self.P
+        w = {}
+        w["counters"] = torch.zeros(8, **i64)
+        w["b_src"], w["b_dst"], w["b_t"] = (torch.zeros(B, **i64) for _ in range(3))
+        w["seeds"] = torch.zeros(n_seeds, **i64)
+        w["pair_src"], w["pair_dst"] = torch.zeros(P, **i64), torch.zeros(P, **i64)
+        w["frontier"] = torch.zeros(max(K - 1, 1) * N, **i64)
+        w["frontier_cnt"] = torch.zeros(8, device=dev, dtype=torch.int32)
+        w["counts"] = torch.zeros(8, device=dev, dtype=torch.int32)
+        w["n_id"] = torch.zeros(N, **i64)
+        w["rowptr"] = torch.zeros(N + 1, device=dev, dtype=torch.int32)
+        w["esrc"], w["edst"], w["eid"] = (torch.zeros(E, **i64) for _ in range(3))
+        w["ins_ws"] = torch.zeros(4 * B, device=dev, dtype=torch.int32)
+        w["rel"] = torch.zeros(E, **f32)
+        w["z0"] = torch.zeros((N, D + self.Fn), **f32)
+        w["X"] = torch.zeros((K + 1, N, D), **f32)
+        w["EP"] = torch.zeros((E, D), **f32)
+        w["A"] = torch.zeros((D, D), **f32)
+        w["QKVA"] = torch.zeros((K, N, 4 * D), **f32)
+        w["TH"] = torch.zeros((K, N, D), **f32)
+        w["ALPHA"] = torch.zeros((K, E), **f32)
+        w["Z"] = torch.zeros((N, D), **f32) if self.final_tanh else None
+        w["H"] = torch.zeros((P, self.Hd), **f32)
+        w["OUT"] = torch.zeros((P, self.O), **f32)
+        w["dOUT"] = torch.zeros((P, self.O), **f32)
+        w["loss_hist"] = torch.zeros(self.hist_cap, **f32)
+        # backward
+        w["dHid"] = torch.zeros((P, self.Hd), **f32)
+        w["dZ"] = torch.zeros((N, D), **f32)
+        w["gA"], w["gB"] = torch.zeros((N, D), **f32), torch.zeros((N, D), **f32)
+        w["DQKVA"] = torch.zeros((N, 4 * D), **f32)
+        w["dEP"] = torch.zeros((E, D), **f32)
+        w["DS"] = torch.zeros(E, **f32)
+        w["dTenc"] = torch.zeros((E, max(self.T, 1)), **f32)
+        w["dA"] = torch.zeros((D, D), **f32)
+        self.w = w
+        self._Nd = w["counts"][0:1]
+        self._Ed = w["counts"][1:2]
+
+    # ------------------------------------------------------------------ state
+    def reset(self, reset_optimizer: bool = False):
+        """Fresh memory + empty graph + cursor at event 0 (train_link.py:226-227)."""
+        self.model.reset_memory()
+        self.loader.reset_state()
+        self.w["counters"].zero_()
+        self.w["counts"].zero_()
+        if reset_optimizer:
+            self.adam_m.zero_()
+            self.adam_v.zero_()
+
+    def set_cursor(self, event_index: int):
+        self.w["counters"][0] = int(event_index)
+        self.loader.cur_e_id = int(event_index)
+
+    @property
+    def cursor(self) -> int:
+        return int(self.w["counters"][0].item())
+
+    # ------------------------------------------------------------------ one step = one stream of launches
+    def _launch(self, train: bool):
+        w, m, ld = self.w, self.model, self.loader
+        B, D, K, S, Fe, Fn, T = self.B, self.D, self.K, self.S, self.Fe, self.Fn, self.T
+        Hd, O, P = self.Hd, self.O, self.P
+        N, E = self.n_cap, self.e_cap
+        Nd, Ed = ptr(self._Nd), ptr(self._Ed)
+        (Wenc, benc, Wq, bq, Wk, bk, Wv, bv, We, W, b, tw, tb, Wsrc, bsrc, Wdst, bdst, Wfin,
+         bfin) = (ptr(t) for t in self.p)
+        mem, lu = m.memory.memory, m.memory.last_update
+        cur1 = ptr(w["counters"]) + 8                       # &counters[1]: current batch start
+        xf = ptr(self.x) if Fn else None
+        call("ctan_stage_batch", ptr(self.src), ptr(self.dst), ptr(self.t), ptr(self.neg), self.n_neg, B,
+             ptr(w["counters"]), 0 if self.host_staged else 1, ptr(w["b_src"]), ptr(w["b_dst"]), ptr(w["b_t"]),
+             ptr(w["seeds"]), ptr(w["pair_src"]), ptr(w["pair_dst"]))
+        call("ctan_nbr_lookup", ptr(ld.neighbors), ptr(ld._deg), self.num_nodes, S, ptr(w["seeds"]), self.n_seeds,
+             None, K, ptr(ld._bitmap), ptr(ld._cbitmap), ptr(w["frontier"]), ptr(w["frontier_cnt"]), N,
+             ptr(w["n_id"]), N, ptr(ld._assoc), ptr(w["rowptr"]), E, ptr(w["counts"]))
+        call("ctan_nbr_fill", ptr(ld.neighbors), ptr(ld.e_id), S, ptr(w["n_id"]), ptr(w["rowptr"]), ptr(ld._assoc),
+             N, Nd, ptr(w["esrc"]), ptr(w["edst"]), ptr(w["eid"]), ptr(ld._bitmap), ptr(ld._cbitmap))
+        call("ctan_edge_rel", ptr(lu), ptr(w["n_id"]), ptr(w["esrc"]), ptr(self.t), ptr(w["eid"]), E, Ed,
+             float(m.gnn.mean_delta_t), float(m.gnn.std_delta_t), ptr(w["rel"]))
+        if train:
+            call("ctan_gather_rows2", ptr(mem), D, xf, Fn, ptr(w["n_id"]), N, Nd, ptr(w["z0"]))
+            call("ctan_enc_fwd", None, D, None, Fn, None, ptr(w["z0"]), N, Nd, Wenc, benc, ptr(w["X"][0]))
+        else:
+            call("ctan_enc_fwd", ptr(mem), D, xf, Fn, ptr(w["n_id"]), None, N, Nd, Wenc, benc, ptr(w["X"][0]))
+        call("ctan_eproj_fwd", ptr(self.msg), Fe, ptr(w["eid"]), ptr(w["rel"]), tw, tb, T, We, E, Ed, D, ptr(w["EP"]))
+        call("ctan_antisym_prep", W, float(m.gnn.aconv.gamma), D, ptr(w["A"]))
+        eps = float(m.gnn.aconv.epsilon)
+        for k in range(K):
+            xi = w["X"][k] if train else w["X"][k & 1]
+            xo = w["X"][k + 1] if train else w["X"][(k + 1) & 1]
+            qk = w["QKVA"][k] if train else w["QKVA"][0]
+            call("ctan_qkva_fwd", ptr(xi), N, Nd, D, Wq, Wk, Wv, ptr(w["A"]), bq, bk, bv, b, ptr(qk))
+            last = k == K - 1
+            call("ctan_edge_fwd", ptr(qk), ptr(w["EP"]), ptr(w["rowptr"]), ptr(w["esrc"]), N, Nd, D, ptr(xi), eps,
+                 ptr(xo), ptr(w["TH"][k]) if train else None, ptr(w["ALPHA"][k]) if train else None,
+                 ptr(w["Z"]) if (last and self.final_tanh) else None)
+        xk = w["X"][K] if train else w["X"][K & 1]
+        z = w["Z"] if self.final_tanh else xk
+        self._z = z
+        call("ctan_readout_fwd", ptr(z), D, ptr(w["pair_src"]), ptr(w["pair_dst"]), ptr(ld._assoc), P, None, Hd, O,
+             Wsrc, bsrc, Wdst, bdst, Wfin, bfin, ptr(w["H"]), ptr(w["OUT"]))
+        call("ctan_bce_loss", ptr(w["OUT"]), B, P - B, ptr(w["dOUT"]) if train else None, ptr(w["loss_hist"]),
+             self.hist_cap, ptr(w["counters"]))
+        # ground-truth state update (train_link.py:276-277); the backward below only reads saved copies
+        call("ctan_mem_update", ptr(mem), ptr(lu), D, ptr(w["b_src"]), ptr(w["b_dst"]), ptr(w["b_t"]), B, None,
+             None, ptr(z), ptr(ld._assoc))
+        call("ctan_nbr_insert", ptr(ld.neighbors), ptr(ld.e_id), ptr(ld._deg), ptr(w["b_src"]), ptr(w["b_dst"]), B,
+             0, cur1, S, ptr(w["ins_ws"]))
+        if not train:
+            return
+        (gWenc, gbenc, gWq, gbq, gWk, gbk, gWv, gbv, gWe, gW, gb, gtw, gtb, gWsrc, gbsrc, gWdst, gbdst, gWfin,
+         gbfin) = (ptr(t) for t in self.g)
+        self.flat_g.zero_()
+        w["dZ"].zero_()
+        w["dA"].zero_()
+        call("ctan_readout_bwd", ptr(w["dOUT"]), ptr(w["H"]), ptr(z), D, ptr(w["pair_src"]), ptr(w["pair_dst"]),
+             ptr(ld._assoc), P, None, Hd, O, Wsrc, Wdst, Wfin, ptr(w["dHid"]), ptr(w["dZ"]), gWsrc, gbsrc, gWdst,
+             gbdst, gWfin, gbfin)
+        g = w["dZ"]
+        if self.final_tanh:
+            call("ctan_tanh_bwd", ptr(w["dZ"]), ptr(z), N, Nd, D, ptr(w["gA"]))
+            g = w["gA"]
+        for k in range(K - 1, -1, -1):
+            w["DQKVA"].zero_()
+            call("ctan_edge_bwd", ptr(w["QKVA"][k]), ptr(w["EP"]), ptr(w["rowptr"]), ptr(w["esrc"]), N, Nd, D, ptr(g),
+                 ptr(w["TH"][k]), ptr(w["ALPHA"][k]), eps, ptr(w["DQKVA"]), ptr(w["dEP"]), int(k != K - 1),
+                 ptr(w["DS"]))
+            gn = w["gB"] if g is not w["gB"] else w["gA"]
+            call("ctan_qkva_bwd", ptr(w["DQKVA"]), ptr(w["X"][k]), ptr(g), N, Nd, D, Wq, Wk, Wv, ptr(w["A"]), ptr(gn),
+                 gWq, gWk, gWv, ptr(w["dA"]), gbq, gbk, gbv, gb)
+            g = gn
+        call("ctan_enc_bwd", ptr(g), ptr(w["z0"]), N, Nd, D, Fn, gWenc, gbenc)
+        call("ctan_eproj_bwd", ptr(w["dEP"]), ptr(self.msg), Fe, ptr(w["eid"]), ptr(w["rel"]), tw, tb, T, We, E, Ed,
+             D, gWe, ptr(w["dTenc"]))
+        call("ctan_tenc_bwd", ptr(w["dTenc"]), ptr(w["rel"]), tw, tb, E, Ed, T, gtw, gtb)
+        call("ctan_antisym_bwd", ptr(w["dA"]), D, gW)
+        call("ctan_adam_step", ptr(self.flat_p), ptr(self.flat_g), ptr(self.adam_m), ptr(self.adam_v),
+             self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 0, ptr(w["counters"]))
+
+    # ------------------------------------------------------------------ public stepping API
+    def _graph(self, train: bool):
+        key = bool(train)
+        if key not in self._graphs:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch(train)
+            self._graphs[key] = g
+        return self._graphs[key]
+
+    def warmup(self):
+        """Run one throw-away training + inference step eagerly (loads every kernel before graph
+        capture) and restore the fresh state.  Call on a freshly reset engine only."""
+        keep = self.flat_p.clone()
+        with torch.cuda.device(self.dev):
+            self._launch(True)
+            self._launch(False)
+        torch.cuda.synchronize(self.dev)
+        self.flat_p.copy_(keep)
+        self.reset(reset_optimizer=True)
+        self.w["loss_hist"].zero_()
+
+    def run(self, n_steps: int, train: bool = True):
+        """Advance n_steps full batches from the cursor (no host synchronisation)."""
+        with torch.cuda.device(self.dev):
+            if self.use_graph:
+                g = self._graph(train)
+                for _ in range(n_steps):
+                    g.replay()
+            else:
+                for _ in range(n_steps):
+                    self._launch(train)
+        self.loader.cur_e_id += n_steps * self.B
+
+    def losses(self, n: int) -> torch.Tensor:
+        """Last n recorded per-step losses (device tensor; reading it synchronises)."""
+        steps = int(self.w["counters"][3].item())
+        idx = torch.arange(steps - n, steps, device=self.dev) % self.hist_cap
+        return self.w["loss_hist"][idx]
+
+    def check(self):
+        """Raise if any lookup overflowed its workspace during the run (device flag, one sync)."""
+        err = int(self.w["counts"][3].item())
+        if err:
+            raise _lib.CtanLibraryError(f"neighbor lookup overflowed the engine workspace (code {err})")

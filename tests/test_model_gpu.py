@@ -80,8 +80,11 @@ def _run_steps(st, tgb, K, D, T, H, final_act, S, n_steps, B=200, train=True, lr
                 assert set(go) == set(gm), set(go) ^ set(gm)
                 for k in go:
                     assert gm[k].shape == go[k].shape, k
-                    err = _rel_err(gm[k], go[k])
-                    assert err < 5e-4, (k, err, it)
+                    # lin_key.bias has an exactly-zero true gradient (softmax is shift invariant): both
+                    # sides hold rounding noise there, so the bound is relative to the largest gradient
+                    scale = max(float(v.abs().max()) for v in go.values())
+                    diff = float((gm[k].cpu() - go[k]).abs().max())
+                    assert diff < 5e-4 * float(go[k].abs().max()) + 1e-6 * scale, (k, diff, it)
             opt_mine.step()
             mm.detach_memory()
             assert abs(float(loss) - float(l_ref)) <= RTOL * abs(float(l_ref)) + 1e-6, (it, float(loss), float(l_ref))
