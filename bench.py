@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Benchmark of the CTAN per-event-batch hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N = 1  : train events/sec of the full per-batch step (lookup -> forward -> loss -> update+insert ->
+         backward -> Adam) on the Wikipedia-shaped synthetic stream (BASELINE.json configs[1]); a "step"
+         is one 200-event batch.  Extra keys carry infer events/sec, the single-GPU TGB-eval queries/sec,
+         the eager-PyTorch-on-GPU baseline and the CPU baseline.
+N > 1  : TGB one-vs-many evaluation (tgb_test val/test semantics, train_link.py:111-199) with the
+         queries of every 200-event batch sharded over N ranks and ONE NCCL all-gather per batch
+         (launched by torchrun, one rank per GPU); value = queries/sec of the whole job.
+--impl reference : the reference algorithm's CPU implementation (oracle port: /root/reference is pure
+         Python and cannot travel to the GPU box) timed on the host cores for the same workload.
+Prints ONE JSON line on rank 0."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WIKI = dict(D=128, T=16, S=5, H=64, B=200, Fe=172, eps=0.1, gamma=0.1, lr=1e-3)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, smax, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if "Active" in v and "Not" not in v:
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def make_workload(n_events, seed=0):
+    import ctan_b200  # noqa: F401
+    from ctan_b200 import synth
+    st = synth.make_stream("wiki", n_events=n_events, seed=seed)
+    st["neg"] = synth.draw_negatives(st)[:, 0]
+    n_train = int(0.7 * n_events)
+    mean, std = synth.delta_t_stats(st, min(n_train, 20000))
+    return st, mean, std
+
+
+def model_kwargs(st, K, mean, std, cfg=WIKI):
+    return dict(num_nodes=st["num_nodes"], edge_dim=st["msg"].size(1), memory_dim=cfg["D"], time_dim=cfg["T"],
+                node_dim=1, num_iters=K, epsilon=cfg["eps"], gamma=cfg["gamma"], readout_hidden=cfg["H"],
+                mean_delta_t=mean, std_delta_t=std, final_act=None)
+
+
+# ------------------------------------------------------------------------------------------ baselines
+def oracle_train_rate(st, K, mean, std, device, n_steps, warmup, threads=None):
+    """events/sec of the restated reference training loop (oracle) on `device`."""
+    from oracle import ctan_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    cfg = WIKI
+    torch.manual_seed(0)
+    om = O.OracleCTAN(**model_kwargs(st, K, mean, std)).to(device)
+    ld = O.TorchNeighborLoader(st["num_nodes"], cfg["S"], device=device)
+    h = torch.zeros(st["num_nodes"], dtype=torch.long, device=device)
+    opt = torch.optim.Adam(om.parameters(), lr=cfg["lr"])
+    g = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in st.items()}
+    B = cfg["B"]
+
+    def sync():
+        if device != "cpu":
+            torch.cuda.synchronize()
+    for it in range(warmup):
+        O.train_step_ref(om, ld, h, opt, g, it * B, (it + 1) * B, g["neg"][it * B:(it + 1) * B])
+    sync()
+    t0 = time.perf_counter()
+    for it in range(warmup, warmup + n_steps):
+        O.train_step_ref(om, ld, h, opt, g, it * B, (it + 1) * B, g["neg"][it * B:(it + 1) * B])
+    sync()
+    dt = time.perf_counter() - t0
+    return n_steps * B / dt, dt / n_steps * 1e3
+
+
+# ------------------------------------------------------------------------------------------ ours, N=1
+def build_engine(st, K, mean, std, dev, host_staged=False):
+    import ctan_b200  # noqa: F401
+    from ctan_b200.engine import StepEngine
+    from ctan_b200.models import CTAN, LastNeighborLoader
+    cfg = WIKI
+    torch.manual_seed(0)
+    model = CTAN(**model_kwargs(st, K, mean, std)).to(dev)
+    loader = LastNeighborLoader(st["num_nodes"], cfg["S"], device=dev)
+    if host_staged:
+        g = dict(st)                                           # stays on the host; batches are pushed per step
+    else:
+        g = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in st.items()}
+        g["neg"] = st["neg"].view(-1, 1).to(dev)
+    eng = StepEngine(model, loader, g, batch_size=cfg["B"], n_neg=1, lr=cfg["lr"], host_staged=host_staged)
+    eng.reset(reset_optimizer=True)
+    eng.warmup()
+    return eng
+
+
+def time_steps(eng, n_steps, train, flush_buf):
+    """Per-step CUDA events with an L2 flush (write of a >L2 buffer) between timed steps."""
+    g = eng._graph(train)
+    evs = []
+    for _ in range(n_steps):
+        if flush_buf is not None:
+            flush_buf.add_(1.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    eng.loader.cur_e_id += n_steps * eng.B
+    return [a.elapsed_time(b) for a, b in evs]
+
+
+def time_back_to_back(eng, n_steps, train):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    eng.run(n_steps, train=train)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def per_kernel_profile(eng, n_steps, train=True):
+    """Eager (non-graph) steps with a CUDA-event pair around every C-ABI call: live per-call device
+    durations on the launching stream."""
+    from ctan_b200 import _lib
+    _lib.TRACE = []
+    for _ in range(n_steps):
+        eng._launch(train)
+    torch.cuda.synchronize()
+    eng.loader.cur_e_id += n_steps * eng.B
+    agg = {}
+    for name, a, b in _lib.TRACE:
+        d = agg.setdefault(name, [0.0, 0])
+        d[0] += a.elapsed_time(b)
+        d[1] += 1
+    _lib.TRACE = None
+    return {k: {"ms_per_call": v[0] / v[1], "calls_per_step": v[1] / n_steps} for k, v in agg.items()}
+
+
+def run_e2e(st, K, mean, std, dev, n_steps, warmup):
+    """Same step driven with HOST buffers through the public engine API: every step copies the batch
+    (src,dst,t,neg ids + msg rows) from pinned host memory, runs the step, and reads the loss back."""
+    eng = build_engine(st, K, mean, std, dev, host_staged=True)
+    B = eng.B
+    pin = {k: st[k].pin_memory() for k in ("src", "dst", "t", "msg")}
+    pin["neg"] = st["neg"].view(-1, 1).pin_memory()
+    loss_host = torch.zeros(1).pin_memory()
+    h2d = 0
+
+    def step(it):
+        nonlocal h2d
+        lo, hi = it * B, (it + 1) * B
+        h2d = eng.push_batch(pin["src"][lo:hi], pin["dst"][lo:hi], pin["t"][lo:hi], pin["neg"][lo:hi], pin["msg"][lo:hi])
+        eng.run(1, train=True)
+        slot = it % eng.hist_cap
+        loss_host.copy_(eng.w["loss_hist"][slot:slot + 1], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(loss_host[0])
+    for it in range(warmup):
+        step(it)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    last = 0.0
+    for it in range(warmup, warmup + n_steps):
+        last = step(it)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    eng.check()
+    return n_steps * B / dt, h2d, 4, last
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--iters", type=int, default=1, help="CTAN num_iters (K)")
+    ap.add_argument("--no-baselines", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    W = max(args.warmup, 3)
+    K = args.iters
+    B = WIKI["B"]
+    cfg_desc = {"workload": "wiki-shaped synthetic link prediction: 9227 nodes, 157474 events, 172-d msgs, batch 200; "
+                            f"CTAN D=128 T=16 S=5 K={K} H=64, 1 negative/positive, full train step incl. Adam",
+                "l2": "flushed between timed steps (256 MiB write), per-step CUDA events summed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n_steps = min(args.steps, 300)
+        st, mean, std = make_workload((W + n_steps + 2) * B)
+        cores = os.cpu_count() or 1
+        v, ms = oracle_train_rate(st, K, mean, std, "cpu", n_steps, W, threads=cores)
+        print(json.dumps({"impl": "reference", "metric": "train_events_per_sec", "value": v, "unit": "events/s",
+                          "n_gpus": args.gpus, "steps": n_steps, "warmup": W, "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": cfg_desc,
+                          "cpu_baseline": {"value": v, "unit": "events/s", "cores": cores, "kind": "port",
+                                           "sample": f"{n_steps} consecutive 200-event training batches of the same "
+                                                     "stream after warm-up (oracle port of train_link.py:237-282)"},
+                          "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    if world > 1 or args.gpus > 1:
+        from bench_tgb import run_tgb_eval_bench        # multi-GPU path: sharded TGB evaluation
+        run_tgb_eval_bench(args, rank, world)
+        return
+
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    from ctan_b200 import _lib
+    n_events = max(157474, (W + args.steps + 64) * B)          # the stream is lengthened only if K asks for more
+    if n_events != 157474:
+        cfg_desc["workload"] += f" (stream lengthened to {n_events} events to fit --steps)"
+    st, mean, std = make_workload(n_events)
+    eng = build_engine(st, K, mean, std, dev)
+    flush = torch.zeros(64 * 1024 * 1024, device=dev)           # 256 MiB > 126 MB L2
+    # ---- phase A: warm-up, then K timed training steps (L2 flushed between steps)
+    eng.run(W, train=True)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    ms_list = time_steps(eng, args.steps, True, flush)
+    clocks = sampler.stop()
+    total_ms = sum(ms_list)
+    value = args.steps * B / (total_ms * 1e-3)
+    eng.check()
+    losses = eng.losses(5).cpu().tolist()
+    # ---- phase B: 20 eager steps with events around every C-ABI call (per-kernel live durations)
+    _lib.N_LAUNCHES = 0
+    prof = per_kernel_profile(eng, 20, train=True)
+    launches_per_step = _lib.N_LAUNCHES // 20
+    counts = eng.w["counts"].cpu().tolist()
+    # ---- phase C: same stream from a fresh state, back-to-back replays (L2 warm, as in production)
+    eng.reset(reset_optimizer=True)
+    eng.run(W, train=True)
+    warm_ms = time_back_to_back(eng, args.steps, True)
+    warm_value = args.steps * B / (warm_ms * 1e-3)
+    # ---- phase D: inference (no-grad) steps from a fresh state
+    eng.reset()
+    eng.run(W, train=False)
+    inf_ms = sum(time_steps(eng, args.steps, False, flush))
+    infer_value = args.steps * B / (inf_ms * 1e-3)
+    eng.check()
+
+    # ---- roofline of the dominant kernel (by live per-call device time)
+    peak, peak_src = load_peaks()
+    N_last, E_last = counts[0], counts[1]
+    top = sorted(prof.items(), key=lambda kv: -kv[1]["ms_per_call"] * kv[1]["calls_per_step"])
+    top_name, top_v = top[0]
+    D, Fe, T, Hd = eng.D, eng.Fe, eng.T, eng.Hd
+    alg_bytes = {
+        "ctan_eproj_fwd": E_last * (4 * Fe + 8 + 4) + 4 * D * (Fe + T) + E_last * D * 4,
+        "ctan_eproj_bwd": E_last * (4 * Fe + 8 + 4 + 4 * D) + 2 * 4 * D * (Fe + T) + E_last * T * 4,
+        "ctan_qkva_fwd": N_last * D * 4 + 4 * D * D * 4 + N_last * 4 * D * 4,
+        "ctan_qkva_bwd": N_last * (4 * D + D + D) * 4 + 2 * 4 * D * D * 4 + N_last * D * 4,
+        "ctan_edge_fwd": N_last * (4 * D + 2 * D) * 4 + E_last * (2 * D * 4 + D * 4 + 8 + 4),
+        "ctan_edge_bwd": N_last * (4 * D + 3 * D + 4 * D) * 4 + E_last * (3 * D * 4 + 2 * D * 4 + 8 + 8),
+        "ctan_readout_fwd": eng.P * (2 * D + Hd + 1) * 4 + 2 * Hd * D * 4,
+        "ctan_readout_bwd": eng.P * (4 * D + 3 * Hd + 2) * 4 + 4 * Hd * D * 4,
+        "ctan_enc_fwd": N_last * (2 * D + 1) * 4 + D * (D + 1) * 4,
+        "ctan_enc_bwd": N_last * (2 * D + 1) * 4 + D * (D + 1) * 4,
+    }.get(top_name)
+    roof = {"bound": "hbm", "kernel": top_name, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
+            "traffic": None, "peak_source": peak_src, "ms_per_launch": top_v["ms_per_call"],
+            "note": "per-batch work is ~2 MB / ~0.2 GFLOP: latency-bound at B=200 (see DESIGN.md)"}
+    if alg_bytes:
+        ach = alg_bytes / (top_v["ms_per_call"] * 1e-3) / 1e9
+        roof.update(achieved=ach, frac=ach / peak, algorithmic_bytes=alg_bytes)
+    # whole-step algorithmic bytes (SURVEY.md S8d formula)
+    U = 2 * B
+    Pw = eng.n_params
+    step_bytes = (16 * eng.S * N_last + N_last * (4 * D + 8 + 4) + E_last * (4 * Fe + 8) + 4 * Pw + 4 * eng.P
+                  + U * (4 * D + 8) + 2 * 16 * eng.S * U + 24 * B + 8 * Pw)
+    step_ms = total_ms / args.steps
+    roof["step"] = {"algorithmic_bytes": step_bytes, "achieved_gbs": step_bytes / (step_ms * 1e-3) / 1e9,
+                    "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak, "N": N_last, "E": E_last}
+
+    out = {"metric": "train_events_per_sec", "value": value, "unit": "events/s", "n_gpus": 1, "steps": args.steps,
+           "warmup": W, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic", "config": cfg_desc, "clocks": clocks,
+           "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+           "value_l2_warm_back_to_back": warm_value, "infer_events_per_sec": infer_value,
+           "last_losses": losses, "roofline": roof,
+           "kernel_ms_per_step": {k: round(v["ms_per_call"] * v["calls_per_step"], 5) for k, v in top[:12]}}
+
+    # ---- end to end with host buffers
+    e2e_v, h2d, d2h, last_loss = run_e2e(st, K, mean, std, dev, min(args.steps, 400), W)
+    out["e2e"] = {"value": e2e_v, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                  "api": "StepEngine(host_staged=True).run(1) per batch: pinned-host batch -> device, one step, loss -> host"}
+
+    if not args.no_baselines:
+        gv, gms = oracle_train_rate(st, K, mean, std, "cuda:0", 100, 10)
+        out["torch_gpu_baseline"] = {"value": gv, "unit": "events/s", "ms_per_step": gms,
+                                     "what": "restated reference loop, eager PyTorch ops on the same B200 (fp32)"}
+        cores = os.cpu_count() or 1
+        cv, cms = oracle_train_rate(st, K, mean, std, "cpu", 120, 5, threads=cores)
+        out["cpu_baseline"] = {"value": cv, "unit": "events/s", "cores": cores, "kind": "port",
+                               "sample": "120 consecutive 200-event training batches of the same stream (oracle port)"}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

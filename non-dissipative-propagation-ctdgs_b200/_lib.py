@@ -108,9 +108,27 @@ def ptr(t, dtype=None):
     return t.data_ptr()
 
 
+# kernels launched by each C entry point (for launch accounting; ctan_nbr_lookup adds one per hop)
+LAUNCHES = {"ctan_nbr_insert": 2, "ctan_nbr_lookup": 1, "ctan_readout_fwd": 2, "ctan_readout_bwd": 5,
+            "ctan_qkva_bwd": 2, "ctan_eproj_bwd": 2}
+
+# Optional instrumentation (bench.py): TRACE = list -> every call appends (name, start_event, end_event)
+TRACE = None
+N_LAUNCHES = 0
+
+
 def call(name: str, *args):
+    global N_LAUNCHES
     fn = getattr(lib(), name)
-    rc = fn(*args, stream_ptr())
+    N_LAUNCHES += LAUNCHES.get(name, 1) + (args[7] if name == "ctan_nbr_lookup" else 0)
+    if TRACE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args, stream_ptr())
+        e1.record()
+        TRACE.append((name, e0, e1))
+    else:
+        rc = fn(*args, stream_ptr())
     if rc != 0:
         raise CtanLibraryError(f"{name} failed with code {rc}"
                                + (f" ({_cuda_err(rc)})" if rc > 0 else " (bad argument / unsupported size)"))

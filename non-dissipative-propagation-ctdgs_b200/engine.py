@@ -52,17 +52,27 @@ class StepEngine:
         self.num_nodes = model.num_nodes
         self.final_tanh = model.final_act == "tanh"
         st = stream
-        for k in ("src", "dst", "t", "msg"):
-            if not st[k].is_cuda:
-                raise _lib.CtanLibraryError(f"stream['{k}'] must be device resident")
-        self.src, self.dst, self.t = st["src"].contiguous(), st["dst"].contiguous(), st["t"].contiguous()
-        self.msg = st["msg"].float().contiguous()
-        self.neg = st["neg"].contiguous().view(self.src.numel(), -1)
-        assert self.neg.size(1) == self.n_neg
+        self.n_events = int(st["src"].numel())
+        self.Fe = int(st["msg"].size(1))
+        if host_staged:
+            # batches arrive from the host: fixed device staging buffers + event tables filled as they come
+            self.src, self.dst, self.t = (torch.zeros(self.B, dtype=torch.long, device=dev) for _ in range(3))
+            self.neg = torch.zeros((self.B, self.n_neg), dtype=torch.long, device=dev)
+            self.t_tab = torch.zeros(self.n_events, dtype=torch.long, device=dev)
+            self.msg = torch.zeros((self.n_events, self.Fe), device=dev)
+            self._host_cursor = 0
+        else:
+            for k in ("src", "dst", "t", "msg", "neg"):
+                if not st[k].is_cuda:
+                    raise _lib.CtanLibraryError(f"stream['{k}'] must be device resident")
+            self.src, self.dst, self.t = st["src"].contiguous(), st["dst"].contiguous(), st["t"].contiguous()
+            self.t_tab = self.t
+            self.msg = st["msg"].float().contiguous()
+            self.neg = st["neg"].contiguous().view(self.n_events, -1)
+            assert self.neg.size(1) == self.n_neg
         self.x = st.get("x")
         if self.x is not None:
             self.x = (self.x.squeeze(0) if self.x.dim() == 3 else self.x).to(dev).float().contiguous()
-        self.Fe = self.msg.size(1)
         self.Fn = self.x.size(1) if self.x is not None else 0
         self.T = model.gnn.time_enc.lin.bias.numel()
         self.Hd = model.readout.lin_src.weight.size(0)
@@ -150,9 +160,25 @@ class StepEngine:
         self.loader.reset_state()
         self.w["counters"].zero_()
         self.w["counts"].zero_()
+        if self.host_staged:
+            self._host_cursor = 0
         if reset_optimizer:
             self.adam_m.zero_()
             self.adam_v.zero_()
+
+    def push_batch(self, src, dst, t, neg, msg):
+        """host_staged mode: copy one batch (pinned host tensors) to the device -- the ids/times into the
+        staging buffers the step reads, the message rows and times into the event tables."""
+        lo = self._host_cursor
+        hi = lo + self.B
+        self.src.copy_(src, non_blocking=True)
+        self.dst.copy_(dst, non_blocking=True)
+        self.t.copy_(t, non_blocking=True)
+        self.neg.copy_(neg.view(self.B, -1), non_blocking=True)
+        self.msg[lo:hi].copy_(msg, non_blocking=True)
+        self.t_tab[lo:hi].copy_(t, non_blocking=True)
+        self._host_cursor = hi
+        return self.B * (8 * (3 + self.n_neg) + 4 * self.Fe)
 
     def set_cursor(self, event_index: int):
         self.w["counters"][0] = int(event_index)
@@ -182,7 +208,7 @@ class StepEngine:
              ptr(w["n_id"]), N, ptr(ld._assoc), ptr(w["rowptr"]), E, ptr(w["counts"]))
         call("ctan_nbr_fill", ptr(ld.neighbors), ptr(ld.e_id), S, ptr(w["n_id"]), ptr(w["rowptr"]), ptr(ld._assoc),
              N, Nd, ptr(w["esrc"]), ptr(w["edst"]), ptr(w["eid"]), ptr(ld._bitmap), ptr(ld._cbitmap))
-        call("ctan_edge_rel", ptr(lu), ptr(w["n_id"]), ptr(w["esrc"]), ptr(self.t), ptr(w["eid"]), E, Ed,
+        call("ctan_edge_rel", ptr(lu), ptr(w["n_id"]), ptr(w["esrc"]), ptr(self.t_tab), ptr(w["eid"]), E, Ed,
              float(m.gnn.mean_delta_t), float(m.gnn.std_delta_t), ptr(w["rel"]))
         if train:
             call("ctan_gather_rows2", ptr(mem), D, xf, Fn, ptr(w["n_id"]), N, Nd, ptr(w["z0"]))
@@ -268,6 +294,8 @@ class StepEngine:
 
     def run(self, n_steps: int, train: bool = True):
         """Advance n_steps full batches from the cursor (no host synchronisation)."""
+        if self.loader.cur_e_id + n_steps * self.B > self.n_events:
+            raise ValueError(f"stream exhausted: cursor {self.loader.cur_e_id} + {n_steps}x{self.B} > {self.n_events}")
         with torch.cuda.device(self.dev):
             if self.use_graph:
                 g = self._graph(train)

@@ -1,0 +1,96 @@
+"""The zero-sync StepEngine (CUDA-graph replay of the whole per-batch step) against the oracle's
+restated training / inference loops (train_link.py:237-282, 361-405) on the same stream."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(st, tgb, K, D, T, H, final_act, S, B, use_graph, eps=0.5):
+    from ctan_b200.engine import StepEngine
+    from ctan_b200.models import CTAN, CTAN_tgb, LastNeighborLoader
+    from oracle import ctan_oracle as O
+    dev = torch.device("cuda:0")
+    kw = dict(num_nodes=st["num_nodes"], edge_dim=st["msg"].size(1), memory_dim=D, time_dim=T, node_dim=1,
+              num_iters=K, epsilon=eps, gamma=0.1, readout_hidden=H, mean_delta_t=np.float64(1234.5),
+              std_delta_t=np.float64(4567.8), final_act=final_act)
+    torch.manual_seed(0)
+    om = O.OracleCTAN(**kw, tgb=tgb)
+    torch.manual_seed(0)
+    mm = (CTAN_tgb if tgb else CTAN)(**kw).to(dev)
+    ld = LastNeighborLoader(st["num_nodes"], S, device=dev)
+    g = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in st.items()}
+    g["neg"] = st["neg"].view(-1, 1).to(dev)
+    eng = StepEngine(mm, ld, g, batch_size=B, n_neg=1, lr=1e-3, use_graph=use_graph)
+    eng.reset(reset_optimizer=True)
+    eng.warmup()
+    return om, mm, ld, eng
+
+
+@pytest.mark.parametrize("tgb,K,final_act,use_graph", [(False, 1, None, True), (True, 2, "tanh", True),
+                                                        (False, 3, "tanh", False)])
+def test_engine_training_matches_oracle(small_stream, tgb, K, final_act, use_graph):
+    from oracle import ctan_oracle as O
+    st = small_stream
+    B, S, steps = 200, 5, 10
+    om, mm, ld, eng = _setup(st, tgb, K, 32, 8, 16, final_act, S, B, use_graph)
+    lo_ref = O.TorchNeighborLoader(st["num_nodes"], S)
+    h = torch.zeros(st["num_nodes"], dtype=torch.long)
+    opt = torch.optim.Adam(om.parameters(), lr=1e-3)
+    ref_losses = []
+    for it in range(steps):
+        l, _, _ = O.train_step_ref(om, lo_ref, h, opt, st, it * B, (it + 1) * B, st["neg"][it * B:(it + 1) * B])
+        ref_losses.append(float(l))
+    eng.run(steps, train=True)
+    torch.cuda.synchronize()
+    eng.check()
+    mine = eng.losses(steps).cpu().tolist()
+    for a, b in zip(mine, ref_losses):
+        assert abs(a - b) <= 2e-4 * abs(b) + 1e-6, (mine, ref_losses)
+    assert eng.cursor == steps * B and ld.cur_e_id == steps * B
+    assert torch.equal(ld.e_id.cpu(), lo_ref.e_id)
+    assert torch.equal(mm.memory.last_update.cpu(), om.memory.last_update)
+    mo = om.memory.memory
+    assert float((mm.memory.memory.cpu() - mo).abs().max()) <= 5e-4 * float(mo.abs().max())
+    po = dict(om.named_parameters())
+    for k, p in mm.named_parameters():
+        if "lin_skip" in k:
+            continue
+        d = float((p.detach().cpu() - po[k].detach()).abs().max())
+        assert d <= 5e-4 * float(po[k].abs().max()) + 1e-6, (k, d)
+
+
+def test_engine_inference_matches_oracle(small_stream):
+    from oracle import ctan_oracle as O
+    st = small_stream
+    B, S, steps = 200, 10, 8
+    om, mm, ld, eng = _setup(st, True, 1, 64, 16, 64, None, S, B, True)
+    lo_ref = O.TorchNeighborLoader(st["num_nodes"], S)
+    h = torch.zeros(st["num_nodes"], dtype=torch.long)
+    crit = torch.nn.BCEWithLogitsLoss()
+    ref = []
+    for it in range(steps):
+        po, no = O.infer_step_ref(om, lo_ref, h, st, it * B, (it + 1) * B, st["neg"][it * B:(it + 1) * B])
+        ref.append(float(crit(po, torch.ones_like(po)) + crit(no, torch.zeros_like(no))))
+    eng.run(steps, train=False)
+    torch.cuda.synchronize()
+    eng.check()
+    mine = eng.losses(steps).cpu().tolist()
+    for a, b in zip(mine, ref):
+        assert abs(a - b) <= 2e-4 * abs(b) + 1e-6, (mine, ref)
+    assert torch.equal(ld.e_id.cpu(), lo_ref.e_id)
+    assert torch.equal(mm.memory.last_update.cpu(), om.memory.last_update)
+
+
+def test_engine_then_dropin_loop_share_state(small_stream):
+    """The engine mutates the same module objects the drop-in API uses."""
+    st = small_stream
+    B, S = 100, 5
+    om, mm, ld, eng = _setup(st, False, 1, 32, 8, 16, None, S, B, True)
+    eng.run(3, train=True)
+    torch.cuda.synchronize()
+    dev = torch.device("cuda:0")
+    s, d = st["src"][300:400].to(dev), st["dst"][300:400].to(dev)
+    n_id, ei, eid = ld(torch.cat([s, d]).unique())
+    assert int(eid.max()) < 300 and ld.cur_e_id == 300
