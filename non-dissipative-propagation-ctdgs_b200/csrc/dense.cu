@@ -118,17 +118,22 @@ extern "C" int ctan_readout_bwd(const float* dOUT, const float* H, const float* 
                                 float* dWsrc, float* dbsrc, float* dWdst, float* dbdst, float* dWfin, float* dbfin,
                                 cudaStream_t stream) {
     if (P <= 0) return 0;
-    head_bwd_kernel<<<ctan_grid((long long)P * Hd, 256), 256, 0, stream>>>(dOUT, H, P, P_dev, Hd, O, Wfin, dHid);
-    CTAN_CHECK_LAUNCH();
+    // Two independent halves (so a caller can put them on different streams):
+    //   dZ != NULL    -> dHid = head backward, then the two scatter contractions into dZ
+    //   dWdst != NULL -> the weight/bias gradients (reads dHid computed by the first half)
+    if (dZ) {
+        head_bwd_kernel<<<ctan_grid((long long)P * Hd, 256), 256, 0, stream>>>(dOUT, H, P, P_dev, Hd, O, Wfin, dHid);
+        CTAN_CHECK_LAUNCH();
+    }
     int rc;
-    {   // dWfin[O,Hd] += dOUT^T relu(H);  dbfin += colsum(dOUT)
+    if (dWdst) {   // dWfin[O,Hd] += dOUT^T relu(H);  dbfin += colsum(dOUT)
         AColMajor A{dOUT, O};
         BRelu B{H, Hd};
         EpiAtomic epi{dWfin, Hd, dbfin};
         rc = launch(A, B, epi, O, nullptr, Hd, P, P_dev, pick_splits(O, Hd, P), stream);
         if (rc) return rc;
     }
-    {   // [dWsrc | dWdst] += dHid^T [z[src] | z[dst]];  dbsrc,dbdst += colsum(dHid)
+    if (dWdst) {   // [dWsrc | dWdst] += dHid^T [z[src] | z[dst]];  dbsrc,dbdst += colsum(dHid)
         const int K1 = Wsrc ? D : 0;
         AColMajor A{dHid, Hd};
         BGather2 B{Z, D, src, K1, Z, D, dst, map};
@@ -136,7 +141,7 @@ extern "C" int ctan_readout_bwd(const float* dOUT, const float* H, const float* 
         rc = launch(A, B, epi, Hd, nullptr, K1 + D, P, P_dev, pick_splits(Hd, K1 + D, P), stream);
         if (rc) return rc;
     }
-    {   // dZ[row(src)] += dHid Wsrc ; dZ[row(dst)] += dHid Wdst
+    if (dZ) {   // dZ[row(src)] += dHid Wsrc ; dZ[row(dst)] += dHid Wdst
         ARowMajor A{dHid, Hd};
         if (Wsrc) {
             BRowMajor B1{Wsrc, D};
@@ -162,14 +167,14 @@ extern "C" int ctan_qkva_bwd(const float* DQKVA, const float* X, const float* G,
                              float* db, cudaStream_t stream) {
     if (N <= 0) return 0;
     int rc;
-    {
+    if (dXin) {      // either half may be skipped (NULL outputs) so the two can run on different streams
         ARowMajor A{DQKVA, 4 * D};
         BRowSeg4 B{{Wq, Wk, Wv, A_}, D, D};
         EpiStore epi{dXin, D, nullptr, nullptr, G, D};
         rc = launch(A, B, epi, N, N_dev, D, 4 * D, nullptr, 1, stream);
         if (rc) return rc;
     }
-    {
+    if (dWq) {
         AColMajor A{DQKVA, 4 * D};
         BRowMajor B{X, D};
         EpiAtomicSeg4 epi{{dWq, dWk, dWv, dA}, {dbq, dbk, dbv, db}, D, D};

@@ -329,27 +329,41 @@ extern "C" int ctan_tanh_bwd(const float* dZ, const float* Z, int N, const int* 
 __global__ void tenc_bwd_kernel(const float* __restrict__ dTenc, const float* __restrict__ rel,
                                 const float* __restrict__ tw, const float* __restrict__ tb, int E_host,
                                 const int* __restrict__ E_dev, int T, float* __restrict__ dtw, float* __restrict__ dtb) {
+    // block = 256 threads = G groups x Tc columns; a block reduces a slab of 128 edges
+    __shared__ float s_w[256], s_b[256];
     const int E = E_dev ? *E_dev : E_host;
     const int e0 = blockIdx.x * 128, e1 = min(E, e0 + 128);
     if (e0 >= E) return;
-    for (int tau = threadIdx.x; tau < T; tau += blockDim.x) {
-        const float w = tw[tau], b = tb[tau];
+    const int Tc = min(T, 256);
+    const int G = 256 / Tc;
+    const int grp = threadIdx.x / Tc, col = threadIdx.x % Tc;
+    for (int tau0 = 0; tau0 < T; tau0 += Tc) {
+        const int tau = tau0 + col;
         float sw = 0.f, sb = 0.f;
-        for (int e = e0; e < e1; ++e) {
-            const float r = rel[e];
-            const float g = -sinf(fmaf(r, w, b)) * dTenc[(size_t)e * T + tau];
-            sw = fmaf(g, r, sw);
-            sb += g;
+        if (grp < G && tau < T) {
+            const float w = tw[tau], b = tb[tau];
+            for (int e = e0 + grp; e < e1; e += G) {
+                const float r = rel[e];
+                const float g = -sinf(fmaf(r, w, b)) * dTenc[(size_t)e * T + tau];
+                sw = fmaf(g, r, sw);
+                sb += g;
+            }
         }
-        atomicAdd(dtw + tau, sw);
-        atomicAdd(dtb + tau, sb);
+        s_w[threadIdx.x] = sw;
+        s_b[threadIdx.x] = sb;
+        __syncthreads();
+        if (grp == 0 && tau < T) {
+            for (int g2 = 1; g2 < G; ++g2) { sw += s_w[g2 * Tc + col]; sb += s_b[g2 * Tc + col]; }
+            atomicAdd(dtw + tau, sw);
+            atomicAdd(dtb + tau, sb);
+        }
+        __syncthreads();
     }
 }
 extern "C" int ctan_tenc_bwd(const float* dTenc, const float* rel, const float* tw, const float* tb, int E,
                              const int* E_dev, int T, float* dtw, float* dtb, cudaStream_t stream) {
     if (E <= 0 || T <= 0) return 0;
-    const int threads = T >= 256 ? 256 : ((T + 31) / 32) * 32;
-    tenc_bwd_kernel<<<ctan_div_up(E, 128), threads, 0, stream>>>(dTenc, rel, tw, tb, E, E_dev, T, dtw, dtb);
+    tenc_bwd_kernel<<<ctan_div_up(E, 128), 256, 0, stream>>>(dTenc, rel, tw, tb, E, E_dev, T, dtw, dtb);
     CTAN_CHECK_LAUNCH();
     return 0;
 }

@@ -79,16 +79,28 @@ class StepEngine:
         self.O = model.readout.lin_final.weight.size(0)
         if self.O != 1:
             raise NotImplementedError("StepEngine's fused loss is binary (readout_out=1)")
+        self.P = self.B * (1 + self.n_neg)
+        self.n_seeds = self.B * (2 + self.n_neg)
+        self.n_cap = min(self.num_nodes, self.n_seeds * (self.S + 1) ** self.K)
+        c_cap = min(self.num_nodes, self.n_seeds * (self.S + 1) ** (self.K - 1))
+        self.e_cap = max(c_cap * self.S, 1)
         self._flatten_params()
         self._alloc()
         self._graphs = {}
+        self._side = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
 
     # ------------------------------------------------------------------ parameters in one flat buffer
     def _flatten_params(self):
         plist = _param_list(self.model)
         n = sum(p.numel() for p in plist)
         self.flat_p = torch.empty(n, device=self.dev)
-        self.flat_g = torch.zeros(n, device=self.dev)
+        # everything the backward accumulates into lives in ONE buffer so a single memset clears it
+        N, D = self.n_cap, self.D
+        self.zero_buf = torch.zeros(n + D * D + N * D + N * 4 * D, device=self.dev)
+        self.flat_g = self.zero_buf[:n]
+        self._dA = self.zero_buf[n:n + D * D].view(D, D)
+        self._dZ = self.zero_buf[n + D * D:n + D * D + N * D].view(N, D)
+        self._DQKVA = self.zero_buf[n + D * D + N * D:].view(N, 4 * D)
         self.adam_m = torch.zeros(n, device=self.dev)
         self.adam_v = torch.zeros(n, device=self.dev)
         self.p, self.g = [], []
@@ -108,12 +120,7 @@ class StepEngine:
         dev, B, S, K, D = self.dev, self.B, self.S, self.K, self.D
         f32 = dict(device=dev, dtype=torch.float32)
         i64 = dict(device=dev, dtype=torch.long)
-        self.P = B * (1 + self.n_neg)
-        n_seeds = B * (2 + self.n_neg)
-        self.n_seeds = n_seeds
-        self.n_cap = min(self.num_nodes, n_seeds * (S + 1) ** K)
-        c_cap = min(self.num_nodes, n_seeds * (S + 1) ** (K - 1))
-        self.e_cap = max(c_cap * S, 1)
+        n_seeds = self.n_seeds
         N, E, P = self.n_cap, self.e_cap, self.P
         w = {}
         w["counters"] = torch.zeros(8, **i64)
@@ -142,13 +149,13 @@ class StepEngine:
         w["loss_hist"] = torch.zeros(self.hist_cap, **f32)
         # backward
         w["dHid"] = torch.zeros((P, self.Hd), **f32)
-        w["dZ"] = torch.zeros((N, D), **f32)
+        w["dZ"] = self._dZ
         w["gA"], w["gB"] = torch.zeros((N, D), **f32), torch.zeros((N, D), **f32)
-        w["DQKVA"] = torch.zeros((N, 4 * D), **f32)
+        w["DQKVA"] = self._DQKVA
         w["dEP"] = torch.zeros((E, D), **f32)
         w["DS"] = torch.zeros(E, **f32)
         w["dTenc"] = torch.zeros((E, max(self.T, 1)), **f32)
-        w["dA"] = torch.zeros((D, D), **f32)
+        w["dA"] = self._dA
         self.w = w
         self._Nd = w["counts"][0:1]
         self._Ed = w["counts"][1:2]
@@ -188,8 +195,18 @@ class StepEngine:
     def cursor(self) -> int:
         return int(self.w["counters"][0].item())
 
-    # ------------------------------------------------------------------ one step = one stream of launches
+    # ------------------------------------------------------------------ one step = one DAG of launches
+    def _fork(self, i):
+        self._side[i].wait_stream(torch.cuda.current_stream())
+        return torch.cuda.stream(self._side[i])
+
+    def _join(self, i):
+        torch.cuda.current_stream().wait_stream(self._side[i])
+
     def _launch(self, train: bool):
+        """Issue one step.  Work that is off the critical path (edge projection, weight gradients,
+        state write-back) goes to two side streams with fork/join edges; under graph capture these
+        become parallel branches of the captured DAG."""
         w, m, ld = self.w, self.model, self.loader
         B, D, K, S, Fe, Fn, T = self.B, self.D, self.K, self.S, self.Fe, self.Fn, self.T
         Hd, O, P = self.Hd, self.O, self.P
@@ -200,6 +217,7 @@ class StepEngine:
         mem, lu = m.memory.memory, m.memory.last_update
         cur1 = ptr(w["counters"]) + 8                       # &counters[1]: current batch start
         xf = ptr(self.x) if Fn else None
+        eps = float(m.gnn.aconv.epsilon)
         call("ctan_stage_batch", ptr(self.src), ptr(self.dst), ptr(self.t), ptr(self.neg), self.n_neg, B,
              ptr(w["counters"]), 0 if self.host_staged else 1, ptr(w["b_src"]), ptr(w["b_dst"]), ptr(w["b_t"]),
              ptr(w["seeds"]), ptr(w["pair_src"]), ptr(w["pair_dst"]))
@@ -208,16 +226,19 @@ class StepEngine:
              ptr(w["n_id"]), N, ptr(ld._assoc), ptr(w["rowptr"]), E, ptr(w["counts"]))
         call("ctan_nbr_fill", ptr(ld.neighbors), ptr(ld.e_id), S, ptr(w["n_id"]), ptr(w["rowptr"]), ptr(ld._assoc),
              N, Nd, ptr(w["esrc"]), ptr(w["edst"]), ptr(w["eid"]), ptr(ld._bitmap), ptr(ld._cbitmap))
-        call("ctan_edge_rel", ptr(lu), ptr(w["n_id"]), ptr(w["esrc"]), ptr(self.t_tab), ptr(w["eid"]), E, Ed,
-             float(m.gnn.mean_delta_t), float(m.gnn.std_delta_t), ptr(w["rel"]))
+        with self._fork(0):                                  # side 0: A, edge-attr projection, grad memset
+            call("ctan_edge_rel", ptr(lu), ptr(w["n_id"]), ptr(w["esrc"]), ptr(self.t_tab), ptr(w["eid"]), E, Ed,
+                 float(m.gnn.mean_delta_t), float(m.gnn.std_delta_t), ptr(w["rel"]))
+            call("ctan_eproj_fwd", ptr(self.msg), Fe, ptr(w["eid"]), ptr(w["rel"]), tw, tb, T, We, E, Ed, D,
+                 ptr(w["EP"]))
+            call("ctan_antisym_prep", W, float(m.gnn.aconv.gamma), D, ptr(w["A"]))
+            if train:
+                self.zero_buf.zero_()
         if train:
-            call("ctan_gather_rows2", ptr(mem), D, xf, Fn, ptr(w["n_id"]), N, Nd, ptr(w["z0"]))
-            call("ctan_enc_fwd", None, D, None, Fn, None, ptr(w["z0"]), N, Nd, Wenc, benc, ptr(w["X"][0]))
-        else:
-            call("ctan_enc_fwd", ptr(mem), D, xf, Fn, ptr(w["n_id"]), None, N, Nd, Wenc, benc, ptr(w["X"][0]))
-        call("ctan_eproj_fwd", ptr(self.msg), Fe, ptr(w["eid"]), ptr(w["rel"]), tw, tb, T, We, E, Ed, D, ptr(w["EP"]))
-        call("ctan_antisym_prep", W, float(m.gnn.aconv.gamma), D, ptr(w["A"]))
-        eps = float(m.gnn.aconv.epsilon)
+            with self._fork(1):                              # side 1: saved copy of the gathered input rows
+                call("ctan_gather_rows2", ptr(mem), D, xf, Fn, ptr(w["n_id"]), N, Nd, ptr(w["z0"]))
+        call("ctan_enc_fwd", ptr(mem), D, xf, Fn, ptr(w["n_id"]), None, N, Nd, Wenc, benc, ptr(w["X"][0]))
+        self._join(0)
         for k in range(K):
             xi = w["X"][k] if train else w["X"][k & 1]
             xo = w["X"][k + 1] if train else w["X"][(k + 1) & 1]
@@ -234,39 +255,50 @@ class StepEngine:
              Wsrc, bsrc, Wdst, bdst, Wfin, bfin, ptr(w["H"]), ptr(w["OUT"]))
         call("ctan_bce_loss", ptr(w["OUT"]), B, P - B, ptr(w["dOUT"]) if train else None, ptr(w["loss_hist"]),
              self.hist_cap, ptr(w["counters"]))
-        # ground-truth state update (train_link.py:276-277); the backward below only reads saved copies
-        call("ctan_mem_update", ptr(mem), ptr(lu), D, ptr(w["b_src"]), ptr(w["b_dst"]), ptr(w["b_t"]), B, None,
-             None, ptr(z), ptr(ld._assoc))
-        call("ctan_nbr_insert", ptr(ld.neighbors), ptr(ld.e_id), ptr(ld._deg), ptr(w["b_src"]), ptr(w["b_dst"]), B,
-             0, cur1, S, ptr(w["ins_ws"]))
+
+        def state_update():
+            # ground-truth state update (train_link.py:276-277)
+            call("ctan_mem_update", ptr(mem), ptr(lu), D, ptr(w["b_src"]), ptr(w["b_dst"]), ptr(w["b_t"]), B, None,
+                 None, ptr(z), ptr(ld._assoc))
+            call("ctan_nbr_insert", ptr(ld.neighbors), ptr(ld.e_id), ptr(ld._deg), ptr(w["b_src"]), ptr(w["b_dst"]),
+                 B, 0, cur1, S, ptr(w["ins_ws"]))
         if not train:
+            state_update()
             return
+        with self._fork(1):                                  # side 1 (after the z0 gather): state write-back
+            state_update()
         (gWenc, gbenc, gWq, gbq, gWk, gbk, gWv, gbv, gWe, gW, gb, gtw, gtb, gWsrc, gbsrc, gWdst, gbdst, gWfin,
          gbfin) = (ptr(t) for t in self.g)
-        self.flat_g.zero_()
-        w["dZ"].zero_()
-        w["dA"].zero_()
-        call("ctan_readout_bwd", ptr(w["dOUT"]), ptr(w["H"]), ptr(z), D, ptr(w["pair_src"]), ptr(w["pair_dst"]),
-             ptr(ld._assoc), P, None, Hd, O, Wsrc, Wdst, Wfin, ptr(w["dHid"]), ptr(w["dZ"]), gWsrc, gbsrc, gWdst,
-             gbdst, gWfin, gbfin)
+        rb_args = (ptr(w["dOUT"]), ptr(w["H"]), ptr(z), D, ptr(w["pair_src"]), ptr(w["pair_dst"]), ptr(ld._assoc), P,
+                   None, Hd, O, Wsrc, Wdst, Wfin, ptr(w["dHid"]))
+        call("ctan_readout_bwd", *rb_args, ptr(w["dZ"]), None, None, None, None, None, None)
+        with self._fork(0):                                  # side 0: readout weight gradients
+            call("ctan_readout_bwd", *rb_args, None, gWsrc, gbsrc, gWdst, gbdst, gWfin, gbfin)
         g = w["dZ"]
         if self.final_tanh:
             call("ctan_tanh_bwd", ptr(w["dZ"]), ptr(z), N, Nd, D, ptr(w["gA"]))
             g = w["gA"]
         for k in range(K - 1, -1, -1):
-            w["DQKVA"].zero_()
+            if k != K - 1:
+                self._join(0)                                # the previous iteration's dW contraction reads DQKVA
+                w["DQKVA"].zero_()
             call("ctan_edge_bwd", ptr(w["QKVA"][k]), ptr(w["EP"]), ptr(w["rowptr"]), ptr(w["esrc"]), N, Nd, D, ptr(g),
                  ptr(w["TH"][k]), ptr(w["ALPHA"][k]), eps, ptr(w["DQKVA"]), ptr(w["dEP"]), int(k != K - 1),
                  ptr(w["DS"]))
+            qb = (ptr(w["DQKVA"]), ptr(w["X"][k]), ptr(g), N, Nd, D, Wq, Wk, Wv, ptr(w["A"]))
+            with self._fork(0):                              # side 0: weight gradients of this iteration
+                call("ctan_qkva_bwd", *qb, None, gWq, gWk, gWv, ptr(w["dA"]), gbq, gbk, gbv, gb)
+                if k == 0:
+                    call("ctan_eproj_bwd", ptr(w["dEP"]), ptr(self.msg), Fe, ptr(w["eid"]), ptr(w["rel"]), tw, tb, T,
+                         We, E, Ed, D, gWe, ptr(w["dTenc"]))
+                    call("ctan_tenc_bwd", ptr(w["dTenc"]), ptr(w["rel"]), tw, tb, E, Ed, T, gtw, gtb)
+                    call("ctan_antisym_bwd", ptr(w["dA"]), D, gW)
             gn = w["gB"] if g is not w["gB"] else w["gA"]
-            call("ctan_qkva_bwd", ptr(w["DQKVA"]), ptr(w["X"][k]), ptr(g), N, Nd, D, Wq, Wk, Wv, ptr(w["A"]), ptr(gn),
-                 gWq, gWk, gWv, ptr(w["dA"]), gbq, gbk, gbv, gb)
+            call("ctan_qkva_bwd", *qb, ptr(gn), None, None, None, None, None, None, None, None)
             g = gn
+        self._join(1)                                        # z0 is complete (and the state write-back done)
         call("ctan_enc_bwd", ptr(g), ptr(w["z0"]), N, Nd, D, Fn, gWenc, gbenc)
-        call("ctan_eproj_bwd", ptr(w["dEP"]), ptr(self.msg), Fe, ptr(w["eid"]), ptr(w["rel"]), tw, tb, T, We, E, Ed,
-             D, gWe, ptr(w["dTenc"]))
-        call("ctan_tenc_bwd", ptr(w["dTenc"]), ptr(w["rel"]), tw, tb, E, Ed, T, gtw, gtb)
-        call("ctan_antisym_bwd", ptr(w["dA"]), D, gW)
+        self._join(0)
         call("ctan_adam_step", ptr(self.flat_p), ptr(self.flat_g), ptr(self.adam_m), ptr(self.adam_v),
              self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 0, ptr(w["counters"]))
 
