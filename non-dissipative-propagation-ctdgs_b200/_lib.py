@@ -36,11 +36,11 @@ SIGNATURES = {
     "ctan_enc_fwd": [P, I, P, I, P, P, I, P, P, P, P],
     "ctan_eproj_fwd": [P, I, P, P, P, P, I, P, I, P, I, P],
     "ctan_qkva_fwd": [P, I, P, I, P, P, P, P, P, P, P, P, P],
-    "ctan_readout_fwd": [P, I, P, P, P, I, P, I, I, P, P, P, P, P, P, P, P],
+    "ctan_readout_fwd": [P, I, P, P, P, I, P, I, I, P, P, P, P, P, P, P, P, I],
     "ctan_readout_bwd": [P, P, P, I, P, P, P, I, P, I, I, P, P, P, P, P, P, P, P, P, P, P],
-    "ctan_qkva_bwd": [P, P, P, I, P, I, P, P, P, P, P, P, P, P, P, P, P, P, P],
-    "ctan_enc_bwd": [P, P, I, P, I, I, P, P],
-    "ctan_eproj_bwd": [P, P, I, P, P, P, P, I, P, I, P, I, P, P],
+    "ctan_qkva_bwd": [P, P, P, I, P, I, P, P, P, P, P, P, P, P, P, P, P, P, P, I],
+    "ctan_enc_bwd": [P, P, I, P, I, I, P, P, I],
+    "ctan_eproj_bwd": [P, P, I, P, P, P, P, I, P, I, P, I, P, P, I],
 }
 
 _lib = None

@@ -11,19 +11,23 @@
 
 using namespace gemm;
 
+static inline bool v4(const void* p, int ld) { return p && aligned16(p) && (ld % 4 == 0); }
+
 // X0[N,D] = [mem[n_id] | xfeat[n_id]] Wenc^T + benc       (gather fused; n_id int64 global ids)
 // If z0 != nullptr the operand is the already-materialised dense [N, D+Fn] matrix instead.
 extern "C" int ctan_enc_fwd(const float* mem, int D, const float* xfeat, int Fn, const int64_t* n_id,
                             const float* z0, int N, const int* N_dev, const float* Wenc, const float* benc,
                             float* X0, cudaStream_t stream) {
     const int K = D + Fn;
-    BWeight B{Wenc, K};
+    BWeight B{Wenc, K, v4(Wenc, K)};
     EpiStore epi{X0, D, benc, nullptr, nullptr, 0};
     if (z0) {
-        ARowMajor A{z0, K};
+        ARowMajor A{z0, K, v4(z0, K)};
         return launch(A, B, epi, N, N_dev, D, K, nullptr, 1, stream);
     }
-    AGather2 A{mem, D, n_id, D, xfeat, Fn, n_id, nullptr};
+    // the tail segment (node features) is rarely 4-aligned: vector loads only when both segments allow it
+    const bool vec = v4(mem, D) && (Fn == 0 || v4(xfeat, Fn));
+    AGather2 A{mem, D, n_id, D, xfeat, Fn, n_id, nullptr, vec};
     return launch(A, B, epi, N, N_dev, D, K, nullptr, 1, stream);
 }
 
@@ -31,8 +35,8 @@ extern "C" int ctan_enc_fwd(const float* mem, int D, const float* xfeat, int Fn,
 extern "C" int ctan_eproj_fwd(const float* msg, int Fe, const int64_t* eidx, const float* rel, const float* tw,
                               const float* tb, int T, const float* We, int E, const int* E_dev, int D, float* EP,
                               cudaStream_t stream) {
-    AEdgeAttr A{msg, Fe, eidx, Fe, rel, tw, tb};
-    BWeight B{We, Fe + T};
+    AEdgeAttr A{msg, Fe, eidx, Fe, rel, tw, tb, v4(msg, Fe) || Fe == 0};
+    BWeight B{We, Fe + T, v4(We, Fe + T)};
     EpiStore epi{EP, D, nullptr, nullptr, nullptr, 0};
     return launch(A, B, epi, E, E_dev, D, Fe + T, nullptr, 1, stream);
 }
@@ -41,8 +45,8 @@ extern "C" int ctan_eproj_fwd(const float* msg, int Fe, const int64_t* eidx, con
 extern "C" int ctan_qkva_fwd(const float* X, int N, const int* N_dev, int D, const float* Wq, const float* Wk,
                              const float* Wv, const float* A_, const float* bq, const float* bk, const float* bv,
                              const float* b, float* QKVA, cudaStream_t stream) {
-    ARowMajor A{X, D};
-    BWeightSeg4 B{{Wq, Wk, Wv, A_}, D, D};
+    ARowMajor A{X, D, v4(X, D)};
+    BWeightSeg4 B{{Wq, Wk, Wv, A_}, D, D, v4(Wq, D) && v4(Wk, D) && v4(Wv, D) && v4(A_, D)};
     EpiStoreSeg4 epi{QKVA, 4 * D, {bq, bk, bv, b}, D};
     return launch(A, B, epi, N, N_dev, 4 * D, D, nullptr, 1, stream);
 }
@@ -66,16 +70,37 @@ __global__ void head_fwd_kernel(const float* __restrict__ H, int P_host, const i
     }
 }
 
+struct EpiAtomicBias2 {            // split-K: C += acc (+ bias + bias2 once)
+    static constexpr bool HAS_ROWSUM = false;
+    float* C; int ldc; const float* bias; const float* bias2;
+    __device__ __forceinline__ void operator()(int m, int n, float v, bool first) const {
+        if (first) {
+            if (bias) v += __ldg(bias + n);
+            if (bias2) v += __ldg(bias2 + n);
+        }
+        atomicAdd(C + (size_t)m * ldc + n, v);
+    }
+    __device__ __forceinline__ void rowsum(int, float) const {}
+};
+
+// h_zeroed != 0: the caller guarantees H is all zeros, which lets the hidden contraction split K over
+// more CTAs (P is a few hundred rows: 7 CTAs otherwise).
 extern "C" int ctan_readout_fwd(const float* Z, int D, const int64_t* src, const int64_t* dst, const int64_t* map,
                                 int P, const int* P_dev, int Hd, int O, const float* Wsrc, const float* bsrc,
                                 const float* Wdst, const float* bdst, const float* Wfin, const float* bfin, float* H,
-                                float* OUT, cudaStream_t stream) {
+                                float* OUT, int h_zeroed, cudaStream_t stream) {
     if (P <= 0) return 0;
     const int K1 = Wsrc ? D : 0;          // Wsrc == nullptr: SequencePredictor (destination row only)
-    AGather2 A{Z, D, src, K1, Z, D, dst, map};
-    BWeightCat2 B{Wsrc, D, K1, Wdst, D};
-    EpiStore epi{H, Hd, bsrc, bdst, nullptr, 0};
-    int rc = launch(A, B, epi, P, P_dev, Hd, K1 + D, nullptr, 1, stream);
+    AGather2 A{Z, D, src, K1, Z, D, dst, map, v4(Z, D)};
+    BWeightCat2 B{Wsrc, D, K1, Wdst, D, v4(Wdst, D) && (!Wsrc || v4(Wsrc, D))};
+    int rc;
+    if (h_zeroed) {
+        EpiAtomicBias2 epi{H, Hd, bsrc, bdst};
+        rc = launch(A, B, epi, P, P_dev, Hd, K1 + D, nullptr, pick_splits(P, Hd, K1 + D), stream);
+    } else {
+        EpiStore epi{H, Hd, bsrc, bdst, nullptr, 0};
+        rc = launch(A, B, epi, P, P_dev, Hd, K1 + D, nullptr, 1, stream);
+    }
     if (rc) return rc;
     head_fwd_kernel<<<ctan_grid((long long)P * 32, 256), 256, 0, stream>>>(H, P, P_dev, Hd, O, Wfin, bfin, OUT);
     CTAN_CHECK_LAUNCH();
@@ -100,7 +125,7 @@ __global__ void head_bwd_kernel(const float* __restrict__ dOUT, const float* __r
 struct EpiAtomicColSeg2 {          // columns split at K1: [C0 | C1] (each row stride D); rowsum added to rs0 and rs1
     static constexpr bool HAS_ROWSUM = true;
     float* C0; float* C1; int K1; int D; float* rs0; float* rs1;
-    __device__ __forceinline__ void operator()(int m, int n, float v) const {
+    __device__ __forceinline__ void operator()(int m, int n, float v, bool) const {
         if (n < K1) atomicAdd(C0 + (size_t)m * D + n, v); else atomicAdd(C1 + (size_t)m * D + (n - K1), v);
     }
     __device__ __forceinline__ void rowsum(int m, float v) const {
@@ -112,73 +137,77 @@ struct EpiAtomicColSeg2 {          // columns split at K1: [C0 | C1] (each row s
 // Gradients of the readout.  All outputs are ACCUMULATED (+=): zero them first.
 //   dZ[N,D] += scatter(dHid Wsrc -> row(src)) + scatter(dHid Wdst -> row(dst))
 //   dWsrc,dWdst [Hd,D], dbsrc,dbdst [Hd], dWfin [O,Hd], dbfin [O];  dHid [P,Hd] is scratch.
+// Two independent halves (so a caller can put them on different streams):
+//   dZ != NULL    -> dHid = head backward, then the two scatter contractions into dZ
+//   dWdst != NULL -> the weight/bias gradients (reads dHid computed by the first half)
 extern "C" int ctan_readout_bwd(const float* dOUT, const float* H, const float* Z, int D, const int64_t* src,
                                 const int64_t* dst, const int64_t* map, int P, const int* P_dev, int Hd, int O,
                                 const float* Wsrc, const float* Wdst, const float* Wfin, float* dHid, float* dZ,
                                 float* dWsrc, float* dbsrc, float* dWdst, float* dbdst, float* dWfin, float* dbfin,
                                 cudaStream_t stream) {
     if (P <= 0) return 0;
-    // Two independent halves (so a caller can put them on different streams):
-    //   dZ != NULL    -> dHid = head backward, then the two scatter contractions into dZ
-    //   dWdst != NULL -> the weight/bias gradients (reads dHid computed by the first half)
+    int rc;
     if (dZ) {
         head_bwd_kernel<<<ctan_grid((long long)P * Hd, 256), 256, 0, stream>>>(dOUT, H, P, P_dev, Hd, O, Wfin, dHid);
         CTAN_CHECK_LAUNCH();
-    }
-    int rc;
-    if (dWdst) {   // dWfin[O,Hd] += dOUT^T relu(H);  dbfin += colsum(dOUT)
-        AColMajor A{dOUT, O};
-        BRelu B{H, Hd};
-        EpiAtomic epi{dWfin, Hd, dbfin};
-        rc = launch(A, B, epi, O, nullptr, Hd, P, P_dev, pick_splits(O, Hd, P), stream);
-        if (rc) return rc;
-    }
-    if (dWdst) {   // [dWsrc | dWdst] += dHid^T [z[src] | z[dst]];  dbsrc,dbdst += colsum(dHid)
-        const int K1 = Wsrc ? D : 0;
-        AColMajor A{dHid, Hd};
-        BGather2 B{Z, D, src, K1, Z, D, dst, map};
-        EpiAtomicColSeg2 epi{dWsrc, dWdst, K1, D, dbsrc, dbdst};
-        rc = launch(A, B, epi, Hd, nullptr, K1 + D, P, P_dev, pick_splits(Hd, K1 + D, P), stream);
-        if (rc) return rc;
-    }
-    if (dZ) {   // dZ[row(src)] += dHid Wsrc ; dZ[row(dst)] += dHid Wdst
-        ARowMajor A{dHid, Hd};
+        // dZ[row(src)] += dHid Wsrc ; dZ[row(dst)] += dHid Wdst
+        ARowMajor A{dHid, Hd, v4(dHid, Hd)};
         if (Wsrc) {
-            BRowMajor B1{Wsrc, D};
+            BRowMajor B1{Wsrc, D, v4(Wsrc, D)};
             EpiScatterAtomic e1{dZ, D, src, map};
-            rc = launch(A, B1, e1, P, P_dev, D, Hd, nullptr, 1, stream);
+            rc = launch(A, B1, e1, P, P_dev, D, Hd, nullptr, pick_splits(P, D, Hd), stream);
             if (rc) return rc;
         }
-        BRowMajor B2{Wdst, D};
+        BRowMajor B2{Wdst, D, v4(Wdst, D)};
         EpiScatterAtomic e2{dZ, D, dst, map};
-        rc = launch(A, B2, e2, P, P_dev, D, Hd, nullptr, 1, stream);
+        rc = launch(A, B2, e2, P, P_dev, D, Hd, nullptr, pick_splits(P, D, Hd), stream);
         if (rc) return rc;
+    }
+    if (dWdst) {
+        {   // dWfin[O,Hd] += dOUT^T relu(H);  dbfin += colsum(dOUT)
+            AColMajor A{dOUT, O, v4(dOUT, O)};
+            BRelu B{H, Hd, v4(H, Hd)};
+            EpiAtomic epi{dWfin, Hd, dbfin, nullptr, 0};
+            rc = launch(A, B, epi, O, nullptr, Hd, P, P_dev, pick_splits(O, Hd, P), stream);
+            if (rc) return rc;
+        }
+        {   // [dWsrc | dWdst] += dHid^T [z[src] | z[dst]];  dbsrc,dbdst += colsum(dHid)
+            const int K1 = Wsrc ? D : 0;
+            AColMajor A{dHid, Hd, v4(dHid, Hd)};
+            BGather2 B{Z, D, src, K1, Z, D, dst, map, v4(Z, D)};
+            EpiAtomicColSeg2 epi{dWsrc, dWdst, K1, D, dbsrc, dbdst};
+            rc = launch(A, B, epi, Hd, nullptr, K1 + D, P, P_dev, pick_splits(Hd, K1 + D, P), stream);
+            if (rc) return rc;
+        }
     }
     return 0;
 }
 
 // ---------------------------------------------------------------------------------------- embed backward
 // One anti-symmetric iteration, given DQKVA[N,4D] (from ctan_edge_bwd) and G = dL/dx_out:
-//   dXin[N,D] = G + DQKVA [Wq;Wk;Wv;A]
+//   dXin[N,D] += G + DQKVA [Wq;Wk;Wv;A]          (dXin must be ZERO on entry: the contraction splits K)
 //   dWq,dWk,dWv,dA [D,D] += DQKVA_seg^T X ;  dbq,dbk,dbv,db [D] += colsum(DQKVA_seg)     (accumulated)
+// Either half may be skipped (NULL outputs) so the two can run on different streams.
+// n_typ: typical true N when N is only an upper bound (sizes the K split); 0 = N.
 extern "C" int ctan_qkva_bwd(const float* DQKVA, const float* X, const float* G, int N, const int* N_dev, int D,
                              const float* Wq, const float* Wk, const float* Wv, const float* A_, float* dXin,
                              float* dWq, float* dWk, float* dWv, float* dA, float* dbq, float* dbk, float* dbv,
-                             float* db, cudaStream_t stream) {
+                             float* db, int n_typ, cudaStream_t stream) {
     if (N <= 0) return 0;
+    if (n_typ <= 0 || n_typ > N) n_typ = N;
     int rc;
-    if (dXin) {      // either half may be skipped (NULL outputs) so the two can run on different streams
-        ARowMajor A{DQKVA, 4 * D};
-        BRowSeg4 B{{Wq, Wk, Wv, A_}, D, D};
-        EpiStore epi{dXin, D, nullptr, nullptr, G, D};
-        rc = launch(A, B, epi, N, N_dev, D, 4 * D, nullptr, 1, stream);
+    if (dXin) {
+        ARowMajor A{DQKVA, 4 * D, v4(DQKVA, 4 * D)};
+        BRowSeg4 B{{Wq, Wk, Wv, A_}, D, D, v4(Wq, D) && v4(Wk, D) && v4(Wv, D) && v4(A_, D)};
+        EpiAtomic epi{dXin, D, nullptr, G, D};
+        rc = launch(A, B, epi, N, N_dev, D, 4 * D, nullptr, pick_splits(n_typ, D, 4 * D), stream);
         if (rc) return rc;
     }
     if (dWq) {
-        AColMajor A{DQKVA, 4 * D};
-        BRowMajor B{X, D};
+        AColMajor A{DQKVA, 4 * D, v4(DQKVA, 4 * D)};
+        BRowMajor B{X, D, v4(X, D)};
         EpiAtomicSeg4 epi{{dWq, dWk, dWv, dA}, {dbq, dbk, dbv, db}, D, D};
-        rc = launch(A, B, epi, 4 * D, nullptr, D, N, N_dev, pick_splits(4 * D, D, N), stream);
+        rc = launch(A, B, epi, 4 * D, nullptr, D, N, N_dev, pick_splits(4 * D, D, n_typ), stream);
         if (rc) return rc;
     }
     return 0;
@@ -186,30 +215,32 @@ extern "C" int ctan_qkva_bwd(const float* DQKVA, const float* X, const float* G,
 
 // dWenc[D, D+Fn] += dX0^T Z0 ; dbenc[D] += colsum(dX0)          (Z0 = materialised [mem|x] rows)
 extern "C" int ctan_enc_bwd(const float* dX0, const float* Z0, int N, const int* N_dev, int D, int Fn, float* dWenc,
-                            float* dbenc, cudaStream_t stream) {
+                            float* dbenc, int n_typ, cudaStream_t stream) {
     if (N <= 0) return 0;
-    AColMajor A{dX0, D};
-    BRowMajor B{Z0, D + Fn};
-    EpiAtomic epi{dWenc, D + Fn, dbenc};
-    return launch(A, B, epi, D, nullptr, D + Fn, N, N_dev, pick_splits(D, D + Fn, N), stream);
+    if (n_typ <= 0 || n_typ > N) n_typ = N;
+    AColMajor A{dX0, D, v4(dX0, D)};
+    BRowMajor B{Z0, D + Fn, v4(Z0, D + Fn)};
+    EpiAtomic epi{dWenc, D + Fn, dbenc, nullptr, 0};
+    return launch(A, B, epi, D, nullptr, D + Fn, N, N_dev, pick_splits(D, D + Fn, n_typ), stream);
 }
 
 // dWe[D, Fe+T] += dEP^T [msg | cos(.)] ;  dTenc[E,T] = dEP We[:,Fe:]   (scratch for ctan_tenc_bwd)
 extern "C" int ctan_eproj_bwd(const float* dEP, const float* msg, int Fe, const int64_t* eidx, const float* rel,
                               const float* tw, const float* tb, int T, const float* We, int E, const int* E_dev, int D,
-                              float* dWe, float* dTenc, cudaStream_t stream) {
+                              float* dWe, float* dTenc, int e_typ, cudaStream_t stream) {
     if (E <= 0) return 0;
+    if (e_typ <= 0 || e_typ > E) e_typ = E;
     int rc;
     {
-        AColMajor A{dEP, D};
-        BEdgeAttr B{msg, Fe, eidx, Fe, rel, tw, tb};
-        EpiAtomic epi{dWe, Fe + T, nullptr};
-        rc = launch(A, B, epi, D, nullptr, Fe + T, E, E_dev, pick_splits(D, Fe + T, E), stream);
+        AColMajor A{dEP, D, v4(dEP, D)};
+        BEdgeAttr B{msg, Fe, eidx, Fe, rel, tw, tb, v4(msg, Fe) || Fe == 0};
+        EpiAtomic epi{dWe, Fe + T, nullptr, nullptr, 0};
+        rc = launch(A, B, epi, D, nullptr, Fe + T, E, E_dev, pick_splits(D, Fe + T, e_typ), stream);
         if (rc) return rc;
     }
     if (T > 0 && dTenc) {
-        ARowMajor A{dEP, D};
-        BRowMajor B{We + Fe, Fe + T};
+        ARowMajor A{dEP, D, v4(dEP, D)};
+        BRowMajor B{We + Fe, Fe + T, v4(We + Fe, Fe + T)};
         EpiStore epi{dTenc, T, nullptr, nullptr, nullptr, 0};
         rc = launch(A, B, epi, E, E_dev, T, D, nullptr, 1, stream);
         if (rc) return rc;

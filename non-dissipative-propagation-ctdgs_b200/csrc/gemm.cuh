@@ -3,12 +3,14 @@
 // functor epilogues (bias / residual / atomic split-K / scatter).
 //
 // The per-batch contractions of the reference configs are 10^7-10^8 flop on a few hundred rows:
-// they are bound by load LATENCY, not by flops or bandwidth.  Hence: a 4-stage cp.async (LDGSTS)
-// shared-memory ring so four k-tiles of loads are in flight per CTA, and two tile shapes -- 64x64
-// (256 threads) and 32x32 (64 threads) -- the small one chosen when the big one would leave most of
-// the 148 SMs idle.  True-fp32 FMA keeps the 1e-4 parity bar of the fp32 path.
-// Sizes may live on the device (produced by the lookup kernels): CTAs past the real extent exit
-// before touching memory.
+// they are bound by load LATENCY and by how many SMs get a CTA, not by flops or bandwidth.  Hence:
+//   * every thread moves one 128-bit vector of A and one of B per k-tile (along the operand's
+//     contiguous dimension), fetched one tile ahead into registers while the current tile is
+//     multiplied out of a double-buffered shared-memory tile (one barrier per k-tile);
+//   * split-K over gridDim.z (atomic epilogues) so that short-and-wide problems still put a CTA on
+//     every SM; 64x64x16 tiles, 256 threads, 4x4 register micro-tile.
+// True-fp32 FMA keeps the 1e-4 parity bar of the fp32 path.  Sizes may live on the device (produced
+// by the lookup kernels): CTAs past the real extent exit before touching memory.
 #pragma once
 #include "common.cuh"
 
@@ -21,38 +23,37 @@ __device__ __forceinline__ P sel4(const P (&p)[4], int s) {
     return s == 0 ? p[0] : (s == 1 ? p[1] : (s == 2 ? p[2] : p[3]));
 }
 
-constexpr int BK = 16, PAD = 4, STAGES = 4;
+constexpr int BM = 64, BN = 64, BK = 16, PAD = 4, THREADS = 256;
 
-__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // Every operand functor provides
-//   ptr(r,c): address of the element when it is a plain memory element (-> cp.async), else nullptr
-//   val(r,c): the element's value when it has to be computed (only called when ptr() == nullptr)
+//   vec        : host-computed flag: 16-byte vector loads along the contiguous dimension are legal
+//   fast4(r,c) : elements (r, c..c+3) [K_CONTIG: c is k] or (c..c+3 rows, fixed other index) -- see below
+//   elem(r,c)  : one element, no alignment assumptions
+// For A operands the arguments are (m, k); for B operands (k, n).  The 4-vector always runs along the
+// operand's contiguous dimension: k when K_CONTIG, otherwise m (A) / n (B).
 // ----------------------------------------------------------------------------- A operands a(m,k)
 struct ARowMajor {                 // a(m,k) = p[m*ld + k]
     static constexpr bool K_CONTIG = true;
-    const float* p; int ld;
-    __device__ __forceinline__ const float* ptr(int m, int k) const { return p + (size_t)m * ld + k; }
-    __device__ __forceinline__ float val(int, int) const { return 0.f; }
+    const float* p; int ld; bool vec;
+    __device__ __forceinline__ float4 fast4(int m, int k) const { return ldg4(p + (size_t)m * ld + k); }
+    __device__ __forceinline__ float elem(int m, int k) const { return __ldg(p + (size_t)m * ld + k); }
 };
-struct AColMajor {                 // a(m,k) = p[k*ld + m]        (A = Y^T)
+struct AColMajor {                 // a(m,k) = p[k*ld + m]        (A = Y^T), vector along m
     static constexpr bool K_CONTIG = false;
-    const float* p; int ld;
-    __device__ __forceinline__ const float* ptr(int m, int k) const { return p + (size_t)k * ld + m; }
-    __device__ __forceinline__ float val(int, int) const { return 0.f; }
+    const float* p; int ld; bool vec;
+    __device__ __forceinline__ float4 fast4(int m, int k) const { return ldg4(p + (size_t)k * ld + m); }
+    __device__ __forceinline__ float elem(int m, int k) const { return __ldg(p + (size_t)k * ld + m); }
 };
 struct AGather2 {                  // a(m,k) = k<K1 ? t1[row1(m)][k] : t2[row2(m)][k-K1];  row = map ? map[idx[m]] : idx[m]
     static constexpr bool K_CONTIG = true;
     const float* t1; int ld1; const int64_t* idx1; int K1;
     const float* t2; int ld2; const int64_t* idx2;
-    const int64_t* map;
-    __device__ __forceinline__ const float* ptr(int m, int k) const {
+    const int64_t* map; bool vec;
+    __device__ __forceinline__ const float* at(int m, int k) const {
         if (k < K1) {
             int64_t r = __ldg(idx1 + m); if (map) r = __ldg(map + r);
             return t1 + (size_t)r * ld1 + k;
@@ -60,65 +61,74 @@ struct AGather2 {                  // a(m,k) = k<K1 ? t1[row1(m)][k] : t2[row2(m
         int64_t r = __ldg(idx2 + m); if (map) r = __ldg(map + r);
         return t2 + (size_t)r * ld2 + (k - K1);
     }
-    __device__ __forceinline__ float val(int, int) const { return 0.f; }
+    __device__ __forceinline__ float4 fast4(int m, int k) const { return ldg4(at(m, k)); }
+    __device__ __forceinline__ float elem(int m, int k) const { return __ldg(at(m, k)); }
 };
 struct AEdgeAttr {                 // a(e,k) = k<Fe ? msg[row(e)][k] : cos(w[k-Fe]*rel[e] + b[k-Fe])
     static constexpr bool K_CONTIG = true;
     const float* msg; int ldm; const int64_t* eidx; int Fe;
-    const float* rel; const float* tw; const float* tb;
-    __device__ __forceinline__ const float* ptr(int e, int k) const {
-        if (k >= Fe) return nullptr;
-        const int64_t r = eidx ? __ldg(eidx + e) : (int64_t)e;
-        return msg + (size_t)r * ldm + k;
-    }
-    __device__ __forceinline__ float val(int e, int k) const {
+    const float* rel; const float* tw; const float* tb; bool vec;
+    __device__ __forceinline__ float tenc(int e, int k) const {
         return cosf(fmaf(__ldg(rel + e), __ldg(tw + (k - Fe)), __ldg(tb + (k - Fe))));
+    }
+    __device__ __forceinline__ float4 fast4(int e, int k) const {     // vec => Fe % 4 == 0: no straddle
+        if (k < Fe) {
+            const int64_t r = eidx ? __ldg(eidx + e) : (int64_t)e;
+            return ldg4(msg + (size_t)r * ldm + k);
+        }
+        return make_float4(tenc(e, k), tenc(e, k + 1), tenc(e, k + 2), tenc(e, k + 3));
+    }
+    __device__ __forceinline__ float elem(int e, int k) const {
+        if (k < Fe) {
+            const int64_t r = eidx ? __ldg(eidx + e) : (int64_t)e;
+            return __ldg(msg + (size_t)r * ldm + k);
+        }
+        return tenc(e, k);
     }
 };
 
 // ----------------------------------------------------------------------------- B operands b(k,n)
 struct BWeight {                   // b(k,n) = W[n*ld + k]          (torch Linear weight [out,in])
     static constexpr bool K_CONTIG = true;
-    const float* p; int ld;
-    __device__ __forceinline__ const float* ptr(int k, int n) const { return p + (size_t)n * ld + k; }
-    __device__ __forceinline__ float val(int, int) const { return 0.f; }
+    const float* p; int ld; bool vec;
+    __device__ __forceinline__ float4 fast4(int k, int n) const { return ldg4(p + (size_t)n * ld + k); }
+    __device__ __forceinline__ float elem(int k, int n) const { return __ldg(p + (size_t)n * ld + k); }
 };
 struct BWeightSeg4 {               // four [D,ld] weights stacked along n
     static constexpr bool K_CONTIG = true;
-    const float* p[4]; int D; int ld;
-    __device__ __forceinline__ const float* ptr(int k, int n) const {
-        return sel4(p, n / D) + (size_t)(n % D) * ld + k;
-    }
-    __device__ __forceinline__ float val(int, int) const { return 0.f; }
+    const float* p[4]; int D; int ld; bool vec;
+    __device__ __forceinline__ const float* at(int k, int n) const { return sel4(p, n / D) + (size_t)(n % D) * ld + k; }
+    __device__ __forceinline__ float4 fast4(int k, int n) const { return ldg4(at(k, n)); }
+    __device__ __forceinline__ float elem(int k, int n) const { return __ldg(at(k, n)); }
 };
 struct BWeightCat2 {               // b(k,n) = k<K1 ? W1[n][k] : W2[n][k-K1]
     static constexpr bool K_CONTIG = true;
-    const float* p1; int ld1; int K1; const float* p2; int ld2;
-    __device__ __forceinline__ const float* ptr(int k, int n) const {
+    const float* p1; int ld1; int K1; const float* p2; int ld2; bool vec;
+    __device__ __forceinline__ const float* at(int k, int n) const {
         return k < K1 ? p1 + (size_t)n * ld1 + k : p2 + (size_t)n * ld2 + (k - K1);
     }
-    __device__ __forceinline__ float val(int, int) const { return 0.f; }
+    __device__ __forceinline__ float4 fast4(int k, int n) const { return ldg4(at(k, n)); }
+    __device__ __forceinline__ float elem(int k, int n) const { return __ldg(at(k, n)); }
 };
-struct BRowMajor {                 // b(k,n) = X[k*ld + n]
+struct BRowMajor {                 // b(k,n) = X[k*ld + n], vector along n
     static constexpr bool K_CONTIG = false;
-    const float* p; int ld;
-    __device__ __forceinline__ const float* ptr(int k, int n) const { return p + (size_t)k * ld + n; }
-    __device__ __forceinline__ float val(int, int) const { return 0.f; }
+    const float* p; int ld; bool vec;
+    __device__ __forceinline__ float4 fast4(int k, int n) const { return ldg4(p + (size_t)k * ld + n); }
+    __device__ __forceinline__ float elem(int k, int n) const { return __ldg(p + (size_t)k * ld + n); }
 };
 struct BRowSeg4 {                  // four [D,ld] matrices stacked along k
     static constexpr bool K_CONTIG = false;
-    const float* p[4]; int D; int ld;
-    __device__ __forceinline__ const float* ptr(int k, int n) const {
-        return sel4(p, k / D) + (size_t)(k % D) * ld + n;
-    }
-    __device__ __forceinline__ float val(int, int) const { return 0.f; }
+    const float* p[4]; int D; int ld; bool vec;
+    __device__ __forceinline__ const float* at(int k, int n) const { return sel4(p, k / D) + (size_t)(k % D) * ld + n; }
+    __device__ __forceinline__ float4 fast4(int k, int n) const { return ldg4(at(k, n)); }
+    __device__ __forceinline__ float elem(int k, int n) const { return __ldg(at(k, n)); }
 };
 struct BGather2 {                  // b(k,n) = n<K1 ? t1[row1(k)][n] : t2[row2(k)][n-K1]
     static constexpr bool K_CONTIG = false;
     const float* t1; int ld1; const int64_t* idx1; int K1;
     const float* t2; int ld2; const int64_t* idx2;
-    const int64_t* map;
-    __device__ __forceinline__ const float* ptr(int k, int n) const {
+    const int64_t* map; bool vec;
+    __device__ __forceinline__ const float* at(int k, int n) const {
         if (n < K1) {
             int64_t r = __ldg(idx1 + k); if (map) r = __ldg(map + r);
             return t1 + (size_t)r * ld1 + n;
@@ -126,33 +136,48 @@ struct BGather2 {                  // b(k,n) = n<K1 ? t1[row1(k)][n] : t2[row2(k
         int64_t r = __ldg(idx2 + k); if (map) r = __ldg(map + r);
         return t2 + (size_t)r * ld2 + (n - K1);
     }
-    __device__ __forceinline__ float val(int, int) const { return 0.f; }
+    __device__ __forceinline__ float4 fast4(int k, int n) const { return ldg4(at(k, n)); }
+    __device__ __forceinline__ float elem(int k, int n) const { return __ldg(at(k, n)); }
 };
 struct BEdgeAttr {                 // b(e,n) = n<Fe ? msg[row(e)][n] : cos(w*rel+b)
     static constexpr bool K_CONTIG = false;
     const float* msg; int ldm; const int64_t* eidx; int Fe;
-    const float* rel; const float* tw; const float* tb;
-    __device__ __forceinline__ const float* ptr(int e, int n) const {
-        if (n >= Fe) return nullptr;
-        const int64_t r = eidx ? __ldg(eidx + e) : (int64_t)e;
-        return msg + (size_t)r * ldm + n;
-    }
-    __device__ __forceinline__ float val(int e, int n) const {
+    const float* rel; const float* tw; const float* tb; bool vec;
+    __device__ __forceinline__ float tenc(int e, int n) const {
         return cosf(fmaf(__ldg(rel + e), __ldg(tw + (n - Fe)), __ldg(tb + (n - Fe))));
+    }
+    __device__ __forceinline__ float4 fast4(int e, int n) const {
+        if (n < Fe) {
+            const int64_t r = eidx ? __ldg(eidx + e) : (int64_t)e;
+            return ldg4(msg + (size_t)r * ldm + n);
+        }
+        return make_float4(tenc(e, n), tenc(e, n + 1), tenc(e, n + 2), tenc(e, n + 3));
+    }
+    __device__ __forceinline__ float elem(int e, int n) const {
+        if (n < Fe) {
+            const int64_t r = eidx ? __ldg(eidx + e) : (int64_t)e;
+            return __ldg(msg + (size_t)r * ldm + n);
+        }
+        return tenc(e, n);
     }
 };
 struct BRelu {                     // b(k,n) = max(H[k*ld+n], 0)
     static constexpr bool K_CONTIG = false;
-    const float* p; int ld;
-    __device__ __forceinline__ const float* ptr(int, int) const { return nullptr; }
-    __device__ __forceinline__ float val(int k, int n) const { return fmaxf(__ldg(p + (size_t)k * ld + n), 0.f); }
+    const float* p; int ld; bool vec;
+    __device__ __forceinline__ float4 fast4(int k, int n) const {
+        const float4 v = ldg4(p + (size_t)k * ld + n);
+        return make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+    }
+    __device__ __forceinline__ float elem(int k, int n) const { return fmaxf(__ldg(p + (size_t)k * ld + n), 0.f); }
 };
 
 // ----------------------------------------------------------------------------- epilogues
+// split(): true when the epilogue accumulates atomically (legal with gridDim.z > 1).
+// first : this CTA owns the k-range starting at 0 (adds bias / residual exactly once).
 struct EpiStore {                  // C = acc + bias[n] + bias2[n] + res[m][n]
     static constexpr bool HAS_ROWSUM = false;
     float* C; int ldc; const float* bias; const float* bias2; const float* res; int ldr;
-    __device__ __forceinline__ void operator()(int m, int n, float v) const {
+    __device__ __forceinline__ void operator()(int m, int n, float v, bool) const {
         if (bias) v += __ldg(bias + n);
         if (bias2) v += __ldg(bias2 + n);
         if (res) v += res[(size_t)m * ldr + n];
@@ -163,23 +188,26 @@ struct EpiStore {                  // C = acc + bias[n] + bias2[n] + res[m][n]
 struct EpiStoreSeg4 {              // C = acc + bias_seg[n/D][n%D]
     static constexpr bool HAS_ROWSUM = false;
     float* C; int ldc; const float* bias[4]; int D;
-    __device__ __forceinline__ void operator()(int m, int n, float v) const {
+    __device__ __forceinline__ void operator()(int m, int n, float v, bool) const {
         const float* b = sel4(bias, n / D);
         if (b) v += __ldg(b + (n % D));
         C[(size_t)m * ldc + n] = v;
     }
     __device__ __forceinline__ void rowsum(int, float) const {}
 };
-struct EpiAtomic {                 // split-K accumulate: C[m][n] += acc ; rs[m] += sum_k a(m,k)
+struct EpiAtomic {                 // split-K accumulate: C[m][n] += acc (+ res[m][n] once); rs[m] += sum_k a(m,k)
     static constexpr bool HAS_ROWSUM = true;
-    float* C; int ldc; float* rs;
-    __device__ __forceinline__ void operator()(int m, int n, float v) const { atomicAdd(C + (size_t)m * ldc + n, v); }
+    float* C; int ldc; float* rs; const float* res; int ldr;
+    __device__ __forceinline__ void operator()(int m, int n, float v, bool first) const {
+        if (res && first) v += res[(size_t)m * ldr + n];
+        atomicAdd(C + (size_t)m * ldc + n, v);
+    }
     __device__ __forceinline__ void rowsum(int m, float v) const { if (rs) atomicAdd(rs + m, v); }
 };
 struct EpiAtomicSeg4 {             // rows split into 4 segments of D rows, each with its own output / bias-grad
     static constexpr bool HAS_ROWSUM = true;
     float* C[4]; float* rs[4]; int D; int ldc;
-    __device__ __forceinline__ void operator()(int m, int n, float v) const {
+    __device__ __forceinline__ void operator()(int m, int n, float v, bool) const {
         atomicAdd(sel4(C, m / D) + (size_t)(m % D) * ldc + n, v);
     }
     __device__ __forceinline__ void rowsum(int m, float v) const {
@@ -190,7 +218,7 @@ struct EpiAtomicSeg4 {             // rows split into 4 segments of D rows, each
 struct EpiScatterAtomic {          // C[row(m)][n] += acc      (row = map ? map[idx[m]] : idx[m])
     static constexpr bool HAS_ROWSUM = false;
     float* C; int ldc; const int64_t* idx; const int64_t* map;
-    __device__ __forceinline__ void operator()(int m, int n, float v) const {
+    __device__ __forceinline__ void operator()(int m, int n, float v, bool) const {
         int64_t r = idx[m]; if (map) r = map[r];
         atomicAdd(C + (size_t)r * ldc + n, v);
     }
@@ -198,54 +226,62 @@ struct EpiScatterAtomic {          // C[row(m)][n] += acc      (row = map ? map[
 };
 
 // ----------------------------------------------------------------------------- kernel
-// BT x BT output tile, (BT/4)^2 threads, 4x4 register micro-tile per thread.
-template <int BT, class AL, class BL, class EP>
-__global__ void __launch_bounds__((BT / 4) * (BT / 4))
+// Operand tile fetch: one float4 per thread.  K_CONTIG: thread -> (row = t/4, k = 4*(t%4));
+// otherwise: thread -> (k = t/16, row4 = 4*(t%16)).  `lim_r` bounds the row index (M or N), [k0,ke) the k range.
+template <class L, bool IS_A>
+__device__ __forceinline__ float4 fetch4(const L& op, int t, int r0, int lim_r, int k0, int ke) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (L::K_CONTIG) {
+        const int r = r0 + (t >> 2), k = k0 + ((t & 3) << 2);
+        if (r < lim_r && k < ke) {
+            if (op.vec && k + 3 < ke) {
+                v = IS_A ? op.fast4(r, k) : op.fast4(k, r);
+            } else {
+                v.x = IS_A ? op.elem(r, k) : op.elem(k, r);
+                if (k + 1 < ke) v.y = IS_A ? op.elem(r, k + 1) : op.elem(k + 1, r);
+                if (k + 2 < ke) v.z = IS_A ? op.elem(r, k + 2) : op.elem(k + 2, r);
+                if (k + 3 < ke) v.w = IS_A ? op.elem(r, k + 3) : op.elem(k + 3, r);
+            }
+        }
+    } else {
+        const int k = k0 + (t >> 4), r = r0 + ((t & 15) << 2);
+        if (k < ke && r < lim_r) {
+            if (op.vec && r + 3 < lim_r) {
+                v = IS_A ? op.fast4(r, k) : op.fast4(k, r);
+            } else {
+                v.x = IS_A ? op.elem(r, k) : op.elem(k, r);
+                if (r + 1 < lim_r) v.y = IS_A ? op.elem(r + 1, k) : op.elem(k, r + 1);
+                if (r + 2 < lim_r) v.z = IS_A ? op.elem(r + 2, k) : op.elem(k, r + 2);
+                if (r + 3 < lim_r) v.w = IS_A ? op.elem(r + 3, k) : op.elem(k, r + 3);
+            }
+        }
+    }
+    return v;
+}
+
+template <bool K_CONTIG>
+__device__ __forceinline__ void stash4(float (*S)[BM + PAD], int t, const float4& v) {
+    if (K_CONTIG) {
+        const int r = t >> 2, k = (t & 3) << 2;
+        S[k][r] = v.x; S[k + 1][r] = v.y; S[k + 2][r] = v.z; S[k + 3][r] = v.w;
+    } else {
+        *reinterpret_cast<float4*>(&S[t >> 4][(t & 15) << 2]) = v;
+    }
+}
+
+template <class AL, class BL, class EP>
+__global__ void __launch_bounds__(THREADS)
 gemm_kernel(const AL A, const BL Bm, const EP epi, int M_host, const int* __restrict__ M_dev, int N, int K_host,
             const int* __restrict__ K_dev, int k_chunk) {
-    constexpr int TPR = BT / 4;                 // threads per tile row/col
-    constexpr int THREADS = TPR * TPR;
-    constexpr int EPT = BT * BK / THREADS;      // elements per thread per operand tile
-    __shared__ __align__(16) float As[STAGES][BK][BT + PAD];
-    __shared__ __align__(16) float Bs[STAGES][BK][BT + PAD];
+    __shared__ __align__(16) float As[2][BK][BM + PAD];
+    __shared__ __align__(16) float Bs[2][BK][BN + PAD];
     const int M = M_dev ? *M_dev : M_host;
     const int K = K_dev ? *K_dev : K_host;
-    const int m0 = blockIdx.y * BT, n0 = blockIdx.x * BT;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int kb = blockIdx.z * k_chunk;
     const int ke = min(K, kb + k_chunk);
     if (m0 >= M || n0 >= N || kb >= ke) return;        // block-uniform, before any barrier
-    const int t = threadIdx.x, ty = t / TPR, tx = t % TPR;
-
-    auto fetch_tile = [&](int k0, int st) {
-#pragma unroll
-        for (int i = 0; i < EPT; ++i) {
-            int r, k;                                   // r: row within the tile (m or n), k: within BK
-            if (AL::K_CONTIG) { k = t % BK; r = t / BK + i * (THREADS / BK); }
-            else              { r = t % BT; k = t / BT + i * (THREADS / BT); }
-            float* dst = &As[st][k][r];
-            const int m = m0 + r, kk = k0 + k;
-            if (m < M && kk < ke) {
-                const float* p = A.ptr(m, kk);
-                if (p) cp_async4(dst, p); else *dst = A.val(m, kk);
-            } else {
-                *dst = 0.f;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < EPT; ++i) {
-            int r, k;
-            if (BL::K_CONTIG) { k = t % BK; r = t / BK + i * (THREADS / BK); }
-            else              { r = t % BT; k = t / BT + i * (THREADS / BT); }
-            float* dst = &Bs[st][k][r];
-            const int n = n0 + r, kk = k0 + k;
-            if (n < N && kk < ke) {
-                const float* p = Bm.ptr(kk, n);
-                if (p) cp_async4(dst, p); else *dst = Bm.val(kk, n);
-            } else {
-                *dst = 0.f;
-            }
-        }
-    };
+    const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
 
     float acc[4][4];
 #pragma unroll
@@ -255,18 +291,25 @@ gemm_kernel(const AL A, const BL Bm, const EP epi, int M_host, const int* __rest
     float rsum[4] = {0.f, 0.f, 0.f, 0.f};
 
     const int n_tiles = (ke - kb + BK - 1) / BK;
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < n_tiles) fetch_tile(kb + s * BK, s);
-        cp_async_commit();                              // one group per stage, empty or not
+    float4 ra = fetch4<AL, true>(A, t, m0, M, kb, ke);
+    float4 rb = fetch4<BL, false>(Bm, t, n0, N, kb, ke);
+    stash4<AL::K_CONTIG>(As[0], t, ra);
+    stash4<BL::K_CONTIG>(Bs[0], t, rb);
+    if (n_tiles > 1) {
+        ra = fetch4<AL, true>(A, t, m0, M, kb + BK, ke);
+        rb = fetch4<BL, false>(Bm, t, n0, N, kb + BK, ke);
     }
+    __syncthreads();
     for (int kt = 0; kt < n_tiles; ++kt) {
-        cp_async_wait<STAGES - 2>();                    // tile kt has landed (own copies) ...
-        __syncthreads();                                // ... and everyone's; tile kt-1's stage is free
-        const int nxt = kt + STAGES - 1;
-        if (nxt < n_tiles) fetch_tile(kb + nxt * BK, nxt % STAGES);
-        cp_async_commit();
-        const int st = kt % STAGES;
+        const int st = kt & 1;
+        if (kt + 1 < n_tiles) {                         // tile kt+1 (in registers) -> the other buffer;
+            stash4<AL::K_CONTIG>(As[st ^ 1], t, ra);    // it was last read in iteration kt-1 (barrier below)
+            stash4<BL::K_CONTIG>(Bs[st ^ 1], t, rb);
+        }
+        if (kt + 2 < n_tiles) {                         // tile kt+2 -> registers, in flight during the FMAs
+            ra = fetch4<AL, true>(A, t, m0, M, kb + (kt + 2) * BK, ke);
+            rb = fetch4<BL, false>(Bm, t, n0, N, kb + (kt + 2) * BK, ke);
+        }
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
             const float4 a4 = *reinterpret_cast<const float4*>(&As[st][k][ty * 4]);
@@ -283,8 +326,9 @@ gemm_kernel(const AL A, const BL Bm, const EP epi, int M_host, const int* __rest
                 for (int i = 0; i < 4; ++i) rsum[i] += a[i];
             }
         }
+        __syncthreads();
     }
-    cp_async_wait<0>();
+    const bool first = blockIdx.z == 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int m = m0 + ty * 4 + i;
@@ -292,14 +336,13 @@ gemm_kernel(const AL A, const BL Bm, const EP epi, int M_host, const int* __rest
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
-            if (n < N) epi(m, n, acc[i][j]);
+            if (n < N) epi(m, n, acc[i][j], first);
         }
         if (EP::HAS_ROWSUM && blockIdx.x == 0 && tx == 0) epi.rowsum(m, rsum[i]);
     }
 }
 
 // M_max bounds the grid when the true M lives on the device; splits > 1 needs an atomic epilogue.
-// m_hint: the typical true M (<= M_max) used only to pick the tile shape.
 template <class AL, class BL, class EP>
 static inline int launch(const AL& A, const BL& B, const EP& epi, int M_max, const int* M_dev, int N, int K_max,
                          const int* K_dev, int splits, cudaStream_t stream) {
@@ -308,23 +351,17 @@ static inline int launch(const AL& A, const BL& B, const EP& epi, int M_max, con
     int k_chunk = (K_max + splits - 1) / splits;
     k_chunk = ((k_chunk + BK - 1) / BK) * BK;
     splits = (K_max + k_chunk - 1) / k_chunk;
-    const long long big_tiles = (long long)((N + 63) / 64) * ((M_max + 63) / 64) * splits;
-    if (big_tiles >= 2 * CTAN_SM_COUNT) {
-        dim3 grid((N + 63) / 64, (M_max + 63) / 64, splits);
-        gemm_kernel<64, AL, BL, EP><<<grid, 256, 0, stream>>>(A, B, epi, M_max, M_dev, N, K_max, K_dev, k_chunk);
-    } else {
-        dim3 grid((N + 31) / 32, (M_max + 31) / 32, splits);
-        gemm_kernel<32, AL, BL, EP><<<grid, 64, 0, stream>>>(A, B, epi, M_max, M_dev, N, K_max, K_dev, k_chunk);
-    }
+    dim3 grid((N + BN - 1) / BN, (M_max + BM - 1) / BM, splits);
+    gemm_kernel<AL, BL, EP><<<grid, THREADS, 0, stream>>>(A, B, epi, M_max, M_dev, N, K_max, K_dev, k_chunk);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
 
-// number of K splits that fills the chip for a reduce-over-rows contraction (32x32 tiles)
-static inline int pick_splits(int M, int N, int K) {
-    const int tiles = ((M + 31) / 32) * ((N + 31) / 32);
+// number of K splits that puts ~2 CTAs on every SM; m_typ = the typical true M when M_max is only a bound
+static inline int pick_splits(int m_typ, int N, int K, int min_k = 2 * BK) {
+    const int tiles = ((m_typ + BM - 1) / BM) * ((N + BN - 1) / BN);
     int s = (2 * CTAN_SM_COUNT + tiles - 1) / tiles;
-    const int max_s = (K + 4 * BK - 1) / (4 * BK);     // at least 64 rows per split
+    const int max_s = (K + min_k - 1) / min_k;
     if (s > max_s) s = max_s;
     if (s < 1) s = 1;
     return s;

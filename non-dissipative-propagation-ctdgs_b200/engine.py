@@ -13,6 +13,8 @@ are an INPUT, drawn by the caller exactly like train_link.py:245-251 / negative_
 first event, train_link.py:265), so `msg[e_id]`/`t[e_id]` are gathers from the same tables."""
 from __future__ import annotations
 
+import contextlib
+
 import torch
 
 from . import _lib
@@ -84,6 +86,9 @@ class StepEngine:
         self.n_cap = min(self.num_nodes, self.n_seeds * (self.S + 1) ** self.K)
         c_cap = min(self.num_nodes, self.n_seeds * (self.S + 1) ** (self.K - 1))
         self.e_cap = max(c_cap * self.S, 1)
+        # typical sizes (only used to size split-K grids): a third of the bound, at least the seed count
+        self.n_typ = max(min(self.n_cap, self.n_seeds), self.n_cap // 4)
+        self.e_typ = max(min(self.e_cap, 2 * self.n_seeds), self.e_cap // 4)
         self._flatten_params()
         self._alloc()
         self._graphs = {}
@@ -96,11 +101,14 @@ class StepEngine:
         self.flat_p = torch.empty(n, device=self.dev)
         # everything the backward accumulates into lives in ONE buffer so a single memset clears it
         N, D = self.n_cap, self.D
-        self.zero_buf = torch.zeros(n + D * D + N * D + N * 4 * D, device=self.dev)
+        K = self.K
+        self.zero_buf = torch.zeros(n + D * D + N * D + N * 4 * D + K * N * D, device=self.dev)
         self.flat_g = self.zero_buf[:n]
-        self._dA = self.zero_buf[n:n + D * D].view(D, D)
-        self._dZ = self.zero_buf[n + D * D:n + D * D + N * D].view(N, D)
-        self._DQKVA = self.zero_buf[n + D * D + N * D:].view(N, 4 * D)
+        o = n
+        self._dA = self.zero_buf[o:o + D * D].view(D, D); o += D * D
+        self._dZ = self.zero_buf[o:o + N * D].view(N, D); o += N * D
+        self._DQKVA = self.zero_buf[o:o + N * 4 * D].view(N, 4 * D); o += N * 4 * D
+        self._DX = self.zero_buf[o:o + K * N * D].view(K, N, D)      # dL/dx_k, accumulated by split-K
         self.adam_m = torch.zeros(n, device=self.dev)
         self.adam_v = torch.zeros(n, device=self.dev)
         self.p, self.g = [], []
@@ -150,7 +158,7 @@ class StepEngine:
         # backward
         w["dHid"] = torch.zeros((P, self.Hd), **f32)
         w["dZ"] = self._dZ
-        w["gA"], w["gB"] = torch.zeros((N, D), **f32), torch.zeros((N, D), **f32)
+        w["gA"] = torch.zeros((N, D), **f32)
         w["DQKVA"] = self._DQKVA
         w["dEP"] = torch.zeros((E, D), **f32)
         w["DS"] = torch.zeros(E, **f32)
@@ -196,12 +204,17 @@ class StepEngine:
         return int(self.w["counters"][0].item())
 
     # ------------------------------------------------------------------ one step = one DAG of launches
+    parallel = True                # False: issue everything on one stream (profiling / experiments)
+
     def _fork(self, i):
+        if not self.parallel:
+            return contextlib.nullcontext()
         self._side[i].wait_stream(torch.cuda.current_stream())
         return torch.cuda.stream(self._side[i])
 
     def _join(self, i):
-        torch.cuda.current_stream().wait_stream(self._side[i])
+        if self.parallel:
+            torch.cuda.current_stream().wait_stream(self._side[i])
 
     def _launch(self, train: bool):
         """Issue one step.  Work that is off the critical path (edge projection, weight gradients,
@@ -232,6 +245,7 @@ class StepEngine:
             call("ctan_eproj_fwd", ptr(self.msg), Fe, ptr(w["eid"]), ptr(w["rel"]), tw, tb, T, We, E, Ed, D,
                  ptr(w["EP"]))
             call("ctan_antisym_prep", W, float(m.gnn.aconv.gamma), D, ptr(w["A"]))
+            w["H"].zero_()
             if train:
                 self.zero_buf.zero_()
         if train:
@@ -252,7 +266,7 @@ class StepEngine:
         z = w["Z"] if self.final_tanh else xk
         self._z = z
         call("ctan_readout_fwd", ptr(z), D, ptr(w["pair_src"]), ptr(w["pair_dst"]), ptr(ld._assoc), P, None, Hd, O,
-             Wsrc, bsrc, Wdst, bdst, Wfin, bfin, ptr(w["H"]), ptr(w["OUT"]))
+             Wsrc, bsrc, Wdst, bdst, Wfin, bfin, ptr(w["H"]), ptr(w["OUT"]), 1)
         call("ctan_bce_loss", ptr(w["OUT"]), B, P - B, ptr(w["dOUT"]) if train else None, ptr(w["loss_hist"]),
              self.hist_cap, ptr(w["counters"]))
 
@@ -287,17 +301,17 @@ class StepEngine:
                  ptr(w["DS"]))
             qb = (ptr(w["DQKVA"]), ptr(w["X"][k]), ptr(g), N, Nd, D, Wq, Wk, Wv, ptr(w["A"]))
             with self._fork(0):                              # side 0: weight gradients of this iteration
-                call("ctan_qkva_bwd", *qb, None, gWq, gWk, gWv, ptr(w["dA"]), gbq, gbk, gbv, gb)
+                call("ctan_qkva_bwd", *qb, None, gWq, gWk, gWv, ptr(w["dA"]), gbq, gbk, gbv, gb, self.n_typ)
                 if k == 0:
                     call("ctan_eproj_bwd", ptr(w["dEP"]), ptr(self.msg), Fe, ptr(w["eid"]), ptr(w["rel"]), tw, tb, T,
-                         We, E, Ed, D, gWe, ptr(w["dTenc"]))
+                         We, E, Ed, D, gWe, ptr(w["dTenc"]), self.e_typ)
                     call("ctan_tenc_bwd", ptr(w["dTenc"]), ptr(w["rel"]), tw, tb, E, Ed, T, gtw, gtb)
                     call("ctan_antisym_bwd", ptr(w["dA"]), D, gW)
-            gn = w["gB"] if g is not w["gB"] else w["gA"]
-            call("ctan_qkva_bwd", *qb, ptr(gn), None, None, None, None, None, None, None, None)
+            gn = self._DX[k]
+            call("ctan_qkva_bwd", *qb, ptr(gn), None, None, None, None, None, None, None, None, self.n_typ)
             g = gn
         self._join(1)                                        # z0 is complete (and the state write-back done)
-        call("ctan_enc_bwd", ptr(g), ptr(w["z0"]), N, Nd, D, Fn, gWenc, gbenc)
+        call("ctan_enc_bwd", ptr(g), ptr(w["z0"]), N, Nd, D, Fn, gWenc, gbenc, self.n_typ)
         self._join(0)
         call("ctan_adam_step", ptr(self.flat_p), ptr(self.flat_g), ptr(self.adam_m), ptr(self.adam_v),
              self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 0, ptr(w["counters"]))

@@ -102,15 +102,15 @@ class _EmbedFn(torch.autograd.Function):
                 DQKVA.zero_()
                 call("ctan_edge_bwd", ptr(QKVA[k]), ptr(EP), ptr(rowptr), ptr(esrc), N, None, D, ptr(g), ptr(TH[k]),
                      ptr(ALPHA[k]), float(eps), ptr(DQKVA), ptr(dEP), int(k != K - 1), ptr(DS))
-                gn = torch.empty((N, D), device=dev)
+                gn = torch.zeros((N, D), device=dev)        # the dX contraction splits K and accumulates
                 call("ctan_qkva_bwd", ptr(DQKVA), ptr(X[k]), ptr(g), N, None, D, ptr(Wq), ptr(Wk), ptr(Wv), ptr(A),
-                     ptr(gn), ptr(dWq), ptr(dWk), ptr(dWv), ptr(dA), ptr(dbq), ptr(dbk), ptr(dbv), ptr(db))
+                     ptr(gn), ptr(dWq), ptr(dWk), ptr(dWv), ptr(dA), ptr(dbq), ptr(dbk), ptr(dbv), ptr(db), 0)
                 g = gn
-            call("ctan_enc_bwd", ptr(g), ptr(z0), N, None, D, Kin - D, ptr(dWenc), ptr(dbenc))
+            call("ctan_enc_bwd", ptr(g), ptr(z0), N, None, D, Kin - D, ptr(dWenc), ptr(dbenc), 0)
             if E > 0:
                 dTenc = torch.empty((E, T), device=dev)
                 call("ctan_eproj_bwd", ptr(dEP), ptr(msg), Fe, None, ptr(rel), ptr(tw), ptr(tb), T, ptr(We), E, None,
-                     D, ptr(dWe), ptr(dTenc))
+                     D, ptr(dWe), ptr(dTenc), 0)
                 call("ctan_tenc_bwd", ptr(dTenc), ptr(rel), ptr(tw), ptr(tb), E, None, T, ptr(dtw), ptr(dtb))
             dW = torch.empty((D, D), device=dev)
             call("ctan_antisym_bwd", ptr(dA), D, ptr(dW))
@@ -136,12 +136,12 @@ class _ReadoutFn(torch.autograd.Function):
         Hd, O = Wdst.size(0), Wfin.size(0)
         dev = z.device
         with torch.cuda.device(dev):
-            H = torch.empty((P, Hd), device=dev)
+            H = torch.zeros((P, Hd), device=dev)         # zeroed: the hidden contraction splits K
             out = torch.empty((P, O), device=dev)
             call("ctan_readout_fwd", ptr(z), D, ptr(src, torch.long) if src is not None else ptr(dst, torch.long),
                  ptr(dst, torch.long), ptr(id_map, torch.long) if id_map is not None else None, P, None, Hd, O,
                  ptr(Wsrc) if Wsrc is not None else None, ptr(bsrc) if bsrc is not None else None, ptr(Wdst),
-                 ptr(bdst), ptr(Wfin), ptr(bfin), ptr(H), ptr(out))
+                 ptr(bdst), ptr(Wfin), ptr(bfin), ptr(H), ptr(out), 1)
         ctx.save_for_backward(z, src, dst, id_map, H, Wsrc, Wdst, Wfin)
         return out
 
