@@ -26,7 +26,8 @@ extern "C" int ctan_enc_fwd(const float* mem, int D, const float* xfeat, int Fn,
         return launch(A, B, epi, N, N_dev, D, K, nullptr, 1, stream);
     }
     // the tail segment (node features) is rarely 4-aligned: vector loads only when both segments allow it
-    const bool vec = v4(mem, D) && (Fn == 0 || v4(xfeat, Fn));
+    // vectors never straddle the segment boundary when D % 4 == 0; a tail shorter than 4 is always scalar
+    const bool vec = v4(mem, D) && (Fn < 4 || v4(xfeat, Fn));
     AGather2 A{mem, D, n_id, D, xfeat, Fn, n_id, nullptr, vec};
     return launch(A, B, epi, N, N_dev, D, K, nullptr, 1, stream);
 }

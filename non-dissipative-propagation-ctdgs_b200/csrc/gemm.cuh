@@ -23,7 +23,7 @@ __device__ __forceinline__ P sel4(const P (&p)[4], int s) {
     return s == 0 ? p[0] : (s == 1 ? p[1] : (s == 2 ? p[2] : p[3]));
 }
 
-constexpr int BM = 64, BN = 64, BK = 16, PAD = 4, THREADS = 256;
+constexpr int BM = 64, BN = 64, BK = 16, PAD = 4;
 
 static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
@@ -226,13 +226,15 @@ struct EpiScatterAtomic {          // C[row(m)][n] += acc      (row = map ? map[
 };
 
 // ----------------------------------------------------------------------------- kernel
-// Operand tile fetch: one float4 per thread.  K_CONTIG: thread -> (row = t/4, k = 4*(t%4));
-// otherwise: thread -> (k = t/16, row4 = 4*(t%16)).  `lim_r` bounds the row index (M or N), [k0,ke) the k range.
+// Tile shapes: BT x BT output tile with (BT/4)^2 threads (4x4 register micro-tile each):
+//   BT = 64 -> 256 threads (1 operand vector per thread per k-tile), BT = 32 -> 64 threads (2 vectors).
+// The small tile is used when the big one would leave most SMs without a CTA (latency-bound shapes).
+// Operand tile fetch: float4 index f -> K_CONTIG: (row = f/4, k = 4*(f%4)); otherwise (k = f/(BT/4),
+// row4 = 4*(f%(BT/4))).  `lim_r` bounds the row index (M or N), [k0,ke) the k range.
 template <class L, bool IS_A>
-__device__ __forceinline__ float4 fetch4(const L& op, int t, int r0, int lim_r, int k0, int ke) {
+__device__ __forceinline__ float4 fetch4(const L& op, int r, int k, int lim_r, int ke) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (L::K_CONTIG) {
-        const int r = r0 + (t >> 2), k = k0 + ((t & 3) << 2);
         if (r < lim_r && k < ke) {
             if (op.vec && k + 3 < ke) {
                 v = IS_A ? op.fast4(r, k) : op.fast4(k, r);
@@ -244,7 +246,6 @@ __device__ __forceinline__ float4 fetch4(const L& op, int t, int r0, int lim_r, 
             }
         }
     } else {
-        const int k = k0 + (t >> 4), r = r0 + ((t & 15) << 2);
         if (k < ke && r < lim_r) {
             if (op.vec && r + 3 < lim_r) {
                 v = IS_A ? op.fast4(r, k) : op.fast4(k, r);
@@ -259,29 +260,21 @@ __device__ __forceinline__ float4 fetch4(const L& op, int t, int r0, int lim_r, 
     return v;
 }
 
-template <bool K_CONTIG>
-__device__ __forceinline__ void stash4(float (*S)[BM + PAD], int t, const float4& v) {
-    if (K_CONTIG) {
-        const int r = t >> 2, k = (t & 3) << 2;
-        S[k][r] = v.x; S[k + 1][r] = v.y; S[k + 2][r] = v.z; S[k + 3][r] = v.w;
-    } else {
-        *reinterpret_cast<float4*>(&S[t >> 4][(t & 15) << 2]) = v;
-    }
-}
-
-template <class AL, class BL, class EP>
-__global__ void __launch_bounds__(THREADS)
+template <int BT, class AL, class BL, class EP>
+__global__ void __launch_bounds__((BT / 4) * (BT / 4))
 gemm_kernel(const AL A, const BL Bm, const EP epi, int M_host, const int* __restrict__ M_dev, int N, int K_host,
             const int* __restrict__ K_dev, int k_chunk) {
-    __shared__ __align__(16) float As[2][BK][BM + PAD];
-    __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+    constexpr int TPR = BT / 4, NT = TPR * TPR;         // threads per tile row, threads per CTA
+    constexpr int VPT = (BT * BK / 4) / NT;             // operand vectors per thread per k-tile (1 or 2)
+    __shared__ __align__(16) float As[2][BK][BT + PAD];
+    __shared__ __align__(16) float Bs[2][BK][BT + PAD];
     const int M = M_dev ? *M_dev : M_host;
     const int K = K_dev ? *K_dev : K_host;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int m0 = blockIdx.y * BT, n0 = blockIdx.x * BT;
     const int kb = blockIdx.z * k_chunk;
     const int ke = min(K, kb + k_chunk);
     if (m0 >= M || n0 >= N || kb >= ke) return;        // block-uniform, before any barrier
-    const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+    const int t = threadIdx.x, ty = t / TPR, tx = t % TPR;
 
     float acc[4][4];
 #pragma unroll
@@ -289,27 +282,46 @@ gemm_kernel(const AL A, const BL Bm, const EP epi, int M_host, const int* __rest
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     float rsum[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 ra[VPT], rb[VPT];
+
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+            const int f = t + i * NT;
+            if (AL::K_CONTIG) ra[i] = fetch4<AL, true>(A, m0 + (f >> 2), k0 + ((f & 3) << 2), M, ke);
+            else              ra[i] = fetch4<AL, true>(A, m0 + ((f % TPR) << 2), k0 + f / TPR, M, ke);
+            if (BL::K_CONTIG) rb[i] = fetch4<BL, false>(Bm, n0 + (f >> 2), k0 + ((f & 3) << 2), N, ke);
+            else              rb[i] = fetch4<BL, false>(Bm, n0 + ((f % TPR) << 2), k0 + f / TPR, N, ke);
+        }
+    };
+    auto stash = [&](int st) {
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+            const int f = t + i * NT;
+            if (AL::K_CONTIG) {
+                const int r = f >> 2, k = (f & 3) << 2;
+                As[st][k][r] = ra[i].x; As[st][k + 1][r] = ra[i].y; As[st][k + 2][r] = ra[i].z; As[st][k + 3][r] = ra[i].w;
+            } else {
+                *reinterpret_cast<float4*>(&As[st][f / TPR][(f % TPR) << 2]) = ra[i];
+            }
+            if (BL::K_CONTIG) {
+                const int r = f >> 2, k = (f & 3) << 2;
+                Bs[st][k][r] = rb[i].x; Bs[st][k + 1][r] = rb[i].y; Bs[st][k + 2][r] = rb[i].z; Bs[st][k + 3][r] = rb[i].w;
+            } else {
+                *reinterpret_cast<float4*>(&Bs[st][f / TPR][(f % TPR) << 2]) = rb[i];
+            }
+        }
+    };
 
     const int n_tiles = (ke - kb + BK - 1) / BK;
-    float4 ra = fetch4<AL, true>(A, t, m0, M, kb, ke);
-    float4 rb = fetch4<BL, false>(Bm, t, n0, N, kb, ke);
-    stash4<AL::K_CONTIG>(As[0], t, ra);
-    stash4<BL::K_CONTIG>(Bs[0], t, rb);
-    if (n_tiles > 1) {
-        ra = fetch4<AL, true>(A, t, m0, M, kb + BK, ke);
-        rb = fetch4<BL, false>(Bm, t, n0, N, kb + BK, ke);
-    }
+    fetch(kb);
+    stash(0);
+    if (n_tiles > 1) fetch(kb + BK);
     __syncthreads();
     for (int kt = 0; kt < n_tiles; ++kt) {
         const int st = kt & 1;
-        if (kt + 1 < n_tiles) {                         // tile kt+1 (in registers) -> the other buffer;
-            stash4<AL::K_CONTIG>(As[st ^ 1], t, ra);    // it was last read in iteration kt-1 (barrier below)
-            stash4<BL::K_CONTIG>(Bs[st ^ 1], t, rb);
-        }
-        if (kt + 2 < n_tiles) {                         // tile kt+2 -> registers, in flight during the FMAs
-            ra = fetch4<AL, true>(A, t, m0, M, kb + (kt + 2) * BK, ke);
-            rb = fetch4<BL, false>(Bm, t, n0, N, kb + (kt + 2) * BK, ke);
-        }
+        if (kt + 1 < n_tiles) stash(st ^ 1);            // tile kt+1 (registers) -> the buffer read in iteration kt-1
+        if (kt + 2 < n_tiles) fetch(kb + (kt + 2) * BK);  // tile kt+2 -> registers, in flight during the FMAs
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
             const float4 a4 = *reinterpret_cast<const float4*>(&As[st][k][ty * 4]);
@@ -342,7 +354,8 @@ gemm_kernel(const AL A, const BL Bm, const EP epi, int M_host, const int* __rest
     }
 }
 
-// M_max bounds the grid when the true M lives on the device; splits > 1 needs an atomic epilogue.
+// M_max bounds the grid when the true M lives on the device (the typical M is then taken as M_max/4 when
+// choosing the tile shape); splits > 1 needs an atomic epilogue.
 template <class AL, class BL, class EP>
 static inline int launch(const AL& A, const BL& B, const EP& epi, int M_max, const int* M_dev, int N, int K_max,
                          const int* K_dev, int splits, cudaStream_t stream) {
@@ -351,16 +364,23 @@ static inline int launch(const AL& A, const BL& B, const EP& epi, int M_max, con
     int k_chunk = (K_max + splits - 1) / splits;
     k_chunk = ((k_chunk + BK - 1) / BK) * BK;
     splits = (K_max + k_chunk - 1) / k_chunk;
-    dim3 grid((N + BN - 1) / BN, (M_max + BM - 1) / BM, splits);
-    gemm_kernel<AL, BL, EP><<<grid, THREADS, 0, stream>>>(A, B, epi, M_max, M_dev, N, K_max, K_dev, k_chunk);
+    const int m_typ = M_dev ? (M_max / 4 > 64 ? M_max / 4 : 64) : M_max;
+    const long long big = (long long)((N + 63) / 64) * ((m_typ + 63) / 64) * splits;
+    if (big >= 2 * CTAN_SM_COUNT) {
+        dim3 grid((N + 63) / 64, (M_max + 63) / 64, splits);
+        gemm_kernel<64, AL, BL, EP><<<grid, 256, 0, stream>>>(A, B, epi, M_max, M_dev, N, K_max, K_dev, k_chunk);
+    } else {
+        dim3 grid((N + 31) / 32, (M_max + 31) / 32, splits);
+        gemm_kernel<32, AL, BL, EP><<<grid, 64, 0, stream>>>(A, B, epi, M_max, M_dev, N, K_max, K_dev, k_chunk);
+    }
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
 
 // number of K splits that puts ~2 CTAs on every SM; m_typ = the typical true M when M_max is only a bound
 static inline int pick_splits(int m_typ, int N, int K, int min_k = 2 * BK) {
-    const int tiles = ((m_typ + BM - 1) / BM) * ((N + BN - 1) / BN);
-    int s = (2 * CTAN_SM_COUNT + tiles - 1) / tiles;
+    const int tiles = ((m_typ + 31) / 32) * ((N + 31) / 32);      // small tiles are used when the grid is thin
+    int s = (3 * CTAN_SM_COUNT + tiles - 1) / tiles;
     const int max_s = (K + min_k - 1) / min_k;
     if (s > max_s) s = max_s;
     if (s < 1) s = 1;
