@@ -355,6 +355,13 @@ def main():
         cv, cms = oracle_train_rate(st, K, mean, std, "cpu", 120, 5, threads=cores)
         out["cpu_baseline"] = {"value": cv, "unit": "events/s", "cores": cores, "kind": "port",
                                "sample": "120 consecutive 200-event training batches of the same stream (oracle port)"}
+        # single-GPU point of the TGB-eval scaling curve (the N>1 runs report this metric as `value`)
+        import types
+        from bench_tgb import run_tgb_eval_bench
+        del eng
+        torch.cuda.empty_cache()
+        r = run_tgb_eval_bench(types.SimpleNamespace(steps=min(args.steps, 100), warmup=5), 0, 1, quiet=True)
+        out["tgb_eval"] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "mrr", "rank0_subgraph")}
     print(json.dumps(out))
 
 

@@ -1,0 +1,106 @@
+"""TGB one-vs-many evaluation benchmark (BASELINE.json configs[4]: tgbl-comment-shaped stream, 994 790
+nodes, 2-d messages, 20 negatives per query, CTAN_tgb D=T=256, S=32, K=1), sharded over N ranks.
+
+Launched by bench.py (directly for N=1, under torchrun for N>1).  A "step" is one 200-event batch =
+200 queries; value = queries/sec of the whole job (strong scaling: the batch is split over the ranks),
+timed on the device between two barriers, max over ranks."""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import numpy as np
+import torch
+
+COMMENT = dict(D=256, T=256, S=32, K=1, B=200, n_neg=20, eps=1.0, gamma=0.1)
+WARM_EVENTS = 400_000          # events inserted into the neighbour/memory state before the timed window
+
+
+def build_eval(rank, world, dev, n_batches, shape="comment", cfg=COMMENT, n_nodes_scale=1.0, warm=WARM_EVENTS):
+    import ctan_b200  # noqa: F401
+    from ctan_b200 import synth
+    from ctan_b200._lib import call, ptr
+    from ctan_b200.models import CTAN_tgb, LastNeighborLoader
+    from ctan_b200.tgb_eval import TGBEvalEngine
+    B = cfg["B"]
+    n_events = warm + (n_batches + 4) * B
+    st = synth.make_stream(shape, n_events=n_events, seed=0, tgb=True, n_nodes_scale=n_nodes_scale)
+    g = torch.Generator().manual_seed(1)
+    neg = torch.randint(st["min_dst"], st["max_dst"] + 1, (n_events, cfg["n_neg"]), generator=g)
+    mean, std = synth.delta_t_stats(st, 20000)
+    torch.manual_seed(0)
+    model = CTAN_tgb(num_nodes=st["num_nodes"], edge_dim=st["msg"].size(1), memory_dim=cfg["D"], time_dim=cfg["T"],
+                     node_dim=1, num_iters=cfg["K"], epsilon=cfg["eps"], gamma=cfg["gamma"], mean_delta_t=mean,
+                     std_delta_t=std).to(dev)
+    loader = LastNeighborLoader(st["num_nodes"], cfg["S"], device=dev)
+    gs = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in st.items()}
+    gs["neg"] = neg.to(dev)
+    group = None
+    eng = TGBEvalEngine(model, loader, gs, batch_size=B, n_neg=cfg["n_neg"], rank=rank, world=world, group=group)
+    eng.warmup()
+    # warm state: insert the first `warm` events and give the touched nodes a non-trivial memory
+    # (replicated identically on every rank; deterministic)
+    model.reset_memory()
+    loader.reset_state()
+    chunk = 2000
+    ws = torch.zeros(4 * chunk, dtype=torch.int32, device=dev)
+    for lo in range(0, warm, chunk):
+        loader.insert(gs["src"][lo:lo + chunk], gs["dst"][lo:lo + chunk])
+    gen = torch.Generator(device="cpu").manual_seed(7)
+    touched = torch.unique(torch.cat([st["src"][:warm], st["dst"][:warm]]))
+    model.memory.memory[touched.to(dev)] = (0.1 * torch.randn(touched.numel(), cfg["D"], generator=gen)).to(dev)
+    model.memory.last_update[touched.to(dev)] = gs["t"][warm - 1] // 2
+    eng.set_cursor(warm)
+    return eng, st
+
+
+def run_tgb_eval_bench(args, rank, world, quiet=False):
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+    steps = args.steps
+    eng, st = build_eval(rank, world, dev, W + steps)
+    B = eng.B
+    eng.run(W)
+    torch.cuda.synchronize()
+    sampler = None
+    if rank == 0:
+        from bench import ClockSampler
+        sampler = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.run(steps)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    eng.check()
+    mrr = eng.mrr()
+    clocks = sampler.stop() if sampler else None
+    counts = eng.w["counts"].cpu().tolist()
+    out = {"metric": "tgb_eval_queries_per_sec", "value": steps * B / (ms * 1e-3), "unit": "queries/s",
+           "n_gpus": world, "steps": steps, "warmup": W, "ms_per_step": ms / steps, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "tgbl-comment-shaped TGB one-vs-many eval: 994790 nodes, 2-d msgs, 200 queries/batch "
+                                  "x 20 negatives, CTAN_tgb D=T=256 S=32 K=1; queries of each batch sharded over the "
+                                  f"ranks, one NCCL all-gather per batch; {WARM_EVENTS} events warm state",
+                      "l2": "state tables (1.0 GB memory + 0.5 GB neighbour rows) exceed L2; no flush"},
+           "clocks": clocks, "mrr": mrr, "rank0_subgraph": {"N": counts[0], "E": counts[1]},
+           "gpu_launches": steps * 15}
+    if rank == 0 and not quiet:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return out

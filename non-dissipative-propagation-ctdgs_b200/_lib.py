@@ -20,7 +20,7 @@ SIGNATURES = {
     "ctan_nbr_insert": [P, P, P, P, P, I, L, P, I, P],
     "ctan_nbr_lookup": [P, P, L, I, P, I, P, I, P, P, P, P, I, P, I, P, P, I, P],
     "ctan_nbr_fill": [P, P, I, P, P, P, I, P, P, P, P, P, P],
-    "ctan_mem_update": [P, P, I, P, P, P, I, P, P, P, P],
+    "ctan_mem_update": [P, P, I, P, P, P, I, P, P, I, P, P],
     "ctan_mem_reset": [P, P, L, I, L],
     # edge.cu
     "ctan_edge_rel": [P, P, P, P, P, I, P, F, F, P],
@@ -77,6 +77,9 @@ SIGNATURES.update({
     "ctan_bce_loss": [P, I, I, P, P, I, P],
     "ctan_adam_step": [P, P, P, P, I, F, F, F, F, F, L, P],
     "ctan_mrr": [P, P, I, I, P],
+    "ctan_stage_eval": [P, P, P, P, I, I, I, I, P, P, P, P, P, P, P],
+    "ctan_pack_eval": [P, P, P, P, P, I, I, I, P],
+    "ctan_accum_col": [P, I, I, I, P],
 })
 
 

@@ -366,7 +366,10 @@ static inline int launch(const AL& A, const BL& B, const EP& epi, int M_max, con
     splits = (K_max + k_chunk - 1) / k_chunk;
     const int m_typ = M_dev ? (M_max / 4 > 64 ? M_max / 4 : 64) : M_max;
     const long long big = (long long)((N + 63) / 64) * ((m_typ + 63) / 64) * splits;
-    if (big >= 2 * CTAN_SM_COUNT) {
+    static const int force_tile = [] { const char* e = getenv("CTAN_GEMM_TILE"); return e ? atoi(e) : 0; }();
+    // measured on B200 (scripts/micro_kernels.py): the 32x32 tile only wins on thin, long-K problems
+    const bool use_big = force_tile == 64 ? true : (force_tile == 32 ? false : (big >= 24 || K_max < 512));
+    if (use_big) {
         dim3 grid((N + 63) / 64, (M_max + 63) / 64, splits);
         gemm_kernel<64, AL, BL, EP><<<grid, 256, 0, stream>>>(A, B, epi, M_max, M_dev, N, K_max, K_dev, k_chunk);
     } else {

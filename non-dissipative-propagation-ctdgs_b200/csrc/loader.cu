@@ -356,7 +356,7 @@ extern "C" int ctan_nbr_fill(const int64_t* nbr, const int64_t* eid, int S, cons
 __global__ void mem_update_kernel(float* __restrict__ mem, int64_t* __restrict__ last_update, int D,
                                   const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
                                   const int64_t* __restrict__ t, int B, const float* __restrict__ emb_src,
-                                  const float* __restrict__ emb_dst, const float* __restrict__ z,
+                                  const float* __restrict__ emb_dst, int emb_ld, const float* __restrict__ z,
                                   const int64_t* __restrict__ assoc) {
     const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
     const int n = 2 * B;
@@ -379,7 +379,7 @@ __global__ void mem_update_kernel(float* __restrict__ mem, int64_t* __restrict__
         if (beaten) continue;
         const float* row;
         if (z) row = z + (size_t)assoc[u] * D;
-        else row = p < B ? emb_src + (size_t)p * D : emb_dst + (size_t)(p - B) * D;
+        else row = p < B ? emb_src + (size_t)p * emb_ld : emb_dst + (size_t)(p - B) * emb_ld;
         float* out = mem + (size_t)u * D;
         for (int d = lane; d < D; d += 32) out[d] = row[d];
         if (lane == 0) last_update[u] = tp;
@@ -387,14 +387,14 @@ __global__ void mem_update_kernel(float* __restrict__ mem, int64_t* __restrict__
 }
 
 extern "C" int ctan_mem_update(float* mem, int64_t* last_update, int D, const int64_t* src, const int64_t* dst,
-                               const int64_t* t, int B, const float* emb_src, const float* emb_dst, const float* z,
-                               const int64_t* assoc, cudaStream_t stream) {
+                               const int64_t* t, int B, const float* emb_src, const float* emb_dst, int emb_ld,
+                               const float* z, const int64_t* assoc, cudaStream_t stream) {
     if (B < 0 || D <= 0) return CTAN_ERR_BAD_ARG;
     if (B == 0) return 0;
     if (!z && (!emb_src || !emb_dst)) return CTAN_ERR_BAD_ARG;
     const int wpb = 4;
     mem_update_kernel<<<ctan_grid(2LL * B, wpb), wpb * 32, 0, stream>>>(mem, last_update, D, src, dst, t, B, emb_src,
-                                                                       emb_dst, z, assoc);
+                                                                       emb_dst, emb_ld > 0 ? emb_ld : D, z, assoc);
     CTAN_CHECK_LAUNCH();
     return 0;
 }

@@ -152,3 +152,116 @@ extern "C" int ctan_mrr(const float* pos, const float* neg, int Q, int n_neg, fl
     CTAN_CHECK_LAUNCH();
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// TGB one-vs-many evaluation (tgb_test 'val'/'test', train_link.py:111-159), union-of-seeds form:
+// the memory / neighbour state is frozen within a 200-event batch, so node embeddings do not depend on
+// the query and ONE forward over the union of this rank's seeds serves all of its queries.
+// stage_eval: this rank owns queries [q0,q1) of the batch.  Writes the whole batch's (src,dst,t) for the
+// state update, the rank's seed list, and its scored pairs in per-query order [pos, neg_1..neg_n].
+// ------------------------------------------------------------------------------------------
+__global__ void stage_eval_kernel(const int64_t* __restrict__ src_all, const int64_t* __restrict__ dst_all,
+                                  const int64_t* __restrict__ t_all, const int64_t* __restrict__ neg_all, int n_neg,
+                                  int B, int q0, int q1, int64_t* __restrict__ counters, int64_t* __restrict__ b_src,
+                                  int64_t* __restrict__ b_dst, int64_t* __restrict__ b_t, int64_t* __restrict__ seeds,
+                                  int64_t* __restrict__ pair_src, int64_t* __restrict__ pair_dst) {
+    __shared__ int64_t s_off;
+    if (threadIdx.x == 0) {
+        const int64_t cur = counters[0];
+        counters[0] = cur + B;
+        counters[1] = cur;
+        counters[3] += 1;
+        s_off = cur;
+    }
+    __syncthreads();
+    const int64_t off = s_off;
+    const int Q = q1 - q0, L = 1 + n_neg;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        b_src[i] = src_all[off + i]; b_dst[i] = dst_all[off + i]; b_t[i] = t_all[off + i];
+    }
+    for (int i = threadIdx.x; i < Q; i += blockDim.x) {
+        const int64_t s = src_all[off + q0 + i], d = dst_all[off + q0 + i];
+        seeds[i] = s; seeds[Q + i] = d;
+        pair_src[(size_t)i * L] = s; pair_dst[(size_t)i * L] = d;
+    }
+    for (int i = threadIdx.x; i < Q * n_neg; i += blockDim.x) {
+        const int q = i / n_neg, j = i % n_neg;
+        const int64_t ng = neg_all[(off + q0 + q) * n_neg + j];
+        seeds[2 * Q + i] = ng;
+        pair_src[(size_t)q * L + 1 + j] = src_all[off + q0 + q];
+        pair_dst[(size_t)q * L + 1 + j] = ng;
+    }
+}
+
+extern "C" int ctan_stage_eval(const int64_t* src_all, const int64_t* dst_all, const int64_t* t_all,
+                               const int64_t* neg_all, int n_neg, int B, int q0, int q1, int64_t* counters,
+                               int64_t* b_src, int64_t* b_dst, int64_t* b_t, int64_t* seeds, int64_t* pair_src,
+                               int64_t* pair_dst, cudaStream_t stream) {
+    if (B <= 0 || n_neg < 1 || q0 < 0 || q1 > B || q1 < q0) return CTAN_ERR_BAD_ARG;
+    stage_eval_kernel<<<1, 512, 0, stream>>>(src_all, dst_all, t_all, neg_all, n_neg, B, q0, q1, counters, b_src, b_dst,
+                                             b_t, seeds, pair_src, pair_dst);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+// pack_eval: one warp per local query q -> row [ 1/rank | scores(1+n_neg) | z[src_q] (D) | z[dst_q] (D) ]
+// (the row every rank needs: reciprocal rank for the metric, embeddings for the identical state update).
+__global__ void pack_eval_kernel(const float* __restrict__ OUT, const float* __restrict__ z,
+                                 const int64_t* __restrict__ assoc, const int64_t* __restrict__ pair_src,
+                                 const int64_t* __restrict__ pair_dst, int Q, int n_neg, int D,
+                                 float* __restrict__ rows) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const int L = 1 + n_neg, W = 1 + L + 2 * D;
+    for (int q = warp; q < Q; q += nw) {
+        const float* o = OUT + (size_t)q * L;
+        float* r = rows + (size_t)q * W;
+        const float p = o[0];
+        int ge = 0, gt = 0;
+        for (int i = 1 + lane; i < L; i += 32) {
+            const float x = o[i];
+            ge += x >= p;
+            gt += x > p;
+        }
+        ge = warp_sum_i(ge); gt = warp_sum_i(gt);
+        if (lane == 0) r[0] = 1.0f / (0.5f * (float)(ge + gt) + 1.0f);
+        for (int i = lane; i < L; i += 32) r[1 + i] = o[i];
+        const float* zs = z + (size_t)assoc[pair_src[(size_t)q * L]] * D;
+        const float* zd = z + (size_t)assoc[pair_dst[(size_t)q * L]] * D;
+        for (int d = lane; d < D; d += 32) {
+            r[1 + L + d] = zs[d];
+            r[1 + L + D + d] = zd[d];
+        }
+    }
+}
+
+extern "C" int ctan_pack_eval(const float* OUT, const float* z, const int64_t* assoc, const int64_t* pair_src,
+                              const int64_t* pair_dst, int Q, int n_neg, int D, float* rows, cudaStream_t stream) {
+    if (Q <= 0) return 0;
+    pack_eval_kernel<<<ctan_grid((long long)Q * 32, 128), 128, 0, stream>>>(OUT, z, assoc, pair_src, pair_dst, Q, n_neg,
+                                                                            D, rows);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+// acc[0] += sum_r rows[r*ld + col]; acc[1] += R    (running sum of reciprocal ranks and query count)
+__global__ void accum_col_kernel(const float* __restrict__ rows, int R, int ld, int col, double* __restrict__ acc) {
+    __shared__ float red[32];
+    float s = 0.f;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) s += rows[(size_t)r * ld + col];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) { acc[0] += (double)v; acc[1] += (double)R; }
+    }
+}
+
+extern "C" int ctan_accum_col(const float* rows, int R, int ld, int col, double* acc, cudaStream_t stream) {
+    if (R <= 0) return 0;
+    accum_col_kernel<<<1, 256, 0, stream>>>(rows, R, ld, col, acc);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}

@@ -273,7 +273,7 @@ class StepEngine:
         def state_update():
             # ground-truth state update (train_link.py:276-277)
             call("ctan_mem_update", ptr(mem), ptr(lu), D, ptr(w["b_src"]), ptr(w["b_dst"]), ptr(w["b_t"]), B, None,
-                 None, ptr(z), ptr(ld._assoc))
+                 None, 0, ptr(z), ptr(ld._assoc))
             call("ctan_nbr_insert", ptr(ld.neighbors), ptr(ld.e_id), ptr(ld._deg), ptr(w["b_src"]), ptr(w["b_dst"]),
                  B, 0, cur1, S, ptr(w["ins_ws"]))
         if not train:

@@ -167,7 +167,7 @@ class SimpleMemory(torch.nn.Module):
         with torch.cuda.device(self.memory.device):
             call("ctan_mem_update", ptr(self.memory), ptr(self.last_update), self.memory_dim,
                  ptr(src.contiguous(), torch.long), ptr(pos_dst.contiguous(), torch.long),
-                 ptr(t.contiguous(), torch.long), B, ptr(se), ptr(de), None, None)
+                 ptr(t.contiguous(), torch.long), B, ptr(se), ptr(de), 0, None, None)
 
     def reset_state(self):
         _require_cuda(self.memory, "SimpleMemory.reset_state")

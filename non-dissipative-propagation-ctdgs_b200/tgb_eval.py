@@ -1,0 +1,237 @@
+"""TGB one-vs-many evaluation (tgb_test, split_mode 'val'/'test': train_link.py:111-159, 197-201) on our
+kernels, restructured B200-first:
+
+  * the reference runs one model forward PER QUERY (200 per batch); the memory and neighbour tables are
+    frozen inside a batch (they are only updated at train_link.py:198-199), so node embeddings are
+    query-independent: we run ONE forward per batch over the union of the seeds;
+  * the queries of a batch are sharded over the ranks (rank r owns a contiguous slice); each rank scores
+    its queries, then ONE all-gather per batch (NCCL over NVLink) exchanges, per query,
+    [1/rank | scores | src embedding | dst embedding]; every rank then applies the identical memory
+    write-back and neighbour insert, so the replicas stay bit-identical;
+  * the MRR (TGB/tgb/linkproppred/evaluate.py:109-120) is computed on the device.
+
+Embeddings are a deterministic function of a node's K-hop neighbourhood and are computed with the same
+arithmetic order on every rank, so a sharded run reproduces the 1-GPU run exactly."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr
+from .modules import CTAN_tgb
+from .neighbor_loader import LastNeighborLoader
+
+
+def shard_range(B: int, rank: int, world: int):
+    """Contiguous, balanced slice [q0,q1) of a batch's B queries owned by `rank`."""
+    base, rem = divmod(B, world)
+    q0 = rank * base + min(rank, rem)
+    return q0, q0 + base + (1 if rank < rem else 0)
+
+
+def exchange_rows(send: torch.Tensor, recv: torch.Tensor, rows: torch.Tensor, B: int, world: int, group=None):
+    """The single collective of a batch: all-gather every rank's packed query rows (`send`
+    [Qmax,row], padded) into `recv` [world*Qmax,row], then compact the per-rank slices (shards may differ
+    by one query) into batch order `rows` [B,row].  Works on any backend (NCCL on GPU, gloo in CPU tests)."""
+    import torch.distributed as dist
+    qmax = send.size(0)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    for rk in range(world):
+        a0, a1 = shard_range(B, rk, world)
+        if a1 > a0:
+            rows[a0:a1].copy_(recv[rk * qmax: rk * qmax + (a1 - a0)])
+    return rows
+
+
+class TGBEvalEngine:
+    def __init__(self, model: CTAN_tgb, loader: LastNeighborLoader, stream: dict, batch_size: int, n_neg: int,
+                 rank: int = 0, world: int = 1, group=None, use_graph: bool = True):
+        dev = model.memory.memory.device
+        if dev.type != "cuda":
+            raise _lib.CtanLibraryError("TGBEvalEngine needs the model on a CUDA device")
+        _lib.lib()
+        self.model, self.loader, self.dev = model, loader, dev
+        self.rank, self.world, self.group, self.use_graph = rank, world, group, use_graph
+        self.B, self.n_neg = int(batch_size), int(n_neg)
+        self.q0, self.q1 = shard_range(self.B, rank, world)
+        self.Q = self.q1 - self.q0
+        self.Qmax = shard_range(self.B, 0, world)[1]                 # largest shard (all-gather row count)
+        self.K, self.D, self.S = model.num_gnn_layers, model.memory.memory_dim, loader.size
+        self.num_nodes = model.num_nodes
+        self.final_tanh = model.final_act == "tanh"
+        st = stream
+        for k in ("src", "dst", "t", "msg", "neg"):
+            if not st[k].is_cuda:
+                raise _lib.CtanLibraryError(f"stream['{k}'] must be device resident")
+        self.src, self.dst, self.t = st["src"].contiguous(), st["dst"].contiguous(), st["t"].contiguous()
+        self.msg = st["msg"].float().contiguous()
+        self.n_events = self.src.numel()
+        self.neg = st["neg"].contiguous().view(self.n_events, self.n_neg)
+        self.x = st.get("x")
+        if self.x is not None:
+            self.x = (self.x.squeeze(0) if self.x.dim() == 3 else self.x).to(dev).float().contiguous()
+        self.Fe, self.Fn = self.msg.size(1), (self.x.size(1) if self.x is not None else 0)
+        self.T = model.gnn.time_enc.lin.bias.numel()
+        r = model.readout
+        self.Hd, self.O = r.lin_src.weight.size(0), r.lin_final.weight.size(0)
+        assert self.O == 1
+        self.L = 1 + self.n_neg
+        self.P = max(self.Q, 1) * self.L
+        self.n_seeds = max(self.Q, 1) * (2 + self.n_neg)
+        self.n_cap = min(self.num_nodes, self.n_seeds * (self.S + 1) ** self.K)
+        c_cap = min(self.num_nodes, self.n_seeds * (self.S + 1) ** (self.K - 1))
+        self.e_cap = max(c_cap * self.S, 1)
+        self.row = 1 + self.L + 2 * self.D                          # packed per-query row
+        self._alloc()
+        self._graph = None
+        self._side = torch.cuda.Stream(device=dev)
+
+    def _alloc(self):
+        dev, B, K, D = self.dev, self.B, self.K, self.D
+        N, E, P = self.n_cap, self.e_cap, self.P
+        f32 = dict(device=dev, dtype=torch.float32)
+        i64 = dict(device=dev, dtype=torch.long)
+        w = {}
+        w["counters"] = torch.zeros(8, **i64)
+        w["b_src"], w["b_dst"], w["b_t"] = (torch.zeros(B, **i64) for _ in range(3))
+        w["seeds"] = torch.zeros(self.n_seeds, **i64)
+        w["pair_src"], w["pair_dst"] = torch.zeros(P, **i64), torch.zeros(P, **i64)
+        w["frontier"] = torch.zeros(max(K - 1, 1) * N, **i64)
+        w["frontier_cnt"] = torch.zeros(8, device=dev, dtype=torch.int32)
+        w["counts"] = torch.zeros(8, device=dev, dtype=torch.int32)
+        w["n_id"] = torch.zeros(N, **i64)
+        w["rowptr"] = torch.zeros(N + 1, device=dev, dtype=torch.int32)
+        w["esrc"], w["edst"], w["eid"] = (torch.zeros(E, **i64) for _ in range(3))
+        w["ins_ws"] = torch.zeros(4 * B, device=dev, dtype=torch.int32)
+        w["rel"] = torch.zeros(E, **f32)
+        w["X"] = torch.zeros((2, N, D), **f32)
+        w["EP"] = torch.zeros((E, D), **f32)
+        w["A"] = torch.zeros((D, D), **f32)
+        w["QKVA"] = torch.zeros((N, 4 * D), **f32)
+        w["Z"] = torch.zeros((N, D), **f32) if self.final_tanh else None
+        w["H"] = torch.zeros((P, self.Hd), **f32)
+        w["OUT"] = torch.zeros((P, self.O), **f32)
+        w["send"] = torch.zeros((self.Qmax, self.row), **f32)
+        w["recv"] = torch.zeros((self.world * self.Qmax, self.row), **f32) if self.world > 1 else w["send"]
+        w["rows"] = torch.zeros((B, self.row), **f32) if self.world > 1 else w["send"]
+        w["acc"] = torch.zeros(2, device=dev, dtype=torch.float64)   # [sum of 1/rank, #queries]
+        self.w = w
+        self._Nd, self._Ed = w["counts"][0:1], w["counts"][1:2]
+
+    # ------------------------------------------------------------------ state
+    def set_cursor(self, event_index: int):
+        self.w["counters"][0] = int(event_index)
+        self.loader.cur_e_id = int(event_index)
+
+    def reset_metric(self):
+        self.w["acc"].zero_()
+
+    def mrr(self) -> float:
+        a = self.w["acc"].cpu()
+        return float(a[0] / a[1]) if float(a[1]) > 0 else float("nan")
+
+    # ------------------------------------------------------------------ one batch
+    def _launch(self, dry: bool = False):
+        w, m, ld = self.w, self.model, self.loader
+        B, D, K, S, Fe, Fn, T, Hd, O, P, Q = self.B, self.D, self.K, self.S, self.Fe, self.Fn, self.T, self.Hd, self.O, self.P, self.Q
+        N, E = self.n_cap, self.e_cap
+        Nd, Ed = ptr(self._Nd), ptr(self._Ed)
+        g, a, r = m.gnn, m.gnn.aconv, m.readout
+        ph = a.phi
+        mem, lu = m.memory.memory, m.memory.last_update
+        xf = ptr(self.x) if Fn else None
+        eps = float(a.epsilon)
+        call("ctan_stage_eval", ptr(self.src), ptr(self.dst), ptr(self.t), ptr(self.neg), self.n_neg, B, self.q0,
+             self.q1, ptr(w["counters"]), ptr(w["b_src"]), ptr(w["b_dst"]), ptr(w["b_t"]), ptr(w["seeds"]),
+             ptr(w["pair_src"]), ptr(w["pair_dst"]))
+        if Q > 0:
+            call("ctan_nbr_lookup", ptr(ld.neighbors), ptr(ld._deg), self.num_nodes, S, ptr(w["seeds"]),
+                 Q * (2 + self.n_neg), None, K, ptr(ld._bitmap), ptr(ld._cbitmap), ptr(w["frontier"]),
+                 ptr(w["frontier_cnt"]), N, ptr(w["n_id"]), N, ptr(ld._assoc), ptr(w["rowptr"]), E, ptr(w["counts"]))
+            call("ctan_nbr_fill", ptr(ld.neighbors), ptr(ld.e_id), S, ptr(w["n_id"]), ptr(w["rowptr"]),
+                 ptr(ld._assoc), N, Nd, ptr(w["esrc"]), ptr(w["edst"]), ptr(w["eid"]), ptr(ld._bitmap),
+                 ptr(ld._cbitmap))
+            self._side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._side):
+                call("ctan_edge_rel", ptr(lu), ptr(w["n_id"]), ptr(w["esrc"]), ptr(self.t), ptr(w["eid"]), E, Ed,
+                     float(g.mean_delta_t), float(g.std_delta_t), ptr(w["rel"]))
+                call("ctan_eproj_fwd", ptr(self.msg), Fe, ptr(w["eid"]), ptr(w["rel"]), ptr(g.time_enc.lin.weight),
+                     ptr(g.time_enc.lin.bias), T, ptr(ph.lin_edge.weight), E, Ed, D, ptr(w["EP"]))
+                call("ctan_antisym_prep", ptr(a.W), float(a.gamma), D, ptr(w["A"]))
+                w["H"].zero_()
+            call("ctan_enc_fwd", ptr(mem), D, xf, Fn, ptr(w["n_id"]), None, N, Nd, ptr(g.enc_x.weight),
+                 ptr(g.enc_x.bias), ptr(w["X"][0]))
+            torch.cuda.current_stream().wait_stream(self._side)
+            for k in range(K):
+                xi, xo = w["X"][k & 1], w["X"][(k + 1) & 1]
+                call("ctan_qkva_fwd", ptr(xi), N, Nd, D, ptr(ph.lin_query.weight), ptr(ph.lin_key.weight),
+                     ptr(ph.lin_value.weight), ptr(w["A"]), ptr(ph.lin_query.bias), ptr(ph.lin_key.bias),
+                     ptr(ph.lin_value.bias), ptr(a.bias), ptr(w["QKVA"]))
+                last = k == K - 1
+                call("ctan_edge_fwd", ptr(w["QKVA"]), ptr(w["EP"]), ptr(w["rowptr"]), ptr(w["esrc"]), N, Nd, D,
+                     ptr(xi), eps, ptr(xo), None, None, ptr(w["Z"]) if (last and self.final_tanh) else None)
+            z = w["Z"] if self.final_tanh else w["X"][K & 1]
+            call("ctan_readout_fwd", ptr(z), D, ptr(w["pair_src"]), ptr(w["pair_dst"]), ptr(ld._assoc), Q * self.L,
+                 None, Hd, O, ptr(r.lin_src.weight), ptr(r.lin_src.bias), ptr(r.lin_dst.weight), ptr(r.lin_dst.bias),
+                 ptr(r.lin_final.weight), ptr(r.lin_final.bias), ptr(w["H"]), ptr(w["OUT"]), 1)
+            call("ctan_pack_eval", ptr(w["OUT"]), ptr(z), ptr(ld._assoc), ptr(w["pair_src"]), ptr(w["pair_dst"]), Q,
+                 self.n_neg, D, ptr(w["send"]))
+        rows = w["send"]
+        if self.world > 1:
+            rows = exchange_rows(w["send"], w["recv"], w["rows"], B, self.world, self.group)   # the one collective
+        call("ctan_accum_col", ptr(rows), B, self.row, 0, ptr(w["acc"]))
+        emb = ptr(rows) + 4 * (1 + self.L)
+        if dry:      # warm-up: same kernels, but the state update goes to scratch tables
+            sm, sl, sn, se, sd = self._scratch
+            call("ctan_mem_update", ptr(sm), ptr(sl), D, ptr(sl), ptr(sl), ptr(sl), 1, emb, emb + 4 * D, self.row,
+                 None, None)
+            call("ctan_nbr_insert", ptr(sn), ptr(se), ptr(sd), ptr(sl), ptr(sl), 1, 0, None, S, ptr(w["ins_ws"]))
+            return
+        call("ctan_mem_update", ptr(mem), ptr(lu), D, ptr(w["b_src"]), ptr(w["b_dst"]), ptr(w["b_t"]), B, emb,
+             emb + 4 * D, self.row, None, None)
+        call("ctan_nbr_insert", ptr(ld.neighbors), ptr(ld.e_id), ptr(ld._deg), ptr(w["b_src"]), ptr(w["b_dst"]), B, 0,
+             ptr(w["counters"]) + 8, S, ptr(w["ins_ws"]))
+
+    def warmup(self):
+        """One eager dry batch: loads every kernel and initialises the communicator before graph capture.
+        Side-effect free: the state update of the dry batch is redirected to scratch tables and the cursor
+        and metric accumulators are restored."""
+        dev = self.dev
+        self._scratch = (torch.zeros((2, self.D), device=dev), torch.zeros(2, dtype=torch.long, device=dev),
+                         torch.zeros((2, self.S), dtype=torch.long, device=dev),
+                         torch.full((2, self.S), -1, dtype=torch.long, device=dev),
+                         torch.zeros(2, dtype=torch.int32, device=dev))
+        cur = self.w["counters"].clone()
+        with torch.cuda.device(dev):
+            self._launch(dry=True)
+        torch.cuda.synchronize(dev)
+        self.w["counters"].copy_(cur)
+        self.w["acc"].zero_()
+
+    def run(self, n_batches: int):
+        if self.loader.cur_e_id + n_batches * self.B > self.n_events:
+            raise ValueError("stream exhausted")
+        with torch.cuda.device(self.dev):
+            if self.use_graph:
+                if self._graph is None:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._launch()
+                    self._graph = g
+                    # capture does not execute: restore the cursor the captured stage kernel will advance
+                for _ in range(n_batches):
+                    self._graph.replay()
+            else:
+                for _ in range(n_batches):
+                    self._launch()
+        self.loader.cur_e_id += n_batches * self.B
+
+    def scores(self) -> torch.Tensor:
+        """[B, 1+n_neg] scores of the last batch (column 0 = positive), batch order."""
+        rows = self.w["rows"] if self.world > 1 else self.w["send"]
+        return rows[: self.B, 1:1 + self.L]
+
+    def check(self):
+        err = int(self.w["counts"][3].item())
+        if err:
+            raise _lib.CtanLibraryError(f"neighbor lookup overflowed the engine workspace (code {err})")

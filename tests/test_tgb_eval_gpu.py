@@ -1,0 +1,80 @@
+"""TGB one-vs-many evaluation: our union-forward engine against the oracle's per-query restatement of
+tgb_test 'val' (train_link.py:111-159,197-201): scores, per-batch MRR, memory and neighbour state."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _neg_table(st, n_neg, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(st["min_dst"], st["max_dst"] + 1, (st["src"].numel(), n_neg), generator=g)
+
+
+@pytest.mark.parametrize("K,final_act,n_neg", [(1, None, 20), (2, "tanh", 7)])
+def test_eval_matches_per_query_oracle(small_stream, K, final_act, n_neg):
+    from ctan_b200.models import CTAN_tgb, LastNeighborLoader
+    from ctan_b200.tgb_eval import TGBEvalEngine
+    from oracle import ctan_oracle as O
+    st = small_stream
+    dev = torch.device("cuda:0")
+    B, S, D = 50, 8, 32
+    neg = _neg_table(st, n_neg)
+    neg[3, :5] = st["dst"][3]            # negatives equal to the positive -> rank ties
+    kw = dict(num_nodes=st["num_nodes"], edge_dim=st["msg"].size(1), memory_dim=D, time_dim=8, node_dim=1,
+              num_iters=K, epsilon=0.5, gamma=0.1, mean_delta_t=np.float64(1234.5), std_delta_t=np.float64(4567.8),
+              final_act=final_act)
+    torch.manual_seed(0)
+    om = O.OracleCTAN(**kw, tgb=True)
+    torch.manual_seed(0)
+    mm = CTAN_tgb(**kw).to(dev)
+    lo_ref = O.TorchNeighborLoader(st["num_nodes"], S)
+    ld = LastNeighborLoader(st["num_nodes"], S, device=dev)
+    h = torch.zeros(st["num_nodes"], dtype=torch.long)
+    g = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in st.items()}
+    g["neg"] = neg.to(dev)
+    eng = TGBEvalEngine(mm, ld, g, batch_size=B, n_neg=n_neg)
+    eng.warmup()
+    # warm both states with the same 600 events through the no-grad inference loop of each side
+    for it in range(12):
+        lo, hi = it * B, (it + 1) * B
+        O.infer_step_ref(om, lo_ref, h, st, lo, hi, st["neg"][lo:hi])
+        s, d, t, msg, ng = g["src"][lo:hi], g["dst"][lo:hi], g["t"][lo:hi], g["msg"][lo:hi], st["neg"][lo:hi].to(dev)
+        n_id, ei, eid, _ = ld.lookup_khop(torch.cat([s, d, ng]), K)
+        hm = torch.zeros(st["num_nodes"], dtype=torch.long, device=dev)
+        hm[n_id] = torch.arange(n_id.numel(), device=dev)
+        with torch.no_grad():
+            po, no, se, de = mm(O.Batch(src=torch.cat([s, s]), dst=torch.cat([d, ng]), n_neg=B, x=g["x"]), n_id,
+                                g["msg"][eid], g["t"][eid], ei, hm)
+        mm.update(s, d, t, msg, se, de)
+        ld.insert(s, d)
+    eng.set_cursor(12 * B)
+    all_ref = []
+    for it in range(12, 18):
+        lo, hi = it * B, (it + 1) * B
+        mrrs, pos_s, neg_s = O.tgb_eval_batch_ref(om, lo_ref, h, st, lo, hi, [neg[q].tolist() for q in range(lo, hi)])
+        all_ref += mrrs
+        eng.run(1)
+        sc = eng.scores().cpu()
+        ref = torch.cat([pos_s.view(-1, 1), torch.stack(neg_s)], 1)
+        assert float((sc - ref).abs().max()) <= 2e-4 * float(ref.abs().max()) + 1e-6, it
+        assert torch.equal(ld.e_id.cpu(), lo_ref.e_id)
+        assert torch.equal(mm.memory.last_update.cpu(), om.memory.last_update)
+        mo = om.memory.memory
+        assert float((mm.memory.memory.cpu() - mo).abs().max()) <= 5e-4 * float(mo.abs().max())
+    eng.check()
+    ref_mrr = float(torch.tensor(all_ref).mean())
+    assert abs(eng.mrr() - ref_mrr) <= 1e-4 * ref_mrr + 1e-6, (eng.mrr(), ref_mrr)
+
+
+def test_mrr_kernel_matches_golden():
+    import os
+    from ctan_b200._lib import call, ptr
+    dev = torch.device("cuda:0")
+    cases = torch.load(os.path.join(os.path.dirname(__file__), "golden", "mrr_golden.pt"))
+    for c in cases:
+        pos, neg = c["pos"].to(dev), c["neg"].to(dev).contiguous()
+        rr = torch.zeros(1, device=dev)
+        call("ctan_mrr", ptr(pos), ptr(neg), 1, neg.numel(), ptr(rr))
+        assert abs(float(rr) - c["mrr"]) < 1e-7
