@@ -132,6 +132,12 @@ class TGBEvalEngine:
 
     # ------------------------------------------------------------------ one batch
     def _launch(self, dry: bool = False):
+        self._compute()
+        self._exchange()
+        self._update(dry)
+
+    def _compute(self):
+        """stage -> lookup -> forward -> scores -> packed per-query rows of this rank's shard."""
         w, m, ld = self.w, self.model, self.loader
         B, D, K, S, Fe, Fn, T, Hd, O, P, Q = self.B, self.D, self.K, self.S, self.Fe, self.Fn, self.T, self.Hd, self.O, self.P, self.Q
         N, E = self.n_cap, self.e_cap
@@ -176,9 +182,20 @@ class TGBEvalEngine:
                  ptr(r.lin_final.weight), ptr(r.lin_final.bias), ptr(w["H"]), ptr(w["OUT"]), 1)
             call("ctan_pack_eval", ptr(w["OUT"]), ptr(z), ptr(ld._assoc), ptr(w["pair_src"]), ptr(w["pair_dst"]), Q,
                  self.n_neg, D, ptr(w["send"]))
-        rows = w["send"]
+
+    def _exchange(self):
+        """The one collective of the batch (kept OUT of CUDA-graph capture: torch's NCCL process group and
+        stream capture do not mix reliably; it is still stream-ordered and needs no host sync)."""
         if self.world > 1:
-            rows = exchange_rows(w["send"], w["recv"], w["rows"], B, self.world, self.group)   # the one collective
+            w = self.w
+            exchange_rows(w["send"], w["recv"], w["rows"], self.B, self.world, self.group)
+
+    def _update(self, dry: bool = False):
+        """metric accumulation + the identical ground-truth state update on every rank."""
+        w, m, ld = self.w, self.model, self.loader
+        B, D, S = self.B, self.D, self.S
+        mem, lu = m.memory.memory, m.memory.last_update
+        rows = w["rows"] if self.world > 1 else w["send"]
         call("ctan_accum_col", ptr(rows), B, self.row, 0, ptr(w["acc"]))
         emb = ptr(rows) + 4 * (1 + self.L)
         if dry:      # warm-up: same kernels, but the state update goes to scratch tables
@@ -214,13 +231,21 @@ class TGBEvalEngine:
         with torch.cuda.device(self.dev):
             if self.use_graph:
                 if self._graph is None:
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
-                        self._launch()
-                    self._graph = g
-                    # capture does not execute: restore the cursor the captured stage kernel will advance
+                    ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(ga):
+                        self._compute()
+                        if self.world == 1:
+                            self._update()
+                    if self.world > 1:
+                        with torch.cuda.graph(gb):
+                            self._update()
+                    self._graph = (ga, gb)
+                ga, gb = self._graph
                 for _ in range(n_batches):
-                    self._graph.replay()
+                    ga.replay()
+                    if self.world > 1:
+                        self._exchange()
+                        gb.replay()
             else:
                 for _ in range(n_batches):
                     self._launch()
