@@ -136,12 +136,14 @@ class _ReadoutFn(torch.autograd.Function):
         Hd, O = Wdst.size(0), Wfin.size(0)
         dev = z.device
         with torch.cuda.device(dev):
-            H = torch.zeros((P, Hd), device=dev)         # zeroed: the hidden contraction splits K
+            # training: split-K (atomic, needs a zeroed H); no-grad scoring: plain stores, bit-reproducible
+            split = any(ctx.needs_input_grad)
+            H = torch.zeros((P, Hd), device=dev) if split else torch.empty((P, Hd), device=dev)
             out = torch.empty((P, O), device=dev)
             call("ctan_readout_fwd", ptr(z), D, ptr(src, torch.long) if src is not None else ptr(dst, torch.long),
                  ptr(dst, torch.long), ptr(id_map, torch.long) if id_map is not None else None, P, None, Hd, O,
                  ptr(Wsrc) if Wsrc is not None else None, ptr(bsrc) if bsrc is not None else None, ptr(Wdst),
-                 ptr(bdst), ptr(Wfin), ptr(bfin), ptr(H), ptr(out), 1)
+                 ptr(bdst), ptr(Wfin), ptr(bfin), ptr(H), ptr(out), int(split))
         ctx.save_for_backward(z, src, dst, id_map, H, Wsrc, Wdst, Wfin)
         return out
 

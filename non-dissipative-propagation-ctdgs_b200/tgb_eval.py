@@ -179,7 +179,7 @@ class TGBEvalEngine:
             z = w["Z"] if self.final_tanh else w["X"][K & 1]
             call("ctan_readout_fwd", ptr(z), D, ptr(w["pair_src"]), ptr(w["pair_dst"]), ptr(ld._assoc), Q * self.L,
                  None, Hd, O, ptr(r.lin_src.weight), ptr(r.lin_src.bias), ptr(r.lin_dst.weight), ptr(r.lin_dst.bias),
-                 ptr(r.lin_final.weight), ptr(r.lin_final.bias), ptr(w["H"]), ptr(w["OUT"]), 1)
+                 ptr(r.lin_final.weight), ptr(r.lin_final.bias), ptr(w["H"]), ptr(w["OUT"]), 0)   # no split-K: scores must not depend on atomic order
             call("ctan_pack_eval", ptr(w["OUT"]), ptr(z), ptr(ld._assoc), ptr(w["pair_src"]), ptr(w["pair_dst"]), Q,
                  self.n_neg, D, ptr(w["send"]))
 
