@@ -20,6 +20,7 @@ SIGNATURES = {
     "ctan_nbr_insert": [P, P, P, P, P, I, L, P, I, P],
     "ctan_nbr_lookup": [P, P, L, I, P, I, P, I, P, P, P, P, I, P, I, P, P, I, P],
     "ctan_nbr_fill": [P, P, I, P, P, P, I, P, P, P, P, P, P],
+    "ctan_nbr_fill_rel": [P, P, I, P, P, P, I, P, P, P, P, P, P, P, P, F, F, P],
     "ctan_mem_update": [P, P, I, P, P, P, I, P, P, I, P, P],
     "ctan_mem_reset": [P, P, L, I, L],
     # edge.cu
@@ -37,7 +38,8 @@ SIGNATURES = {
     "ctan_eproj_fwd": [P, I, P, P, P, P, I, P, I, P, I, P],
     "ctan_qkva_fwd": [P, I, P, I, P, P, P, P, P, P, P, P, P],
     "ctan_readout_fwd": [P, I, P, P, P, I, P, I, I, P, P, P, P, P, P, P, P, I],
-    "ctan_readout_bwd": [P, P, P, I, P, P, P, I, P, I, I, P, P, P, P, P, P, P, P, P, P, P],
+    "ctan_readout_bwd": [P, P, P, I, P, P, P, I, P, I, I, P, P, P, P, P, P, P, P, P, P, P, I],
+    "ctan_head_loss": [P, I, I, P, P, I, P, P, P, P, I, P],
     "ctan_qkva_bwd": [P, P, P, I, P, I, P, P, P, P, P, P, P, P, P, P, P, P, P, I],
     "ctan_enc_bwd": [P, P, I, P, I, I, P, P, I],
     "ctan_eproj_bwd": [P, P, I, P, P, P, P, I, P, I, P, I, P, P, I],
@@ -73,7 +75,7 @@ OPTIONAL_SIGNATURES = {}
 
 SIGNATURES.update({
     # step.cu
-    "ctan_stage_batch": [P, P, P, P, I, I, P, I, P, P, P, P, P, P],
+    "ctan_stage_batch": [P, P, P, P, I, I, P, I, P, P, P, P, P, P, P, I],
     "ctan_bce_loss": [P, I, I, P, P, I, P],
     "ctan_adam_step": [P, P, P, P, I, F, F, F, F, F, L, P],
     "ctan_mrr": [P, P, I, I, P],
@@ -112,7 +114,7 @@ def ptr(t, dtype=None):
 
 
 # kernels launched by each C entry point (for launch accounting; ctan_nbr_lookup adds one per hop)
-LAUNCHES = {"ctan_nbr_insert": 2, "ctan_nbr_lookup": 1, "ctan_readout_fwd": 2, "ctan_readout_bwd": 5,
+LAUNCHES = {"ctan_nbr_insert": 2, "ctan_nbr_lookup": 1, "ctan_readout_fwd": 2, "ctan_readout_bwd": 2,
             "ctan_qkva_bwd": 2, "ctan_eproj_bwd": 2}
 
 # Optional instrumentation (bench.py): TRACE = list -> every call appends (name, start_event, end_event)

@@ -103,10 +103,84 @@ extern "C" int ctan_readout_fwd(const float* Z, int D, const int64_t* src, const
         rc = launch(A, B, epi, P, P_dev, Hd, K1 + D, nullptr, 1, stream);
     }
     if (rc) return rc;
+    if (!OUT) return 0;                 // hidden layer only (the caller fuses the head with the loss)
     head_fwd_kernel<<<ctan_grid((long long)P * 32, 256), 256, 0, stream>>>(H, P, P_dev, Hd, O, Wfin, bfin, OUT);
     CTAN_CHECK_LAUNCH();
     return 0;
 }
+
+// Fused binary head + loss + their gradients (O = 1), one warp per scored pair:
+//   OUT[p]  = relu(H[p]) . Wfin + bfin
+//   loss   += softplus(-OUT[p])/n_pos (p < n_pos)  |  softplus(OUT[p])/n_neg (else)      (train_link.py:269-270)
+//   dOUT[p] = dloss/dOUT[p];  dHid[p,h] = (H[p,h] > 0) dOUT[p] Wfin[h]
+// loss is accumulated (atomicAdd) into loss_hist[(counters[3]-1) % hist_cap], which must be zero on entry
+// (ctan_stage_batch clears it).  dOUT/dHid may be NULL (inference: loss only).
+__global__ void head_loss_kernel(const float* __restrict__ H, int P, int Hd, const float* __restrict__ Wfin,
+                                 const float* __restrict__ bfin, int n_pos, float* __restrict__ OUT,
+                                 float* __restrict__ dOUT, float* __restrict__ dHid, float* __restrict__ loss_hist,
+                                 int hist_cap, const int64_t* __restrict__ counters) {
+    __shared__ float s_loss[8];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int p = blockIdx.x * (blockDim.x >> 5) + wib;
+    float my = 0.f;
+    if (p < P) {
+        float s = 0.f;
+        for (int h = lane; h < Hd; h += 32) s = fmaf(fmaxf(H[(size_t)p * Hd + h], 0.f), __ldg(Wfin + h), s);
+        const float x = warp_sum(s) + __ldg(bfin);
+        const int n_neg = P - n_pos;
+        float dx;
+        if (p < n_pos) {
+            my = (fmaxf(-x, 0.f) + log1pf(expf(-fabsf(x)))) / (float)n_pos;
+            dx = -1.f / (1.f + expf(x)) / (float)n_pos;
+        } else {
+            my = (fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)))) / (float)n_neg;
+            dx = 1.f / (1.f + expf(-x)) / (float)n_neg;
+        }
+        if (lane == 0) { OUT[p] = x; if (dOUT) dOUT[p] = dx; }
+        if (dHid)
+            for (int h = lane; h < Hd; h += 32)
+                dHid[(size_t)p * Hd + h] = H[(size_t)p * Hd + h] > 0.f ? dx * __ldg(Wfin + h) : 0.f;
+    }
+    if (lane == 0) s_loss[wib] = my;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_loss[i];
+        long long slot = counters ? (long long)counters[3] - 1 : 0;
+        if (slot < 0) slot = 0;
+        atomicAdd(loss_hist + (slot % hist_cap), t);
+    }
+}
+
+extern "C" int ctan_head_loss(const float* H, int P, int Hd, const float* Wfin, const float* bfin, int n_pos,
+                              float* OUT, float* dOUT, float* dHid, float* loss_hist, int hist_cap,
+                              const int64_t* counters, cudaStream_t stream) {
+    if (P <= 0 || n_pos <= 0 || n_pos >= P || hist_cap <= 0) return CTAN_ERR_BAD_ARG;
+    head_loss_kernel<<<ctan_div_up(P, 8), 256, 0, stream>>>(H, P, Hd, Wfin, bfin, n_pos, OUT, dOUT, dHid, loss_hist,
+                                                            hist_cap, counters);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+struct BRowCat2 {                  // b(k,n) = n<D ? W1[k*ld+n] : W2[k*ld+n-D]   (vector along n)
+    static constexpr bool K_CONTIG = false;
+    const float* p1; const float* p2; int D; int ld; bool vec;
+    __device__ __forceinline__ const float* at(int k, int n) const {
+        return n < D ? p1 + (size_t)k * ld + n : p2 + (size_t)k * ld + (n - D);
+    }
+    __device__ __forceinline__ float4 fast4(int k, int n) const { return ldg4(at(k, n)); }
+    __device__ __forceinline__ float elem(int k, int n) const { return __ldg(at(k, n)); }
+};
+struct EpiScatterAtomic2 {         // n<D: C[row(idx1[m])][n] += v ; else C[row(idx2[m])][n-D] += v
+    static constexpr bool HAS_ROWSUM = false;
+    float* C; int D; const int64_t* idx1; const int64_t* idx2; const int64_t* map;
+    __device__ __forceinline__ void operator()(int m, int n, float v, bool) const {
+        int64_t r = n < D ? idx1[m] : idx2[m];
+        if (map) r = map[r];
+        atomicAdd(C + (size_t)r * D + (n < D ? n : n - D), v);
+    }
+    __device__ __forceinline__ void rowsum(int, float) const {}
+};
 
 // dHid[p,h] = (H>0) * sum_o dOUT[p,o] Wfin[o,h]
 __global__ void head_bwd_kernel(const float* __restrict__ dOUT, const float* __restrict__ H, int P_host,
@@ -145,23 +219,26 @@ extern "C" int ctan_readout_bwd(const float* dOUT, const float* H, const float* 
                                 const int64_t* dst, const int64_t* map, int P, const int* P_dev, int Hd, int O,
                                 const float* Wsrc, const float* Wdst, const float* Wfin, float* dHid, float* dZ,
                                 float* dWsrc, float* dbsrc, float* dWdst, float* dbdst, float* dWfin, float* dbfin,
-                                cudaStream_t stream) {
+                                int dhid_ready, cudaStream_t stream) {
     if (P <= 0) return 0;
     int rc;
     if (dZ) {
-        head_bwd_kernel<<<ctan_grid((long long)P * Hd, 256), 256, 0, stream>>>(dOUT, H, P, P_dev, Hd, O, Wfin, dHid);
-        CTAN_CHECK_LAUNCH();
-        // dZ[row(src)] += dHid Wsrc ; dZ[row(dst)] += dHid Wdst
+        if (!dhid_ready) {              // (ctan_head_loss already produced dHid in the fused training step)
+            head_bwd_kernel<<<ctan_grid((long long)P * Hd, 256), 256, 0, stream>>>(dOUT, H, P, P_dev, Hd, O, Wfin,
+                                                                                  dHid);
+            CTAN_CHECK_LAUNCH();
+        }
+        // dZ[row(src)] += dHid Wsrc ; dZ[row(dst)] += dHid Wdst   -- one contraction against [Wsrc | Wdst]
         ARowMajor A{dHid, Hd, v4(dHid, Hd)};
         if (Wsrc) {
-            BRowMajor B1{Wsrc, D, v4(Wsrc, D)};
-            EpiScatterAtomic e1{dZ, D, src, map};
-            rc = launch(A, B1, e1, P, P_dev, D, Hd, nullptr, pick_splits(P, D, Hd), stream);
-            if (rc) return rc;
+            BRowCat2 B{Wsrc, Wdst, D, D, v4(Wsrc, D) && v4(Wdst, D)};
+            EpiScatterAtomic2 e{dZ, D, src, dst, map};
+            rc = launch(A, B, e, P, P_dev, 2 * D, Hd, nullptr, pick_splits(P, 2 * D, Hd), stream);
+        } else {
+            BRowMajor B2{Wdst, D, v4(Wdst, D)};
+            EpiScatterAtomic e2{dZ, D, dst, map};
+            rc = launch(A, B2, e2, P, P_dev, D, Hd, nullptr, pick_splits(P, D, Hd), stream);
         }
-        BRowMajor B2{Wdst, D, v4(Wdst, D)};
-        EpiScatterAtomic e2{dZ, D, dst, map};
-        rc = launch(A, B2, e2, P, P_dev, D, Hd, nullptr, pick_splits(P, D, Hd), stream);
         if (rc) return rc;
     }
     if (dWdst) {

@@ -272,7 +272,9 @@ __global__ void lk_fill_kernel(const int64_t* __restrict__ nbr, const int64_t* _
                                const int64_t* __restrict__ assoc, int n_host, const int32_t* __restrict__ n_dev,
                                int64_t* __restrict__ edge_src, int64_t* __restrict__ edge_dst,
                                int64_t* __restrict__ e_id_out, uint32_t* __restrict__ bitmap,
-                               uint32_t* __restrict__ cbitmap) {
+                               uint32_t* __restrict__ cbitmap, const int64_t* __restrict__ last_update,
+                               const int64_t* __restrict__ t_tab, float mean, float stdv,
+                               float* __restrict__ rel) {
     const int N = n_dev ? *n_dev : n_host;
     const int gpw = 32 / lpi;
     const int lane = threadIdx.x & 31, g = lane / lpi, gl = lane % lpi;
@@ -282,9 +284,15 @@ __global__ void lk_fill_kernel(const int64_t* __restrict__ nbr, const int64_t* _
         const int64_t node = n_id[r];
         const int off = rowptr[r], d = rowptr[r + 1] - off;
         for (int s = gl; s < d; s += lpi) {
-            edge_src[off + s] = assoc[nbr[node * S + s]];
+            const int64_t nb = nbr[node * S + s], ev = eid[node * S + s];
+            edge_src[off + s] = assoc[nb];
             edge_dst[off + s] = r;
-            e_id_out[off + s] = eid[node * S + s];
+            e_id_out[off + s] = ev;
+            if (rel) {      // fused delta-t normalisation (gnn_layers.py:94-95): |last_update[src] - t_e|
+                long long dt = last_update[nb] - t_tab[ev];
+                if (dt < 0) dt = -dt;
+                rel[off + s] = __fdiv_rn(__ll2float_rn(dt) - mean, stdv);
+            }
         }
         if (gl == 0) { bitmap[node >> 5] = 0u; cbitmap[node >> 5] = 0u; }
     }
@@ -341,7 +349,25 @@ extern "C" int ctan_nbr_fill(const int64_t* nbr, const int64_t* eid, int S, cons
     const int lpi = lanes_per_item(S);
     lk_fill_kernel<<<ctan_grid((long long)n * lpi, 256), 256, 0, stream>>>(nbr, eid, S, lpi, n_id, rowptr, assoc, n,
                                                                            n_dev, edge_src, edge_dst, e_id_out,
-                                                                           bitmap, cbitmap);
+                                                                           bitmap, cbitmap, nullptr, nullptr, 0.f, 1.f,
+                                                                           nullptr);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+// Same as ctan_nbr_fill, and also writes rel[e] = ((|last_update[src_e] - t_tab[e_id_e]| - mean)/std) as fp32
+// (the delta-t input of the time encoder) while the row is in registers: saves a dependent launch.
+extern "C" int ctan_nbr_fill_rel(const int64_t* nbr, const int64_t* eid, int S, const int64_t* n_id,
+                                 const int32_t* rowptr, const int64_t* assoc, int n, const int32_t* n_dev,
+                                 int64_t* edge_src, int64_t* edge_dst, int64_t* e_id_out, uint32_t* bitmap,
+                                 uint32_t* cbitmap, const int64_t* last_update, const int64_t* t_tab, float mean,
+                                 float stdv, float* rel, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    const int lpi = lanes_per_item(S);
+    lk_fill_kernel<<<ctan_grid((long long)n * lpi, 256), 256, 0, stream>>>(nbr, eid, S, lpi, n_id, rowptr, assoc, n,
+                                                                           n_dev, edge_src, edge_dst, e_id_out,
+                                                                           bitmap, cbitmap, last_update, t_tab, mean,
+                                                                           stdv, rel);
     CTAN_CHECK_LAUNCH();
     return 0;
 }

@@ -15,7 +15,8 @@ __global__ void stage_batch_kernel(const int64_t* __restrict__ src_all, const in
                                    int n_neg, int B, int64_t* __restrict__ counters, int use_cursor,
                                    int64_t* __restrict__ b_src, int64_t* __restrict__ b_dst,
                                    int64_t* __restrict__ b_t, int64_t* __restrict__ seeds,
-                                   int64_t* __restrict__ pair_src, int64_t* __restrict__ pair_dst) {
+                                   int64_t* __restrict__ pair_src, int64_t* __restrict__ pair_dst,
+                                   float* __restrict__ loss_hist, int hist_cap) {
     // single block; negatives are laid out [event][n_neg]
     __shared__ int64_t s_off;
     if (threadIdx.x == 0) {
@@ -24,6 +25,7 @@ __global__ void stage_batch_kernel(const int64_t* __restrict__ src_all, const in
         counters[1] = cur;
         counters[2] += 1;
         counters[3] += 1;
+        if (loss_hist) loss_hist[(counters[3] - 1) % hist_cap] = 0.f;   // slot the fused head+loss accumulates into
         s_off = use_cursor ? cur : 0;                 // 0: the arrays ARE the batch (host-staged buffers)
     }
     __syncthreads();
@@ -49,10 +51,11 @@ __global__ void stage_batch_kernel(const int64_t* __restrict__ src_all, const in
 extern "C" int ctan_stage_batch(const int64_t* src_all, const int64_t* dst_all, const int64_t* t_all,
                                 const int64_t* neg_all, int n_neg, int B, int64_t* counters, int use_cursor,
                                 int64_t* b_src, int64_t* b_dst, int64_t* b_t, int64_t* seeds, int64_t* pair_src,
-                                int64_t* pair_dst, cudaStream_t stream) {
+                                int64_t* pair_dst, float* loss_hist, int hist_cap, cudaStream_t stream) {
     if (B <= 0 || n_neg < 0) return CTAN_ERR_BAD_ARG;
     stage_batch_kernel<<<1, 256, 0, stream>>>(src_all, dst_all, t_all, neg_all, n_neg, B, counters, use_cursor, b_src,
-                                              b_dst, b_t, seeds, pair_src, pair_dst);
+                                              b_dst, b_t, seeds, pair_src, pair_dst, loss_hist,
+                                              hist_cap > 0 ? hist_cap : 1);
     CTAN_CHECK_LAUNCH();
     return 0;
 }
@@ -98,15 +101,22 @@ extern "C" int ctan_bce_loss(const float* OUT, int n_pos, int n_negs, float* dOU
     return 0;
 }
 
-// torch.optim.Adam (amsgrad=False, maximize=False) on a flat parameter vector.
+// torch.optim.Adam (amsgrad=False, maximize=False) on a flat parameter vector.  The bias corrections
+// need double-precision pow(): one thread per block computes them (FP64 is slow on this part, and every
+// thread doing it cost more than the update itself).
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int n, float lr, float beta1, float beta2, float eps, float wd,
                             int64_t step_host, const int64_t* __restrict__ counters) {
-    const int64_t step = counters ? counters[2] : step_host;
-    const double bc1 = 1.0 - pow((double)beta1, (double)step);
-    const double bc2 = 1.0 - pow((double)beta2, (double)step);
-    const float step_size = (float)((double)lr / bc1);
-    const float bc2_sqrt = (float)sqrt(bc2);
+    __shared__ float s_step_size, s_bc2_sqrt;
+    if (threadIdx.x == 0) {
+        const int64_t step = counters ? counters[2] : step_host;
+        const double bc1 = 1.0 - pow((double)beta1, (double)step);
+        const double bc2 = 1.0 - pow((double)beta2, (double)step);
+        s_step_size = (float)((double)lr / bc1);
+        s_bc2_sqrt = (float)sqrt(bc2);
+    }
+    __syncthreads();
+    const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float gi = g[i];
         const float pi = p[i];
@@ -122,7 +132,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 extern "C" int ctan_adam_step(float* p, const float* g, float* m, float* v, int n, float lr, float beta1, float beta2,
                               float eps, float wd, int64_t step, const int64_t* counters, cudaStream_t stream) {
     if (n <= 0) return 0;
-    adam_kernel<<<ctan_grid(n, 256), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, step, counters);
+    adam_kernel<<<ctan_grid(n, 1024, 1), 1024, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, step, counters);
     CTAN_CHECK_LAUNCH();
     return 0;
 }

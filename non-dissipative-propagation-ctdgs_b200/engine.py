@@ -233,15 +233,14 @@ class StepEngine:
         eps = float(m.gnn.aconv.epsilon)
         call("ctan_stage_batch", ptr(self.src), ptr(self.dst), ptr(self.t), ptr(self.neg), self.n_neg, B,
              ptr(w["counters"]), 0 if self.host_staged else 1, ptr(w["b_src"]), ptr(w["b_dst"]), ptr(w["b_t"]),
-             ptr(w["seeds"]), ptr(w["pair_src"]), ptr(w["pair_dst"]))
+             ptr(w["seeds"]), ptr(w["pair_src"]), ptr(w["pair_dst"]), ptr(w["loss_hist"]), self.hist_cap)
         call("ctan_nbr_lookup", ptr(ld.neighbors), ptr(ld._deg), self.num_nodes, S, ptr(w["seeds"]), self.n_seeds,
              None, K, ptr(ld._bitmap), ptr(ld._cbitmap), ptr(w["frontier"]), ptr(w["frontier_cnt"]), N,
              ptr(w["n_id"]), N, ptr(ld._assoc), ptr(w["rowptr"]), E, ptr(w["counts"]))
-        call("ctan_nbr_fill", ptr(ld.neighbors), ptr(ld.e_id), S, ptr(w["n_id"]), ptr(w["rowptr"]), ptr(ld._assoc),
-             N, Nd, ptr(w["esrc"]), ptr(w["edst"]), ptr(w["eid"]), ptr(ld._bitmap), ptr(ld._cbitmap))
+        call("ctan_nbr_fill_rel", ptr(ld.neighbors), ptr(ld.e_id), S, ptr(w["n_id"]), ptr(w["rowptr"]),
+             ptr(ld._assoc), N, Nd, ptr(w["esrc"]), ptr(w["edst"]), ptr(w["eid"]), ptr(ld._bitmap), ptr(ld._cbitmap),
+             ptr(lu), ptr(self.t_tab), float(m.gnn.mean_delta_t), float(m.gnn.std_delta_t), ptr(w["rel"]))
         with self._fork(0):                                  # side 0: A, edge-attr projection, grad memset
-            call("ctan_edge_rel", ptr(lu), ptr(w["n_id"]), ptr(w["esrc"]), ptr(self.t_tab), ptr(w["eid"]), E, Ed,
-                 float(m.gnn.mean_delta_t), float(m.gnn.std_delta_t), ptr(w["rel"]))
             call("ctan_eproj_fwd", ptr(self.msg), Fe, ptr(w["eid"]), ptr(w["rel"]), tw, tb, T, We, E, Ed, D,
                  ptr(w["EP"]))
             call("ctan_antisym_prep", W, float(m.gnn.aconv.gamma), D, ptr(w["A"]))
@@ -266,9 +265,10 @@ class StepEngine:
         z = w["Z"] if self.final_tanh else xk
         self._z = z
         call("ctan_readout_fwd", ptr(z), D, ptr(w["pair_src"]), ptr(w["pair_dst"]), ptr(ld._assoc), P, None, Hd, O,
-             Wsrc, bsrc, Wdst, bdst, Wfin, bfin, ptr(w["H"]), ptr(w["OUT"]), 1)
-        call("ctan_bce_loss", ptr(w["OUT"]), B, P - B, ptr(w["dOUT"]) if train else None, ptr(w["loss_hist"]),
-             self.hist_cap, ptr(w["counters"]))
+             Wsrc, bsrc, Wdst, bdst, Wfin, bfin, ptr(w["H"]), None, 1)
+        # head + BCE loss + dOUT + dHid in one launch (the loss slot was cleared by the stage kernel)
+        call("ctan_head_loss", ptr(w["H"]), P, Hd, Wfin, bfin, B, ptr(w["OUT"]), ptr(w["dOUT"]) if train else None,
+             ptr(w["dHid"]) if train else None, ptr(w["loss_hist"]), self.hist_cap, ptr(w["counters"]))
 
         def state_update():
             # ground-truth state update (train_link.py:276-277)
@@ -285,9 +285,9 @@ class StepEngine:
          gbfin) = (ptr(t) for t in self.g)
         rb_args = (ptr(w["dOUT"]), ptr(w["H"]), ptr(z), D, ptr(w["pair_src"]), ptr(w["pair_dst"]), ptr(ld._assoc), P,
                    None, Hd, O, Wsrc, Wdst, Wfin, ptr(w["dHid"]))
-        call("ctan_readout_bwd", *rb_args, ptr(w["dZ"]), None, None, None, None, None, None)
+        call("ctan_readout_bwd", *rb_args, ptr(w["dZ"]), None, None, None, None, None, None, 1)
         with self._fork(0):                                  # side 0: readout weight gradients
-            call("ctan_readout_bwd", *rb_args, None, gWsrc, gbsrc, gWdst, gbdst, gWfin, gbfin)
+            call("ctan_readout_bwd", *rb_args, None, gWsrc, gbsrc, gWdst, gbdst, gWfin, gbfin, 1)
         g = w["dZ"]
         if self.final_tanh:
             call("ctan_tanh_bwd", ptr(w["dZ"]), ptr(z), N, Nd, D, ptr(w["gA"]))

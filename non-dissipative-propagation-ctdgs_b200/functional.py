@@ -168,7 +168,7 @@ class _ReadoutFn(torch.autograd.Function):
             call("ctan_readout_bwd", ptr(dout), ptr(H), ptr(z), D, ptr(src) if src is not None else ptr(dst), ptr(dst),
                  ptr(id_map) if id_map is not None else None, P, None, Hd, O, ptr(Wsrc) if has_src else None,
                  ptr(Wdst), ptr(Wfin), ptr(dHid), ptr(dz), ptr(dWsrc) if has_src else None,
-                 ptr(dbsrc) if has_src else None, ptr(dWdst), ptr(dbdst), ptr(dWfin), ptr(dbfin))
+                 ptr(dbsrc) if has_src else None, ptr(dWdst), ptr(dbdst), ptr(dWfin), ptr(dbfin), 0)
         return (dz, None, None, None, dWsrc if has_src else None, dbsrc if has_src else None, dWdst, dbdst,
                 dWfin, dbfin)
 

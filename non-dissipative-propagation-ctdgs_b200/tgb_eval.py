@@ -154,13 +154,11 @@ class TGBEvalEngine:
             call("ctan_nbr_lookup", ptr(ld.neighbors), ptr(ld._deg), self.num_nodes, S, ptr(w["seeds"]),
                  Q * (2 + self.n_neg), None, K, ptr(ld._bitmap), ptr(ld._cbitmap), ptr(w["frontier"]),
                  ptr(w["frontier_cnt"]), N, ptr(w["n_id"]), N, ptr(ld._assoc), ptr(w["rowptr"]), E, ptr(w["counts"]))
-            call("ctan_nbr_fill", ptr(ld.neighbors), ptr(ld.e_id), S, ptr(w["n_id"]), ptr(w["rowptr"]),
+            call("ctan_nbr_fill_rel", ptr(ld.neighbors), ptr(ld.e_id), S, ptr(w["n_id"]), ptr(w["rowptr"]),
                  ptr(ld._assoc), N, Nd, ptr(w["esrc"]), ptr(w["edst"]), ptr(w["eid"]), ptr(ld._bitmap),
-                 ptr(ld._cbitmap))
+                 ptr(ld._cbitmap), ptr(lu), ptr(self.t), float(g.mean_delta_t), float(g.std_delta_t), ptr(w["rel"]))
             self._side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._side):
-                call("ctan_edge_rel", ptr(lu), ptr(w["n_id"]), ptr(w["esrc"]), ptr(self.t), ptr(w["eid"]), E, Ed,
-                     float(g.mean_delta_t), float(g.std_delta_t), ptr(w["rel"]))
                 call("ctan_eproj_fwd", ptr(self.msg), Fe, ptr(w["eid"]), ptr(w["rel"]), ptr(g.time_enc.lin.weight),
                      ptr(g.time_enc.lin.bias), T, ptr(ph.lin_edge.weight), E, Ed, D, ptr(w["EP"]))
                 call("ctan_antisym_prep", ptr(a.W), float(a.gamma), D, ptr(w["A"]))
