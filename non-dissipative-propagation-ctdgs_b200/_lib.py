@@ -82,6 +82,7 @@ SIGNATURES.update({
     "ctan_stage_eval": [P, P, P, P, I, I, I, I, P, P, P, P, P, P, P],
     "ctan_pack_eval": [P, P, P, P, P, I, I, I, P],
     "ctan_accum_col": [P, I, I, I, P],
+    "ctan_probe": [P, I],
 })
 
 
@@ -122,9 +123,23 @@ TRACE = None
 N_LAUNCHES = 0
 
 
+# Optional timeline probing (scripts/timeline_step.py): PROBE = (ts_tensor, names_list) -> after every call made
+# on the stream that was current when probing was switched on, a probe kernel stores %globaltimer.
+PROBE = None
+
+
 def call(name: str, *args):
     global N_LAUNCHES
     fn = getattr(lib(), name)
+    if PROBE is not None and name != "ctan_probe":
+        ts, names, main = PROBE
+        rc = fn(*args, stream_ptr())
+        if rc != 0:
+            raise CtanLibraryError(f"{name} failed with code {rc}")
+        if torch.cuda.current_stream().cuda_stream == main:
+            lib().ctan_probe(ts.data_ptr(), len(names), stream_ptr())
+            names.append(name)
+        return
     N_LAUNCHES += LAUNCHES.get(name, 1) + (args[7] if name == "ctan_nbr_lookup" else 0)
     if TRACE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -275,3 +275,16 @@ extern "C" int ctan_accum_col(const float* rows, int R, int ld, int col, double*
     CTAN_CHECK_LAUNCH();
     return 0;
 }
+
+// Timeline probe (profiling aid): ts[idx] = %globaltimer in ns.  Placed between the nodes of the step DAG
+// it gives per-stage device timestamps inside a CUDA-graph replay without a profiler.
+__global__ void probe_kernel(unsigned long long* __restrict__ ts, int idx) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    ts[idx] = t;
+}
+extern "C" int ctan_probe(unsigned long long* ts, int idx, cudaStream_t stream) {
+    probe_kernel<<<1, 1, 0, stream>>>(ts, idx);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}

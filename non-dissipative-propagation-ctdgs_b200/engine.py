@@ -92,7 +92,7 @@ class StepEngine:
         self._flatten_params()
         self._alloc()
         self._graphs = {}
-        self._side = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        self._side = [torch.cuda.Stream(device=dev) for _ in range(4)]
 
     # ------------------------------------------------------------------ parameters in one flat buffer
     def _flatten_params(self):
@@ -231,6 +231,11 @@ class StepEngine:
         cur1 = ptr(w["counters"]) + 8                       # &counters[1]: current batch start
         xf = ptr(self.x) if Fn else None
         eps = float(m.gnn.aconv.epsilon)
+        with self._fork(2):                                  # side 2: work with no dependence on the batch
+            call("ctan_antisym_prep", W, float(m.gnn.aconv.gamma), D, ptr(w["A"]))
+            w["H"].zero_()
+            if train:
+                self.zero_buf.zero_()
         call("ctan_stage_batch", ptr(self.src), ptr(self.dst), ptr(self.t), ptr(self.neg), self.n_neg, B,
              ptr(w["counters"]), 0 if self.host_staged else 1, ptr(w["b_src"]), ptr(w["b_dst"]), ptr(w["b_t"]),
              ptr(w["seeds"]), ptr(w["pair_src"]), ptr(w["pair_dst"]), ptr(w["loss_hist"]), self.hist_cap)
@@ -240,18 +245,15 @@ class StepEngine:
         call("ctan_nbr_fill_rel", ptr(ld.neighbors), ptr(ld.e_id), S, ptr(w["n_id"]), ptr(w["rowptr"]),
              ptr(ld._assoc), N, Nd, ptr(w["esrc"]), ptr(w["edst"]), ptr(w["eid"]), ptr(ld._bitmap), ptr(ld._cbitmap),
              ptr(lu), ptr(self.t_tab), float(m.gnn.mean_delta_t), float(m.gnn.std_delta_t), ptr(w["rel"]))
-        with self._fork(0):                                  # side 0: A, edge-attr projection, grad memset
+        with self._fork(0):                                  # side 0: edge-attribute projection (|| enc_x)
             call("ctan_eproj_fwd", ptr(self.msg), Fe, ptr(w["eid"]), ptr(w["rel"]), tw, tb, T, We, E, Ed, D,
                  ptr(w["EP"]))
-            call("ctan_antisym_prep", W, float(m.gnn.aconv.gamma), D, ptr(w["A"]))
-            w["H"].zero_()
-            if train:
-                self.zero_buf.zero_()
         if train:
             with self._fork(1):                              # side 1: saved copy of the gathered input rows
                 call("ctan_gather_rows2", ptr(mem), D, xf, Fn, ptr(w["n_id"]), N, Nd, ptr(w["z0"]))
         call("ctan_enc_fwd", ptr(mem), D, xf, Fn, ptr(w["n_id"]), None, N, Nd, Wenc, benc, ptr(w["X"][0]))
         self._join(0)
+        self._join(2)
         for k in range(K):
             xi = w["X"][k] if train else w["X"][k & 1]
             xo = w["X"][k + 1] if train else w["X"][(k + 1) & 1]
@@ -286,7 +288,7 @@ class StepEngine:
         rb_args = (ptr(w["dOUT"]), ptr(w["H"]), ptr(z), D, ptr(w["pair_src"]), ptr(w["pair_dst"]), ptr(ld._assoc), P,
                    None, Hd, O, Wsrc, Wdst, Wfin, ptr(w["dHid"]))
         call("ctan_readout_bwd", *rb_args, ptr(w["dZ"]), None, None, None, None, None, None, 1)
-        with self._fork(0):                                  # side 0: readout weight gradients
+        with self._fork(2):                                  # side 2: readout weight gradients
             call("ctan_readout_bwd", *rb_args, None, gWsrc, gbsrc, gWdst, gbdst, gWfin, gbfin, 1)
         g = w["dZ"]
         if self.final_tanh:
@@ -303,16 +305,20 @@ class StepEngine:
             with self._fork(0):                              # side 0: weight gradients of this iteration
                 call("ctan_qkva_bwd", *qb, None, gWq, gWk, gWv, ptr(w["dA"]), gbq, gbk, gbv, gb, self.n_typ)
                 if k == 0:
+                    call("ctan_antisym_bwd", ptr(w["dA"]), D, gW)
+            if k == 0:
+                with self._fork(3):                          # side 3: lin_edge / time-encoder gradients
                     call("ctan_eproj_bwd", ptr(w["dEP"]), ptr(self.msg), Fe, ptr(w["eid"]), ptr(w["rel"]), tw, tb, T,
                          We, E, Ed, D, gWe, ptr(w["dTenc"]), self.e_typ)
                     call("ctan_tenc_bwd", ptr(w["dTenc"]), ptr(w["rel"]), tw, tb, E, Ed, T, gtw, gtb)
-                    call("ctan_antisym_bwd", ptr(w["dA"]), D, gW)
             gn = self._DX[k]
             call("ctan_qkva_bwd", *qb, ptr(gn), None, None, None, None, None, None, None, None, self.n_typ)
             g = gn
         self._join(1)                                        # z0 is complete (and the state write-back done)
         call("ctan_enc_bwd", ptr(g), ptr(w["z0"]), N, Nd, D, Fn, gWenc, gbenc, self.n_typ)
         self._join(0)
+        self._join(2)
+        self._join(3)
         call("ctan_adam_step", ptr(self.flat_p), ptr(self.flat_g), ptr(self.adam_m), ptr(self.adam_v),
              self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 0, ptr(w["counters"]))
 
