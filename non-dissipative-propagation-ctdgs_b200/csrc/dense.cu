@@ -285,7 +285,7 @@ extern "C" int ctan_qkva_bwd(const float* DQKVA, const float* X, const float* G,
         AColMajor A{DQKVA, 4 * D, v4(DQKVA, 4 * D)};
         BRowMajor B{X, D, v4(X, D)};
         EpiAtomicSeg4 epi{{dWq, dWk, dWv, dA}, {dbq, dbk, dbv, db}, D, D};
-        rc = launch(A, B, epi, 4 * D, nullptr, D, N, N_dev, pick_splits(4 * D, D, n_typ), stream);
+        rc = launch(A, B, epi, 4 * D, nullptr, D, N, N_dev, pick_splits(4 * D, D, n_typ), stream, n_typ);
         if (rc) return rc;
     }
     return 0;
@@ -299,7 +299,7 @@ extern "C" int ctan_enc_bwd(const float* dX0, const float* Z0, int N, const int*
     AColMajor A{dX0, D, v4(dX0, D)};
     BRowMajor B{Z0, D + Fn, v4(Z0, D + Fn)};
     EpiAtomic epi{dWenc, D + Fn, dbenc, nullptr, 0};
-    return launch(A, B, epi, D, nullptr, D + Fn, N, N_dev, pick_splits(D, D + Fn, n_typ), stream);
+    return launch(A, B, epi, D, nullptr, D + Fn, N, N_dev, pick_splits(D, D + Fn, n_typ), stream, n_typ);
 }
 
 // dWe[D, Fe+T] += dEP^T [msg | cos(.)] ;  dTenc[E,T] = dEP We[:,Fe:]   (scratch for ctan_tenc_bwd)
@@ -313,7 +313,7 @@ extern "C" int ctan_eproj_bwd(const float* dEP, const float* msg, int Fe, const 
         AColMajor A{dEP, D, v4(dEP, D)};
         BEdgeAttr B{msg, Fe, eidx, Fe, rel, tw, tb, v4(msg, Fe) || Fe == 0};
         EpiAtomic epi{dWe, Fe + T, nullptr, nullptr, 0};
-        rc = launch(A, B, epi, D, nullptr, Fe + T, E, E_dev, pick_splits(D, Fe + T, e_typ), stream);
+        rc = launch(A, B, epi, D, nullptr, Fe + T, E, E_dev, pick_splits(D, Fe + T, e_typ), stream, e_typ);
         if (rc) return rc;
     }
     if (T > 0 && dTenc) {

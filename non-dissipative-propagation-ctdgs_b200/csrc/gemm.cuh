@@ -322,20 +322,29 @@ gemm_kernel(const AL A, const BL Bm, const EP epi, int M_host, const int* __rest
         const int st = kt & 1;
         if (kt + 1 < n_tiles) stash(st ^ 1);            // tile kt+1 (registers) -> the buffer read in iteration kt-1
         if (kt + 2 < n_tiles) fetch(kb + (kt + 2) * BK);  // tile kt+2 -> registers, in flight during the FMAs
+        // shared-memory operands are read four k-steps at a time (8 LDS.128 in flight, then 64 FMAs): ncu
+        // showed short-scoreboard (LDS latency) as the top stall when every k-step waited on its own pair
 #pragma unroll
-        for (int k = 0; k < BK; ++k) {
-            const float4 a4 = *reinterpret_cast<const float4*>(&As[st][k][ty * 4]);
-            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[st][k][tx * 4]);
-            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
-            const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+        for (int k0 = 0; k0 < BK; k0 += 4) {
+            float4 a4[4], b4[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            for (int u = 0; u < 4; ++u) {
+                a4[u] = *reinterpret_cast<const float4*>(&As[st][k0 + u][ty * 4]);
+                b4[u] = *reinterpret_cast<const float4*>(&Bs[st][k0 + u][tx * 4]);
             }
-            if (EP::HAS_ROWSUM) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) rsum[i] += a[i];
+            for (int u = 0; u < 4; ++u) {
+                const float a[4] = {a4[u].x, a4[u].y, a4[u].z, a4[u].w};
+                const float b[4] = {b4[u].x, b4[u].y, b4[u].z, b4[u].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                }
+                if (EP::HAS_ROWSUM) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) rsum[i] += a[i];
+                }
             }
         }
         __syncthreads();
@@ -358,10 +367,13 @@ gemm_kernel(const AL A, const BL Bm, const EP epi, int M_host, const int* __rest
 // choosing the tile shape); splits > 1 needs an atomic epilogue.
 template <class AL, class BL, class EP>
 static inline int launch(const AL& A, const BL& B, const EP& epi, int M_max, const int* M_dev, int N, int K_max,
-                         const int* K_dev, int splits, cudaStream_t stream) {
+                         const int* K_dev, int splits, cudaStream_t stream, int k_typ = 0) {
     if (M_max <= 0 || N <= 0 || K_max <= 0) return 0;
     if (splits < 1) splits = 1;
-    int k_chunk = (K_max + splits - 1) / splits;
+    // k_typ: the typical true K when K_max is only an upper bound (device-sized K): the chunk is cut from the
+    // typical extent so that the ACTIVE splits cover it; splits past the true K exit immediately
+    const int k_ref = (K_dev && k_typ > 0 && k_typ < K_max) ? k_typ : K_max;
+    int k_chunk = (k_ref + splits - 1) / splits;
     k_chunk = ((k_chunk + BK - 1) / BK) * BK;
     splits = (K_max + k_chunk - 1) / k_chunk;
     const int m_typ = M_dev ? (M_max / 4 > 64 ? M_max / 4 : 64) : M_max;
