@@ -83,6 +83,9 @@ SIGNATURES.update({
     "ctan_pack_eval": [P, P, P, P, P, I, I, I, P],
     "ctan_accum_col": [P, I, I, I, P],
     "ctan_probe": [P, I],
+    # tc_gemm.cu
+    "ctan_wcat_prep": [P, P, P, P, F, I, P, P, P],
+    "ctan_qkva_fwd_tc": [P, I, P, I, P, P, P, P, P, P, P],
 })
 
 

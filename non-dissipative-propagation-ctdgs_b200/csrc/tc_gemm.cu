@@ -1,0 +1,279 @@
+// Tensor-core projection for the large-batch shapes: QKVA[N,4D] = X [Wq;Wk;Wv;A]^T + bias on the 5th-gen
+// tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM) with operands staged by TMA
+// (cp.async.bulk.tensor, 128-byte swizzle) -- the "once the batch is large enough" path of the north star.
+//
+// fp32 parity: 3xTF32 error compensation.  Each fp32 operand is split as x = hi + lo with hi = x truncated
+// to TF32 (10-bit mantissa) and lo = x - hi; the product is accumulated as lo*hi' + hi*lo' + hi*hi' in the
+// fp32 TMEM accumulator (relative error ~2^-21, inside the 1e-4 bar; plain TF32 would be ~5e-4).
+// The weights are split once per step by ctan_wcat_prep (which also forms A = W - W^T - gamma I); the
+// activation tile is split in shared memory right after its TMA load (an element-wise rewrite keeps the
+// swizzled layout).
+//
+// One CTA = one 128x128 output tile, 128 threads.  K advances in 128-byte (32-float) blocks through a
+// 2-stage smem ring: full[s] (TMA bytes landed) / empty[s] (tcgen05.commit: the MMAs reading stage s are done).
+// Thread 0 issues TMA and MMA; all four warps split the A tile and run the epilogue
+// (tcgen05.ld 32x32b -> +bias -> global).  Replaces the same reference code as ctan_qkva_fwd.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BKF = 32, STAGES = 2;
+constexpr int TILE_BYTES = BM * BKF * 4;                 // 16 KB (A and B tiles have the same shape)
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;              // A_hi, A_lo, B_hi, B_lo
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%1], %0;" ::"r"(count), "r"(smem_u32(bar)));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a lost arrival must never hang the GPU -- trap instead (the launch then fails loudly).
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int crd_inner,
+                                            int crd_outer) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(crd_inner), "r"(crd_outer)
+        : "memory");
+}
+// K-major operand tile, 128-byte swizzle: rows 128 B apart, 8-row groups 1024 B apart (SBO), version 1.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M=128, N=128
+__device__ __forceinline__ uint32_t instr_desc_tf32() {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct Bias4 { const float* p[4]; int D; };
+
+__global__ void __launch_bounds__(128)
+qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+               const __grid_constant__ CUtensorMap tmBlo, Bias4 bias, float* __restrict__ C, int ldc, int M_host,
+               const int* __restrict__ M_dev, int N, int K) {
+    extern __shared__ uint8_t smem_raw[];
+    const int M = M_dev ? *M_dev : M_host;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    if (m0 >= M) return;                                              // uniform, before any allocation
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* done = empty + STAGES;
+    uint32_t* tmem_holder = (uint32_t*)(done + 1);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+
+    if (t == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
+                     "r"((uint32_t)BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_holder;
+
+    const int n_kb = K / BKF;
+    auto stage_ptr = [&](int s, int which) { return smem + s * STAGE_BYTES + which * TILE_BYTES; };
+    auto issue_loads = [&](int kb, int s) {
+        mbar_expect_tx(&full[s], 3 * TILE_BYTES);
+        tma_load_2d(stage_ptr(s, 0), &tmA, &full[s], kb * BKF, m0);
+        tma_load_2d(stage_ptr(s, 2), &tmBhi, &full[s], kb * BKF, n0);
+        tma_load_2d(stage_ptr(s, 3), &tmBlo, &full[s], kb * BKF, n0);
+    };
+    if (t == 0)
+        for (int s = 0; s < STAGES && s < n_kb; ++s) issue_loads(s, s);
+
+    const uint32_t idesc = instr_desc_tf32();
+    for (int kb = 0; kb < n_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        // split the activation tile in place: A_hi <- trunc_tf32(x), A_lo <- x - A_hi (same swizzled offsets)
+        float4* ahi = (float4*)stage_ptr(s, 0);
+        float4* alo = (float4*)stage_ptr(s, 1);
+#pragma unroll
+        for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
+            const float4 v = ahi[t + i * 128];
+            float4 h, l;
+            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+            ahi[t + i * 128] = h;
+            alo[t + i * 128] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+        __syncthreads();
+        if (t == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = smem_u32(stage_ptr(s, 0)), a_lo = smem_u32(stage_ptr(s, 1));
+            const uint32_t b_hi = smem_u32(stage_ptr(s, 2)), b_lo = smem_u32(stage_ptr(s, 3));
+#pragma unroll
+            for (int k = 0; k < BKF / 8; ++k) {                        // UMMA_K = 8 tf32 = 32 bytes inside the swizzle atom
+                const uint32_t off = k * 32;
+                mma_tf32(tmem_base, smem_desc_sw128(a_lo + off), smem_desc_sw128(b_hi + off), idesc, (kb | k) ? 1u : 0u);
+                mma_tf32(tmem_base, smem_desc_sw128(a_hi + off), smem_desc_sw128(b_lo + off), idesc, 1u);
+                mma_tf32(tmem_base, smem_desc_sw128(a_hi + off), smem_desc_sw128(b_hi + off), idesc, 1u);
+            }
+            mma_commit(&empty[s]);                                      // arrives when these MMAs have read stage s
+            if (kb + STAGES < n_kb) {
+                mbar_wait(&empty[s], ph);
+                issue_loads(kb + STAGES, s);
+            }
+        }
+    }
+    if (t == 0) mma_commit(done);
+    mbar_wait(done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // epilogue: warp w owns TMEM lanes [32w, 32w+32) = output rows m0 + 32w + lane
+    const int row = m0 + warp * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+        uint32_t v[16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < M) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int n = n0 + c + j;
+                if (n < N) {
+                    const int seg = n / bias.D;
+                    const float* bp = seg == 0 ? bias.p[0] : (seg == 1 ? bias.p[1] : (seg == 2 ? bias.p[2] : bias.p[3]));
+                    const float bv = bp ? __ldg(bp + (n - seg * bias.D)) : 0.f;
+                    C[(size_t)row * ldc + n] = __uint_as_float(v[j]) + bv;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN));
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// row-major fp32 [rows, K] matrix, box = 128 rows x 32 floats, 128-byte swizzle
+static int make_map(CUtensorMap* m, const float* base, int rows, int K) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return CTAN_ERR_UNSUPPORTED;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+    cuuint32_t box[2] = {(cuuint32_t)BKF, (cuuint32_t)BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : CTAN_ERR_BAD_ARG;
+}
+
+}  // namespace tc
+
+// Wcat_hi/Wcat_lo [4D, D]: TF32 split of the stacked weights [Wq; Wk; Wv; A], A = W - W^T - gamma I.
+// A_out [D,D] (optional) receives the un-split A for the CUDA-core backward.
+__global__ void wcat_prep_kernel(const float* __restrict__ Wq, const float* __restrict__ Wk,
+                                 const float* __restrict__ Wv, const float* __restrict__ W, float gamma, int D,
+                                 float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ A_out) {
+    const int n = 4 * D * D;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int seg = i / (D * D), r = i - seg * D * D;
+        float x;
+        if (seg == 0) x = Wq[r];
+        else if (seg == 1) x = Wk[r];
+        else if (seg == 2) x = Wv[r];
+        else {
+            const int a = r / D, b = r % D;
+            x = W[r] - W[b * D + a] - (a == b ? gamma : 0.f);
+            if (A_out) A_out[r] = x;
+        }
+        const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+        hi[i] = h;
+        lo[i] = x - h;
+    }
+}
+
+extern "C" int ctan_wcat_prep(const float* Wq, const float* Wk, const float* Wv, const float* W, float gamma, int D,
+                              float* Wcat_hi, float* Wcat_lo, float* A_out, cudaStream_t stream) {
+    if (D <= 0) return CTAN_ERR_BAD_ARG;
+    wcat_prep_kernel<<<ctan_grid(4LL * D * D, 256), 256, 0, stream>>>(Wq, Wk, Wv, W, gamma, D, Wcat_hi, Wcat_lo, A_out);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+// QKVA[N,4D] = X Wcat^T + [bq;bk;bv;b] on tcgen05 (3xTF32).  Requirements: D % 32 == 0, X has at least
+// ceil(N/128)*128 addressable rows or N rows (TMA zero-fills out-of-bounds rows), 16-byte aligned bases.
+// Returns CTAN_ERR_UNSUPPORTED when the shape does not qualify (the caller then uses ctan_qkva_fwd).
+extern "C" int ctan_qkva_fwd_tc(const float* X, int N, const int* N_dev, int D, const float* Wcat_hi,
+                                const float* Wcat_lo, const float* bq, const float* bk, const float* bv,
+                                const float* b, float* QKVA, cudaStream_t stream) {
+    if (N <= 0) return 0;
+    if (D % tc::BKF != 0 || ((4 * D) % tc::BN) != 0 || (((uintptr_t)X | (uintptr_t)Wcat_hi | (uintptr_t)Wcat_lo) & 15))
+        return CTAN_ERR_UNSUPPORTED;
+    CUtensorMap tmA, tmBhi, tmBlo;
+    int rc = tc::make_map(&tmA, X, N, D);
+    if (!rc) rc = tc::make_map(&tmBhi, Wcat_hi, 4 * D, D);
+    if (!rc) rc = tc::make_map(&tmBlo, Wcat_lo, 4 * D, D);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc::qkva_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             tc::SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    tc::Bias4 bias{{bq, bk, bv, b}, D};
+    dim3 grid((4 * D) / tc::BN, (N + tc::BM - 1) / tc::BM);
+    tc::qkva_tc_kernel<<<grid, 128, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, bias, QKVA, 4 * D, N, N_dev, 4 * D, D);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}

@@ -36,6 +36,11 @@ REF = {
     "ctan_stage_eval": "per-query batch assembly of tgb_test -- train_link.py:111-142",
     "ctan_pack_eval": "per-query MRR + src/pos_dst embeddings kept for the state update -- train_link.py:150-158",
     "ctan_accum_col": "mean of the per-query metric -- train_link.py:201",
+    "ctan_nbr_fill_rel": "LastNeighborLoader.__call__ edge list + CTANEmbedding delta-t -- TGB/modules/neighbor_loader.py:28-39, models/gnn_layers.py:94-95",
+    "ctan_head_loss": "predictor head + BCEWithLogitsLoss + their gradients -- models/predictors.py:18-19, train_link.py:269-270,279",
+    "ctan_probe": "(profiling aid, no reference counterpart)",
+    "ctan_wcat_prep": "AntiSymmetricConv W - W^T - gamma*I, packed with the q/k/v weights and split for 3xTF32 -- PyG 2.3.1",
+    "ctan_qkva_fwd_tc": "TransformerConv lin_query/lin_key/lin_value + x @ A^T + bias on tcgen05 tensor cores -- PyG 2.3.1 (SURVEY.md App. A.5)",
 }
 out = ['''/* ctan_sm100.h -- C ABI of libctan_sm100.so (hand-written CUDA for sm_100a, NVIDIA B200).
  *
@@ -64,7 +69,7 @@ extern "C" {
 #endif
 ''']
 names = []
-for f in ("loader.cu", "edge.cu", "dense.cu", "step.cu"):
+for f in ("loader.cu", "edge.cu", "dense.cu", "step.cu", "tc_gemm.cu"):
     src = open(os.path.join(CSRC, f)).read()
     out.append(f"/* ---------------------------------------------------------------- {f} */")
     for m in re.finditer(r'((?:^//[^\n]*\n)*)extern "C" int (\w+)\(([^{]*?)\)\s*\{', src, re.M):

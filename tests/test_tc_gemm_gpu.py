@@ -1,0 +1,58 @@
+"""tcgen05/TMA projection (csrc/tc_gemm.cu, 3xTF32) against the CUDA-core fp32 contraction and a float64
+reference: it must stay inside the fp32 path's 1e-4 bar (north_star), far tighter than plain TF32."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("N,D", [(700, 128), (5000, 256), (129, 64), (128, 32)])
+def test_qkva_tc_matches_fp32(N, D):
+    from ctan_b200._lib import call, ptr
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(N + D)
+    X = torch.randn(N, D, generator=g).to(dev)
+    Ws = [(torch.randn(D, D, generator=g) / D ** 0.5).to(dev) for _ in range(4)]     # Wq, Wk, Wv, W
+    bs = [torch.randn(D, generator=g).to(dev) for _ in range(4)]
+    gamma = 0.1
+    hi = torch.empty(4 * D, D, device=dev)
+    lo = torch.empty(4 * D, D, device=dev)
+    A = torch.empty(D, D, device=dev)
+    call("ctan_wcat_prep", ptr(Ws[0]), ptr(Ws[1]), ptr(Ws[2]), ptr(Ws[3]), gamma, D, ptr(hi), ptr(lo), ptr(A))
+    A_ref = Ws[3] - Ws[3].t() - gamma * torch.eye(D, device=dev)
+    assert torch.equal(A, A_ref)
+    assert torch.equal(hi + lo, torch.cat([Ws[0], Ws[1], Ws[2], A_ref]))                # exact split
+    out_tc = torch.full((N, 4 * D), float("nan"), device=dev)
+    call("ctan_qkva_fwd_tc", ptr(X), N, None, D, ptr(hi), ptr(lo), ptr(bs[0]), ptr(bs[1]), ptr(bs[2]), ptr(bs[3]),
+         ptr(out_tc))
+    out_fp = torch.empty((N, 4 * D), device=dev)
+    call("ctan_qkva_fwd", ptr(X), N, None, D, ptr(Ws[0]), ptr(Ws[1]), ptr(Ws[2]), ptr(A), ptr(bs[0]), ptr(bs[1]),
+         ptr(bs[2]), ptr(bs[3]), ptr(out_fp))
+    torch.cuda.synchronize()
+    Wcat = torch.cat([Ws[0], Ws[1], Ws[2], A_ref]).double()
+    ref = X.double() @ Wcat.t() + torch.cat(bs).double()
+    scale = float(ref.abs().max())
+    e_tc = float((out_tc.double() - ref).abs().max()) / scale
+    e_fp = float((out_fp.double() - ref).abs().max()) / scale
+    assert not torch.isnan(out_tc).any()
+    assert e_fp < 2e-6, e_fp
+    assert e_tc < 5e-6, (e_tc, e_fp)          # 3xTF32: ~fp32 accuracy (plain TF32 would be ~5e-4)
+
+
+def test_qkva_tc_device_sized_rows():
+    """N read on the device (engine mode): rows past the true N are neither computed nor written."""
+    from ctan_b200._lib import call, ptr
+    dev = torch.device("cuda:0")
+    D, cap, n_true = 128, 1024, 300
+    X = torch.randn(cap, D, device=dev)
+    W = [torch.randn(D, D, device=dev) / 11 for _ in range(4)]
+    hi, lo = torch.empty(4 * D, D, device=dev), torch.empty(4 * D, D, device=dev)
+    call("ctan_wcat_prep", ptr(W[0]), ptr(W[1]), ptr(W[2]), ptr(W[3]), 0.1, D, ptr(hi), ptr(lo), None)
+    out = torch.full((cap, 4 * D), 7.0, device=dev)
+    n_dev = torch.tensor([n_true], dtype=torch.int32, device=dev)
+    call("ctan_qkva_fwd_tc", ptr(X), cap, ptr(n_dev), D, ptr(hi), ptr(lo), None, None, None, None, ptr(out))
+    torch.cuda.synchronize()
+    ref = X[:n_true].double() @ (hi + lo).double().t()
+    assert float((out[:n_true].double() - ref).abs().max()) < 5e-5
+    assert bool((out[384:] == 7.0).all())           # whole tiles past n_true untouched
+    assert bool((out[n_true:384] == 7.0).all())     # rows past n_true inside the last tile untouched
