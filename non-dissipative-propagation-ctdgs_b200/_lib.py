@@ -85,7 +85,7 @@ SIGNATURES.update({
     "ctan_probe": [P, I],
     # tc_gemm.cu
     "ctan_wcat_prep": [P, P, P, P, F, I, P, P, P],
-    "ctan_qkva_fwd_tc": [P, I, P, I, P, P, P, P, P, P, P],
+    "ctan_qkva_fwd_tc": [P, I, P, I, P, P, P, P, P, P, P, I],
 })
 
 

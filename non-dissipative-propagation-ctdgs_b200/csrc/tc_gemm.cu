@@ -9,16 +9,15 @@
 // activation tile is split in shared memory right after its TMA load (an element-wise rewrite keeps the
 // swizzled layout).
 //
-// One CTA = one 128x128 output tile, 128 threads.  K advances in 128-byte (32-float) blocks through a
-// 2-stage smem ring: full[s] (TMA bytes landed) / empty[s] (tcgen05.commit: the MMAs reading stage s are done).
-// Thread 0 issues TMA and MMA; all four warps split the A tile and run the epilogue
-// (tcgen05.ld 32x32b -> +bias -> global).  Replaces the same reference code as ctan_qkva_fwd.
+// One CTA = one 128x128 output tile, 192 threads, warp-specialised (TMA producer / MMA issuer / 4 transform+
+// epilogue warps).  K advances in 128-byte (32-float) blocks through a 3-stage smem ring of mbarriers.
+// Epilogue: tcgen05.ld 32x32b -> +bias -> 128-bit stores.  Replaces the same reference code as ctan_qkva_fwd.
 #include "common.cuh"
 #include <cuda.h>
 
 namespace tc {
 
-constexpr int BM = 128, BN = 128, BKF = 32, STAGES = 2;
+constexpr int BM = 128, BN = 128, BKF = 32, STAGES = 3;
 constexpr int TILE_BYTES = BM * BKF * 4;                 // 16 KB (A and B tiles have the same shape)
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;              // A_hi, A_lo, B_hi, B_lo
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -72,29 +71,41 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
                  : "memory");
 }
 
-struct Bias4 { const float* p[4]; int D; };
+struct Bias4 { const float* p[4]; int D; int vec; };
 
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Warp-specialised: warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer (one lane),
+// warps 2..5 = operand transform (3xTF32 split of the activation tile in smem) and epilogue.
+//   raw[s]   : TMA bytes of stage s have landed            (1 arrival + tx bytes)
+//   ready[s] : the 128 transform threads have split stage s (128 arrivals)          [mode 0 only]
+//   empty[s] : the MMAs that read stage s have completed    (tcgen05.commit)
+//   done     : every MMA of the tile has completed          (tcgen05.commit)
+// mode 0: 3xTF32 (fp32 parity path); mode 1: single TF32 pass (1e-2 path; no split, no lo tiles).
+__global__ void __launch_bounds__(192)
 qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                const __grid_constant__ CUtensorMap tmBlo, Bias4 bias, float* __restrict__ C, int ldc, int M_host,
-               const int* __restrict__ M_dev, int N, int K) {
+               const int* __restrict__ M_dev, int N, int K, int mode) {
     extern __shared__ uint8_t smem_raw[];
     const int M = M_dev ? *M_dev : M_host;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     if (m0 >= M) return;                                              // uniform, before any allocation
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
-    uint64_t* empty = full + STAGES;
+    uint64_t* raw = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+    uint64_t* ready = raw + STAGES;
+    uint64_t* empty = ready + STAGES;
     uint64_t* done = empty + STAGES;
     uint32_t* tmem_holder = (uint32_t*)(done + 1);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
 
     if (t == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&raw[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], 1); }
         mbar_init(done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
+    if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
                      "r"((uint32_t)BN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -103,89 +114,111 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_holder;
-
     const int n_kb = K / BKF;
     auto stage_ptr = [&](int s, int which) { return smem + s * STAGE_BYTES + which * TILE_BYTES; };
-    auto issue_loads = [&](int kb, int s) {
-        mbar_expect_tx(&full[s], 3 * TILE_BYTES);
-        tma_load_2d(stage_ptr(s, 0), &tmA, &full[s], kb * BKF, m0);
-        tma_load_2d(stage_ptr(s, 2), &tmBhi, &full[s], kb * BKF, n0);
-        tma_load_2d(stage_ptr(s, 3), &tmBlo, &full[s], kb * BKF, n0);
-    };
-    if (t == 0)
-        for (int s = 0; s < STAGES && s < n_kb; ++s) issue_loads(s, s);
 
-    const uint32_t idesc = instr_desc_tf32();
-    for (int kb = 0; kb < n_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full[s], ph);
-        // split the activation tile in place: A_hi <- trunc_tf32(x), A_lo <- x - A_hi (same swizzled offsets)
-        float4* ahi = (float4*)stage_ptr(s, 0);
-        float4* alo = (float4*)stage_ptr(s, 1);
-#pragma unroll
-        for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
-            const float4 v = ahi[t + i * 128];
-            float4 h, l;
-            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-            ahi[t + i * 128] = h;
-            alo[t + i * 128] = l;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
-        __syncthreads();
-        if (t == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_hi = smem_u32(stage_ptr(s, 0)), a_lo = smem_u32(stage_ptr(s, 1));
-            const uint32_t b_hi = smem_u32(stage_ptr(s, 2)), b_lo = smem_u32(stage_ptr(s, 3));
-#pragma unroll
-            for (int k = 0; k < BKF / 8; ++k) {                        // UMMA_K = 8 tf32 = 32 bytes inside the swizzle atom
-                const uint32_t off = k * 32;
-                mma_tf32(tmem_base, smem_desc_sw128(a_lo + off), smem_desc_sw128(b_hi + off), idesc, (kb | k) ? 1u : 0u);
-                mma_tf32(tmem_base, smem_desc_sw128(a_hi + off), smem_desc_sw128(b_lo + off), idesc, 1u);
-                mma_tf32(tmem_base, smem_desc_sw128(a_hi + off), smem_desc_sw128(b_hi + off), idesc, 1u);
-            }
-            mma_commit(&empty[s]);                                      // arrives when these MMAs have read stage s
-            if (kb + STAGES < n_kb) {
-                mbar_wait(&empty[s], ph);
-                issue_loads(kb + STAGES, s);
+    if (warp == 0) {
+        // ------------------------------------------------ TMA producer
+        if (lane == 0) {
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int s = kb % STAGES;
+                if (kb >= STAGES) mbar_wait(&empty[s], ((kb / STAGES) - 1) & 1);
+                mbar_expect_tx(&raw[s], (mode == 0 ? 3 : 2) * TILE_BYTES);
+                tma_load_2d(stage_ptr(s, 0), &tmA, &raw[s], kb * BKF, m0);
+                tma_load_2d(stage_ptr(s, 2), &tmBhi, &raw[s], kb * BKF, n0);
+                if (mode == 0) tma_load_2d(stage_ptr(s, 3), &tmBlo, &raw[s], kb * BKF, n0);
             }
         }
-    }
-    if (t == 0) mma_commit(done);
-    mbar_wait(done, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-    // epilogue: warp w owns TMEM lanes [32w, 32w+32) = output rows m0 + 32w + lane
-    const int row = m0 + warp * 32 + lane;
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = instr_desc_tf32();
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(mode == 0 ? &ready[s] : &raw[s], (kb / STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_hi = smem_u32(stage_ptr(s, 0)), a_lo = smem_u32(stage_ptr(s, 1));
+                const uint32_t b_hi = smem_u32(stage_ptr(s, 2)), b_lo = smem_u32(stage_ptr(s, 3));
+#pragma unroll
+                for (int k = 0; k < BKF / 8; ++k) {                    // UMMA_K = 8 tf32 = 32 bytes inside the swizzle atom
+                    const uint32_t off = k * 32;
+                    if (mode == 0) {
+                        mma_tf32(tmem_base, smem_desc_sw128(a_lo + off), smem_desc_sw128(b_hi + off), idesc, (kb | k) ? 1u : 0u);
+                        mma_tf32(tmem_base, smem_desc_sw128(a_hi + off), smem_desc_sw128(b_lo + off), idesc, 1u);
+                        mma_tf32(tmem_base, smem_desc_sw128(a_hi + off), smem_desc_sw128(b_hi + off), idesc, 1u);
+                    } else {
+                        mma_tf32(tmem_base, smem_desc_sw128(a_hi + off), smem_desc_sw128(b_hi + off), idesc, (kb | k) ? 1u : 0u);
+                    }
+                }
+                mma_commit(&empty[s]);                                  // arrives when these MMAs have read stage s
+            }
+            mma_commit(done);
+        }
+    } else {
+        // ------------------------------------------------ transform (3xTF32 split of A) then epilogue
+        const int te = t - 64;                                          // 0..127
+        if (mode == 0) {
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&raw[s], (kb / STAGES) & 1);
+                float4* ahi = (float4*)stage_ptr(s, 0);
+                float4* alo = (float4*)stage_ptr(s, 1);
+#pragma unroll
+                for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
+                    const float4 v = ahi[te + i * 128];
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+                    ahi[te + i * 128] = h;
+                    alo[te + i * 128] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA
+                mbar_arrive(&ready[s]);
+            }
+        }
+        mbar_wait(done, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // warp w may touch TMEM lanes [32*(w%4), +32): warps 2,3,4,5 cover quarters 2,3,0,1
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 16) {
-        uint32_t v[16];
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row < M) {
+        for (int c = 0; c < BN; c += 16) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int n = n0 + c;                                       // 16-column chunk: inside one bias segment (D % 32 == 0)
+            if (row < M && n < N) {
+                const int seg = n / bias.D;
+                const float* bp = seg == 0 ? bias.p[0] : (seg == 1 ? bias.p[1] : (seg == 2 ? bias.p[2] : bias.p[3]));
+                float* out = C + (size_t)row * ldc + n;
+                if (bias.vec && n + 15 < N) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int n = n0 + c + j;
-                if (n < N) {
-                    const int seg = n / bias.D;
-                    const float* bp = seg == 0 ? bias.p[0] : (seg == 1 ? bias.p[1] : (seg == 2 ? bias.p[2] : bias.p[3]));
-                    const float bv = bp ? __ldg(bp + (n - seg * bias.D)) : 0.f;
-                    C[(size_t)row * ldc + n] = __uint_as_float(v[j]) + bv;
+                    for (int j = 0; j < 16; j += 4) {
+                        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (bp) bv = __ldg(reinterpret_cast<const float4*>(bp + (n - seg * bias.D) + j));
+                        float4 o;
+                        o.x = __uint_as_float(v[j]) + bv.x; o.y = __uint_as_float(v[j + 1]) + bv.y;
+                        o.z = __uint_as_float(v[j + 2]) + bv.z; o.w = __uint_as_float(v[j + 3]) + bv.w;
+                        *reinterpret_cast<float4*>(out + j) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (n + j < N) out[j] = __uint_as_float(v[j]) + (bp ? __ldg(bp + (n - seg * bias.D) + j) : 0.f);
                 }
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0)
+    if (warp == 1)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN));
 }
 
@@ -255,7 +288,7 @@ extern "C" int ctan_wcat_prep(const float* Wq, const float* Wk, const float* Wv,
 // Returns CTAN_ERR_UNSUPPORTED when the shape does not qualify (the caller then uses ctan_qkva_fwd).
 extern "C" int ctan_qkva_fwd_tc(const float* X, int N, const int* N_dev, int D, const float* Wcat_hi,
                                 const float* Wcat_lo, const float* bq, const float* bk, const float* bv,
-                                const float* b, float* QKVA, cudaStream_t stream) {
+                                const float* b, float* QKVA, int mode, cudaStream_t stream) {
     if (N <= 0) return 0;
     if (D % tc::BKF != 0 || ((4 * D) % tc::BN) != 0 || (((uintptr_t)X | (uintptr_t)Wcat_hi | (uintptr_t)Wcat_lo) & 15))
         return CTAN_ERR_UNSUPPORTED;
@@ -271,9 +304,11 @@ extern "C" int ctan_qkva_fwd_tc(const float* X, int N, const int* N_dev, int D, 
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    tc::Bias4 bias{{bq, bk, bv, b}, D};
+    const uintptr_t ball = (uintptr_t)bq | (uintptr_t)bk | (uintptr_t)bv | (uintptr_t)b | (uintptr_t)QKVA;
+    tc::Bias4 bias{{bq, bk, bv, b}, D, (ball & 15) == 0 ? 1 : 0};
     dim3 grid((4 * D) / tc::BN, (N + tc::BM - 1) / tc::BM);
-    tc::qkva_tc_kernel<<<grid, 128, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, bias, QKVA, 4 * D, N, N_dev, 4 * D, D);
+    tc::qkva_tc_kernel<<<grid, 192, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, bias, QKVA, 4 * D, N, N_dev, 4 * D, D,
+                                                              mode);
     CTAN_CHECK_LAUNCH();
     return 0;
 }

@@ -24,7 +24,7 @@ def test_qkva_tc_matches_fp32(N, D):
     assert torch.equal(hi + lo, torch.cat([Ws[0], Ws[1], Ws[2], A_ref]))                # exact split
     out_tc = torch.full((N, 4 * D), float("nan"), device=dev)
     call("ctan_qkva_fwd_tc", ptr(X), N, None, D, ptr(hi), ptr(lo), ptr(bs[0]), ptr(bs[1]), ptr(bs[2]), ptr(bs[3]),
-         ptr(out_tc))
+         ptr(out_tc), 0)
     out_fp = torch.empty((N, 4 * D), device=dev)
     call("ctan_qkva_fwd", ptr(X), N, None, D, ptr(Ws[0]), ptr(Ws[1]), ptr(Ws[2]), ptr(A), ptr(bs[0]), ptr(bs[1]),
          ptr(bs[2]), ptr(bs[3]), ptr(out_fp))
@@ -37,6 +37,12 @@ def test_qkva_tc_matches_fp32(N, D):
     assert not torch.isnan(out_tc).any()
     assert e_fp < 2e-6, e_fp
     assert e_tc < 5e-6, (e_tc, e_fp)          # 3xTF32: ~fp32 accuracy (plain TF32 would be ~5e-4)
+    out_1x = torch.full((N, 4 * D), float("nan"), device=dev)
+    call("ctan_qkva_fwd_tc", ptr(X), N, None, D, ptr(hi), ptr(lo), ptr(bs[0]), ptr(bs[1]), ptr(bs[2]), ptr(bs[3]),
+         ptr(out_1x), 1)
+    torch.cuda.synchronize()
+    e_1x = float((out_1x.double() - ref).abs().max()) / scale
+    assert 1e-5 < e_1x < 5e-3, e_1x           # single-pass TF32: the 1e-2 path
 
 
 def test_qkva_tc_device_sized_rows():
@@ -50,7 +56,7 @@ def test_qkva_tc_device_sized_rows():
     call("ctan_wcat_prep", ptr(W[0]), ptr(W[1]), ptr(W[2]), ptr(W[3]), 0.1, D, ptr(hi), ptr(lo), None)
     out = torch.full((cap, 4 * D), 7.0, device=dev)
     n_dev = torch.tensor([n_true], dtype=torch.int32, device=dev)
-    call("ctan_qkva_fwd_tc", ptr(X), cap, ptr(n_dev), D, ptr(hi), ptr(lo), None, None, None, None, ptr(out))
+    call("ctan_qkva_fwd_tc", ptr(X), cap, ptr(n_dev), D, ptr(hi), ptr(lo), None, None, None, None, ptr(out), 0)
     torch.cuda.synchronize()
     ref = X[:n_true].double() @ (hi + lo).double().t()
     assert float((out[:n_true].double() - ref).abs().max()) < 5e-5
