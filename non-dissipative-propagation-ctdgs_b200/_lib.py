@@ -100,6 +100,16 @@ def exported_symbols():
     return list(SIGNATURES) + list(OPTIONAL_SIGNATURES)
 
 
+def use_tensor_cores(D: int) -> bool:
+    """The tcgen05/TMA projection needs D % 32 == 0 (128-byte K blocks, 128-wide N tiles).  CTAN_NO_TC=1
+    forces the CUDA-core contraction (A/B comparisons)."""
+    return D % 32 == 0 and os.environ.get("CTAN_NO_TC", "0") != "1"
+
+
+# precision of the tensor-core projection: 0 = 3xTF32 (fp32 parity, 1e-4 bar), 1 = single-pass TF32 (1e-2 bar)
+TC_MODE = int(os.environ.get("CTAN_TC_MODE", "0"))
+
+
 def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 

@@ -147,6 +147,8 @@ class StepEngine:
         w["X"] = torch.zeros((K + 1, N, D), **f32)
         w["EP"] = torch.zeros((E, D), **f32)
         w["A"] = torch.zeros((D, D), **f32)
+        self.use_tc = _lib.use_tensor_cores(D)
+        w["Wcat_hi"], w["Wcat_lo"] = torch.zeros((4 * D, D), **f32), torch.zeros((4 * D, D), **f32)
         w["QKVA"] = torch.zeros((K, N, 4 * D), **f32)
         w["TH"] = torch.zeros((K, N, D), **f32)
         w["ALPHA"] = torch.zeros((K, E), **f32)
@@ -232,7 +234,11 @@ class StepEngine:
         xf = ptr(self.x) if Fn else None
         eps = float(m.gnn.aconv.epsilon)
         with self._fork(2):                                  # side 2: work with no dependence on the batch
-            call("ctan_antisym_prep", W, float(m.gnn.aconv.gamma), D, ptr(w["A"]))
+            if self.use_tc:      # A = W - W^T - gamma I, packed with q/k/v weights and split for 3xTF32
+                call("ctan_wcat_prep", Wq, Wk, Wv, W, float(m.gnn.aconv.gamma), D, ptr(w["Wcat_hi"]),
+                     ptr(w["Wcat_lo"]), ptr(w["A"]))
+            else:
+                call("ctan_antisym_prep", W, float(m.gnn.aconv.gamma), D, ptr(w["A"]))
             w["H"].zero_()
             if train:
                 self.zero_buf.zero_()
@@ -258,7 +264,11 @@ class StepEngine:
             xi = w["X"][k] if train else w["X"][k & 1]
             xo = w["X"][k + 1] if train else w["X"][(k + 1) & 1]
             qk = w["QKVA"][k] if train else w["QKVA"][0]
-            call("ctan_qkva_fwd", ptr(xi), N, Nd, D, Wq, Wk, Wv, ptr(w["A"]), bq, bk, bv, b, ptr(qk))
+            if self.use_tc:      # tcgen05 + TMA projection
+                call("ctan_qkva_fwd_tc", ptr(xi), N, Nd, D, ptr(w["Wcat_hi"]), ptr(w["Wcat_lo"]), bq, bk, bv, b,
+                     ptr(qk), _lib.TC_MODE)
+            else:
+                call("ctan_qkva_fwd", ptr(xi), N, Nd, D, Wq, Wk, Wv, ptr(w["A"]), bq, bk, bv, b, ptr(qk))
             last = k == K - 1
             call("ctan_edge_fwd", ptr(qk), ptr(w["EP"]), ptr(w["rowptr"]), ptr(w["esrc"]), N, Nd, D, ptr(xi), eps,
                  ptr(xo), ptr(w["TH"][k]) if train else None, ptr(w["ALPHA"][k]) if train else None,

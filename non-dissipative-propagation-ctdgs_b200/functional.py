@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import torch
 
+from . import _lib
 from ._lib import call, ptr
 
 
@@ -42,7 +43,12 @@ class _EmbedFn(torch.autograd.Function):
             EP = torch.empty((E, D), device=dev)
             call("ctan_eproj_fwd", ptr(msg), Fe, None, ptr(rel), ptr(tw), ptr(tb), T, ptr(We), E, None, D, ptr(EP))
             A = torch.empty((D, D), device=dev)
-            call("ctan_antisym_prep", ptr(W), float(gamma), D, ptr(A))
+            use_tc = _lib.use_tensor_cores(D)
+            if use_tc:
+                Whi, Wlo = torch.empty((4 * D, D), device=dev), torch.empty((4 * D, D), device=dev)
+                call("ctan_wcat_prep", ptr(Wq), ptr(Wk), ptr(Wv), ptr(W), float(gamma), D, ptr(Whi), ptr(Wlo), ptr(A))
+            else:
+                call("ctan_antisym_prep", ptr(W), float(gamma), D, ptr(A))
             QKVA = torch.empty((max(nk, 1), N, 4 * D), device=dev)
             TH = torch.empty((K, N, D), device=dev) if need_grad else None
             ALPHA = torch.empty((K, max(E, 1)), device=dev) if need_grad else None
@@ -51,8 +57,12 @@ class _EmbedFn(torch.autograd.Function):
                 xi = X[k] if need_grad else X[k & 1]
                 xo = X[k + 1] if need_grad else X[(k + 1) & 1]
                 qk = QKVA[k] if need_grad else QKVA[0]
-                call("ctan_qkva_fwd", ptr(xi), N, None, D, ptr(Wq), ptr(Wk), ptr(Wv), ptr(A), ptr(bq), ptr(bk),
-                     ptr(bv), ptr(b), ptr(qk))
+                if use_tc:
+                    call("ctan_qkva_fwd_tc", ptr(xi), N, None, D, ptr(Whi), ptr(Wlo), ptr(bq), ptr(bk), ptr(bv),
+                         ptr(b), ptr(qk), _lib.TC_MODE)
+                else:
+                    call("ctan_qkva_fwd", ptr(xi), N, None, D, ptr(Wq), ptr(Wk), ptr(Wv), ptr(A), ptr(bq), ptr(bk),
+                         ptr(bv), ptr(b), ptr(qk))
                 last = k == K - 1
                 call("ctan_edge_fwd", ptr(qk), ptr(EP), ptr(rowptr, torch.int32), ptr(esrc), N, None, D, ptr(xi),
                      float(eps), ptr(xo), ptr(TH[k]) if need_grad else None, ptr(ALPHA[k]) if need_grad else None,

@@ -107,6 +107,8 @@ class TGBEvalEngine:
         w["X"] = torch.zeros((2, N, D), **f32)
         w["EP"] = torch.zeros((E, D), **f32)
         w["A"] = torch.zeros((D, D), **f32)
+        self.use_tc = _lib.use_tensor_cores(D)
+        w["Wcat_hi"], w["Wcat_lo"] = torch.zeros((4 * D, D), **f32), torch.zeros((4 * D, D), **f32)
         w["QKVA"] = torch.zeros((N, 4 * D), **f32)
         w["Z"] = torch.zeros((N, D), **f32) if self.final_tanh else None
         w["H"] = torch.zeros((P, self.Hd), **f32)
@@ -161,14 +163,23 @@ class TGBEvalEngine:
             with torch.cuda.stream(self._side):
                 call("ctan_eproj_fwd", ptr(self.msg), Fe, ptr(w["eid"]), ptr(w["rel"]), ptr(g.time_enc.lin.weight),
                      ptr(g.time_enc.lin.bias), T, ptr(ph.lin_edge.weight), E, Ed, D, ptr(w["EP"]))
-                call("ctan_antisym_prep", ptr(a.W), float(a.gamma), D, ptr(w["A"]))
+                if self.use_tc:
+                    call("ctan_wcat_prep", ptr(ph.lin_query.weight), ptr(ph.lin_key.weight), ptr(ph.lin_value.weight),
+                         ptr(a.W), float(a.gamma), D, ptr(w["Wcat_hi"]), ptr(w["Wcat_lo"]), ptr(w["A"]))
+                else:
+                    call("ctan_antisym_prep", ptr(a.W), float(a.gamma), D, ptr(w["A"]))
                 w["H"].zero_()
             call("ctan_enc_fwd", ptr(mem), D, xf, Fn, ptr(w["n_id"]), None, N, Nd, ptr(g.enc_x.weight),
                  ptr(g.enc_x.bias), ptr(w["X"][0]))
             torch.cuda.current_stream().wait_stream(self._side)
             for k in range(K):
                 xi, xo = w["X"][k & 1], w["X"][(k + 1) & 1]
-                call("ctan_qkva_fwd", ptr(xi), N, Nd, D, ptr(ph.lin_query.weight), ptr(ph.lin_key.weight),
+                if self.use_tc:
+                    call("ctan_qkva_fwd_tc", ptr(xi), N, Nd, D, ptr(w["Wcat_hi"]), ptr(w["Wcat_lo"]),
+                         ptr(ph.lin_query.bias), ptr(ph.lin_key.bias), ptr(ph.lin_value.bias), ptr(a.bias),
+                         ptr(w["QKVA"]), _lib.TC_MODE)
+                else:
+                  call("ctan_qkva_fwd", ptr(xi), N, Nd, D, ptr(ph.lin_query.weight), ptr(ph.lin_key.weight),
                      ptr(ph.lin_value.weight), ptr(w["A"]), ptr(ph.lin_query.bias), ptr(ph.lin_key.bias),
                      ptr(ph.lin_value.bias), ptr(a.bias), ptr(w["QKVA"]))
                 last = k == K - 1
