@@ -84,7 +84,8 @@ SIGNATURES.update({
     "ctan_accum_col": [P, I, I, I, P],
     "ctan_probe": [P, I],
     # tc_gemm.cu
-    "ctan_wcat_prep": [P, P, P, P, F, I, P, P, P],
+    "ctan_wcat_prep": [P, P, P, P, F, I, P, P, P, P, P],
+    "ctan_dx_tc": [P, P, I, P, I, P, P, P, I],
     "ctan_qkva_fwd_tc": [P, I, P, I, P, P, P, P, P, P, P, I],
 })
 

@@ -71,7 +71,7 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
                  : "memory");
 }
 
-struct Bias4 { const float* p[4]; int D; int vec; };
+struct Bias4 { const float* p[4]; int D; int vec; const float* res; int ldr; };   // + optional residual res[m][n]
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -198,11 +198,16 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int seg = n / bias.D;
                 const float* bp = seg == 0 ? bias.p[0] : (seg == 1 ? bias.p[1] : (seg == 2 ? bias.p[2] : bias.p[3]));
                 float* out = C + (size_t)row * ldc + n;
+                const float* rp = bias.res ? bias.res + (size_t)row * bias.ldr + n : nullptr;
                 if (bias.vec && n + 15 < N) {
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
                         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (bp) bv = __ldg(reinterpret_cast<const float4*>(bp + (n - seg * bias.D) + j));
+                        if (rp) {
+                            const float4 rv = *reinterpret_cast<const float4*>(rp + j);
+                            bv.x += rv.x; bv.y += rv.y; bv.z += rv.z; bv.w += rv.w;
+                        }
                         float4 o;
                         o.x = __uint_as_float(v[j]) + bv.x; o.y = __uint_as_float(v[j + 1]) + bv.y;
                         o.z = __uint_as_float(v[j + 2]) + bv.z; o.w = __uint_as_float(v[j + 3]) + bv.w;
@@ -211,7 +216,8 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 } else {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (n + j < N) out[j] = __uint_as_float(v[j]) + (bp ? __ldg(bp + (n - seg * bias.D) + j) : 0.f);
+                        if (n + j < N)
+                            out[j] = __uint_as_float(v[j]) + (bp ? __ldg(bp + (n - seg * bias.D) + j) : 0.f) + (rp ? rp[j] : 0.f);
                 }
             }
         }
@@ -256,7 +262,8 @@ static int make_map(CUtensorMap* m, const float* base, int rows, int K) {
 // A_out [D,D] (optional) receives the un-split A for the CUDA-core backward.
 __global__ void wcat_prep_kernel(const float* __restrict__ Wq, const float* __restrict__ Wk,
                                  const float* __restrict__ Wv, const float* __restrict__ W, float gamma, int D,
-                                 float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ A_out) {
+                                 float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ A_out,
+                                 float* __restrict__ hiT, float* __restrict__ loT) {
     const int n = 4 * D * D;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int seg = i / (D * D), r = i - seg * D * D;
@@ -272,13 +279,21 @@ __global__ void wcat_prep_kernel(const float* __restrict__ Wq, const float* __re
         const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
         hi[i] = h;
         lo[i] = x - h;
+        if (hiT) {      // Wcat^T [D, 4D] (K-major operand of dX = DQKVA Wcat): element (c, seg*D + a) = Wcat[seg*D + a][c]
+            const int a = r / D, c = r % D;
+            const size_t o = (size_t)c * 4 * D + seg * D + a;
+            hiT[o] = h;
+            loT[o] = x - h;
+        }
     }
 }
 
 extern "C" int ctan_wcat_prep(const float* Wq, const float* Wk, const float* Wv, const float* W, float gamma, int D,
-                              float* Wcat_hi, float* Wcat_lo, float* A_out, cudaStream_t stream) {
+                              float* Wcat_hi, float* Wcat_lo, float* A_out, float* WcatT_hi, float* WcatT_lo,
+                              cudaStream_t stream) {
     if (D <= 0) return CTAN_ERR_BAD_ARG;
-    wcat_prep_kernel<<<ctan_grid(4LL * D * D, 256), 256, 0, stream>>>(Wq, Wk, Wv, W, gamma, D, Wcat_hi, Wcat_lo, A_out);
+    wcat_prep_kernel<<<ctan_grid(4LL * D * D, 256), 256, 0, stream>>>(Wq, Wk, Wv, W, gamma, D, Wcat_hi, Wcat_lo, A_out,
+                                                                      WcatT_hi, WcatT_lo);
     CTAN_CHECK_LAUNCH();
     return 0;
 }
@@ -305,10 +320,33 @@ extern "C" int ctan_qkva_fwd_tc(const float* X, int N, const int* N_dev, int D, 
         attr_set = true;
     }
     const uintptr_t ball = (uintptr_t)bq | (uintptr_t)bk | (uintptr_t)bv | (uintptr_t)b | (uintptr_t)QKVA;
-    tc::Bias4 bias{{bq, bk, bv, b}, D, (ball & 15) == 0 ? 1 : 0};
+    tc::Bias4 bias{{bq, bk, bv, b}, D, (ball & 15) == 0 ? 1 : 0, nullptr, 0};
     dim3 grid((4 * D) / tc::BN, (N + tc::BM - 1) / tc::BM);
     tc::qkva_tc_kernel<<<grid, 192, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, bias, QKVA, 4 * D, N, N_dev, 4 * D, D,
                                                               mode);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+// dXin[N,D] = G + DQKVA[N,4D] Wcat   on tcgen05 (3xTF32): the activation-gradient contraction of one
+// anti-symmetric iteration (ctan_qkva_bwd's first half), as A = DQKVA (K = 4D) against the K-major operand
+// Wcat^T [D,4D] prepared by ctan_wcat_prep.  Plain stores: no atomics, dXin need not be zeroed.
+// Requirements: D % 128 == 0 (one or more 128-wide output tiles); else CTAN_ERR_UNSUPPORTED.
+extern "C" int ctan_dx_tc(const float* DQKVA, const float* G, int N, const int* N_dev, int D, const float* WcatT_hi,
+                          const float* WcatT_lo, float* dXin, int mode, cudaStream_t stream) {
+    if (N <= 0) return 0;
+    if (D % tc::BN != 0 || (((uintptr_t)DQKVA | (uintptr_t)WcatT_hi | (uintptr_t)WcatT_lo | (uintptr_t)G | (uintptr_t)dXin) & 15))
+        return CTAN_ERR_UNSUPPORTED;
+    CUtensorMap tmA, tmBhi, tmBlo;
+    int rc = tc::make_map(&tmA, DQKVA, N, 4 * D);
+    if (!rc) rc = tc::make_map(&tmBhi, WcatT_hi, D, 4 * D);
+    if (!rc) rc = tc::make_map(&tmBlo, WcatT_lo, D, 4 * D);
+    if (rc) return rc;
+    cudaError_t e = cudaFuncSetAttribute(tc::qkva_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    tc::Bias4 epi{{nullptr, nullptr, nullptr, nullptr}, D, 1, G, D};
+    dim3 grid(D / tc::BN, (N + tc::BM - 1) / tc::BM);
+    tc::qkva_tc_kernel<<<grid, 192, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, epi, dXin, D, N, N_dev, D, 4 * D, mode);
     CTAN_CHECK_LAUNCH();
     return 0;
 }

@@ -149,6 +149,8 @@ class StepEngine:
         w["A"] = torch.zeros((D, D), **f32)
         self.use_tc = _lib.use_tensor_cores(D)
         w["Wcat_hi"], w["Wcat_lo"] = torch.zeros((4 * D, D), **f32), torch.zeros((4 * D, D), **f32)
+        self.use_tc_dx = self.use_tc and D % 128 == 0          # dX contraction on tcgen05 needs 128-wide output tiles
+        w["WcatT_hi"], w["WcatT_lo"] = torch.zeros((D, 4 * D), **f32), torch.zeros((D, 4 * D), **f32)
         w["QKVA"] = torch.zeros((K, N, 4 * D), **f32)
         w["TH"] = torch.zeros((K, N, D), **f32)
         w["ALPHA"] = torch.zeros((K, E), **f32)
@@ -236,7 +238,8 @@ class StepEngine:
         with self._fork(2):                                  # side 2: work with no dependence on the batch
             if self.use_tc:      # A = W - W^T - gamma I, packed with q/k/v weights and split for 3xTF32
                 call("ctan_wcat_prep", Wq, Wk, Wv, W, float(m.gnn.aconv.gamma), D, ptr(w["Wcat_hi"]),
-                     ptr(w["Wcat_lo"]), ptr(w["A"]))
+                     ptr(w["Wcat_lo"]), ptr(w["A"]), ptr(w["WcatT_hi"]) if (train and self.use_tc_dx) else None,
+                     ptr(w["WcatT_lo"]) if (train and self.use_tc_dx) else None)
             else:
                 call("ctan_antisym_prep", W, float(m.gnn.aconv.gamma), D, ptr(w["A"]))
             w["H"].zero_()
@@ -322,7 +325,11 @@ class StepEngine:
                          We, E, Ed, D, gWe, ptr(w["dTenc"]), self.e_typ)
                     call("ctan_tenc_bwd", ptr(w["dTenc"]), ptr(w["rel"]), tw, tb, E, Ed, T, gtw, gtb)
             gn = self._DX[k]
-            call("ctan_qkva_bwd", *qb, ptr(gn), None, None, None, None, None, None, None, None, self.n_typ)
+            if self.use_tc_dx:   # dX = G + DQKVA Wcat on tcgen05 (plain stores)
+                call("ctan_dx_tc", ptr(w["DQKVA"]), ptr(g), N, Nd, D, ptr(w["WcatT_hi"]), ptr(w["WcatT_lo"]), ptr(gn),
+                     _lib.TC_MODE)
+            else:
+                call("ctan_qkva_bwd", *qb, ptr(gn), None, None, None, None, None, None, None, None, self.n_typ)
             g = gn
         self._join(1)                                        # z0 is complete (and the state write-back done)
         call("ctan_enc_bwd", ptr(g), ptr(w["z0"]), N, Nd, D, Fn, gWenc, gbenc, self.n_typ)

@@ -46,7 +46,7 @@ class _EmbedFn(torch.autograd.Function):
             use_tc = _lib.use_tensor_cores(D)
             if use_tc:
                 Whi, Wlo = torch.empty((4 * D, D), device=dev), torch.empty((4 * D, D), device=dev)
-                call("ctan_wcat_prep", ptr(Wq), ptr(Wk), ptr(Wv), ptr(W), float(gamma), D, ptr(Whi), ptr(Wlo), ptr(A))
+                call("ctan_wcat_prep", ptr(Wq), ptr(Wk), ptr(Wv), ptr(W), float(gamma), D, ptr(Whi), ptr(Wlo), ptr(A), None, None)
             else:
                 call("ctan_antisym_prep", ptr(W), float(gamma), D, ptr(A))
             QKVA = torch.empty((max(nk, 1), N, 4 * D), device=dev)

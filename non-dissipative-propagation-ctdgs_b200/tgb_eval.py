@@ -165,7 +165,7 @@ class TGBEvalEngine:
                      ptr(g.time_enc.lin.bias), T, ptr(ph.lin_edge.weight), E, Ed, D, ptr(w["EP"]))
                 if self.use_tc:
                     call("ctan_wcat_prep", ptr(ph.lin_query.weight), ptr(ph.lin_key.weight), ptr(ph.lin_value.weight),
-                         ptr(a.W), float(a.gamma), D, ptr(w["Wcat_hi"]), ptr(w["Wcat_lo"]), ptr(w["A"]))
+                         ptr(a.W), float(a.gamma), D, ptr(w["Wcat_hi"]), ptr(w["Wcat_lo"]), ptr(w["A"]), None, None)
                 else:
                     call("ctan_antisym_prep", ptr(a.W), float(a.gamma), D, ptr(w["A"]))
                 w["H"].zero_()

@@ -40,6 +40,7 @@ REF = {
     "ctan_head_loss": "predictor head + BCEWithLogitsLoss + their gradients -- models/predictors.py:18-19, train_link.py:269-270,279",
     "ctan_probe": "(profiling aid, no reference counterpart)",
     "ctan_wcat_prep": "AntiSymmetricConv W - W^T - gamma*I, packed with the q/k/v weights and split for 3xTF32 -- PyG 2.3.1",
+    "ctan_dx_tc": "gradient of the projections w.r.t. the node state (autograd in the reference) on tcgen05",
     "ctan_qkva_fwd_tc": "TransformerConv lin_query/lin_key/lin_value + x @ A^T + bias on tcgen05 tensor cores -- PyG 2.3.1 (SURVEY.md App. A.5)",
 }
 out = ['''/* ctan_sm100.h -- C ABI of libctan_sm100.so (hand-written CUDA for sm_100a, NVIDIA B200).

@@ -11,7 +11,7 @@ for N, D in [(700, 128), (3000, 128), (6000, 256), (40000, 256)]:
     W = [torch.randn(D, D, device=dev) / D ** 0.5 for _ in range(4)]
     b = [torch.randn(D, device=dev) for _ in range(4)]
     hi, lo, A = torch.empty(4 * D, D, device=dev), torch.empty(4 * D, D, device=dev), torch.empty(D, D, device=dev)
-    call("ctan_wcat_prep", ptr(W[0]), ptr(W[1]), ptr(W[2]), ptr(W[3]), 0.1, D, ptr(hi), ptr(lo), ptr(A))
+    call("ctan_wcat_prep", ptr(W[0]), ptr(W[1]), ptr(W[2]), ptr(W[3]), 0.1, D, ptr(hi), ptr(lo), ptr(A), None, None)
     out = torch.empty(N, 4 * D, device=dev)
     fns = {"tc3x": lambda: call("ctan_qkva_fwd_tc", ptr(X), N, None, D, ptr(hi), ptr(lo), ptr(b[0]), ptr(b[1]), ptr(b[2]), ptr(b[3]), ptr(out), 0),
            "tc1x": lambda: call("ctan_qkva_fwd_tc", ptr(X), N, None, D, ptr(hi), ptr(lo), ptr(b[0]), ptr(b[1]), ptr(b[2]), ptr(b[3]), ptr(out), 1),

@@ -18,7 +18,7 @@ def test_qkva_tc_matches_fp32(N, D):
     hi = torch.empty(4 * D, D, device=dev)
     lo = torch.empty(4 * D, D, device=dev)
     A = torch.empty(D, D, device=dev)
-    call("ctan_wcat_prep", ptr(Ws[0]), ptr(Ws[1]), ptr(Ws[2]), ptr(Ws[3]), gamma, D, ptr(hi), ptr(lo), ptr(A))
+    call("ctan_wcat_prep", ptr(Ws[0]), ptr(Ws[1]), ptr(Ws[2]), ptr(Ws[3]), gamma, D, ptr(hi), ptr(lo), ptr(A), None, None)
     A_ref = Ws[3] - Ws[3].t() - gamma * torch.eye(D, device=dev)
     assert torch.equal(A, A_ref)
     assert torch.equal(hi + lo, torch.cat([Ws[0], Ws[1], Ws[2], A_ref]))                # exact split
@@ -53,7 +53,7 @@ def test_qkva_tc_device_sized_rows():
     X = torch.randn(cap, D, device=dev)
     W = [torch.randn(D, D, device=dev) / 11 for _ in range(4)]
     hi, lo = torch.empty(4 * D, D, device=dev), torch.empty(4 * D, D, device=dev)
-    call("ctan_wcat_prep", ptr(W[0]), ptr(W[1]), ptr(W[2]), ptr(W[3]), 0.1, D, ptr(hi), ptr(lo), None)
+    call("ctan_wcat_prep", ptr(W[0]), ptr(W[1]), ptr(W[2]), ptr(W[3]), 0.1, D, ptr(hi), ptr(lo), None, None, None)
     out = torch.full((cap, 4 * D), 7.0, device=dev)
     n_dev = torch.tensor([n_true], dtype=torch.int32, device=dev)
     call("ctan_qkva_fwd_tc", ptr(X), cap, ptr(n_dev), D, ptr(hi), ptr(lo), None, None, None, None, ptr(out), 0)
@@ -62,3 +62,30 @@ def test_qkva_tc_device_sized_rows():
     assert float((out[:n_true].double() - ref).abs().max()) < 5e-5
     assert bool((out[384:] == 7.0).all())           # whole tiles past n_true untouched
     assert bool((out[n_true:384] == 7.0).all())     # rows past n_true inside the last tile untouched
+
+
+@pytest.mark.parametrize("N,D", [(700, 128), (1300, 256)])
+def test_dx_tc_matches_fp32(N, D):
+    """dX = G + DQKVA Wcat on tcgen05 vs the CUDA-core split-K contraction and float64."""
+    from ctan_b200._lib import call, ptr
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(N)
+    DQ = torch.randn(N, 4 * D, generator=g).to(dev)
+    G = torch.randn(N, D, generator=g).to(dev)
+    Ws = [(torch.randn(D, D, generator=g) / D ** 0.5).to(dev) for _ in range(4)]
+    hi, lo = torch.empty(4 * D, D, device=dev), torch.empty(4 * D, D, device=dev)
+    hiT, loT = torch.empty(D, 4 * D, device=dev), torch.empty(D, 4 * D, device=dev)
+    A = torch.empty(D, D, device=dev)
+    call("ctan_wcat_prep", ptr(Ws[0]), ptr(Ws[1]), ptr(Ws[2]), ptr(Ws[3]), 0.1, D, ptr(hi), ptr(lo), ptr(A), ptr(hiT),
+         ptr(loT))
+    assert torch.equal(hiT, hi.t().contiguous()) and torch.equal(loT, lo.t().contiguous())
+    out_tc = torch.full((N, D), float("nan"), device=dev)
+    call("ctan_dx_tc", ptr(DQ), ptr(G), N, None, D, ptr(hiT), ptr(loT), ptr(out_tc), 0)
+    out_fp = torch.zeros((N, D), device=dev)
+    call("ctan_qkva_bwd", ptr(DQ), ptr(DQ), ptr(G), N, None, D, ptr(Ws[0]), ptr(Ws[1]), ptr(Ws[2]), ptr(A), ptr(out_fp),
+         None, None, None, None, None, None, None, None, 0)
+    torch.cuda.synchronize()
+    ref = G.double() + DQ.double() @ (hi + lo).double()
+    scale = float(ref.abs().max())
+    assert float((out_fp.double() - ref).abs().max()) / scale < 2e-6
+    assert float((out_tc.double() - ref).abs().max()) / scale < 5e-6
