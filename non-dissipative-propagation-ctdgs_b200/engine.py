@@ -102,13 +102,19 @@ class StepEngine:
         # everything the backward accumulates into lives in ONE buffer so a single memset clears it
         N, D = self.n_cap, self.D
         K = self.K
-        self.zero_buf = torch.zeros(n + D * D + N * D + N * 4 * D + K * N * D, device=self.dev)
+
+        def pad(v):                      # every region starts on a 256-byte boundary (128-bit loads, TMA bases)
+            return (v + 63) // 64 * 64
+        o_dA = pad(n)
+        o_dZ = o_dA + pad(D * D)
+        o_DQ = o_dZ + pad(N * D)
+        o_DX = o_DQ + pad(N * 4 * D)
+        self.zero_buf = torch.zeros(o_DX + K * N * D, device=self.dev)
         self.flat_g = self.zero_buf[:n]
-        o = n
-        self._dA = self.zero_buf[o:o + D * D].view(D, D); o += D * D
-        self._dZ = self.zero_buf[o:o + N * D].view(N, D); o += N * D
-        self._DQKVA = self.zero_buf[o:o + N * 4 * D].view(N, 4 * D); o += N * 4 * D
-        self._DX = self.zero_buf[o:o + K * N * D].view(K, N, D)      # dL/dx_k, accumulated by split-K
+        self._dA = self.zero_buf[o_dA:o_dA + D * D].view(D, D)
+        self._dZ = self.zero_buf[o_dZ:o_dZ + N * D].view(N, D)
+        self._DQKVA = self.zero_buf[o_DQ:o_DQ + N * 4 * D].view(N, 4 * D)
+        self._DX = self.zero_buf[o_DX:o_DX + K * N * D].view(K, N, D)      # dL/dx_k, accumulated by split-K
         self.adam_m = torch.zeros(n, device=self.dev)
         self.adam_v = torch.zeros(n, device=self.dev)
         self.p, self.g = [], []
