@@ -14,6 +14,7 @@ first event, train_link.py:265), so `msg[e_id]`/`t[e_id]` are gathers from the s
 from __future__ import annotations
 
 import contextlib
+import os
 
 import torch
 
@@ -155,7 +156,8 @@ class StepEngine:
         w["A"] = torch.zeros((D, D), **f32)
         self.use_tc = _lib.use_tensor_cores(D)
         w["Wcat_hi"], w["Wcat_lo"] = torch.zeros((4 * D, D), **f32), torch.zeros((4 * D, D), **f32)
-        self.use_tc_dx = self.use_tc and D % 128 == 0          # dX contraction on tcgen05 needs 128-wide output tiles
+        self.use_tc_dx = (self.use_tc and D % 128 == 0          # dX contraction on tcgen05 needs 128-wide output tiles
+                          and os.environ.get("CTAN_TC_DX", "1") == "1")
         w["WcatT_hi"], w["WcatT_lo"] = torch.zeros((D, 4 * D), **f32), torch.zeros((D, 4 * D), **f32)
         w["QKVA"] = torch.zeros((K, N, 4 * D), **f32)
         w["TH"] = torch.zeros((K, N, D), **f32)

@@ -88,4 +88,4 @@ def test_dx_tc_matches_fp32(N, D):
     ref = G.double() + DQ.double() @ (hi + lo).double()
     scale = float(ref.abs().max())
     assert float((out_fp.double() - ref).abs().max()) / scale < 2e-6
-    assert float((out_tc.double() - ref).abs().max()) / scale < 5e-6
+    assert float((out_tc.double() - ref).abs().max()) / scale < 1e-5      # K = 4D up to 1024 terms
