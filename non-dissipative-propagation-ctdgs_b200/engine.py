@@ -93,7 +93,10 @@ class StepEngine:
         self._flatten_params()
         self._alloc()
         self._graphs = {}
-        self._side = [torch.cuda.Stream(device=dev) for _ in range(4)]
+        # critical path on a high-priority stream, off-critical-path branches on normal-priority streams: when
+        # both have CTAs pending, the block scheduler serves the critical path first
+        self._main = torch.cuda.Stream(device=dev, priority=-1)
+        self._side = [torch.cuda.Stream(device=dev, priority=0) for _ in range(4)]
 
     # ------------------------------------------------------------------ parameters in one flat buffer
     def _flatten_params(self):
@@ -352,7 +355,7 @@ class StepEngine:
         key = bool(train)
         if key not in self._graphs:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=self._main):
                 self._launch(train)
             self._graphs[key] = g
         return self._graphs[key]
