@@ -117,41 +117,34 @@ __global__ void edge_fwd_kernel(const float* __restrict__ QKVA, const float* __r
                 const int d = lane + 32 * v;
                 q[v] = d < D ? QKVA[(size_t)i * ld + d] : 0.f;
             }
+            // ONE pass over the row's edges (every k_j / v_j / EP row is read from HBM exactly once): online
+            // softmax -- running max mx, running denominator den and running weighted sum phi are rescaled
+            // by exp(mx_old - mx_new) whenever the max grows.  Raw scores are parked in ALPHA (lane e%32 writes
+            // and later re-reads its own entries) and normalised once the row's max and sum are final.
             float mx = -INFINITY, den = 0.f;
-            for (int c0 = r0; c0 < r1; c0 += 32) {
-                const int cnt = min(32, r1 - c0);
-                float s_keep = -INFINITY;
-                for (int c = 0; c < cnt; ++c) {
-                    const int e = c0 + c;
-                    const int64_t j = esrc[e];
-                    float part = 0.f;
+            for (int e = r0; e < r1; ++e) {
+                const int64_t j = esrc[e];
+                float kj[MAXV], vj[MAXV], ep[MAXV];
 #pragma unroll
-                    for (int v = 0; v < MAXV; ++v) {
-                        const int d = lane + 32 * v;
-                        if (d < D) part = fmaf(q[v], QKVA[(size_t)j * ld + D + d] + EP[(size_t)e * D + d], part);
-                    }
-                    const float s = warp_sum(part) * inv_sqrt_d;
-                    if (lane == c) s_keep = s;
+                for (int v = 0; v < MAXV; ++v) {
+                    const int d = lane + 32 * v;
+                    const bool in = d < D;
+                    kj[v] = in ? QKVA[(size_t)j * ld + D + d] : 0.f;
+                    vj[v] = in ? QKVA[(size_t)j * ld + 2 * D + d] : 0.f;
+                    ep[v] = in ? EP[(size_t)e * D + d] : 0.f;
                 }
-                if (ALPHA && lane < cnt) ALPHA[c0 + lane] = s_keep;       // raw score, normalised below
-                const float nmx = fmaxf(mx, warp_max(s_keep));
+                float part = 0.f;
+#pragma unroll
+                for (int v = 0; v < MAXV; ++v) part = fmaf(q[v], kj[v] + ep[v], part);
+                const float s = warp_sum(part) * inv_sqrt_d;
+                if (ALPHA && lane == ((e - r0) & 31)) ALPHA[e] = s;
+                const float nmx = fmaxf(mx, s);
                 const float scale = (mx == -INFINITY) ? 0.f : expf(mx - nmx);
-                den *= scale;
+                const float p = expf(s - nmx);
+                den = fmaf(den, scale, p);
 #pragma unroll
-                for (int v = 0; v < MAXV; ++v) phi[v] *= scale;
+                for (int v = 0; v < MAXV; ++v) phi[v] = fmaf(phi[v], scale, p * (vj[v] + ep[v]));
                 mx = nmx;
-                const float p_keep = lane < cnt ? expf(s_keep - mx) : 0.f;
-                for (int c = 0; c < cnt; ++c) {
-                    const int e = c0 + c;
-                    const int64_t j = esrc[e];
-                    const float p = __shfl_sync(0xffffffffu, p_keep, c);
-                    den += p;
-#pragma unroll
-                    for (int v = 0; v < MAXV; ++v) {
-                        const int d = lane + 32 * v;
-                        if (d < D) phi[v] = fmaf(p, QKVA[(size_t)j * ld + 2 * D + d] + EP[(size_t)e * D + d], phi[v]);
-                    }
-                }
             }
             const float inv = 1.f / (den + 1e-16f);
 #pragma unroll
