@@ -175,22 +175,68 @@ def time_back_to_back(eng, n_steps, train):
     return e0.elapsed_time(e1)
 
 
-def per_kernel_profile(eng, n_steps, train=True):
-    """Eager (non-graph) steps with a CUDA-event pair around every C-ABI call: live per-call device
-    durations on the launching stream."""
+def stage_timeline(eng, n_replays, train=True):
+    """Live per-stage device durations INSIDE the CUDA-graph replay: a one-thread probe kernel storing
+    %globaltimer is captured after every C-ABI call of the critical-path stream (side-stream work overlaps
+    and shows up only where the critical path has to join it).  Returns ({call: us}, launches_per_step)."""
     from ctan_b200 import _lib
-    _lib.TRACE = []
-    for _ in range(n_steps):
+    ts = torch.zeros(256, dtype=torch.int64, device=eng.dev)
+    names = []
+    g = torch.cuda.CUDAGraph()
+    _lib.N_LAUNCHES = 0
+    with torch.cuda.graph(g):
+        _lib.lib().ctan_probe(ts.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+        names.append("start")
+        _lib.PROBE = (ts, names, torch.cuda.current_stream().cuda_stream)
         eng._launch(train)
+        _lib.PROBE = None
+    launches = _lib.N_LAUNCHES
+    acc = torch.zeros(len(names), dtype=torch.float64)
+    for _ in range(n_replays):
+        g.replay()
+        torch.cuda.synchronize()
+        t = ts[:len(names)].cpu().double()
+        acc += t - t[0]
+    eng.loader.cur_e_id += n_replays * eng.B
+    acc = (acc / n_replays / 1e3).tolist()
+    out = {}
+    for i in range(1, len(names)):
+        out[names[i]] = out.get(names[i], 0.0) + max(acc[i] - acc[i - 1] - 1.3, 0.1)   # ~1.3 us is the probe itself
+    return out, launches
+
+
+def saturating_edge_roofline(dev, N=100_000, S=16, D=256, iters=10):
+    """The fused edge kernel (logits + segmented softmax + aggregation + tanh update) on a shape that
+    saturates the memory system: N rows of degree S gathering from a node table larger than L2.
+    Algorithmic bytes: 16*D per node (q, xA+b, x_in, x_out) + (12*D+8) per edge (k_j, v_j, EP row, src id)."""
+    from ctan_b200._lib import call, ptr
+    E = N * S
+    g = torch.Generator(device="cpu").manual_seed(0)
+    QKVA = torch.randn(N, 4 * D, device=dev)
+    EP = torch.randn(E, D, device=dev)
+    X = torch.randn(N, D, device=dev)
+    Xo = torch.empty(N, D, device=dev)
+    rowptr = (torch.arange(N + 1, dtype=torch.int32) * S).to(dev)
+    esrc = torch.randint(0, N, (E,), generator=g).to(dev)
+
+    def fn():
+        call("ctan_edge_fwd", ptr(QKVA), ptr(EP), ptr(rowptr), ptr(esrc), N, None, D, ptr(X), 0.5, ptr(Xo), None, None,
+             None)
+    for _ in range(3):
+        fn()
     torch.cuda.synchronize()
-    eng.loader.cur_e_id += n_steps * eng.B
-    agg = {}
-    for name, a, b in _lib.TRACE:
-        d = agg.setdefault(name, [0.0, 0])
-        d[0] += a.elapsed_time(b)
-        d[1] += 1
-    _lib.TRACE = None
-    return {k: {"ms_per_call": v[0] / v[1], "calls_per_step": v[1] / n_steps} for k, v in agg.items()}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    alg = N * 16 * D + E * (12 * D + 8)
+    del QKVA, EP, X, Xo
+    torch.cuda.empty_cache()
+    return {"kernel": "edge_fwd_kernel", "shape": {"N": N, "E": E, "D": D}, "ms_per_launch": ms,
+            "algorithmic_bytes": alg, "achieved": alg / (ms * 1e-3) / 1e9}
 
 
 def run_e2e(st, K, mean, std, dev, n_steps, warmup):
@@ -284,10 +330,8 @@ def main():
     value = args.steps * B / (total_ms * 1e-3)
     eng.check()
     losses = eng.losses(5).cpu().tolist()
-    # ---- phase B: 20 eager steps with events around every C-ABI call (per-kernel live durations)
-    _lib.N_LAUNCHES = 0
-    prof = per_kernel_profile(eng, 20, train=True)
-    launches_per_step = _lib.N_LAUNCHES // 20
+    # ---- phase B: per-stage device timeline inside the graph replay (probe kernels on the critical path)
+    prof, launches_per_step = stage_timeline(eng, 50, train=True)
     counts = eng.w["counts"].cpu().tolist()
     # ---- phase C: same stream from a fresh state, back-to-back replays (L2 warm, as in production)
     eng.reset(reset_optimizer=True)
@@ -304,13 +348,15 @@ def main():
     # ---- roofline of the dominant kernel (by live per-call device time)
     peak, peak_src = load_peaks()
     N_last, E_last = counts[0], counts[1]
-    top = sorted(prof.items(), key=lambda kv: -kv[1]["ms_per_call"] * kv[1]["calls_per_step"])
-    top_name, top_v = top[0]
+    top = sorted(prof.items(), key=lambda kv: -kv[1])
+    top_name, top_us = top[0]
     D, Fe, T, Hd = eng.D, eng.Fe, eng.T, eng.Hd
     alg_bytes = {
         "ctan_eproj_fwd": E_last * (4 * Fe + 8 + 4) + 4 * D * (Fe + T) + E_last * D * 4,
         "ctan_eproj_bwd": E_last * (4 * Fe + 8 + 4 + 4 * D) + 2 * 4 * D * (Fe + T) + E_last * T * 4,
         "ctan_qkva_fwd": N_last * D * 4 + 4 * D * D * 4 + N_last * 4 * D * 4,
+        "ctan_qkva_fwd_tc": N_last * D * 4 + 2 * 4 * D * D * 4 + N_last * 4 * D * 4,
+        "ctan_dx_tc": N_last * (4 * D + D + D) * 4 + 2 * 4 * D * D * 4,
         "ctan_qkva_bwd": N_last * (4 * D + D + D) * 4 + 2 * 4 * D * D * 4 + N_last * D * 4,
         "ctan_edge_fwd": N_last * (4 * D + 2 * D) * 4 + E_last * (2 * D * 4 + D * 4 + 8 + 4),
         "ctan_edge_bwd": N_last * (4 * D + 3 * D + 4 * D) * 4 + E_last * (3 * D * 4 + 2 * D * 4 + 8 + 8),
@@ -320,10 +366,12 @@ def main():
         "ctan_enc_bwd": N_last * (2 * D + 1) * 4 + D * (D + 1) * 4,
     }.get(top_name)
     roof = {"bound": "hbm", "kernel": top_name, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
-            "traffic": None, "peak_source": peak_src, "ms_per_launch": top_v["ms_per_call"],
-            "note": "per-batch work is ~2 MB / ~0.2 GFLOP: latency-bound at B=200 (see DESIGN.md)"}
+            "traffic": None, "peak_source": peak_src, "ms_per_launch": top_us * 1e-3,
+            "how": "longest stage of the in-graph critical-path timeline (globaltimer probes, 50 replays)",
+            "note": "per-batch work is ~3 MB / ~0.2 GFLOP: every kernel of the step is latency-bound at B=200 "
+                    "(DESIGN.md S4); the saturating-shape figure is under roofline_saturating"}
     if alg_bytes:
-        ach = alg_bytes / (top_v["ms_per_call"] * 1e-3) / 1e9
+        ach = alg_bytes / (top_us * 1e-6) / 1e9
         roof.update(achieved=ach, frac=ach / peak, algorithmic_bytes=alg_bytes)
     # whole-step algorithmic bytes (SURVEY.md S8d formula)
     U = 2 * B
@@ -340,7 +388,15 @@ def main():
            "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
            "value_l2_warm_back_to_back": warm_value, "infer_events_per_sec": infer_value,
            "last_losses": losses, "roofline": roof,
-           "kernel_ms_per_step": {k: round(v["ms_per_call"] * v["calls_per_step"], 5) for k, v in top[:12]}}
+           "critical_path_us": {k: round(v, 2) for k, v in top}}
+    sat = saturating_edge_roofline(dev)
+    sat.update(bound="hbm", peak=peak, unit="GB/s", frac=sat["achieved"] / peak, traffic=None)
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        tr = json.load(open(tpath)).get("edge_fwd_kernel@saturating(N=100000,E=1600000,D=256)")
+        if tr:
+            sat["traffic"] = tr["traffic_bytes"]
+    out["roofline_saturating"] = sat
 
     # ---- end to end with host buffers
     e2e_v, h2d, d2h, last_loss = run_e2e(st, K, mean, std, dev, min(args.steps, 400), W)
