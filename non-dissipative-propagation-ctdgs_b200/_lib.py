@@ -145,6 +145,7 @@ PROBE = None
 def call(name: str, *args):
     global N_LAUNCHES
     fn = getattr(lib(), name)
+    N_LAUNCHES += LAUNCHES.get(name, 1) + (args[7] if name == "ctan_nbr_lookup" else 0)
     if PROBE is not None and name != "ctan_probe":
         ts, names, main = PROBE
         rc = fn(*args, stream_ptr())
@@ -154,7 +155,6 @@ def call(name: str, *args):
             lib().ctan_probe(ts.data_ptr(), len(names), stream_ptr())
             names.append(name)
         return
-    N_LAUNCHES += LAUNCHES.get(name, 1) + (args[7] if name == "ctan_nbr_lookup" else 0)
     if TRACE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
