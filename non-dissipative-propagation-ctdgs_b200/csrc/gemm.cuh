@@ -270,11 +270,14 @@ gemm_kernel(const AL A, const BL Bm, const EP epi, int M_host, const int* __rest
     __shared__ __align__(16) float Bs[2][BK][BT + PAD];
     const int M = M_dev ? *M_dev : M_host;
     const int K = K_dev ? *K_dev : K_host;
-    const int m0 = blockIdx.y * BT, n0 = blockIdx.x * BT;
+    const int n0 = blockIdx.x * BT;
     const int kb = blockIdx.z * k_chunk;
     const int ke = min(K, kb + k_chunk);
-    if (m0 >= M || n0 >= N || kb >= ke) return;        // block-uniform, before any barrier
+    if (n0 >= N || kb >= ke) return;                   // block-uniform, before any barrier
     const int t = threadIdx.x, ty = t / TPR, tx = t % TPR;
+    // grid.y is bounded by the host (the true M may be far below its upper bound): a CTA walks row tiles
+    // blockIdx.y, blockIdx.y + gridDim.y, ... so no more than a few waves of CTAs are ever launched
+  for (int m0 = blockIdx.y * BT; m0 < M; m0 += gridDim.y * BT) {
 
     float acc[4][4];
 #pragma unroll
@@ -361,6 +364,7 @@ gemm_kernel(const AL A, const BL Bm, const EP epi, int M_host, const int* __rest
         }
         if (EP::HAS_ROWSUM && blockIdx.x == 0 && tx == 0) epi.rowsum(m, rsum[i]);
     }
+  }   // row-tile loop (the k-loop's trailing barrier already protects the smem tiles for the next pass)
 }
 
 // M_max bounds the grid when the true M lives on the device (the typical M is then taken as M_max/4 when
@@ -381,13 +385,16 @@ static inline int launch(const AL& A, const BL& B, const EP& epi, int M_max, con
     static const int force_tile = [] { const char* e = getenv("CTAN_GEMM_TILE"); return e ? atoi(e) : 0; }();
     // measured on B200 (scripts/micro_kernels.py): the 32x32 tile only wins on thin, long-K problems
     const bool use_big = force_tile == 64 ? true : (force_tile == 32 ? false : (big >= 24 || K_max < 512));
-    if (use_big) {
-        dim3 grid((N + 63) / 64, (M_max + 63) / 64, splits);
-        gemm_kernel<64, AL, BL, EP><<<grid, 256, 0, stream>>>(A, B, epi, M_max, M_dev, N, K_max, K_dev, k_chunk);
-    } else {
-        dim3 grid((N + 31) / 32, (M_max + 31) / 32, splits);
-        gemm_kernel<32, AL, BL, EP><<<grid, 64, 0, stream>>>(A, B, epi, M_max, M_dev, N, K_max, K_dev, k_chunk);
+    const int bt = use_big ? 64 : 32;
+    const int gx = (N + bt - 1) / bt;
+    int gy = (M_max + bt - 1) / bt;
+    if (M_dev) {        // device-sized M: launch at most ~6 waves of CTAs, each walks several row tiles
+        const int cap = (6 * CTAN_SM_COUNT) / (gx * splits);
+        if (gy > cap) gy = cap > 1 ? cap : 1;
     }
+    dim3 grid(gx, gy, splits);
+    if (use_big) gemm_kernel<64, AL, BL, EP><<<grid, 256, 0, stream>>>(A, B, epi, M_max, M_dev, N, K_max, K_dev, k_chunk);
+    else         gemm_kernel<32, AL, BL, EP><<<grid, 64, 0, stream>>>(A, B, epi, M_max, M_dev, N, K_max, K_dev, k_chunk);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }

@@ -90,19 +90,24 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const int* __restrict__ M_dev, int N, int K, int mode) {
     extern __shared__ uint8_t smem_raw[];
     const int M = M_dev ? *M_dev : M_host;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    if (m0 >= M) return;                                              // uniform, before any allocation
+    const int n0 = blockIdx.x * BN;
+    if ((int)blockIdx.y * BM >= M) return;                            // uniform, before any allocation
+    // Persistent over row tiles: the true M lives on the device, so the host launches a bounded grid.y and
+    // each CTA walks tiles blockIdx.y, +gridDim.y, ...; the smem ring and its phases run on across tiles,
+    // `done`/`accfree` hand the TMEM accumulator back and forth between the MMA issuer and the epilogue.
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* raw = (uint64_t*)(smem + STAGES * STAGE_BYTES);
     uint64_t* ready = raw + STAGES;
     uint64_t* empty = ready + STAGES;
     uint64_t* done = empty + STAGES;
-    uint32_t* tmem_holder = (uint32_t*)(done + 1);
+    uint64_t* accfree = done + 1;
+    uint32_t* tmem_holder = (uint32_t*)(accfree + 1);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
 
     if (t == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&raw[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], 1); }
         mbar_init(done, 1);
+        mbar_init(accfree, 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -120,9 +125,11 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer
         if (lane == 0) {
-            for (int kb = 0; kb < n_kb; ++kb) {
-                const int s = kb % STAGES;
-                if (kb >= STAGES) mbar_wait(&empty[s], ((kb / STAGES) - 1) & 1);
+            int it = 0;                                                 // k-blocks issued so far (all tiles)
+            for (int m0 = blockIdx.y * BM; m0 < M; m0 += gridDim.y * BM)
+            for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                const int s = it % STAGES;
+                if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);
                 mbar_expect_tx(&raw[s], (mode == 0 ? 3 : 2) * TILE_BYTES);
                 tma_load_2d(stage_ptr(s, 0), &tmA, &raw[s], kb * BKF, m0);
                 tma_load_2d(stage_ptr(s, 2), &tmBhi, &raw[s], kb * BKF, n0);
@@ -133,9 +140,15 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ------------------------------------------------ MMA issuer
         if (lane == 0) {
             const uint32_t idesc = instr_desc_tf32();
-            for (int kb = 0; kb < n_kb; ++kb) {
-                const int s = kb % STAGES;
-                mbar_wait(mode == 0 ? &ready[s] : &raw[s], (kb / STAGES) & 1);
+            int it = 0, tile = 0;
+            for (int m0 = blockIdx.y * BM; m0 < M; m0 += gridDim.y * BM, ++tile) {
+            if (tile > 0) {                                             // the epilogue has drained the accumulator
+                mbar_wait(accfree, (tile - 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(mode == 0 ? &ready[s] : &raw[s], (it / STAGES) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_hi = smem_u32(stage_ptr(s, 0)), a_lo = smem_u32(stage_ptr(s, 1));
                 const uint32_t b_hi = smem_u32(stage_ptr(s, 2)), b_lo = smem_u32(stage_ptr(s, 3));
@@ -152,15 +165,18 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 mma_commit(&empty[s]);                                  // arrives when these MMAs have read stage s
             }
-            mma_commit(done);
+            mma_commit(done);                                           // this tile's accumulator is complete
+            }
         }
     } else {
         // ------------------------------------------------ transform (3xTF32 split of A) then epilogue
         const int te = t - 64;                                          // 0..127
+        int it = 0, tile = 0;
+        for (int m0 = blockIdx.y * BM; m0 < M; m0 += gridDim.y * BM, ++tile) {
         if (mode == 0) {
-            for (int kb = 0; kb < n_kb; ++kb) {
-                const int s = kb % STAGES;
-                mbar_wait(&raw[s], (kb / STAGES) & 1);
+            for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(&raw[s], (it / STAGES) & 1);
                 float4* ahi = (float4*)stage_ptr(s, 0);
                 float4* alo = (float4*)stage_ptr(s, 1);
 #pragma unroll
@@ -178,7 +194,7 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_arrive(&ready[s]);
             }
         }
-        mbar_wait(done, 0);
+        mbar_wait(done, tile & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // warp w may touch TMEM lanes [32*(w%4), +32): warps 2,3,4,5 cover quarters 2,3,0,1
         const int q = warp & 3;
@@ -221,6 +237,9 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(accfree);                                           // TMEM reads of this tile are complete
+        }   // row-tile loop
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -254,6 +273,17 @@ static int make_map(CUtensorMap* m, const float* base, int rows, int K) {
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : CTAN_ERR_BAD_ARG;
+}
+
+// grid.y: every row tile when the size is known on the host; with a device-sized M (upper bound only) at most
+// two CTAs per SM are launched and each walks several row tiles (a CTA holds 193 KB of smem: empty ones are not free)
+static int bounded_rows(int M_max, const int* M_dev, int gx) {
+    int gy = (M_max + BM - 1) / BM;
+    if (M_dev) {
+        const int cap = (2 * CTAN_SM_COUNT) / gx;
+        if (gy > cap) gy = cap > 1 ? cap : 1;
+    }
+    return gy;
 }
 
 }  // namespace tc
@@ -321,7 +351,7 @@ extern "C" int ctan_qkva_fwd_tc(const float* X, int N, const int* N_dev, int D, 
     }
     const uintptr_t ball = (uintptr_t)bq | (uintptr_t)bk | (uintptr_t)bv | (uintptr_t)b | (uintptr_t)QKVA;
     tc::Bias4 bias{{bq, bk, bv, b}, D, (ball & 15) == 0 ? 1 : 0, nullptr, 0};
-    dim3 grid((4 * D) / tc::BN, (N + tc::BM - 1) / tc::BM);
+    dim3 grid((4 * D) / tc::BN, tc::bounded_rows(N, N_dev, (4 * D) / tc::BN));
     tc::qkva_tc_kernel<<<grid, 192, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, bias, QKVA, 4 * D, N, N_dev, 4 * D, D,
                                                               mode);
     CTAN_CHECK_LAUNCH();
@@ -345,7 +375,7 @@ extern "C" int ctan_dx_tc(const float* DQKVA, const float* G, int N, const int* 
     cudaError_t e = cudaFuncSetAttribute(tc::qkva_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     tc::Bias4 epi{{nullptr, nullptr, nullptr, nullptr}, D, 1, G, D};
-    dim3 grid(D / tc::BN, (N + tc::BM - 1) / tc::BM);
+    dim3 grid(D / tc::BN, tc::bounded_rows(N, N_dev, D / tc::BN));
     tc::qkva_tc_kernel<<<grid, 192, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, epi, dXin, D, N, N_dev, D, 4 * D, mode);
     CTAN_CHECK_LAUNCH();
     return 0;
