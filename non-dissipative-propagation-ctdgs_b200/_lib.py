@@ -86,6 +86,10 @@ SIGNATURES.update({
     # tc_gemm.cu
     "ctan_wcat_prep": [P, P, P, P, F, I, P, P, P, P, P],
     "ctan_dx_tc": [P, P, I, P, I, P, P, P, I],
+    "ctan_pack_split": [P, I, I, I, P, P],
+    "ctan_gemm_tc": [P, I, P, I, P, P, I, P, P, P, P, I, P, I, P, I],
+    "ctan_enc_prep": [P, I, P, I, P, I, P, P, P, P],
+    "ctan_head_gather": [P, I, P, P, P, I, P, P, P],
     "ctan_qkva_fwd_tc": [P, I, P, I, P, P, P, P, P, P, P, I],
 })
 

@@ -378,3 +378,61 @@ extern "C" int ctan_csr_from_sorted(const int64_t* edst, int E, int N, int32_t* 
     CTAN_CHECK_LAUNCH();
     return 0;
 }
+
+// Operand preparation of the tensor-core enc_x path: one warp per local node r (global id g = n_id[r])
+//   zmain[r,:] = mem[g,:]                                  (dense, 16-byte aligned rows -> TMA source)
+//   tail[r,n]  = sum_f xfeat[g,f] * Wenc[n, D+f]           (the node-feature columns of enc_x, a rank-Fn update
+//                                                           that the contraction's epilogue adds as a residual)
+__global__ void enc_prep_kernel(const float* __restrict__ mem, int D, const float* __restrict__ xfeat, int Fn,
+                                const int64_t* __restrict__ n_id, int N_host, const int* __restrict__ N_dev,
+                                const float* __restrict__ Wenc, float* __restrict__ zmain, float* __restrict__ tail) {
+    const int N = N_dev ? *N_dev : N_host;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const int ldw = D + Fn;
+    for (int r = warp; r < N; r += nw) {
+        const int64_t g = n_id[r];
+        for (int d = lane; d < D; d += 32) {
+            zmain[(size_t)r * D + d] = __ldg(mem + (size_t)g * D + d);
+            float t = 0.f;
+            for (int f = 0; f < Fn; ++f) t = fmaf(__ldg(xfeat + (size_t)g * Fn + f), __ldg(Wenc + (size_t)d * ldw + D + f), t);
+            tail[(size_t)r * D + d] = t;
+        }
+    }
+}
+extern "C" int ctan_enc_prep(const float* mem, int D, const float* xfeat, int Fn, const int64_t* n_id, int N,
+                             const int* N_dev, const float* Wenc, float* zmain, float* tail, cudaStream_t stream) {
+    if (N <= 0) return 0;
+    enc_prep_kernel<<<ctan_grid((long long)N * 32, 256), 256, 0, stream>>>(mem, D, xfeat, Fn, n_id, N, N_dev, Wenc,
+                                                                           zmain, tail);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+// Readout head on pre-projected node rows (evaluation): Y[N, 2*Hd] = z [Wsrc;Wdst]^T + [bsrc;bdst] is computed
+// once per NODE on the tensor cores; a scored pair only gathers two rows:
+//   OUT[p] = relu(Y[row(src_p), :Hd] + Y[row(dst_p), Hd:]) . Wfin + bfin         (models/predictors.py:16-19)
+__global__ void head_gather_kernel(const float* __restrict__ Y, int Hd, const int64_t* __restrict__ src,
+                                   const int64_t* __restrict__ dst, const int64_t* __restrict__ map, int P,
+                                   const float* __restrict__ Wfin, const float* __restrict__ bfin,
+                                   float* __restrict__ OUT) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int p = warp; p < P; p += nw) {
+        int64_t rs = src[p], rd = dst[p];
+        if (map) { rs = map[rs]; rd = map[rd]; }
+        const float* ys = Y + (size_t)rs * 2 * Hd;
+        const float* yd = Y + (size_t)rd * 2 * Hd + Hd;
+        float s = 0.f;
+        for (int h = lane; h < Hd; h += 32) s = fmaf(fmaxf(ys[h] + yd[h], 0.f), __ldg(Wfin + h), s);
+        s = warp_sum(s);
+        if (lane == 0) OUT[p] = s + __ldg(bfin);
+    }
+}
+extern "C" int ctan_head_gather(const float* Y, int Hd, const int64_t* src, const int64_t* dst, const int64_t* map,
+                                int P, const float* Wfin, const float* bfin, float* OUT, cudaStream_t stream) {
+    if (P <= 0) return 0;
+    head_gather_kernel<<<ctan_grid((long long)P * 32, 256), 256, 0, stream>>>(Y, Hd, src, dst, map, P, Wfin, bfin, OUT);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}

@@ -298,6 +298,125 @@ __global__ void lk_fill_kernel(const int64_t* __restrict__ nbr, const int64_t* _
     }
 }
 
+// Two-level variant of lk_scan_kernel for large id spaces: SCAN_CTAS CTAs each own a contiguous range of bitmap
+// words.  Pass 1 writes per-CTA (nodes, edges, centres) totals; pass 2 turns them into each CTA's base offsets
+// (a 128-entry serial prefix, redone by every CTA) and emits n_id / assoc / rowptr exactly like the 1-CTA kernel.
+constexpr int SCAN_CTAS = 128;
+
+__device__ __forceinline__ void scan_count_words(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ cbitmap,
+                                                 const int32_t* __restrict__ deg, int w0, int w1, int& nn, int& ne,
+                                                 int& nc) {
+    nn = ne = nc = 0;
+    for (int w = w0; w < w1; ++w) {
+        const uint32_t b = bitmap[w];
+        if (!b) continue;
+        nn += __popc(b);
+        uint32_t c = cbitmap[w];
+        nc += __popc(c);
+        while (c) {
+            const int bit = __ffs(c) - 1;
+            c &= c - 1;
+            ne += deg[(long long)w * 32 + bit];
+        }
+    }
+}
+
+// exclusive block scan of (a,b) over 256 threads; returns this thread's exclusive prefixes and the block totals
+__device__ __forceinline__ void block_scan2(int a, int b, int& ea, int& eb, int& ta, int& tb, int* s_a, int* s_b) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int ia = a, ib = b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int x = __shfl_up_sync(0xffffffffu, ia, o), y = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o) { ia += x; ib += y; }
+    }
+    if (lane == 31) { s_a[wid] = ia; s_b[wid] = ib; }
+    __syncthreads();
+    int pa = 0, pb = 0, sa = 0, sb = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+        if (i < wid) { pa += s_a[i]; pb += s_b[i]; }
+        sa += s_a[i]; sb += s_b[i];
+    }
+    ea = ia - a + pa; eb = ib - b + pb; ta = sa; tb = sb;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+lk_scan_partial_kernel(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ cbitmap,
+                       const int32_t* __restrict__ deg, int n_words, int* __restrict__ partials) {
+    __shared__ int s_a[8], s_b[8], s_c[8];
+    const int chunk = (n_words + SCAN_CTAS - 1) / SCAN_CTAS;
+    const int c0 = min(n_words, (int)blockIdx.x * chunk), c1 = min(n_words, c0 + chunk);
+    const int sub = (chunk + 255) / 256;
+    const int w0 = min(c1, c0 + (int)threadIdx.x * sub), w1 = min(c1, w0 + sub);
+    int nn, ne, nc;
+    scan_count_words(bitmap, cbitmap, deg, w0, w1, nn, ne, nc);
+    nn = warp_sum_i(nn); ne = warp_sum_i(ne); nc = warp_sum_i(nc);
+    if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = nn; s_b[threadIdx.x >> 5] = ne; s_c[threadIdx.x >> 5] = nc; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int a = 0, b = 0, c = 0;
+        for (int i = 0; i < 8; ++i) { a += s_a[i]; b += s_b[i]; c += s_c[i]; }
+        partials[blockIdx.x * 3 + 0] = a; partials[blockIdx.x * 3 + 1] = b; partials[blockIdx.x * 3 + 2] = c;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+lk_scan_emit_kernel(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ cbitmap,
+                    const int32_t* __restrict__ deg, int n_words, const int* __restrict__ partials,
+                    int64_t* __restrict__ n_id_out, int64_t* __restrict__ assoc, int32_t* __restrict__ rowptr,
+                    int32_t* __restrict__ counts, int n_cap, int e_cap, int* __restrict__ frontier_cnt,
+                    int n_frontier_cnt) {
+    __shared__ int s_a[8], s_b[8], s_base[5];
+    if (threadIdx.x == 0) {
+        int bn = 0, be = 0, tn = 0, te = 0, tcn = 0;
+        for (int i = 0; i < SCAN_CTAS; ++i) {
+            if (i < (int)blockIdx.x) { bn += partials[i * 3]; be += partials[i * 3 + 1]; }
+            tn += partials[i * 3]; te += partials[i * 3 + 1]; tcn += partials[i * 3 + 2];
+        }
+        s_base[0] = bn; s_base[1] = be; s_base[2] = tn; s_base[3] = te; s_base[4] = tcn;
+    }
+    __syncthreads();
+    const int tot_n = s_base[2], tot_e = s_base[3];
+    const bool fits = (tot_n <= n_cap) && (tot_e <= e_cap);
+    const int chunk = (n_words + SCAN_CTAS - 1) / SCAN_CTAS;
+    const int c0 = min(n_words, (int)blockIdx.x * chunk), c1 = min(n_words, c0 + chunk);
+    const int sub = (chunk + 255) / 256;
+    const int w0 = min(c1, c0 + (int)threadIdx.x * sub), w1 = min(c1, w0 + sub);
+    int nn, ne, nc;
+    scan_count_words(bitmap, cbitmap, deg, w0, w1, nn, ne, nc);
+    int en, ee, tn2, te2;
+    block_scan2(nn, ne, en, ee, tn2, te2, s_a, s_b);
+    int base_n = s_base[0] + en, base_e = s_base[1] + ee;
+    if (fits) {
+        for (int w = w0; w < w1; ++w) {
+            uint32_t b = bitmap[w];
+            if (!b) continue;
+            const uint32_t c = cbitmap[w];
+            while (b) {
+                const int bit = __ffs(b) - 1;
+                b &= b - 1;
+                const long long node = (long long)w * 32 + bit;
+                n_id_out[base_n] = node;
+                assoc[node] = base_n;
+                rowptr[base_n] = base_e;
+                if ((c >> bit) & 1u) base_e += deg[node];
+                ++base_n;
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (fits) rowptr[tot_n] = tot_e;
+        counts[0] = fits ? tot_n : 0;
+        counts[1] = fits ? tot_e : 0;
+        counts[2] = s_base[4];
+        if (!fits) counts[3] = 2;
+        counts[4] = tot_n;
+        counts[5] = tot_e;
+        for (int i = 0; i < n_frontier_cnt; ++i) frontier_cnt[i] = 0;
+    }
+}
+
 static inline int lanes_per_item(int S) {
     int l = 1;
     while (l < S && l < 32) l <<= 1;
@@ -333,8 +452,20 @@ extern "C" int ctan_nbr_lookup(const int64_t* nbr, const int32_t* deg, int64_t n
         cur_list = nxt; cur_cnt_dev = nxt_cnt; cur_n = 0;
     }
     const int n_words = (int)((num_nodes + 31) / 32);
-    lk_scan_kernel<<<1, 1024, 0, stream>>>(bitmap, cbitmap, deg, n_words, n_id_out, assoc, rowptr, counts, n_cap,
-                                           e_cap, frontier_cnt, num_hops > 1 ? num_hops - 1 : 0);
+    // the frontier lists are dead once the last hop has run: their storage doubles as the scan's partial sums
+    int* scan_partials = (frontier && (size_t)frontier_cap * sizeof(int64_t) >= SCAN_CTAS * 3 * sizeof(int))
+                             ? reinterpret_cast<int*>(frontier) : nullptr;
+    if (n_words <= 4096 || !scan_partials) {
+        lk_scan_kernel<<<1, 1024, 0, stream>>>(bitmap, cbitmap, deg, n_words, n_id_out, assoc, rowptr, counts, n_cap,
+                                               e_cap, frontier_cnt, num_hops > 1 ? num_hops - 1 : 0);
+    } else {
+        // large id spaces (e.g. 994k nodes = 31k bitmap words): two-level scan over SCAN_CTAS CTAs
+        lk_scan_partial_kernel<<<SCAN_CTAS, 256, 0, stream>>>(bitmap, cbitmap, deg, n_words, scan_partials);
+        CTAN_CHECK_LAUNCH();
+        lk_scan_emit_kernel<<<SCAN_CTAS, 256, 0, stream>>>(bitmap, cbitmap, deg, n_words, scan_partials, n_id_out, assoc,
+                                                         rowptr, counts, n_cap, e_cap, frontier_cnt,
+                                                         num_hops > 1 ? num_hops - 1 : 0);
+    }
     CTAN_CHECK_LAUNCH();
     return 0;
 }

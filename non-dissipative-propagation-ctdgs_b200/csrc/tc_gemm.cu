@@ -380,3 +380,47 @@ extern "C" int ctan_dx_tc(const float* DQKVA, const float* G, int N, const int* 
     CTAN_CHECK_LAUNCH();
     return 0;
 }
+
+// TF32 split of a row-major [rows, cols] block read with leading dimension ld: packs (and 16-byte aligns) weights
+// such as enc_x.weight[:, :D] (ld = D+Fn) or the readout's lin_src/lin_dst so that TMA can stage them.
+__global__ void pack_split_kernel(const float* __restrict__ src, int rows, int cols, int ld, float* __restrict__ hi,
+                                  float* __restrict__ lo) {
+    const int n = rows * cols;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float x = src[(size_t)(i / cols) * ld + (i % cols)];
+        const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+        hi[i] = h;
+        lo[i] = x - h;
+    }
+}
+extern "C" int ctan_pack_split(const float* src, int rows, int cols, int ld, float* hi, float* lo, cudaStream_t stream) {
+    if (rows <= 0 || cols <= 0) return CTAN_ERR_BAD_ARG;
+    pack_split_kernel<<<ctan_grid((long long)rows * cols, 256), 256, 0, stream>>>(src, rows, cols, ld, hi, lo);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+// Generic tensor-core linear layer: C[M,Nout] = A[M,K] B^T + bias_seg[n/seg][n%seg] + res[m][n]  (3xTF32 / TF32).
+// A row-major [M(max),K] dense, B = packed split weights [Nout,K].  K % 32 == 0, Nout % 128 == 0, seg % 16 == 0.
+extern "C" int ctan_gemm_tc(const float* A, int M, const int* M_dev, int K, const float* Bhi, const float* Blo, int Nout,
+                            const float* b0, const float* b1, const float* b2, const float* b3, int seg,
+                            const float* res, int ldr, float* C, int mode, cudaStream_t stream) {
+    if (M <= 0) return 0;
+    if (K % tc::BKF != 0 || Nout % tc::BN != 0 || seg <= 0 || seg % 16 != 0 ||
+        (((uintptr_t)A | (uintptr_t)Bhi | (uintptr_t)Blo | (uintptr_t)C) & 15))
+        return CTAN_ERR_UNSUPPORTED;
+    CUtensorMap tmA, tmBhi, tmBlo;
+    int rc = tc::make_map(&tmA, A, M, K);
+    if (!rc) rc = tc::make_map(&tmBhi, Bhi, Nout, K);
+    if (!rc) rc = tc::make_map(&tmBlo, Blo, Nout, K);
+    if (rc) return rc;
+    cudaError_t e = cudaFuncSetAttribute(tc::qkva_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    const uintptr_t ball = (uintptr_t)b0 | (uintptr_t)b1 | (uintptr_t)b2 | (uintptr_t)b3 | (uintptr_t)res |
+                           (uintptr_t)(ldr * 4);
+    tc::Bias4 epi{{b0, b1, b2, b3}, seg, (ball & 15) == 0 ? 1 : 0, res, ldr};
+    dim3 grid(Nout / tc::BN, tc::bounded_rows(M, M_dev, Nout / tc::BN));
+    tc::qkva_tc_kernel<<<grid, 192, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, epi, C, Nout, M, M_dev, Nout, K, mode);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}

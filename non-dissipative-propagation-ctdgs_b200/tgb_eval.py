@@ -108,6 +108,15 @@ class TGBEvalEngine:
         w["EP"] = torch.zeros((E, D), **f32)
         w["A"] = torch.zeros((D, D), **f32)
         self.use_tc = _lib.use_tensor_cores(D)
+        # tensor-core enc_x (dense gathered rows + packed weights) and node-projection readout
+        self.use_tc_enc = self.use_tc and D % 128 == 0
+        self.use_tc_ro = self.use_tc and (2 * self.Hd) % 128 == 0 and self.Hd % 16 == 0
+        if self.use_tc_enc:
+            w["zmain"], w["ztail"] = torch.zeros((N, D), **f32), torch.zeros((N, D), **f32)
+            w["Wenc_hi"], w["Wenc_lo"] = torch.zeros((D, D), **f32), torch.zeros((D, D), **f32)
+        if self.use_tc_ro:
+            w["Wro_hi"], w["Wro_lo"] = torch.zeros((2 * self.Hd, D), **f32), torch.zeros((2 * self.Hd, D), **f32)
+            w["Y"] = torch.zeros((N, 2 * self.Hd), **f32)
         w["Wcat_hi"], w["Wcat_lo"] = torch.zeros((4 * D, D), **f32), torch.zeros((4 * D, D), **f32)
         w["QKVA"] = torch.zeros((N, 4 * D), **f32)
         w["Z"] = torch.zeros((N, D), **f32) if self.final_tanh else None
@@ -169,8 +178,19 @@ class TGBEvalEngine:
                 else:
                     call("ctan_antisym_prep", ptr(a.W), float(a.gamma), D, ptr(w["A"]))
                 w["H"].zero_()
-            call("ctan_enc_fwd", ptr(mem), D, xf, Fn, ptr(w["n_id"]), None, N, Nd, ptr(g.enc_x.weight),
-                 ptr(g.enc_x.bias), ptr(w["X"][0]))
+                if self.use_tc_ro:       # [lin_src; lin_dst] packed + split for the node-projection readout
+                    call("ctan_pack_split", ptr(r.lin_src.weight), Hd, D, D, ptr(w["Wro_hi"]), ptr(w["Wro_lo"]))
+                    call("ctan_pack_split", ptr(r.lin_dst.weight), Hd, D, D, ptr(w["Wro_hi"]) + 4 * Hd * D,
+                         ptr(w["Wro_lo"]) + 4 * Hd * D)
+            if self.use_tc_enc:          # gather -> dense rows; enc_x on the tensor cores; node-feature columns as residual
+                call("ctan_pack_split", ptr(g.enc_x.weight), D, D, D + Fn, ptr(w["Wenc_hi"]), ptr(w["Wenc_lo"]))
+                call("ctan_enc_prep", ptr(mem), D, xf, Fn, ptr(w["n_id"]), N, Nd, ptr(g.enc_x.weight), ptr(w["zmain"]),
+                     ptr(w["ztail"]))
+                call("ctan_gemm_tc", ptr(w["zmain"]), N, Nd, D, ptr(w["Wenc_hi"]), ptr(w["Wenc_lo"]), D,
+                     ptr(g.enc_x.bias), None, None, None, D, ptr(w["ztail"]), D, ptr(w["X"][0]), _lib.TC_MODE)
+            else:
+                call("ctan_enc_fwd", ptr(mem), D, xf, Fn, ptr(w["n_id"]), None, N, Nd, ptr(g.enc_x.weight),
+                     ptr(g.enc_x.bias), ptr(w["X"][0]))
             torch.cuda.current_stream().wait_stream(self._side)
             for k in range(K):
                 xi, xo = w["X"][k & 1], w["X"][(k + 1) & 1]
@@ -186,7 +206,14 @@ class TGBEvalEngine:
                 call("ctan_edge_fwd", ptr(w["QKVA"]), ptr(w["EP"]), ptr(w["rowptr"]), ptr(w["esrc"]), N, Nd, D,
                      ptr(xi), eps, ptr(xo), None, None, ptr(w["Z"]) if (last and self.final_tanh) else None)
             z = w["Z"] if self.final_tanh else w["X"][K & 1]
-            call("ctan_readout_fwd", ptr(z), D, ptr(w["pair_src"]), ptr(w["pair_dst"]), ptr(ld._assoc), Q * self.L,
+            if self.use_tc_ro:
+                # project every NODE once (tensor cores), then a scored pair only gathers two rows
+                call("ctan_gemm_tc", ptr(z), N, Nd, D, ptr(w["Wro_hi"]), ptr(w["Wro_lo"]), 2 * Hd, ptr(r.lin_src.bias),
+                     ptr(r.lin_dst.bias), None, None, Hd, None, 0, ptr(w["Y"]), _lib.TC_MODE)
+                call("ctan_head_gather", ptr(w["Y"]), Hd, ptr(w["pair_src"]), ptr(w["pair_dst"]), ptr(ld._assoc),
+                     Q * self.L, ptr(r.lin_final.weight), ptr(r.lin_final.bias), ptr(w["OUT"]))
+            else:
+              call("ctan_readout_fwd", ptr(z), D, ptr(w["pair_src"]), ptr(w["pair_dst"]), ptr(ld._assoc), Q * self.L,
                  None, Hd, O, ptr(r.lin_src.weight), ptr(r.lin_src.bias), ptr(r.lin_dst.weight), ptr(r.lin_dst.bias),
                  ptr(r.lin_final.weight), ptr(r.lin_final.bias), ptr(w["H"]), ptr(w["OUT"]), 0)   # no split-K: scores must not depend on atomic order
             call("ctan_pack_eval", ptr(w["OUT"]), ptr(z), ptr(ld._assoc), ptr(w["pair_src"]), ptr(w["pair_dst"]), Q,

@@ -40,6 +40,10 @@ REF = {
     "ctan_head_loss": "predictor head + BCEWithLogitsLoss + their gradients -- models/predictors.py:18-19, train_link.py:269-270,279",
     "ctan_probe": "(profiling aid, no reference counterpart)",
     "ctan_wcat_prep": "AntiSymmetricConv W - W^T - gamma*I, packed with the q/k/v weights and split for 3xTF32 -- PyG 2.3.1",
+    "ctan_pack_split": "(weight packing + TF32 split for the tensor-core path; no reference counterpart)",
+    "ctan_gemm_tc": "torch.nn.Linear on tcgen05 tensor cores (enc_x: models/gnn_layers.py:96; readout lin_src/lin_dst: models/predictors.py:16-17)",
+    "ctan_enc_prep": "SimpleMemory.forward gather + node-feature columns of enc_x -- models/memory_layers.py:155-156, models/gnn_layers.py:96",
+    "ctan_head_gather": "TGBLinkPredictor.forward on pre-projected node rows -- models/predictors.py:16-19",
     "ctan_dx_tc": "gradient of the projections w.r.t. the node state (autograd in the reference) on tcgen05",
     "ctan_qkva_fwd_tc": "TransformerConv lin_query/lin_key/lin_value + x @ A^T + bias on tcgen05 tensor cores -- PyG 2.3.1 (SURVEY.md App. A.5)",
 }

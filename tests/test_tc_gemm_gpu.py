@@ -89,3 +89,25 @@ def test_dx_tc_matches_fp32(N, D):
     scale = float(ref.abs().max())
     assert float((out_fp.double() - ref).abs().max()) / scale < 2e-6
     assert float((out_tc.double() - ref).abs().max()) / scale < 1e-5      # K = 4D up to 1024 terms
+
+
+def test_qkva_tc_persistent_row_loop():
+    """Device-sized N far below a large bound: the launch is capped and each CTA walks several row tiles
+    (smem ring phases and the TMEM accumulator hand-over run across tiles)."""
+    from ctan_b200._lib import call, ptr
+    dev = torch.device("cuda:0")
+    D, cap, n_true = 128, 60000, 41000
+    X = torch.randn(cap, D, device=dev)
+    W = [torch.randn(D, D, device=dev) / 11 for _ in range(4)]
+    b = [torch.randn(D, device=dev) for _ in range(4)]
+    hi, lo = torch.empty(4 * D, D, device=dev), torch.empty(4 * D, D, device=dev)
+    call("ctan_wcat_prep", ptr(W[0]), ptr(W[1]), ptr(W[2]), ptr(W[3]), 0.1, D, ptr(hi), ptr(lo), None, None, None)
+    out = torch.full((cap, 4 * D), 7.0, device=dev)
+    n_dev = torch.tensor([n_true], dtype=torch.int32, device=dev)
+    call("ctan_qkva_fwd_tc", ptr(X), cap, ptr(n_dev), D, ptr(hi), ptr(lo), ptr(b[0]), ptr(b[1]), ptr(b[2]), ptr(b[3]),
+         ptr(out), 0)
+    torch.cuda.synchronize()
+    ref = X[:n_true].double() @ (hi + lo).double().t() + torch.cat(b).double()
+    err = float((out[:n_true].double() - ref).abs().max()) / float(ref.abs().max())
+    assert err < 5e-6, err
+    assert bool((out[n_true:] == 7.0).all())

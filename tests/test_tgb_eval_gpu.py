@@ -12,14 +12,14 @@ def _neg_table(st, n_neg, seed=5):
     return torch.randint(st["min_dst"], st["max_dst"] + 1, (st["src"].numel(), n_neg), generator=g)
 
 
-@pytest.mark.parametrize("K,final_act,n_neg", [(1, None, 20), (2, "tanh", 7)])
-def test_eval_matches_per_query_oracle(small_stream, K, final_act, n_neg):
+@pytest.mark.parametrize("K,final_act,n_neg,D", [(1, None, 20, 32), (2, "tanh", 7, 32), (1, "tanh", 20, 128)])
+def test_eval_matches_per_query_oracle(small_stream, K, final_act, n_neg, D):
     from ctan_b200.models import CTAN_tgb, LastNeighborLoader
     from ctan_b200.tgb_eval import TGBEvalEngine
     from oracle import ctan_oracle as O
     st = small_stream
     dev = torch.device("cuda:0")
-    B, S, D = 50, 8, 32
+    B, S = 50, 8           # D=128 exercises the tcgen05 enc_x / projection / node-projection readout paths
     neg = _neg_table(st, n_neg)
     neg[3, :5] = st["dst"][3]            # negatives equal to the positive -> rank ties
     kw = dict(num_nodes=st["num_nodes"], edge_dim=st["msg"].size(1), memory_dim=D, time_dim=8, node_dim=1,
