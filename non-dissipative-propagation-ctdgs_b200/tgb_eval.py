@@ -35,6 +35,9 @@ def exchange_rows(send: torch.Tensor, recv: torch.Tensor, rows: torch.Tensor, B:
     by one query) into batch order `rows` [B,row].  Works on any backend (NCCL on GPU, gloo in CPU tests)."""
     import torch.distributed as dist
     qmax = send.size(0)
+    if B % world == 0:                 # equal shards: the gathered buffer already is the batch order
+        dist.all_gather_into_tensor(rows, send, group=group)
+        return rows
     dist.all_gather_into_tensor(recv, send, group=group)
     for rk in range(world):
         a0, a1 = shard_range(B, rk, world)
