@@ -326,14 +326,6 @@ class StepEngine:
                  ptr(w["TH"][k]), ptr(w["ALPHA"][k]), eps, ptr(w["DQKVA"]), ptr(w["dEP"]), int(k != K - 1),
                  ptr(w["DS"]))
             qb = (ptr(w["DQKVA"]), ptr(w["X"][k]), ptr(g), N, Nd, D, Wq, Wk, Wv, ptr(w["A"]))
-            gn = self._DX[k]
-            if self.use_tc_dx:   # dX = G + DQKVA Wcat on tcgen05 (plain stores)
-                call("ctan_dx_tc", ptr(w["DQKVA"]), ptr(g), N, Nd, D, ptr(w["WcatT_hi"]), ptr(w["WcatT_lo"]), ptr(gn),
-                     _lib.TC_MODE)
-            else:
-                call("ctan_qkva_bwd", *qb, ptr(gn), None, None, None, None, None, None, None, None, self.n_typ)
-            # weight gradients are forked AFTER the activation gradient has been issued: they only feed Adam, and
-            # launched first they would occupy the SMs the critical-path contraction needs
             with self._fork(0):                              # side 0: weight gradients of this iteration
                 call("ctan_qkva_bwd", *qb, None, gWq, gWk, gWv, ptr(w["dA"]), gbq, gbk, gbv, gb, self.n_typ)
                 if k == 0:
@@ -343,6 +335,12 @@ class StepEngine:
                     call("ctan_eproj_bwd", ptr(w["dEP"]), ptr(self.msg), Fe, ptr(w["eid"]), ptr(w["rel"]), tw, tb, T,
                          We, E, Ed, D, gWe, ptr(w["dTenc"]), self.e_typ)
                     call("ctan_tenc_bwd", ptr(w["dTenc"]), ptr(w["rel"]), tw, tb, E, Ed, T, gtw, gtb)
+            gn = self._DX[k]
+            if self.use_tc_dx:   # dX = G + DQKVA Wcat on tcgen05 (plain stores)
+                call("ctan_dx_tc", ptr(w["DQKVA"]), ptr(g), N, Nd, D, ptr(w["WcatT_hi"]), ptr(w["WcatT_lo"]), ptr(gn),
+                     _lib.TC_MODE)
+            else:
+                call("ctan_qkva_bwd", *qb, ptr(gn), None, None, None, None, None, None, None, None, self.n_typ)
             g = gn
         self._join(1)                                        # z0 is complete (and the state write-back done)
         call("ctan_enc_bwd", ptr(g), ptr(w["z0"]), N, Nd, D, Fn, gWenc, gbenc, self.n_typ)
