@@ -119,7 +119,10 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_holder;
-    const int n_kb = K / BKF;
+    // split-K over gridDim.z (atomic epilogue): thin problems (few row tiles, long K) get more CTAs
+    const int kb_per = (K / BKF + (int)gridDim.z - 1) / (int)gridDim.z;
+    const int kb0 = (int)blockIdx.z * kb_per;
+    const int n_kb = min(K / BKF - kb0, kb_per);
     auto stage_ptr = [&](int s, int which) { return smem + s * STAGE_BYTES + which * TILE_BYTES; };
 
     if (warp == 0) {
@@ -131,9 +134,9 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int s = it % STAGES;
                 if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);
                 mbar_expect_tx(&raw[s], (mode == 0 ? 3 : 2) * TILE_BYTES);
-                tma_load_2d(stage_ptr(s, 0), &tmA, &raw[s], kb * BKF, m0);
-                tma_load_2d(stage_ptr(s, 2), &tmBhi, &raw[s], kb * BKF, n0);
-                if (mode == 0) tma_load_2d(stage_ptr(s, 3), &tmBlo, &raw[s], kb * BKF, n0);
+                tma_load_2d(stage_ptr(s, 0), &tmA, &raw[s], (kb0 + kb) * BKF, m0);
+                tma_load_2d(stage_ptr(s, 2), &tmBhi, &raw[s], (kb0 + kb) * BKF, n0);
+                if (mode == 0) tma_load_2d(stage_ptr(s, 3), &tmBlo, &raw[s], (kb0 + kb) * BKF, n0);
             }
         }
     } else if (warp == 1) {
@@ -212,10 +215,18 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int n = n0 + c;                                       // 16-column chunk: inside one bias segment (D % 32 == 0)
             if (row < M && n < N) {
                 const int seg = n / bias.D;
-                const float* bp = seg == 0 ? bias.p[0] : (seg == 1 ? bias.p[1] : (seg == 2 ? bias.p[2] : bias.p[3]));
+                const bool first = blockIdx.z == 0;                     // bias / residual are added by one split only
+                const float* bp = !first ? nullptr
+                                         : (seg == 0 ? bias.p[0] : (seg == 1 ? bias.p[1] : (seg == 2 ? bias.p[2] : bias.p[3])));
                 float* out = C + (size_t)row * ldc + n;
-                const float* rp = bias.res ? bias.res + (size_t)row * bias.ldr + n : nullptr;
-                if (bias.vec && n + 15 < N) {
+                const float* rp = (first && bias.res) ? bias.res + (size_t)row * bias.ldr + n : nullptr;
+                if (gridDim.z > 1) {                                    // split-K: accumulate into the zeroed output
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (n + j < N)
+                            atomicAdd(out + j, __uint_as_float(v[j]) + (bp ? __ldg(bp + (n - seg * bias.D) + j) : 0.f) +
+                                                   (rp ? rp[j] : 0.f));
+                } else if (bias.vec && n + 15 < N) {
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
                         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -363,7 +374,7 @@ extern "C" int ctan_qkva_fwd_tc(const float* X, int N, const int* N_dev, int D, 
 // Wcat^T [D,4D] prepared by ctan_wcat_prep.  Plain stores: no atomics, dXin need not be zeroed.
 // Requirements: D % 128 == 0 (one or more 128-wide output tiles); else CTAN_ERR_UNSUPPORTED.
 extern "C" int ctan_dx_tc(const float* DQKVA, const float* G, int N, const int* N_dev, int D, const float* WcatT_hi,
-                          const float* WcatT_lo, float* dXin, int mode, cudaStream_t stream) {
+                          const float* WcatT_lo, float* dXin, int mode, int n_split, cudaStream_t stream) {
     if (N <= 0) return 0;
     if (D % tc::BN != 0 || (((uintptr_t)DQKVA | (uintptr_t)WcatT_hi | (uintptr_t)WcatT_lo | (uintptr_t)G | (uintptr_t)dXin) & 15))
         return CTAN_ERR_UNSUPPORTED;
@@ -375,7 +386,11 @@ extern "C" int ctan_dx_tc(const float* DQKVA, const float* G, int N, const int* 
     cudaError_t e = cudaFuncSetAttribute(tc::qkva_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     tc::Bias4 epi{{nullptr, nullptr, nullptr, nullptr}, D, 1, G, D};
-    dim3 grid(D / tc::BN, tc::bounded_rows(N, N_dev, D / tc::BN));
+    // K = 4D is long and there are few row tiles: split K when the caller provides a zeroed dXin (n_split > 1)
+    const int n_kb = (4 * D) / tc::BKF;
+    int splits = n_split < 1 ? 1 : n_split;
+    while (splits > 1 && (n_kb % splits != 0)) --splits;
+    dim3 grid(D / tc::BN, tc::bounded_rows(N, N_dev, (D / tc::BN) * splits), splits);
     tc::qkva_tc_kernel<<<grid, 192, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, epi, dXin, D, N, N_dev, D, 4 * D, mode);
     CTAN_CHECK_LAUNCH();
     return 0;
