@@ -338,7 +338,7 @@ class StepEngine:
             gn = self._DX[k]
             if self.use_tc_dx:   # dX = G + DQKVA Wcat on tcgen05 (plain stores)
                 call("ctan_dx_tc", ptr(w["DQKVA"]), ptr(g), N, Nd, D, ptr(w["WcatT_hi"]), ptr(w["WcatT_lo"]), ptr(gn),
-                     _lib.TC_MODE)
+                     _lib.TC_MODE, 4 if self.n_typ <= 4096 else 1)     # gn lives in the zeroed buffer
             else:
                 call("ctan_qkva_bwd", *qb, ptr(gn), None, None, None, None, None, None, None, None, self.n_typ)
             g = gn

@@ -80,7 +80,9 @@ def test_dx_tc_matches_fp32(N, D):
          ptr(loT))
     assert torch.equal(hiT, hi.t().contiguous()) and torch.equal(loT, lo.t().contiguous())
     out_tc = torch.full((N, D), float("nan"), device=dev)
-    call("ctan_dx_tc", ptr(DQ), ptr(G), N, None, D, ptr(hiT), ptr(loT), ptr(out_tc), 0)
+    call("ctan_dx_tc", ptr(DQ), ptr(G), N, None, D, ptr(hiT), ptr(loT), ptr(out_tc), 0, 1)
+    out_sp = torch.zeros((N, D), device=dev)                      # split-K variant accumulates into zeros
+    call("ctan_dx_tc", ptr(DQ), ptr(G), N, None, D, ptr(hiT), ptr(loT), ptr(out_sp), 0, 4)
     out_fp = torch.zeros((N, D), device=dev)
     call("ctan_qkva_bwd", ptr(DQ), ptr(DQ), ptr(G), N, None, D, ptr(Ws[0]), ptr(Ws[1]), ptr(Ws[2]), ptr(A), ptr(out_fp),
          None, None, None, None, None, None, None, None, 0)
@@ -89,6 +91,7 @@ def test_dx_tc_matches_fp32(N, D):
     scale = float(ref.abs().max())
     assert float((out_fp.double() - ref).abs().max()) / scale < 2e-6
     assert float((out_tc.double() - ref).abs().max()) / scale < 1e-5      # K = 4D up to 1024 terms
+    assert float((out_sp.double() - ref).abs().max()) / scale < 1e-5
 
 
 def test_qkva_tc_persistent_row_loop():
