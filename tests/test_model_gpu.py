@@ -135,3 +135,111 @@ def test_state_dict_roundtrip_and_cpu_guard():
     m2.load_state_dict(sd)
     with pytest.raises(CtanLibraryError):           # no silent CPU fallback
         m.reset_memory()
+
+
+def test_multiclass_head_pascal_config():
+    """C4 (Temporal Pascal-VOC): no negatives, readout_out=21, CrossEntropyLoss (train_link.py:297-343 with
+    train_neg_sampler=None; conf_pascal.py): logits, loss and every gradient against the oracle."""
+    from ctan_b200.models import CTAN, LastNeighborLoader
+    from oracle import ctan_oracle as O
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(4)
+    num_nodes, n, B, D, Fn = 400, 1024, 256, 74, 14
+    src = torch.randint(0, num_nodes, (n,), generator=g)
+    dst = torch.randint(0, num_nodes, (n,), generator=g)
+    t = torch.sort(torch.randint(0, 5000, (n,), generator=g)).values
+    msg = torch.randn(n, 1, generator=g)
+    x = torch.randn(num_nodes, Fn, generator=g)
+    y = torch.randint(0, 21, (n,), generator=g)
+    kw = dict(num_nodes=num_nodes, edge_dim=1, memory_dim=D, time_dim=1, node_dim=Fn, num_iters=3, epsilon=0.1,
+              gamma=0.1, readout_hidden=D // 2, readout_out=21, mean_delta_t=30.0, std_delta_t=50.0)
+    torch.manual_seed(1)
+    om = O.OracleCTAN(**kw)
+    torch.manual_seed(1)
+    mm = CTAN(**kw).to(dev)
+    lr_, lm = O.TorchNeighborLoader(num_nodes, 5), LastNeighborLoader(num_nodes, 5, device=dev)
+    h_r = torch.zeros(num_nodes, dtype=torch.long)
+    h_m = h_r.to(dev)
+    crit = torch.nn.CrossEntropyLoss()
+    for it in range(4):
+        lo, hi = it * B, (it + 1) * B
+        outs = []
+        for model, loader, helper, d in ((om, lr_, h_r, "cpu"), (mm, lm, h_m, dev)):
+            s, dd, tt, m_, xx, yy = (v[lo:hi].to(d) if v.size(0) == n else v.to(d) for v in (src, dst, t, msg, x, y))
+            model.zero_grad()
+            n_id = torch.cat([s, dd]).unique()
+            for _ in range(model.num_gnn_layers):
+                n_id, ei, eid = loader(n_id)
+            helper[n_id] = torch.arange(n_id.numel(), device=d)
+            pos, neg, se, de = model(O.Batch(src=s, dst=dd, x=xx), n_id, msg.to(d)[eid], t.to(d)[eid], ei, helper)
+            assert neg is None and pos.shape == (B, 21)
+            loss = crit(pos, yy)
+            model.update(s, dd, tt, m_, se, de)
+            loader.insert(s, dd)
+            loss.backward()
+            outs.append((pos.detach().cpu(), float(loss), {k: p.grad.detach().cpu() for k, p in model.named_parameters() if p.grad is not None}))
+        (p_r, l_r, g_r), (p_m, l_m, g_m) = outs
+        assert _rel_err(p_m, p_r) < 5 * RTOL, it
+        assert abs(l_m - l_r) <= RTOL * abs(l_r) + 1e-6
+        scale = max(float(v.abs().max()) for v in g_r.values())
+        assert set(g_r) == set(g_m)
+        for k in g_r:
+            assert float((g_m[k] - g_r[k]).abs().max()) < 5e-4 * float(g_r[k].abs().max()) + 1e-6 * scale, (k, it)
+
+
+def test_sequence_classification_loop():
+    """C1 (Temporal Path Graph, train_sequence.py:16-65): one event per step, x given as [1,num_nodes,F],
+    K lookups with `e_id % seq_len`, only the last prediction enters the loss."""
+    from ctan_b200.models import CTAN, LastNeighborLoader
+    from oracle import ctan_oracle as O
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(9)
+    L, n_seq, F, D, K = 7, 6, 2, 26, 3
+    num_nodes = L * n_seq
+    kw = dict(num_nodes=num_nodes, edge_dim=F, memory_dim=D, time_dim=1, node_dim=F, num_iters=K, epsilon=0.5,
+              gamma=0.1, readout_hidden=D // 2, readout_out=1, mean_delta_t=1.67, std_delta_t=1.49, final_act="tanh")
+    torch.manual_seed(2)
+    om = O.OracleCTAN(**kw)
+    torch.manual_seed(2)
+    mm = CTAN(**kw).to(dev)
+    x = (torch.rand(1, num_nodes, F, generator=g) * 2 - 1)
+    res = []
+    for model, d, Loader in ((om, "cpu", O.TorchNeighborLoader), (mm, dev, LastNeighborLoader)):
+        loader = Loader(num_nodes, 5, device=d) if d != "cpu" else Loader(num_nodes, 5)
+        helper = torch.zeros(num_nodes, dtype=torch.long, device=d)
+        model.reset_memory()
+        preds = []
+        gg = torch.Generator().manual_seed(10)
+        for i in range(n_seq):
+            msg = (torch.rand(L - 1, F, generator=gg) * 2 - 1).to(d)
+            tt = torch.arange(L - 1).to(d)
+            srcs = torch.arange(i * L, i * L + L - 1).to(d)
+            dsts = srcs + 1
+            last = None
+            for e in range(L - 1):
+                s, dd = srcs[e:e + 1], dsts[e:e + 1]
+                n_id = torch.cat([s, dd]).unique()
+                ei = torch.empty((2, 0), dtype=torch.long, device=d)
+                eid = torch.empty(0, dtype=torch.long, device=d)
+                for _ in range(model.num_gnn_layers):
+                    n_id, ei, eid = loader(n_id)
+                    eid = eid % msg.shape[0]
+                helper[n_id] = torch.arange(n_id.numel(), device=d)
+                y_pred, _, se, de = model(O.Batch(src=s, dst=dd, x=x.to(d)), n_id, msg[eid], tt[eid], ei, helper)
+                last = y_pred.squeeze(0)
+                model.update(s, dd, tt[e:e + 1], msg[e:e + 1], se, de)
+                loader.insert(s, dd)
+            preds.append(last)
+        pred = torch.cat(preds, -1)
+        loss = torch.nn.BCEWithLogitsLoss()(pred, (torch.arange(n_seq) % 2).float().to(d))
+        model.zero_grad()
+        loss.backward()
+        res.append((pred.detach().cpu(), float(loss), {k: p.grad.detach().cpu() for k, p in model.named_parameters() if p.grad is not None},
+                    model.memory.memory.detach().cpu()))
+    (p_r, l_r, g_r, m_r), (p_m, l_m, g_m, m_m) = res
+    assert _rel_err(p_m, p_r) < 5 * RTOL
+    assert abs(l_m - l_r) <= RTOL * abs(l_r) + 1e-6
+    assert _rel_err(m_m, m_r) < 5 * RTOL
+    scale = max(float(v.abs().max()) for v in g_r.values())
+    for k in g_r:
+        assert float((g_m[k] - g_r[k]).abs().max()) < 5e-4 * float(g_r[k].abs().max()) + 1e-6 * scale, k
