@@ -154,12 +154,18 @@ class _ReadoutFn(torch.autograd.Function):
                  ptr(dst, torch.long), ptr(id_map, torch.long) if id_map is not None else None, P, None, Hd, O,
                  ptr(Wsrc) if Wsrc is not None else None, ptr(bsrc) if bsrc is not None else None, ptr(Wdst),
                  ptr(bdst), ptr(Wfin), ptr(bfin), ptr(H), ptr(out), int(split))
-        ctx.save_for_backward(z, src, dst, id_map, H, Wsrc, Wdst, Wfin)
+        # the caller's id map (`assoc`) is a scratch table it overwrites on the next batch, while backward may
+        # run many batches later (train_sequence.py:30-65): keep the resolved rows, not the table
+        if id_map is not None:
+            src = id_map[src] if src is not None else None
+            dst = id_map[dst]
+        ctx.save_for_backward(z, src, dst, H, Wsrc, Wdst, Wfin)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        z, src, dst, id_map, H, Wsrc, Wdst, Wfin = ctx.saved_tensors
+        z, src, dst, H, Wsrc, Wdst, Wfin = ctx.saved_tensors
+        id_map = None
         P = dst.numel()
         N, D = z.shape
         Hd, O = Wdst.size(0), Wfin.size(0)
