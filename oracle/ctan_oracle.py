@@ -292,7 +292,8 @@ class OracleCTAN(torch.nn.Module):
                  mean_delta_t=0.0, std_delta_t=1.0, init_time=0, final_act=None, predict_dst=False,
                  conv_type="TransformerConv", separable=False, tgb=False):
         super().__init__()
-        assert conv_type == "TransformerConv" and gnn_act == "tanh" and not predict_dst
+        assert conv_type == "TransformerConv" and gnn_act == "tanh"
+        self.predict_dst = predict_dst
         D, T = memory_dim, time_dim
         self.num_nodes, self.num_gnn_layers, self.tgb = num_nodes, num_iters, tgb
         self.epsilon, self.gamma = epsilon, gamma
@@ -324,7 +325,10 @@ class OracleCTAN(torch.nn.Module):
         self.gnn = gnn
         H = D if readout_hidden is None else readout_hidden
         ro = _Holder()
-        ro.lin_src, ro.lin_dst, ro.lin_final = _Lin(D, H), _Lin(D, H), _Lin(H, readout_out)
+        if predict_dst:                       # SequencePredictor (predictors.py:37-48)
+            ro.lin, ro.lin_final = _Lin(D, H), _Lin(H, readout_out)
+        else:
+            ro.lin_src, ro.lin_dst, ro.lin_final = _Lin(D, H), _Lin(D, H), _Lin(H, readout_out)
         self.readout = ro
         if tgb:                               # CTAN_tgb replaces the readout (ctdg_models.py:502)
             ro = _Holder()
@@ -366,6 +370,10 @@ class OracleCTAN(torch.nn.Module):
             n_neg = batch.n_neg
             out = readout_ref(P, z[id_mapper[src]], z[id_mapper[dst]])
             return out[:-n_neg], out[-n_neg:], z[id_mapper[src[:-n_neg]]], z[id_mapper[dst[:-n_neg]]]
+        if self.predict_dst:                  # ctdg_models.py:460-462
+            h = F.linear(z[id_mapper[dst]], P["readout.lin.weight"], P["readout.lin.bias"]).relu()
+            out = F.linear(h, P["readout.lin_final.weight"], P["readout.lin_final.bias"])
+            return out, None, z[id_mapper[src]], z[id_mapper[dst]]
         neg_dst = getattr(batch, "neg_dst", None)   # ctdg_models.py:463-470
         pos_out = readout_ref(P, z[id_mapper[src]], z[id_mapper[dst]])
         neg_out = readout_ref(P, z[id_mapper[src]], z[id_mapper[neg_dst]]) if neg_dst is not None else None
@@ -460,3 +468,76 @@ def tgb_eval_batch_ref(model: OracleCTAN, loader, helper: Tensor, stream: dict, 
     model.update(src, dst, t, msg, torch.cat(s_embs, 0), torch.cat(d_embs, 0))
     loader.insert(src, dst)
     return mrrs, torch.cat(pos_s), neg_s
+
+
+# ------------------------------------------------------------------ C1: sequence classification loops
+def sequence_pass_ref(model, loader, helper: Tensor, seqs: list, x: Tensor, meta_batches: list, optimizer=None,
+                      criterion=None, reset: bool = True):
+    """train (optimizer given; train_sequence.py:16-65) or eval (optimizer None; train_sequence.py:68-110)
+    over path-graph sequences.  `seqs[i]` = dict(src,dst,t,msg [L-1,...], y [1]); `x` [1,num_nodes,F] is shared.
+    One event per step, K lookups with `e_id % (L-1)`, only the LAST prediction of a sequence enters the
+    loss; memory / neighbour state is reset at the start of a training pass only.  Works for any
+    (model, loader) pair with the reference API.  Returns (logits [n_seq], labels [n_seq])."""
+    criterion = criterion or torch.nn.BCEWithLogitsLoss()
+    dev = helper.device
+    train = optimizer is not None
+    if train and reset:
+        model.reset_memory()
+        loader.reset_state()
+    all_pred, all_true = [], []
+    with torch.set_grad_enabled(train):
+        for idx in meta_batches:
+            if train:
+                optimizer.zero_grad()
+            preds, trues = [], []
+            for i in idx:
+                d = seqs[int(i)]
+                msg_all, t_all = d["msg"].to(dev), d["t"].to(dev)
+                last = None
+                for e in range(d["src"].numel()):
+                    src, dst = d["src"][e:e + 1].to(dev), d["dst"][e:e + 1].to(dev)
+                    n_id = torch.cat([src, dst]).unique()
+                    edge_index = torch.empty((2, 0), dtype=torch.long, device=dev)
+                    e_id = loader.e_id[n_id]
+                    for _ in range(model.num_gnn_layers):
+                        n_id, edge_index, e_id = loader(n_id)
+                        e_id = e_id % msg_all.shape[0]
+                    helper[n_id] = torch.arange(n_id.size(0), device=dev)
+                    y_pred, _, se, de = model(Batch(src=src, dst=dst, x=x.to(dev)), n_id, msg_all[e_id], t_all[e_id],
+                                              edge_index, helper)
+                    last = y_pred.squeeze(0)
+                    model.update(src, dst, t_all[e:e + 1], msg_all[e:e + 1], se, de)
+                    loader.insert(src, dst)
+                preds.append(last)
+                trues.append(d["y"].to(dev))
+            if train:
+                loss = criterion(torch.cat(preds, -1), torch.cat(trues, -1))
+                loss.backward()
+                optimizer.step()
+                model.detach_memory()
+            all_pred += [p.detach() for p in preds]
+            all_true += trues
+    return torch.cat(all_pred), torch.cat(all_true)
+
+
+def path_graph_events(seq_len: int, n_seq: int):
+    """src, dst, t of the Temporal Path Graph generator (datasets/label_prediction_sequence.py:27-57):
+    sequence i is the chain i*L -> i*L+1 -> ... with t = 0..L-2."""
+    base = torch.arange(n_seq).view(-1, 1) * seq_len
+    k = torch.arange(seq_len - 1).view(1, -1)
+    return (base + k).reshape(-1), (base + k + 1).reshape(-1), k.expand(n_seq, -1).reshape(-1)
+
+
+def delta_t_stats_ref(src, dst, t, init_time=0):
+    """`compute_stats` (utils.py:46-92): mean / population std (float64) of `t - last_seen[node]` over BOTH
+    endpoints of every event in order; both endpoints of an event see the table as it was before the event;
+    a node's first occurrence is measured from init_time."""
+    last = {}
+    diffs = []
+    for s, d, tt in zip(src.tolist(), dst.tolist(), t.tolist()):
+        diffs.append(tt - last.get(s, init_time))
+        diffs.append(tt - last.get(d, init_time))
+        last[s] = tt
+        last[d] = tt
+    a = np.asarray(diffs, dtype=np.float64)
+    return float(a.mean()), float(a.std())

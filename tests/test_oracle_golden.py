@@ -93,3 +93,46 @@ def test_memory_update_tie_rule():
     O.memory_update_ref(mem, lu, src, dst, t, se, de)
     assert lu.tolist() == [0, 5, 4, 5, 0, 0]
     assert mem[1].tolist() == [1, 1] and mem[2].tolist() == [3, 3] and mem[3].tolist() == [4, 4]
+
+
+# ------------------------------------------------------------------ C1: the reference's shipped fixture
+def _seq_golden():
+    return torch.load(os.path.join(G, "sequence_golden.pt"), weights_only=False)
+
+
+def test_delta_t_stats_known_answers():
+    """`delta_t_stats.pkl` of the shipped label-sequence fixture = the reference's own known answers of
+    utils.compute_stats for L in {3,...,20} (train split = first int(1000*(1-.15-.15)) sequences)."""
+    g = _seq_golden()
+    assert sorted(g["stats"]) == [3, 5, 7, 9, 11, 13, 15, 20]
+    n_train = int(1000 * (1 - g["split"][0] - g["split"][1]))
+    for L, (mean, std) in g["stats"].items():
+        s, d, t = O.path_graph_events(L, n_train)
+        m, sd = O.delta_t_stats_ref(s, d, t, init_time=0)
+        assert abs(m - mean) < 1e-12 and abs(sd - std) < 1e-12, (L, m, sd)
+
+
+def test_oracle_sequence_loop_matches_reference_run():
+    """The reference's train_sequence.train + eval, run verbatim on the first 16 sequences of its shipped L=7
+    dataset (tests/golden/make_sequence_golden.py): parameters after the optimizer steps, logits, memory."""
+    g = _seq_golden()
+    L, n = g["L"], g["n_seq"]
+    om = O.OracleCTAN(**g["model_kw"])
+    om.load_state_dict(g["init"])
+    src, dst, t = O.path_graph_events(L, n)
+    seqs = [dict(src=src[i * (L - 1):(i + 1) * (L - 1)], dst=dst[i * (L - 1):(i + 1) * (L - 1)],
+                 t=t[i * (L - 1):(i + 1) * (L - 1)], msg=g["msg"][i], y=g["y"][i:i + 1]) for i in range(n)]
+    meta = [range(i, i + g["meta_batch"]) for i in range(0, n, g["meta_batch"])]
+    loader = O.TorchNeighborLoader(g["model_kw"]["num_nodes"], 5)
+    helper = torch.zeros(g["model_kw"]["num_nodes"], dtype=torch.long)
+    opt = torch.optim.Adam(om.parameters(), lr=g["lr"], weight_decay=g["weight_decay"])
+    O.sequence_pass_ref(om, loader, helper, seqs, g["x"], meta, optimizer=opt)
+    sd = om.state_dict()
+    for k, v in g["after_train"].items():
+        if not k.endswith("_assoc"):            # scratch table (torch.empty in the reference)
+            assert torch.allclose(sd[k].to(v.dtype), v, rtol=1e-5, atol=1e-6), k
+    pred, true = O.sequence_pass_ref(om, loader, helper, seqs, g["x"], meta)
+    assert torch.equal(true, g["eval_true"])
+    assert torch.allclose(pred, g["eval_pred"], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(om.memory.memory, g["memory_after_eval"], rtol=1e-5, atol=1e-6)
+    assert torch.equal(om.memory.last_update, g["last_update_after_eval"])
