@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 COMMENT = dict(D=256, T=256, S=32, K=1, B=200, n_neg=20, eps=1.0, gamma=0.1)
-WARM_EVENTS = 400_000          # events inserted into the neighbour/memory state before the timed window
+WARM_EVENTS = 1_000_000         # events inserted into the neighbour/memory state before the timed window
 
 
 def build_eval(rank, world, dev, n_batches, shape="comment", cfg=COMMENT, n_nodes_scale=1.0, warm=WARM_EVENTS):
@@ -95,10 +95,11 @@ def run_tgb_eval_bench(args, rank, world, quiet=False):
            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "tgbl-comment-shaped TGB one-vs-many eval: 994790 nodes, 2-d msgs, 200 queries/batch "
                                   "x 20 negatives, CTAN_tgb D=T=256 S=32 K=1; queries of each batch sharded over the "
-                                  f"ranks, one NCCL all-gather per batch; {WARM_EVENTS} events warm state",
+                                  f"ranks, one NCCL all-gather per batch; timed window follows a {WARM_EVENTS}-event warm "
+                                  "insert (SURVEY.md S8d)",
                       "l2": "state tables (1.0 GB memory + 0.5 GB neighbour rows) exceed L2; no flush"},
            "clocks": clocks, "mrr": mrr, "rank0_subgraph": {"N": counts[0], "E": counts[1]},
-           "gpu_launches": steps * 15}
+           "gpu_launches": steps * eng.launches_per_batch, "launches_per_step": eng.launches_per_batch}
     if rank == 0 and not quiet:
         print(json.dumps(out))
     if world > 1:

@@ -175,18 +175,7 @@ class TGBEvalEngine:
             with torch.cuda.stream(self._side):
                 call("ctan_eproj_fwd", ptr(self.msg), Fe, ptr(w["eid"]), ptr(w["rel"]), ptr(g.time_enc.lin.weight),
                      ptr(g.time_enc.lin.bias), T, ptr(ph.lin_edge.weight), E, Ed, D, ptr(w["EP"]))
-                if self.use_tc:
-                    call("ctan_wcat_prep", ptr(ph.lin_query.weight), ptr(ph.lin_key.weight), ptr(ph.lin_value.weight),
-                         ptr(a.W), float(a.gamma), D, ptr(w["Wcat_hi"]), ptr(w["Wcat_lo"]), ptr(w["A"]), None, None)
-                else:
-                    call("ctan_antisym_prep", ptr(a.W), float(a.gamma), D, ptr(w["A"]))
-                w["H"].zero_()
-                if self.use_tc_ro:       # [lin_src; lin_dst] packed + split for the node-projection readout
-                    call("ctan_pack_split", ptr(r.lin_src.weight), Hd, D, D, ptr(w["Wro_hi"]), ptr(w["Wro_lo"]))
-                    call("ctan_pack_split", ptr(r.lin_dst.weight), Hd, D, D, ptr(w["Wro_hi"]) + 4 * Hd * D,
-                         ptr(w["Wro_lo"]) + 4 * Hd * D)
             if self.use_tc_enc:          # gather -> dense rows; enc_x on the tensor cores; node-feature columns as residual
-                call("ctan_pack_split", ptr(g.enc_x.weight), D, D, D + Fn, ptr(w["Wenc_hi"]), ptr(w["Wenc_lo"]))
                 call("ctan_enc_prep", ptr(mem), D, xf, Fn, ptr(w["n_id"]), N, Nd, ptr(g.enc_x.weight), ptr(w["zmain"]),
                      ptr(w["ztail"]))
                 call("ctan_gemm_tc", ptr(w["zmain"]), N, Nd, D, ptr(w["Wenc_hi"]), ptr(w["Wenc_lo"]), D,
@@ -221,6 +210,27 @@ class TGBEvalEngine:
                  ptr(r.lin_final.weight), ptr(r.lin_final.bias), ptr(w["H"]), ptr(w["OUT"]), 0)   # no split-K: scores must not depend on atomic order
             call("ctan_pack_eval", ptr(w["OUT"]), ptr(z), ptr(ld._assoc), ptr(w["pair_src"]), ptr(w["pair_dst"]), Q,
                  self.n_neg, D, ptr(w["send"]))
+
+    def _prep_weights(self):
+        """Weight-only operands (A = W - W^T - gamma I, the packed / hi-lo split weight panels of the tensor-core
+        contractions).  Evaluation runs with frozen weights (tgb_test is @torch.no_grad, train_link.py:111),
+        so they are formed at the start of every run() call, not once per batch."""
+        w, m = self.w, self.model
+        D, Fn, Hd = self.D, self.Fn, self.Hd
+        g, a, r = m.gnn, m.gnn.aconv, m.readout
+        ph = a.phi
+        with torch.cuda.device(self.dev):
+            if self.use_tc:
+                call("ctan_wcat_prep", ptr(ph.lin_query.weight), ptr(ph.lin_key.weight), ptr(ph.lin_value.weight),
+                     ptr(a.W), float(a.gamma), D, ptr(w["Wcat_hi"]), ptr(w["Wcat_lo"]), ptr(w["A"]), None, None)
+            else:
+                call("ctan_antisym_prep", ptr(a.W), float(a.gamma), D, ptr(w["A"]))
+            if self.use_tc_ro:           # [lin_src; lin_dst] packed + split for the node-projection readout
+                call("ctan_pack_split", ptr(r.lin_src.weight), Hd, D, D, ptr(w["Wro_hi"]), ptr(w["Wro_lo"]))
+                call("ctan_pack_split", ptr(r.lin_dst.weight), Hd, D, D, ptr(w["Wro_hi"]) + 4 * Hd * D,
+                     ptr(w["Wro_lo"]) + 4 * Hd * D)
+            if self.use_tc_enc:
+                call("ctan_pack_split", ptr(g.enc_x.weight), D, D, D + Fn, ptr(w["Wenc_hi"]), ptr(w["Wenc_lo"]))
 
     def _exchange(self):
         """The one collective of the batch (kept OUT of CUDA-graph capture: torch's NCCL process group and
@@ -258,15 +268,20 @@ class TGBEvalEngine:
                          torch.full((2, self.S), -1, dtype=torch.long, device=dev),
                          torch.zeros(2, dtype=torch.int32, device=dev))
         cur = self.w["counters"].clone()
+        from . import _lib
+        self._prep_weights()
+        n0 = _lib.N_LAUNCHES
         with torch.cuda.device(dev):
             self._launch(dry=True)
         torch.cuda.synchronize(dev)
+        self.launches_per_batch = _lib.N_LAUNCHES - n0      # our kernels per batch (the collective is NCCL's)
         self.w["counters"].copy_(cur)
         self.w["acc"].zero_()
 
     def run(self, n_batches: int):
         if self.loader.cur_e_id + n_batches * self.B > self.n_events:
             raise ValueError("stream exhausted")
+        self._prep_weights()          # once per run() call (a whole split), not per batch
         with torch.cuda.device(self.dev):
             if self.use_graph:
                 if self._graph is None:
