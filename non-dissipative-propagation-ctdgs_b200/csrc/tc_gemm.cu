@@ -6,21 +6,28 @@
 // to TF32 (10-bit mantissa) and lo = x - hi; the product is accumulated as lo*hi' + hi*lo' + hi*hi' in the
 // fp32 TMEM accumulator (relative error ~2^-21, inside the 1e-4 bar; plain TF32 would be ~5e-4).
 // The weights are split once per step by ctan_wcat_prep (which also forms A = W - W^T - gamma I); the
-// activation tile is split in shared memory right after its TMA load (an element-wise rewrite keeps the
-// swizzled layout).
+// activation tile is split by the transform warps right after its TMA load.
 //
-// One CTA = one 128x128 output tile, 192 threads, warp-specialised (TMA producer / MMA issuer / 4 transform+
-// epilogue warps).  K advances in 128-byte (32-float) blocks through a 3-stage smem ring of mbarriers.
-// Epilogue: tcgen05.ld 32x32b -> +bias -> 128-bit stores.  Replaces the same reference code as ctan_qkva_fwd.
+// One persistent CTA per SM walks 128x128 output tiles: 320 threads, warp-specialised (TMA producer / MMA issuer /
+// 4 transform warps / 4 epilogue warps).  K advances in 128-byte (32-float) blocks through a 4-stage ring of
+// mbarriers; the activation operand is split in registers and handed to the MMA through TENSOR MEMORY (only the
+// weight tile is read from shared memory: a tf32 MMA is shared-memory-bandwidth bound); two TMEM accumulators let the
+// epilogue of tile i (tcgen05.ld -> smem staging -> +bias/+residual -> full-line stores) overlap the MMAs of tile
+// i+1.  Replaces the same reference code as ctan_qkva_fwd.
 #include "common.cuh"
 #include <cuda.h>
 
 namespace tc {
 
-constexpr int BM = 128, BN = 128, BKF = 32, STAGES = 3;
+constexpr int BM = 128, BN = 128, BKF = 32, STAGES = 4;
 constexpr int TILE_BYTES = BM * BKF * 4;                 // 16 KB (A and B tiles have the same shape)
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;              // A_hi, A_lo, B_hi, B_lo
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int STAGE_BYTES = 3 * TILE_BYTES;              // A (raw fp32), B_hi, B_lo
+constexpr int EPI_LD = 36;                               // staging row pitch in floats (32 + 4: conflict-free float4)
+constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;           // one 32x32 staging block per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int THREADS = 320;                             // TMA | MMA | 4 transform warps | 4 epilogue warps
+// TMEM columns (512 allocated): two 128-column fp32 accumulators, then per stage 32 columns A_hi + 32 columns A_lo
+constexpr uint32_t TMEM_COLS = 512, TM_ACC = 0, TM_A = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -59,16 +66,34 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 __device__ __forceinline__ uint32_t instr_desc_tf32() {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+// D[tmem] (+)= A[tmem] * B[smem]: the activation operand is read from tensor memory (lane = row, one tf32 per
+// column), so only the weight tile goes through the shared-memory read port.
+__device__ __forceinline__ void mma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
 struct Bias4 { const float* p[4]; int D; int vec; const float* res; int ldr; };   // + optional residual res[m][n]
@@ -77,14 +102,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Warp-specialised: warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer (one lane),
-// warps 2..5 = operand transform (3xTF32 split of the activation tile in smem) and epilogue.
-//   raw[s]   : TMA bytes of stage s have landed            (1 arrival + tx bytes)
-//   ready[s] : the 128 transform threads have split stage s (128 arrivals)          [mode 0 only]
-//   empty[s] : the MMAs that read stage s have completed    (tcgen05.commit)
-//   done     : every MMA of the tile has completed          (tcgen05.commit)
-// mode 0: 3xTF32 (fp32 parity path); mode 1: single TF32 pass (1e-2 path; no split, no lo tiles).
-__global__ void __launch_bounds__(192)
+// Warp-specialised, persistent over row tiles (one CTA per SM; the ring and its phases run on across tiles):
+//   warp 0     TMA producer (one lane): A raw fp32, B_hi, B_lo tiles of a k-block -> smem stage s
+//   warp 1     TMEM owner + MMA issuer (one lane)
+//   warps 2-5  operand transform: read the raw A tile from smem, split x = hi + lo (3xTF32) in registers and
+//              write both halves to TENSOR MEMORY (tcgen05.st) -- the MMA then reads A from TMEM and only B from
+//              smem, which halves the shared-memory traffic that bounds a tf32 MMA (8 KB of operands / 67 clk)
+//   warps 6-9  epilogue of the PREVIOUS tile (second accumulator buffer) while the next tile's MMAs run:
+//              tcgen05.ld -> per-warp smem staging -> +bias/+residual -> full-line coalesced stores (or atomics)
+// Barriers: raw[s] TMA landed | ready[s] A of stage s is in TMEM (128 arrivals) | empty[s] MMAs of stage s retired
+//           done[b] accumulator b complete | accfree[b] accumulator b drained (128 arrivals)
+// mode 0: 3xTF32 (fp32 parity path); mode 1: single TF32 pass (1e-2 path; hi only).
+__global__ void __launch_bounds__(THREADS)
 qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                const __grid_constant__ CUtensorMap tmBlo, Bias4 bias, float* __restrict__ C, int ldc, int M_host,
                const int* __restrict__ M_dev, int N, int K, int mode) {
@@ -92,27 +121,24 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int M = M_dev ? *M_dev : M_host;
     const int n0 = blockIdx.x * BN;
     if ((int)blockIdx.y * BM >= M) return;                            // uniform, before any allocation
-    // Persistent over row tiles: the true M lives on the device, so the host launches a bounded grid.y and
-    // each CTA walks tiles blockIdx.y, +gridDim.y, ...; the smem ring and its phases run on across tiles,
-    // `done`/`accfree` hand the TMEM accumulator back and forth between the MMA issuer and the epilogue.
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* raw = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+    float* epi = (float*)(smem + STAGES * STAGE_BYTES);
+    uint64_t* raw = (uint64_t*)(smem + STAGES * STAGE_BYTES + EPI_BYTES);
     uint64_t* ready = raw + STAGES;
     uint64_t* empty = ready + STAGES;
-    uint64_t* done = empty + STAGES;
-    uint64_t* accfree = done + 1;
-    uint32_t* tmem_holder = (uint32_t*)(accfree + 1);
+    uint64_t* done = empty + STAGES;          // [2]
+    uint64_t* accfree = done + 2;             // [2]
+    uint32_t* tmem_holder = (uint32_t*)(accfree + 2);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
 
     if (t == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&raw[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], 1); }
-        mbar_init(done, 1);
-        mbar_init(accfree, 128);
+        for (int b = 0; b < 2; ++b) { mbar_init(&done[b], 1); mbar_init(&accfree[b], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
-                     "r"((uint32_t)BN));
+                     "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -135,8 +161,8 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);
                 mbar_expect_tx(&raw[s], (mode == 0 ? 3 : 2) * TILE_BYTES);
                 tma_load_2d(stage_ptr(s, 0), &tmA, &raw[s], (kb0 + kb) * BKF, m0);
-                tma_load_2d(stage_ptr(s, 2), &tmBhi, &raw[s], (kb0 + kb) * BKF, n0);
-                if (mode == 0) tma_load_2d(stage_ptr(s, 3), &tmBlo, &raw[s], (kb0 + kb) * BKF, n0);
+                tma_load_2d(stage_ptr(s, 1), &tmBhi, &raw[s], (kb0 + kb) * BKF, n0);
+                if (mode == 0) tma_load_2d(stage_ptr(s, 2), &tmBlo, &raw[s], (kb0 + kb) * BKF, n0);
             }
         }
     } else if (warp == 1) {
@@ -145,117 +171,129 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t idesc = instr_desc_tf32();
             int it = 0, tile = 0;
             for (int m0 = blockIdx.y * BM; m0 < M; m0 += gridDim.y * BM, ++tile) {
-            if (tile > 0) {                                             // the epilogue has drained the accumulator
-                mbar_wait(accfree, (tile - 1) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            }
-            for (int kb = 0; kb < n_kb; ++kb, ++it) {
-                const int s = it % STAGES;
-                mbar_wait(mode == 0 ? &ready[s] : &raw[s], (it / STAGES) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_hi = smem_u32(stage_ptr(s, 0)), a_lo = smem_u32(stage_ptr(s, 1));
-                const uint32_t b_hi = smem_u32(stage_ptr(s, 2)), b_lo = smem_u32(stage_ptr(s, 3));
-#pragma unroll
-                for (int k = 0; k < BKF / 8; ++k) {                    // UMMA_K = 8 tf32 = 32 bytes inside the swizzle atom
-                    const uint32_t off = k * 32;
-                    if (mode == 0) {
-                        mma_tf32(tmem_base, smem_desc_sw128(a_lo + off), smem_desc_sw128(b_hi + off), idesc, (kb | k) ? 1u : 0u);
-                        mma_tf32(tmem_base, smem_desc_sw128(a_hi + off), smem_desc_sw128(b_lo + off), idesc, 1u);
-                        mma_tf32(tmem_base, smem_desc_sw128(a_hi + off), smem_desc_sw128(b_hi + off), idesc, 1u);
-                    } else {
-                        mma_tf32(tmem_base, smem_desc_sw128(a_hi + off), smem_desc_sw128(b_hi + off), idesc, (kb | k) ? 1u : 0u);
-                    }
+                const int buf = tile & 1;
+                if (tile >= 2) {                                        // the epilogue has drained this accumulator
+                    mbar_wait(&accfree[buf], ((tile >> 1) - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-                mma_commit(&empty[s]);                                  // arrives when these MMAs have read stage s
+                const uint32_t acc = tmem_base + TM_ACC + (uint32_t)buf * BN;
+                for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&ready[s], (it / STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_hi = tmem_base + TM_A + (uint32_t)s * 64, a_lo = a_hi + 32;
+                    const uint32_t b_hi = smem_u32(stage_ptr(s, 1)), b_lo = smem_u32(stage_ptr(s, 2));
+#pragma unroll
+                    for (int k = 0; k < BKF / 8; ++k) {                // UMMA_K = 8 tf32 = 32 bytes inside the swizzle atom
+                        const uint32_t off = k * 32;
+                        if (mode == 0) {
+                            mma_tf32_ta(acc, a_lo + k * 8, smem_desc_sw128(b_hi + off), idesc, (kb | k) ? 1u : 0u);
+                            mma_tf32_ta(acc, a_hi + k * 8, smem_desc_sw128(b_lo + off), idesc, 1u);
+                            mma_tf32_ta(acc, a_hi + k * 8, smem_desc_sw128(b_hi + off), idesc, 1u);
+                        } else {
+                            mma_tf32_ta(acc, a_hi + k * 8, smem_desc_sw128(b_hi + off), idesc, (kb | k) ? 1u : 0u);
+                        }
+                    }
+                    mma_commit(&empty[s]);                              // arrives when these MMAs have read stage s
+                }
+                mma_commit(&done[buf]);                                 // this tile's accumulator is complete
             }
-            mma_commit(done);                                           // this tile's accumulator is complete
+        }
+    } else if (warp < 6) {
+        // ------------------------------------------------ transform: raw A (smem, swizzled) -> hi/lo in TMEM
+        const int q = warp & 3;                                         // TMEM lane quarter this warp may touch
+        const int r = q * 32 + lane;                                    // tile row = TMEM lane
+        const uint32_t tlane = (uint32_t)(q * 32) << 16;
+        int it = 0;
+        for (int m0 = blockIdx.y * BM; m0 < M; m0 += gridDim.y * BM)
+        for (int kb = 0; kb < n_kb; ++kb, ++it) {
+            const int s = it % STAGES;
+            mbar_wait(&raw[s], (it / STAGES) & 1);
+            const uint8_t* arow = stage_ptr(s, 0) + r * 128;
+            const uint32_t t_hi = tmem_base + tlane + TM_A + (uint32_t)s * 64;
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {                            // 16-byte chunk c of row r sits at chunk c ^ (r & 7)
+                const float4 v0 = *reinterpret_cast<const float4*>(arow + (((c) ^ (r & 7)) << 4));
+                const float4 v1 = *reinterpret_cast<const float4*>(arow + (((c + 1) ^ (r & 7)) << 4));
+                const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                uint32_t h[8], l[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    h[j] = __float_as_uint(x[j]) & 0xFFFFE000u;
+                    l[j] = __float_as_uint(x[j] - __uint_as_float(h[j]));
+                }
+                tmem_st8(t_hi + c * 4, h);
+                if (mode == 0) tmem_st8(t_hi + 32 + c * 4, l);
             }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&ready[s]);
         }
     } else {
-        // ------------------------------------------------ transform (3xTF32 split of A) then epilogue
-        const int te = t - 64;                                          // 0..127
-        int it = 0, tile = 0;
+        // ------------------------------------------------ epilogue (overlaps the next tile's main loop)
+        const int q = warp & 3;                                         // warps 6,7,8,9 -> lane quarters 2,3,0,1
+        float* stg = epi + (warp - 6) * 32 * EPI_LD;
+        const bool first = blockIdx.z == 0;                             // bias / residual are added by one split only
+        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+        int tile = 0;
         for (int m0 = blockIdx.y * BM; m0 < M; m0 += gridDim.y * BM, ++tile) {
-        if (mode == 0) {
-            for (int kb = 0; kb < n_kb; ++kb, ++it) {
-                const int s = it % STAGES;
-                mbar_wait(&raw[s], (it / STAGES) & 1);
-                float4* ahi = (float4*)stage_ptr(s, 0);
-                float4* alo = (float4*)stage_ptr(s, 1);
-#pragma unroll
-                for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
-                    const float4 v = ahi[te + i * 128];
-                    float4 h, l;
-                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-                    ahi[te + i * 128] = h;
-                    alo[te + i * 128] = l;
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA
-                mbar_arrive(&ready[s]);
-            }
-        }
-        mbar_wait(done, tile & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // warp w may touch TMEM lanes [32*(w%4), +32): warps 2,3,4,5 cover quarters 2,3,0,1
-        const int q = warp & 3;
-        const int row = m0 + q * 32 + lane;
+            const int buf = tile & 1;
+            mbar_wait(&done[buf], (tile >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC + (uint32_t)buf * BN;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 16) {
-            uint32_t v[16];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const int n = n0 + c;                                       // 16-column chunk: inside one bias segment (D % 32 == 0)
-            if (row < M && n < N) {
-                const int seg = n / bias.D;
-                const bool first = blockIdx.z == 0;                     // bias / residual are added by one split only
-                const float* bp = !first ? nullptr
-                                         : (seg == 0 ? bias.p[0] : (seg == 1 ? bias.p[1] : (seg == 2 ? bias.p[2] : bias.p[3])));
-                float* out = C + (size_t)row * ldc + n;
-                const float* rp = (first && bias.res) ? bias.res + (size_t)row * bias.ldr + n : nullptr;
-                if (gridDim.z > 1) {                                    // split-K: accumulate into the zeroed output
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tacc + c0, v);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (n + j < N)
-                            atomicAdd(out + j, __uint_as_float(v[j]) + (bp ? __ldg(bp + (n - seg * bias.D) + j) : 0.f) +
-                                                   (rp ? rp[j] : 0.f));
-                } else if (bias.vec && n + 15 < N) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (bp) bv = __ldg(reinterpret_cast<const float4*>(bp + (n - seg * bias.D) + j));
-                        if (rp) {
-                            const float4 rv = *reinterpret_cast<const float4*>(rp + j);
-                            bv.x += rv.x; bv.y += rv.y; bv.z += rv.z; bv.w += rv.w;
-                        }
-                        float4 o;
-                        o.x = __uint_as_float(v[j]) + bv.x; o.y = __uint_as_float(v[j + 1]) + bv.y;
-                        o.z = __uint_as_float(v[j + 2]) + bv.z; o.w = __uint_as_float(v[j + 3]) + bv.w;
-                        *reinterpret_cast<float4*>(out + j) = o;
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(stg + lane * EPI_LD + j) =
+                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                    __uint_as_float(v[j + 3]));
+                __syncwarp();
+                const int n = n0 + c0 + sub_c;                          // 4 columns: inside one bias segment (D % 16 == 0)
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (first && n < N) {
+                    const int seg = n / bias.D;
+                    const float* bp = seg == 0 ? bias.p[0] : (seg == 1 ? bias.p[1] : (seg == 2 ? bias.p[2] : bias.p[3]));
+                    if (bp) {
+                        bp += n - seg * bias.D;
+                        if (bias.vec) bv = __ldg(reinterpret_cast<const float4*>(bp));
+                        else bv = make_float4(__ldg(bp), __ldg(bp + 1), __ldg(bp + 2), __ldg(bp + 3));
                     }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (n + j < N)
-                            out[j] = __uint_as_float(v[j]) + (bp ? __ldg(bp + (n - seg * bias.D) + j) : 0.f) + (rp ? rp[j] : 0.f);
                 }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {                           // 4 rows x 128 B per warp instruction
+                    const int rr = i * 4 + sub_r;
+                    const int row = m0 + q * 32 + rr;
+                    if (row < M && n < N) {
+                        float4 o = *reinterpret_cast<const float4*>(stg + rr * EPI_LD + sub_c);
+                        o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                        if (first && bias.res) {
+                            const float* rp = bias.res + (size_t)row * bias.ldr + n;
+                            if (bias.vec) {
+                                const float4 rv = *reinterpret_cast<const float4*>(rp);
+                                o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+                            } else { o.x += rp[0]; o.y += rp[1]; o.z += rp[2]; o.w += rp[3]; }
+                        }
+                        float* out = C + (size_t)row * ldc + n;
+                        if (gridDim.z > 1) {                            // split-K: accumulate into the zeroed output
+                            atomicAdd(out, o.x); atomicAdd(out + 1, o.y); atomicAdd(out + 2, o.z); atomicAdd(out + 3, o.w);
+                        } else if (bias.vec) {
+                            *reinterpret_cast<float4*>(out) = o;
+                        } else { out[0] = o.x; out[1] = o.y; out[2] = o.z; out[3] = o.w; }
+                    }
+                }
+                __syncwarp();
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&accfree[buf]);                                 // TMEM reads of this tile are complete
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        mbar_arrive(accfree);                                           // TMEM reads of this tile are complete
-        }   // row-tile loop
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -286,14 +324,13 @@ static int make_map(CUtensorMap* m, const float* base, int rows, int K) {
     return r == CUDA_SUCCESS ? 0 : CTAN_ERR_BAD_ARG;
 }
 
-// grid.y: every row tile when the size is known on the host; with a device-sized M (upper bound only) at most
-// two CTAs per SM are launched and each walks several row tiles (a CTA holds 193 KB of smem: empty ones are not free)
+// grid.y: a CTA holds ~212 KB of smem and all 512 TMEM columns, so exactly one is resident per SM; launch at most
+// one wave and let each CTA walk the remaining row tiles (that is also what overlaps epilogue and main loop)
 static int bounded_rows(int M_max, const int* M_dev, int gx) {
+    (void)M_dev;
     int gy = (M_max + BM - 1) / BM;
-    if (M_dev) {
-        const int cap = (2 * CTAN_SM_COUNT) / gx;
-        if (gy > cap) gy = cap > 1 ? cap : 1;
-    }
+    const int cap = CTAN_SM_COUNT / gx;
+    if (gy > cap) gy = cap > 1 ? cap : 1;
     return gy;
 }
 
@@ -363,7 +400,7 @@ extern "C" int ctan_qkva_fwd_tc(const float* X, int N, const int* N_dev, int D, 
     const uintptr_t ball = (uintptr_t)bq | (uintptr_t)bk | (uintptr_t)bv | (uintptr_t)b | (uintptr_t)QKVA;
     tc::Bias4 bias{{bq, bk, bv, b}, D, (ball & 15) == 0 ? 1 : 0, nullptr, 0};
     dim3 grid((4 * D) / tc::BN, tc::bounded_rows(N, N_dev, (4 * D) / tc::BN));
-    tc::qkva_tc_kernel<<<grid, 192, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, bias, QKVA, 4 * D, N, N_dev, 4 * D, D,
+    tc::qkva_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, bias, QKVA, 4 * D, N, N_dev, 4 * D, D,
                                                               mode);
     CTAN_CHECK_LAUNCH();
     return 0;
@@ -391,7 +428,7 @@ extern "C" int ctan_dx_tc(const float* DQKVA, const float* G, int N, const int* 
     int splits = n_split < 1 ? 1 : n_split;
     while (splits > 1 && (n_kb % splits != 0)) --splits;
     dim3 grid(D / tc::BN, tc::bounded_rows(N, N_dev, (D / tc::BN) * splits), splits);
-    tc::qkva_tc_kernel<<<grid, 192, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, epi, dXin, D, N, N_dev, D, 4 * D, mode);
+    tc::qkva_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, epi, dXin, D, N, N_dev, D, 4 * D, mode);
     CTAN_CHECK_LAUNCH();
     return 0;
 }
@@ -435,7 +472,7 @@ extern "C" int ctan_gemm_tc(const float* A, int M, const int* M_dev, int K, cons
                            (uintptr_t)(ldr * 4);
     tc::Bias4 epi{{b0, b1, b2, b3}, seg, (ball & 15) == 0 ? 1 : 0, res, ldr};
     dim3 grid(Nout / tc::BN, tc::bounded_rows(M, M_dev, Nout / tc::BN));
-    tc::qkva_tc_kernel<<<grid, 192, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, epi, C, Nout, M, M_dev, Nout, K, mode);
+    tc::qkva_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, epi, C, Nout, M, M_dev, Nout, K, mode);
     CTAN_CHECK_LAUNCH();
     return 0;
 }
