@@ -87,6 +87,8 @@ SIGNATURES.update({
     "ctan_wcat_prep": [P, P, P, P, F, I, P, P, P, P, P],
     "ctan_dx_tc": [P, P, I, P, I, P, P, P, I, I],
     "ctan_pack_split": [P, I, I, I, P, P],
+    "ctan_pack_split_pad": [P, I, I, I, I, P, P],
+    "ctan_eproj_prep": [P, I, P, P, P, P, I, I, P, I, P],
     "ctan_gemm_tc": [P, I, P, I, P, P, I, P, P, P, P, I, P, I, P, I],
     "ctan_enc_prep": [P, I, P, I, P, I, P, P, P, P],
     "ctan_head_gather": [P, I, P, P, P, I, P, P, P],

@@ -409,6 +409,39 @@ extern "C" int ctan_enc_prep(const float* mem, int D, const float* xfeat, int Fn
     return 0;
 }
 
+// Tensor-core lin_edge (evaluation shapes): edge_attr = [msg[e_id] | cos(w*rel + b)] (models/gnn_layers.py:96-97,
+// TGB/modules/time_enc.py:23-24) written as a dense row-major [E, Kpad] operand (Kpad = Fe+T rounded up to 32, zero
+// padded, 128-byte rows -> TMA source) for ctan_gemm_tc.  One warp per edge.
+__global__ void eproj_prep_kernel(const float* __restrict__ msg, int Fe, const int64_t* __restrict__ eid,
+                                  const float* __restrict__ rel, const float* __restrict__ tw,
+                                  const float* __restrict__ tb, int T, int E_host, const int* __restrict__ E_dev,
+                                  int Kpad, float* __restrict__ A) {
+    const int E = E_dev ? *E_dev : E_host;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int e = warp; e < E; e += nw) {
+        const int64_t g = eid ? eid[e] : e;
+        const float r = rel[e];
+        float* out = A + (size_t)e * Kpad;
+        for (int k = lane; k < Kpad; k += 32) {
+            float v = 0.f;
+            if (k < Fe) v = __ldg(msg + (size_t)g * Fe + k);
+            else if (k < Fe + T) v = cosf(fmaf(r, __ldg(tw + (k - Fe)), __ldg(tb + (k - Fe))));
+            out[k] = v;
+        }
+    }
+}
+extern "C" int ctan_eproj_prep(const float* msg, int Fe, const int64_t* eid, const float* rel, const float* tw,
+                               const float* tb, int T, int E, const int* E_dev, int Kpad, float* A,
+                               cudaStream_t stream) {
+    if (E <= 0) return 0;
+    if (Kpad < Fe + T || Kpad % 32 != 0) return CTAN_ERR_BAD_ARG;
+    eproj_prep_kernel<<<ctan_grid((long long)E * 32, 256), 256, 0, stream>>>(msg, Fe, eid, rel, tw, tb, T, E, E_dev,
+                                                                           Kpad, A);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
 // Readout head on pre-projected node rows (evaluation): Y[N, 2*Hd] = z [Wsrc;Wdst]^T + [bsrc;bdst] is computed
 // once per NODE on the tensor cores; a scored pair only gathers two rows:
 //   OUT[p] = relu(Y[row(src_p), :Hd] + Y[row(dst_p), Hd:]) . Wfin + bfin         (models/predictors.py:16-19)

@@ -435,11 +435,12 @@ extern "C" int ctan_dx_tc(const float* DQKVA, const float* G, int N, const int* 
 
 // TF32 split of a row-major [rows, cols] block read with leading dimension ld: packs (and 16-byte aligns) weights
 // such as enc_x.weight[:, :D] (ld = D+Fn) or the readout's lin_src/lin_dst so that TMA can stage them.
-__global__ void pack_split_kernel(const float* __restrict__ src, int rows, int cols, int ld, float* __restrict__ hi,
-                                  float* __restrict__ lo) {
-    const int n = rows * cols;
+__global__ void pack_split_kernel(const float* __restrict__ src, int rows, int cols, int ld, int ld_out,
+                                  float* __restrict__ hi, float* __restrict__ lo) {
+    const int n = rows * ld_out;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float x = src[(size_t)(i / cols) * ld + (i % cols)];
+        const int r = i / ld_out, c = i - r * ld_out;
+        const float x = c < cols ? src[(size_t)r * ld + c] : 0.f;          // columns [cols, ld_out) are zero padding
         const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
         hi[i] = h;
         lo[i] = x - h;
@@ -447,7 +448,15 @@ __global__ void pack_split_kernel(const float* __restrict__ src, int rows, int c
 }
 extern "C" int ctan_pack_split(const float* src, int rows, int cols, int ld, float* hi, float* lo, cudaStream_t stream) {
     if (rows <= 0 || cols <= 0) return CTAN_ERR_BAD_ARG;
-    pack_split_kernel<<<ctan_grid((long long)rows * cols, 256), 256, 0, stream>>>(src, rows, cols, ld, hi, lo);
+    pack_split_kernel<<<ctan_grid((long long)rows * cols, 256), 256, 0, stream>>>(src, rows, cols, ld, cols, hi, lo);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+// same, into panels whose rows are zero-padded to ld_out >= cols floats (K rounded up to the 32-float k-block)
+extern "C" int ctan_pack_split_pad(const float* src, int rows, int cols, int ld, int ld_out, float* hi, float* lo,
+                                   cudaStream_t stream) {
+    if (rows <= 0 || cols <= 0 || ld_out < cols) return CTAN_ERR_BAD_ARG;
+    pack_split_kernel<<<ctan_grid((long long)rows * ld_out, 256), 256, 0, stream>>>(src, rows, cols, ld, ld_out, hi, lo);
     CTAN_CHECK_LAUNCH();
     return 0;
 }

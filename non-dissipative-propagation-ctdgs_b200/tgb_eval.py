@@ -114,6 +114,11 @@ class TGBEvalEngine:
         # tensor-core enc_x (dense gathered rows + packed weights) and node-projection readout
         self.use_tc_enc = self.use_tc and D % 128 == 0
         self.use_tc_ro = self.use_tc and (2 * self.Hd) % 128 == 0 and self.Hd % 16 == 0
+        self.use_tc_ep = self.use_tc and D % 128 == 0
+        if self.use_tc_ep:               # lin_edge on the tensor cores: dense [E, Kpad] edge_attr operand
+            self.Kep = ((self.Fe + self.T + 31) // 32) * 32
+            w["Aep"] = torch.zeros((self.e_cap + 128, self.Kep), **f32)
+            w["Wep_hi"], w["Wep_lo"] = torch.zeros((D, self.Kep), **f32), torch.zeros((D, self.Kep), **f32)
         if self.use_tc_enc:
             w["zmain"], w["ztail"] = torch.zeros((N, D), **f32), torch.zeros((N, D), **f32)
             w["Wenc_hi"], w["Wenc_lo"] = torch.zeros((D, D), **f32), torch.zeros((D, D), **f32)
@@ -173,8 +178,14 @@ class TGBEvalEngine:
                  ptr(ld._cbitmap), ptr(lu), ptr(self.t), float(g.mean_delta_t), float(g.std_delta_t), ptr(w["rel"]))
             self._side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._side):
-                call("ctan_eproj_fwd", ptr(self.msg), Fe, ptr(w["eid"]), ptr(w["rel"]), ptr(g.time_enc.lin.weight),
-                     ptr(g.time_enc.lin.bias), T, ptr(ph.lin_edge.weight), E, Ed, D, ptr(w["EP"]))
+                if self.use_tc_ep:
+                    call("ctan_eproj_prep", ptr(self.msg), Fe, ptr(w["eid"]), ptr(w["rel"]), ptr(g.time_enc.lin.weight),
+                         ptr(g.time_enc.lin.bias), T, E, Ed, self.Kep, ptr(w["Aep"]))
+                    call("ctan_gemm_tc", ptr(w["Aep"]), E, Ed, self.Kep, ptr(w["Wep_hi"]), ptr(w["Wep_lo"]), D, None,
+                         None, None, None, D, None, 0, ptr(w["EP"]), _lib.TC_MODE)
+                else:
+                    call("ctan_eproj_fwd", ptr(self.msg), Fe, ptr(w["eid"]), ptr(w["rel"]), ptr(g.time_enc.lin.weight),
+                         ptr(g.time_enc.lin.bias), T, ptr(ph.lin_edge.weight), E, Ed, D, ptr(w["EP"]))
             if self.use_tc_enc:          # gather -> dense rows; enc_x on the tensor cores; node-feature columns as residual
                 call("ctan_enc_prep", ptr(mem), D, xf, Fn, ptr(w["n_id"]), N, Nd, ptr(g.enc_x.weight), ptr(w["zmain"]),
                      ptr(w["ztail"]))
@@ -231,6 +242,9 @@ class TGBEvalEngine:
                      ptr(w["Wro_lo"]) + 4 * Hd * D)
             if self.use_tc_enc:
                 call("ctan_pack_split", ptr(g.enc_x.weight), D, D, D + Fn, ptr(w["Wenc_hi"]), ptr(w["Wenc_lo"]))
+            if self.use_tc_ep:
+                call("ctan_pack_split_pad", ptr(ph.lin_edge.weight), D, self.Fe + self.T, self.Fe + self.T, self.Kep,
+                     ptr(w["Wep_hi"]), ptr(w["Wep_lo"]))
 
     def _exchange(self):
         """The one collective of the batch (kept OUT of CUDA-graph capture: torch's NCCL process group and
