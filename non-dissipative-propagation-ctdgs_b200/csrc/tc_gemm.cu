@@ -25,7 +25,8 @@ constexpr int STAGE_BYTES = 3 * TILE_BYTES;              // A (raw fp32), B_hi, 
 constexpr int EPI_LD = 36;                               // staging row pitch in floats (32 + 4: conflict-free float4)
 constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;           // one 32x32 staging block per epilogue warp
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int THREADS = 320;                             // TMA | MMA | 4 transform warps | 4 epilogue warps
+constexpr int TGROUPS = 1;                               // transform warp groups (k-blocks alternate between them)
+constexpr int THREADS = 64 + TGROUPS * 128 + 128;        // TMA | MMA | TGROUPS x 4 transform warps | 4 epilogue warps
 // TMEM columns (512 allocated): two 128-column fp32 accumulators, then per stage 32 columns A_hi + 32 columns A_lo
 constexpr uint32_t TMEM_COLS = 512, TM_ACC = 0, TM_A = 256;
 
@@ -199,14 +200,18 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mma_commit(&done[buf]);                                 // this tile's accumulator is complete
             }
         }
-    } else if (warp < 6) {
+    } else if (warp < 2 + 4 * TGROUPS) {
         // ------------------------------------------------ transform: raw A (smem, swizzled) -> hi/lo in TMEM
+        // TGROUPS > 1 lets groups of four warps take alternate k-blocks (measured: no gain, the ring is bound by
+        // the TMA round trip, not by this chain).
+        const int grp = (warp - 2) >> 2;
         const int q = warp & 3;                                         // TMEM lane quarter this warp may touch
         const int r = q * 32 + lane;                                    // tile row = TMEM lane
         const uint32_t tlane = (uint32_t)(q * 32) << 16;
         int it = 0;
         for (int m0 = blockIdx.y * BM; m0 < M; m0 += gridDim.y * BM)
         for (int kb = 0; kb < n_kb; ++kb, ++it) {
+            if (it % TGROUPS != grp) continue;
             const int s = it % STAGES;
             mbar_wait(&raw[s], (it / STAGES) & 1);
             const uint8_t* arow = stage_ptr(s, 0) + r * 128;
@@ -231,8 +236,8 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {
         // ------------------------------------------------ epilogue (overlaps the next tile's main loop)
-        const int q = warp & 3;                                         // warps 6,7,8,9 -> lane quarters 2,3,0,1
-        float* stg = epi + (warp - 6) * 32 * EPI_LD;
+        const int q = warp & 3;                                         // TMEM lane quarter of this warp
+        float* stg = epi + (warp - (2 + 4 * TGROUPS)) * 32 * EPI_LD;
         const bool first = blockIdx.z == 0;                             // bias / residual are added by one split only
         const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
         int tile = 0;

@@ -38,12 +38,12 @@ def run(M, K, Nout, mode, dev_sized=False):
 
 
 for mode in (0, 1):
-    for K in (32, 256, 512, 1024, 2048):
+    for K in (32, 256, 1024, 2048):
         us = run(148 * 128, K, 128, mode)
         print(f"one tile/SM  mode={mode} K={K:5d} ({K//32:3d} k-blocks): {us:8.2f} us")
 for M, K, Nout in [(6027, 256, 256), (6027, 256, 512), (6027, 256, 1024), (40000, 256, 1024)]:
     for mode in (0, 1):
-        for ds in (False, True):
+        for ds in (True,):
             us = run(M, K, Nout, mode, ds)
             print(f"M={M} K={K} Nout={Nout} mode={mode} dev_sized={ds}: {us:8.2f} us  "
                   f"{2.0 * M * K * Nout / us / 1e6:7.1f} useful TFLOP/s")
