@@ -12,6 +12,7 @@
 // warp-shuffle reductions over the row's <= S edges -- no atomics, no [E,D] intermediates in HBM --
 // and the tanh update x <- x + eps*tanh(x A^T + phi + b) is applied in the same pass.
 #include "common.cuh"
+#include <cstdlib>
 
 // rel[e] = ((|last_update[n_id[src_local[e]]] - t_e| - mean) / std) as fp32   (gnn_layers.py:94-95)
 // n_id == nullptr: last_update is already the gathered per-local-node array.
@@ -95,7 +96,7 @@ extern "C" int ctan_antisym_bwd(const float* dA, int D, float* dW, cudaStream_t 
 //   x_out = x_in + eps * tanh(QKVA[:,3D:] + phi)
 // Saves ALPHA [E] (normalised attention) and TH [N,D] (tanh values) for the backward when non-null.
 // ------------------------------------------------------------------------------------------
-template <int MAXV>
+template <int MAXV, bool PF>
 __global__ void edge_fwd_kernel(const float* __restrict__ QKVA, const float* __restrict__ EP,
                                 const int32_t* __restrict__ rowptr, const int64_t* __restrict__ esrc, int N_host,
                                 const int* __restrict__ N_dev, int D, const float* __restrict__ Xin, float eps,
@@ -122,6 +123,50 @@ __global__ void edge_fwd_kernel(const float* __restrict__ QKVA, const float* __r
             // by exp(mx_old - mx_new) whenever the max grows.  Raw scores are parked in ALPHA (lane e%32 writes
             // and later re-reads its own entries) and normalised once the row's max and sum are final.
             float mx = -INFINITY, den = 0.f;
+            if (PF) {
+                // software-pipelined: the rows of edge e+1 are requested before edge e is reduced, so a row of
+                // degree d costs ~d/2 exposed memory round trips (hub rows at evaluation shapes are latency-bound)
+                float kj[MAXV], vj[MAXV], ep[MAXV];
+                {
+                    const int64_t j = esrc[r0];
+#pragma unroll
+                    for (int v = 0; v < MAXV; ++v) {
+                        const int d = lane + 32 * v;
+                        const bool in = d < D;
+                        kj[v] = in ? QKVA[(size_t)j * ld + D + d] : 0.f;
+                        vj[v] = in ? QKVA[(size_t)j * ld + 2 * D + d] : 0.f;
+                        ep[v] = in ? EP[(size_t)r0 * D + d] : 0.f;
+                    }
+                }
+                for (int e = r0; e < r1; ++e) {
+                    float kn[MAXV], vn[MAXV], en[MAXV];
+                    const int e1 = min(e + 1, r1 - 1);                 // last iteration re-reads its own rows (L1 hit)
+                    const int64_t jn = esrc[e1];
+#pragma unroll
+                    for (int v = 0; v < MAXV; ++v) {
+                        const int d = lane + 32 * v;
+                        const bool in = d < D;
+                        kn[v] = in ? QKVA[(size_t)jn * ld + D + d] : 0.f;
+                        vn[v] = in ? QKVA[(size_t)jn * ld + 2 * D + d] : 0.f;
+                        en[v] = in ? EP[(size_t)e1 * D + d] : 0.f;
+                    }
+                    float part = 0.f;
+#pragma unroll
+                    for (int v = 0; v < MAXV; ++v) part = fmaf(q[v], kj[v] + ep[v], part);
+                    const float s = warp_sum(part) * inv_sqrt_d;
+                    if (ALPHA && lane == ((e - r0) & 31)) ALPHA[e] = s;
+                    const float nmx = fmaxf(mx, s);
+                    const float scale = (mx == -INFINITY) ? 0.f : expf(mx - nmx);
+                    const float p = expf(s - nmx);
+                    den = fmaf(den, scale, p);
+#pragma unroll
+                    for (int v = 0; v < MAXV; ++v) {
+                        phi[v] = fmaf(phi[v], scale, p * (vj[v] + ep[v]));
+                        kj[v] = kn[v]; vj[v] = vn[v]; ep[v] = en[v];
+                    }
+                    mx = nmx;
+                }
+            } else
             for (int e = r0; e < r1; ++e) {
                 const int64_t j = esrc[e];
                 float kj[MAXV], vj[MAXV], ep[MAXV];
@@ -175,10 +220,12 @@ extern "C" int ctan_edge_fwd(const float* QKVA, const float* EP, const int32_t* 
     if (D > 512) return CTAN_ERR_UNSUPPORTED;
     const int grid = ctan_grid((long long)N * 32, 256);
     const float isd = 1.0f / sqrtf((float)D);
-#define LAUNCH(V) edge_fwd_kernel<V><<<grid, 256, 0, stream>>>(QKVA, EP, rowptr, esrc, N, N_dev, D, Xin, eps, Xout, \
-                                                                TH, ALPHA, Zout, isd)
+#define LAUNCH2(V, P) edge_fwd_kernel<V, P><<<grid, 256, 0, stream>>>(QKVA, EP, rowptr, esrc, N, N_dev, D, Xin, eps, \
+                                                                       Xout, TH, ALPHA, Zout, isd)
+#define LAUNCH(V) LAUNCH2(V, true)
     if (D <= 32) LAUNCH(1); else if (D <= 64) LAUNCH(2); else if (D <= 128) LAUNCH(4);
-    else if (D <= 256) LAUNCH(8); else LAUNCH(16);
+    else if (D <= 256) LAUNCH(8); else LAUNCH2(16, false);
+#undef LAUNCH2
 #undef LAUNCH
     CTAN_CHECK_LAUNCH();
     return 0;
