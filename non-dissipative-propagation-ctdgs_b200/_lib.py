@@ -92,6 +92,7 @@ SIGNATURES.update({
     "ctan_gemm_tc": [P, I, P, I, P, P, I, P, P, P, P, I, P, I, P, I],
     "ctan_enc_prep": [P, I, P, I, P, I, P, P, P, P],
     "ctan_head_gather": [P, I, P, P, P, I, P, P, P],
+    "ctan_head_pack": [P, I, P, I, P, P, P, I, I, P, P, P],
     "ctan_qkva_fwd_tc": [P, I, P, I, P, P, P, P, P, P, P, I],
 })
 

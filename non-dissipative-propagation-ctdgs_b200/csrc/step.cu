@@ -254,6 +254,66 @@ extern "C" int ctan_pack_eval(const float* OUT, const float* z, const int64_t* a
     return 0;
 }
 
+// head_pack: readout head on pre-projected node rows + reciprocal rank + packed row, one CTA per query:
+//   score_i = relu(Y[row(src_i), :Hd] + Y[row(dst_i), Hd:]) . Wfin + bfin        (models/predictors.py:16-19)
+//   row q   = [ 1/rank | scores(1+n_neg) | z[src_q] (D) | z[dst_q] (D) ]           (evaluate.py:109-120)
+// Same arithmetic order as ctan_head_gather + ctan_pack_eval (scores are bit-identical), two launches fewer.
+__global__ void head_pack_kernel(const float* __restrict__ Y, int Hd, const float* __restrict__ z, int D,
+                                 const int64_t* __restrict__ assoc, const int64_t* __restrict__ pair_src,
+                                 const int64_t* __restrict__ pair_dst, int Q, int n_neg,
+                                 const float* __restrict__ Wfin, const float* __restrict__ bfin,
+                                 float* __restrict__ rows) {
+    extern __shared__ float sc[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int L = 1 + n_neg, W = 1 + L + 2 * D;
+    for (int q = blockIdx.x; q < Q; q += gridDim.x) {
+        for (int i = warp; i < L; i += nwarp) {
+            const int64_t rs = assoc[pair_src[(size_t)q * L + i]], rd = assoc[pair_dst[(size_t)q * L + i]];
+            const float* ys = Y + (size_t)rs * 2 * Hd;
+            const float* yd = Y + (size_t)rd * 2 * Hd + Hd;
+            float s = 0.f;
+            for (int h = lane; h < Hd; h += 32) s = fmaf(fmaxf(ys[h] + yd[h], 0.f), __ldg(Wfin + h), s);
+            s = warp_sum(s);
+            if (lane == 0) sc[i] = s + __ldg(bfin);
+        }
+        __syncthreads();
+        float* r = rows + (size_t)q * W;
+        if (warp == 0) {
+            const float p = sc[0];
+            int ge = 0, gt = 0;
+            for (int i = 1 + lane; i < L; i += 32) {
+                const float x = sc[i];
+                ge += x >= p;
+                gt += x > p;
+            }
+            ge = warp_sum_i(ge); gt = warp_sum_i(gt);
+            if (lane == 0) r[0] = 1.0f / (0.5f * (float)(ge + gt) + 1.0f);
+        }
+        for (int i = threadIdx.x; i < L; i += blockDim.x) r[1 + i] = sc[i];
+        const float* zs = z + (size_t)assoc[pair_src[(size_t)q * L]] * D;
+        const float* zd = z + (size_t)assoc[pair_dst[(size_t)q * L]] * D;
+        for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            r[1 + L + d] = zs[d];
+            r[1 + L + D + d] = zd[d];
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int ctan_head_pack(const float* Y, int Hd, const float* z, int D, const int64_t* assoc,
+                              const int64_t* pair_src, const int64_t* pair_dst, int Q, int n_neg, const float* Wfin,
+                              const float* bfin, float* rows, cudaStream_t stream) {
+    if (Q <= 0) return 0;
+    if (n_neg < 0 || (size_t)(1 + n_neg) * 4 > 48 * 1024) return CTAN_ERR_UNSUPPORTED;
+    const int grid = Q < 4 * CTAN_SM_COUNT ? Q : 4 * CTAN_SM_COUNT;
+    // one warp per candidate when they fit (each is a chain of dependent gathers: pair -> row id -> projected rows)
+    const int warps = (1 + n_neg) < 32 ? (1 + n_neg) : 32;
+    head_pack_kernel<<<grid, 32 * warps, (1 + n_neg) * sizeof(float), stream>>>(Y, Hd, z, D, assoc, pair_src, pair_dst, Q,
+                                                                         n_neg, Wfin, bfin, rows);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
 // acc[0] += sum_r rows[r*ld + col]; acc[1] += R    (running sum of reciprocal ranks and query count)
 __global__ void accum_col_kernel(const float* __restrict__ rows, int R, int ld, int col, double* __restrict__ acc) {
     __shared__ float red[32];

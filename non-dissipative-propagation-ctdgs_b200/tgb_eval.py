@@ -88,6 +88,7 @@ class TGBEvalEngine:
         self._alloc()
         self._graph = None
         self._side = torch.cuda.Stream(device=dev)
+        self._side2 = torch.cuda.Stream(device=dev)
 
     def _alloc(self):
         dev, B, K, D = self.dev, self.B, self.K, self.D
@@ -151,11 +152,25 @@ class TGBEvalEngine:
 
     # ------------------------------------------------------------------ one batch
     def _launch(self, dry: bool = False):
-        self._compute()
+        self._compute(dry)
         self._exchange()
         self._update(dry)
 
-    def _compute(self):
+    def _insert_branch(self, dry: bool):
+        """The neighbour-table insert of the batch needs only the staged (src, dst) and must follow this batch's
+        lookup/fill (the last readers of the tables): it runs as a parallel branch beside the whole forward and
+        the exchange instead of at the tail of the batch."""
+        w, ld = self.w, self.loader
+        self._side2.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side2):
+            if dry:
+                sm, sl, sn, se, sd = self._scratch
+                call("ctan_nbr_insert", ptr(sn), ptr(se), ptr(sd), ptr(sl), ptr(sl), 1, 0, None, self.S, ptr(w["ins_ws"]))
+            else:
+                call("ctan_nbr_insert", ptr(ld.neighbors), ptr(ld.e_id), ptr(ld._deg), ptr(w["b_src"]), ptr(w["b_dst"]),
+                     self.B, 0, ptr(w["counters"]) + 8, self.S, ptr(w["ins_ws"]))
+
+    def _compute(self, dry: bool = False):
         """stage -> lookup -> forward -> scores -> packed per-query rows of this rank's shard."""
         w, m, ld = self.w, self.model, self.loader
         B, D, K, S, Fe, Fn, T, Hd, O, P, Q = self.B, self.D, self.K, self.S, self.Fe, self.Fn, self.T, self.Hd, self.O, self.P, self.Q
@@ -177,6 +192,7 @@ class TGBEvalEngine:
                  ptr(ld._assoc), N, Nd, ptr(w["esrc"]), ptr(w["edst"]), ptr(w["eid"]), ptr(ld._bitmap),
                  ptr(ld._cbitmap), ptr(lu), ptr(self.t), float(g.mean_delta_t), float(g.std_delta_t), ptr(w["rel"]))
             self._side.wait_stream(torch.cuda.current_stream())
+            self._insert_branch(dry)
             with torch.cuda.stream(self._side):
                 if self.use_tc_ep:
                     call("ctan_eproj_prep", ptr(self.msg), Fe, ptr(w["eid"]), ptr(w["rel"]), ptr(g.time_enc.lin.weight),
@@ -213,14 +229,17 @@ class TGBEvalEngine:
                 # project every NODE once (tensor cores), then a scored pair only gathers two rows
                 call("ctan_gemm_tc", ptr(z), N, Nd, D, ptr(w["Wro_hi"]), ptr(w["Wro_lo"]), 2 * Hd, ptr(r.lin_src.bias),
                      ptr(r.lin_dst.bias), None, None, Hd, None, 0, ptr(w["Y"]), _lib.TC_MODE)
-                call("ctan_head_gather", ptr(w["Y"]), Hd, ptr(w["pair_src"]), ptr(w["pair_dst"]), ptr(ld._assoc),
-                     Q * self.L, ptr(r.lin_final.weight), ptr(r.lin_final.bias), ptr(w["OUT"]))
+                call("ctan_head_pack", ptr(w["Y"]), Hd, ptr(z), D, ptr(ld._assoc), ptr(w["pair_src"]), ptr(w["pair_dst"]),
+                     Q, self.n_neg, ptr(r.lin_final.weight), ptr(r.lin_final.bias), ptr(w["send"]))
             else:
-              call("ctan_readout_fwd", ptr(z), D, ptr(w["pair_src"]), ptr(w["pair_dst"]), ptr(ld._assoc), Q * self.L,
-                 None, Hd, O, ptr(r.lin_src.weight), ptr(r.lin_src.bias), ptr(r.lin_dst.weight), ptr(r.lin_dst.bias),
-                 ptr(r.lin_final.weight), ptr(r.lin_final.bias), ptr(w["H"]), ptr(w["OUT"]), 0)   # no split-K: scores must not depend on atomic order
-            call("ctan_pack_eval", ptr(w["OUT"]), ptr(z), ptr(ld._assoc), ptr(w["pair_src"]), ptr(w["pair_dst"]), Q,
-                 self.n_neg, D, ptr(w["send"]))
+                call("ctan_readout_fwd", ptr(z), D, ptr(w["pair_src"]), ptr(w["pair_dst"]), ptr(ld._assoc), Q * self.L,
+                     None, Hd, O, ptr(r.lin_src.weight), ptr(r.lin_src.bias), ptr(r.lin_dst.weight), ptr(r.lin_dst.bias),
+                     ptr(r.lin_final.weight), ptr(r.lin_final.bias), ptr(w["H"]), ptr(w["OUT"]), 0)   # no split-K: scores must not depend on atomic order
+                call("ctan_pack_eval", ptr(w["OUT"]), ptr(z), ptr(ld._assoc), ptr(w["pair_src"]), ptr(w["pair_dst"]), Q,
+                     self.n_neg, D, ptr(w["send"]))
+        else:
+            self._insert_branch(dry)         # a rank without queries still applies the state update
+        torch.cuda.current_stream().wait_stream(self._side2)
 
     def _prep_weights(self):
         """Weight-only operands (A = W - W^T - gamma I, the packed / hi-lo split weight panels of the tensor-core
@@ -265,12 +284,9 @@ class TGBEvalEngine:
             sm, sl, sn, se, sd = self._scratch
             call("ctan_mem_update", ptr(sm), ptr(sl), D, ptr(sl), ptr(sl), ptr(sl), 1, emb, emb + 4 * D, self.row,
                  None, None)
-            call("ctan_nbr_insert", ptr(sn), ptr(se), ptr(sd), ptr(sl), ptr(sl), 1, 0, None, S, ptr(w["ins_ws"]))
             return
         call("ctan_mem_update", ptr(mem), ptr(lu), D, ptr(w["b_src"]), ptr(w["b_dst"]), ptr(w["b_t"]), B, emb,
              emb + 4 * D, self.row, None, None)
-        call("ctan_nbr_insert", ptr(ld.neighbors), ptr(ld.e_id), ptr(ld._deg), ptr(w["b_src"]), ptr(w["b_dst"]), B, 0,
-             ptr(w["counters"]) + 8, S, ptr(w["ins_ws"]))
 
     def warmup(self):
         """One eager dry batch: loads every kernel and initialises the communicator before graph capture.

@@ -46,6 +46,7 @@ REF = {
     "ctan_gemm_tc": "torch.nn.Linear on tcgen05 tensor cores (enc_x: models/gnn_layers.py:96; readout lin_src/lin_dst: models/predictors.py:16-17)",
     "ctan_enc_prep": "SimpleMemory.forward gather + node-feature columns of enc_x -- models/memory_layers.py:155-156, models/gnn_layers.py:96",
     "ctan_head_gather": "TGBLinkPredictor.forward on pre-projected node rows -- models/predictors.py:16-19",
+    "ctan_head_pack": "TGBLinkPredictor.forward on pre-projected rows + per-query reciprocal rank (TGB/tgb/linkproppred/evaluate.py:109-120) + the packed row every rank exchanges",
     "ctan_dx_tc": "gradient of the projections w.r.t. the node state (autograd in the reference) on tcgen05",
     "ctan_qkva_fwd_tc": "TransformerConv lin_query/lin_key/lin_value + x @ A^T + bias on tcgen05 tensor cores -- PyG 2.3.1 (SURVEY.md App. A.5)",
 }
