@@ -47,6 +47,8 @@ REF = {
     "ctan_enc_prep": "SimpleMemory.forward gather + node-feature columns of enc_x -- models/memory_layers.py:155-156, models/gnn_layers.py:96",
     "ctan_head_gather": "TGBLinkPredictor.forward on pre-projected node rows -- models/predictors.py:16-19",
     "ctan_head_pack": "TGBLinkPredictor.forward on pre-projected rows + per-query reciprocal rank (TGB/tgb/linkproppred/evaluate.py:109-120) + the packed row every rank exchanges",
+    "ctan_delta_t_stats_ws_bytes": "(workspace size of ctan_delta_t_stats; host-side query)",
+    "ctan_delta_t_stats": "compute_stats: mean/std of per-node inter-event times -- utils.py:46-92",
     "ctan_dx_tc": "gradient of the projections w.r.t. the node state (autograd in the reference) on tcgen05",
     "ctan_qkva_fwd_tc": "TransformerConv lin_query/lin_key/lin_value + x @ A^T + bias on tcgen05 tensor cores -- PyG 2.3.1 (SURVEY.md App. A.5)",
 }
@@ -77,7 +79,7 @@ extern "C" {
 #endif
 ''']
 names = []
-for f in ("loader.cu", "edge.cu", "dense.cu", "step.cu", "tc_gemm.cu"):
+for f in ("loader.cu", "edge.cu", "dense.cu", "step.cu", "tc_gemm.cu", "stats.cu"):
     src = open(os.path.join(CSRC, f)).read()
     out.append(f"/* ---------------------------------------------------------------- {f} */")
     for m in re.finditer(r'((?:^//[^\n]*\n)*)extern "C" int (\w+)\(([^{]*?)\)\s*\{', src, re.M):

@@ -285,3 +285,26 @@ def test_sequence_fixture_matches_reference_run():
     assert float((pred.cpu() - g["eval_pred"]).abs().max()) < 2e-3
     assert torch.equal(mm.memory.last_update.cpu(), g["last_update_after_eval"])
     assert float((mm.memory.memory.cpu() - g["memory_after_eval"]).abs().max()) < 2e-3
+
+
+def test_device_compute_stats_known_answers_and_oracle():
+    """f4: compute_stats on the device vs the reference's known answers (delta_t_stats.pkl of the shipped
+    fixture) and vs the oracle on a wiki-shaped stream with hubs, time ties and self-loops."""
+    import os
+    from ctan_b200 import synth
+    from ctan_b200.stats import compute_stats
+    from oracle import ctan_oracle as O
+    dev = torch.device("cuda:0")
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "sequence_golden.pt"), weights_only=False)
+    n_train = int(1000 * (1 - g["split"][0] - g["split"][1]))
+    for L, (mean, std) in g["stats"].items():
+        s, d, t = O.path_graph_events(L, n_train)
+        m, sd = compute_stats(s.to(dev), d.to(dev), t.to(dev), init_time=0)
+        assert abs(m - mean) < 1e-12 and abs(sd - std) < 1e-12, (L, m, sd)
+    st = synth.make_stream("wiki", n_events=20000, seed=2, n_nodes_scale=0.05)
+    src, dst, t = st["src"].clone(), st["dst"].clone(), st["t"]
+    dst[::97] = src[::97]                                  # self-loops: both endpoints see the pre-event state
+    for init in (0, -5):
+        m_ref, s_ref = O.delta_t_stats_ref(src, dst, t, init_time=init)
+        m, sd = compute_stats(src.to(dev), dst.to(dev), t.to(dev), init_time=init)
+        assert abs(m - m_ref) <= 1e-12 * abs(m_ref) and abs(sd - s_ref) <= 1e-11 * abs(s_ref), (m, m_ref, sd, s_ref)
