@@ -84,3 +84,38 @@ def test_mrr_kernel_matches_golden():
         rr = torch.zeros(1, device=dev)
         call("ctan_mrr", ptr(pos), ptr(neg), 1, neg.numel(), ptr(rr))
         assert abs(float(rr) - c["mrr"]) < 1e-7
+
+
+def test_full_size_comment_shape_engine_vs_module_api():
+    """BASELINE config C5 at its full sizes (994 790 nodes, D=T=256, S=32, 20 negatives, 200 queries/batch): no CPU
+    oracle finishes here, so the graph-captured evaluation engine (tcgen05 enc_x / lin_edge / projections /
+    node-projection readout) is checked against the reference-API module path (`CTAN_tgb.forward` on
+    `LastNeighborLoader.lookup_khop`, itself oracle-tested at small sizes) on the SAME state, batch after batch."""
+    import bench_tgb
+    from oracle import ctan_oracle as O
+    dev = torch.device("cuda:0")
+    eng, st = bench_tgb.build_eval(0, 1, dev, n_batches=8, warm=100_000)
+    mm, ld = eng.model, eng.loader
+    B, n_neg = eng.B, eng.n_neg
+    src, dst, t, msg, neg, x = eng.src, eng.dst, eng.t, eng.msg, eng.neg, eng.x
+    cur = ld.cur_e_id
+    assert st["num_nodes"] == 994790
+    for it in range(3):
+        lo, hi = cur + it * B, cur + (it + 1) * B
+        s, d, ng = src[lo:hi], dst[lo:hi], neg[lo:hi]
+        # reference-API path on the current state (no state change)
+        seeds = torch.cat([s, d, ng.reshape(-1)])
+        n_id, ei, eid, _ = ld.lookup_khop(seeds, mm.num_gnn_layers)
+        hm = torch.zeros(st["num_nodes"], dtype=torch.long, device=dev)
+        hm[n_id] = torch.arange(n_id.numel(), device=dev)
+        with torch.no_grad():
+            q_src = s.view(-1, 1).expand(-1, 1 + n_neg).reshape(-1)
+            q_dst = torch.cat([d.view(-1, 1), ng], 1).reshape(-1)
+            out, _, _, _ = mm(O.Batch(src=torch.cat([q_src, q_src[:1]]), dst=torch.cat([q_dst, q_dst[:1]]), n_neg=1, x=x),
+                              n_id, msg[eid], t[eid], ei, hm)
+        ref = out.view(-1)[: B * (1 + n_neg)].view(B, 1 + n_neg)
+        eng.run(1)
+        sc = eng.scores()
+        assert float((sc - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-6, it
+    eng.check()
+    assert 0.0 < eng.mrr() <= 1.0
