@@ -94,3 +94,39 @@ def test_engine_then_dropin_loop_share_state(small_stream):
     s, d = st["src"][300:400].to(dev), st["dst"][300:400].to(dev)
     n_id, ei, eid = ld(torch.cat([s, d]).unique())
     assert int(eid.max()) < 300 and ld.cur_e_id == 300
+
+
+@pytest.mark.parametrize("K", [1, 3])
+def test_bench_configuration_matches_oracle(K):
+    """The exact workload bench.py times (BASELINE configs[1]: wiki-shaped stream, 9 227 nodes, 172-d messages,
+    batch 200, CTAN D=128 T=16 S=5 H=64, tcgen05 projections): 30 warm-up + 12 compared training steps
+    (loss, parameters, memory, neighbour tables) against the oracle on the same events."""
+    import bench
+    from oracle import ctan_oracle as O
+    dev = torch.device("cuda:0")
+    steps, B, S = 42, bench.WIKI["B"], bench.WIKI["S"]
+    st, mean, std = bench.make_workload((steps + 8) * B)
+    eng = bench.build_engine(st, K, mean, std, dev)
+    mm, ld = eng.model, eng.loader
+    torch.manual_seed(0)
+    om = O.OracleCTAN(**bench.model_kwargs(st, K, mean, std))
+    lo_ref = O.TorchNeighborLoader(st["num_nodes"], S)
+    h = torch.zeros(st["num_nodes"], dtype=torch.long)
+    opt = torch.optim.Adam(om.parameters(), lr=bench.WIKI["lr"])
+    ref = [float(O.train_step_ref(om, lo_ref, h, opt, st, it * B, (it + 1) * B, st["neg"][it * B:(it + 1) * B])[0])
+           for it in range(steps)]
+    eng.run(steps, train=True)
+    torch.cuda.synchronize()
+    eng.check()
+    mine = eng.losses(steps).cpu().tolist()
+    for a, b in zip(mine[-12:], ref[-12:]):
+        assert abs(a - b) <= 1e-3 * abs(b) + 1e-6, (mine[-12:], ref[-12:])
+    assert torch.equal(ld.e_id.cpu(), lo_ref.e_id)
+    assert torch.equal(mm.memory.last_update.cpu(), om.memory.last_update)
+    mo = om.memory.memory
+    assert float((mm.memory.memory.cpu() - mo).abs().max()) <= 2e-3 * float(mo.abs().max())
+    po = dict(om.named_parameters())
+    for k, p in mm.named_parameters():
+        if "lin_skip" not in k:
+            d = float((p.detach().cpu() - po[k].detach()).abs().max())
+            assert d <= 2e-3 * float(po[k].abs().max()) + 1e-6, (k, d)
