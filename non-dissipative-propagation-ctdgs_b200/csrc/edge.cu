@@ -96,18 +96,103 @@ extern "C" int ctan_antisym_bwd(const float* dA, int D, float* dW, cudaStream_t 
 //   x_out = x_in + eps * tanh(QKVA[:,3D:] + phi)
 // Saves ALPHA [E] (normalised attention) and TH [N,D] (tanh values) for the backward when non-null.
 // ------------------------------------------------------------------------------------------
-template <int MAXV, bool PF>
-__global__ void edge_fwd_kernel(const float* __restrict__ QKVA, const float* __restrict__ EP,
+// One pass over edges e = e_begin, e_begin + stride, ... < e_end of destination row i (every k_j / v_j / EP row is
+// read from HBM exactly once): online softmax -- running max mx, running denominator den and running weighted
+// sum phi are rescaled by exp(mx_old - mx_new) whenever the max grows.  Software-pipelined: the rows of the next
+// edge are requested before the current one is reduced.  Raw scores are parked in ALPHA (lane (e-r0)%32).
+template <int MAXV>
+__device__ __forceinline__ void edge_partial(const float* __restrict__ QKVA, const float* __restrict__ EP,
+                                             const int64_t* __restrict__ esrc, int D, int ld, int lane,
+                                             const float (&q)[MAXV], int e_begin, int e_end, int stride, int r0,
+                                             float* __restrict__ ALPHA, float inv_sqrt_d, float& mx, float& den,
+                                             float (&phi)[MAXV]) {
+    if (e_begin >= e_end) return;
+    float kj[MAXV], vj[MAXV], ep[MAXV];
+    {
+        const int64_t j = esrc[e_begin];
+#pragma unroll
+        for (int v = 0; v < MAXV; ++v) {
+            const int d = lane + 32 * v;
+            const bool in = d < D;
+            kj[v] = in ? QKVA[(size_t)j * ld + D + d] : 0.f;
+            vj[v] = in ? QKVA[(size_t)j * ld + 2 * D + d] : 0.f;
+            ep[v] = in ? EP[(size_t)e_begin * D + d] : 0.f;
+        }
+    }
+    for (int e = e_begin; e < e_end; e += stride) {
+        float kn[MAXV], vn[MAXV], en[MAXV];
+        const int e1 = (e + stride < e_end) ? e + stride : e;          // last iteration re-reads its own rows (L1 hit)
+        const int64_t jn = esrc[e1];
+#pragma unroll
+        for (int v = 0; v < MAXV; ++v) {
+            const int d = lane + 32 * v;
+            const bool in = d < D;
+            kn[v] = in ? QKVA[(size_t)jn * ld + D + d] : 0.f;
+            vn[v] = in ? QKVA[(size_t)jn * ld + 2 * D + d] : 0.f;
+            en[v] = in ? EP[(size_t)e1 * D + d] : 0.f;
+        }
+        float part = 0.f;
+#pragma unroll
+        for (int v = 0; v < MAXV; ++v) part = fmaf(q[v], kj[v] + ep[v], part);
+        const float s = warp_sum(part) * inv_sqrt_d;
+        if (ALPHA && lane == ((e - r0) & 31)) ALPHA[e] = s;
+        const float nmx = fmaxf(mx, s);
+        const float scale = (mx == -INFINITY) ? 0.f : expf(mx - nmx);
+        const float p = expf(s - nmx);
+        den = fmaf(den, scale, p);
+#pragma unroll
+        for (int v = 0; v < MAXV; ++v) {
+            phi[v] = fmaf(phi[v], scale, p * (vj[v] + ep[v]));
+            kj[v] = kn[v]; vj[v] = vn[v]; ep[v] = en[v];
+        }
+        mx = nmx;
+    }
+}
+
+// x_out = x_in + eps tanh(x A^T + b + phi) for one (row, column)
+__device__ __forceinline__ void edge_finish(const float* __restrict__ QKVA, const float* __restrict__ Xin, float eps,
+                                            float* __restrict__ Xout, float* __restrict__ TH,
+                                            float* __restrict__ Zout, int D, int i, int d, float phi_d) {
+    const float h = QKVA[(size_t)i * 4 * D + 3 * D + d] + phi_d;
+    const float th = tanhf(h);
+    if (TH) TH[(size_t)i * D + d] = th;
+    const float xn = fmaf(eps, th, Xin[(size_t)i * D + d]);
+    Xout[(size_t)i * D + d] = xn;
+    if (Zout) Zout[(size_t)i * D + d] = tanhf(xn);
+}
+
+// Rows of degree > HUB_DEG at small batches are a chain of dependent gathers in ONE warp (a degree-32 row of the
+// TGB evaluation took ~20 us: the whole launch waited for it).  When the caller provides a hub workspace and the
+// launch is in the latency regime (N <= HUB_MAX_N), such rows are appended to a list instead and processed by
+// edge_fwd_hub_kernel: one CTA per hub row, each of its 8 warps taking every 8th edge with its own online-softmax
+// state, the 8 states merged through shared memory in a fixed order.  Bandwidth-bound launches (large N) and
+// callers without a workspace keep the plain warp-per-row path for every row.
+// hub workspace (int32): [0] = number of deferred rows, [1] = CTA ticket of the hub kernel, [2..] = row ids.
+constexpr int HUB_DEG = 8, HUB_MAX_N = 16384, EF_WARPS = 8;
+
+template <int MAXV>
+__global__ void __launch_bounds__(256, MAXV <= 8 ? 3 : 1)               // 3 CTAs/SM: the saturating shape needs the warps
+edge_fwd_kernel(const float* __restrict__ QKVA, const float* __restrict__ EP,
                                 const int32_t* __restrict__ rowptr, const int64_t* __restrict__ esrc, int N_host,
                                 const int* __restrict__ N_dev, int D, const float* __restrict__ Xin, float eps,
                                 float* __restrict__ Xout, float* __restrict__ TH, float* __restrict__ ALPHA,
-                                float* __restrict__ Zout, float inv_sqrt_d) {
+                                float* __restrict__ Zout, float inv_sqrt_d, int* __restrict__ hub, int hub_cap) {
     const int N = N_dev ? *N_dev : N_host;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     const int ld = 4 * D;
+    const bool defer = hub != nullptr && N <= HUB_MAX_N;
     for (int i = warp; i < N; i += nw) {
         const int r0 = rowptr[i], r1 = rowptr[i + 1];
+        if (defer && r1 - r0 > HUB_DEG) {
+            int slot = 0;
+            if (lane == 0) slot = atomicAdd(hub, 1);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (slot < hub_cap) {
+                if (lane == 0) hub[2 + slot] = i;
+                continue;
+            }                                                           // list full: plain path
+        }
         float phi[MAXV];
 #pragma unroll
         for (int v = 0; v < MAXV; ++v) phi[v] = 0.f;
@@ -118,79 +203,8 @@ __global__ void edge_fwd_kernel(const float* __restrict__ QKVA, const float* __r
                 const int d = lane + 32 * v;
                 q[v] = d < D ? QKVA[(size_t)i * ld + d] : 0.f;
             }
-            // ONE pass over the row's edges (every k_j / v_j / EP row is read from HBM exactly once): online
-            // softmax -- running max mx, running denominator den and running weighted sum phi are rescaled
-            // by exp(mx_old - mx_new) whenever the max grows.  Raw scores are parked in ALPHA (lane e%32 writes
-            // and later re-reads its own entries) and normalised once the row's max and sum are final.
             float mx = -INFINITY, den = 0.f;
-            if (PF) {
-                // software-pipelined: the rows of edge e+1 are requested before edge e is reduced, so a row of
-                // degree d costs ~d/2 exposed memory round trips (hub rows at evaluation shapes are latency-bound)
-                float kj[MAXV], vj[MAXV], ep[MAXV];
-                {
-                    const int64_t j = esrc[r0];
-#pragma unroll
-                    for (int v = 0; v < MAXV; ++v) {
-                        const int d = lane + 32 * v;
-                        const bool in = d < D;
-                        kj[v] = in ? QKVA[(size_t)j * ld + D + d] : 0.f;
-                        vj[v] = in ? QKVA[(size_t)j * ld + 2 * D + d] : 0.f;
-                        ep[v] = in ? EP[(size_t)r0 * D + d] : 0.f;
-                    }
-                }
-                for (int e = r0; e < r1; ++e) {
-                    float kn[MAXV], vn[MAXV], en[MAXV];
-                    const int e1 = min(e + 1, r1 - 1);                 // last iteration re-reads its own rows (L1 hit)
-                    const int64_t jn = esrc[e1];
-#pragma unroll
-                    for (int v = 0; v < MAXV; ++v) {
-                        const int d = lane + 32 * v;
-                        const bool in = d < D;
-                        kn[v] = in ? QKVA[(size_t)jn * ld + D + d] : 0.f;
-                        vn[v] = in ? QKVA[(size_t)jn * ld + 2 * D + d] : 0.f;
-                        en[v] = in ? EP[(size_t)e1 * D + d] : 0.f;
-                    }
-                    float part = 0.f;
-#pragma unroll
-                    for (int v = 0; v < MAXV; ++v) part = fmaf(q[v], kj[v] + ep[v], part);
-                    const float s = warp_sum(part) * inv_sqrt_d;
-                    if (ALPHA && lane == ((e - r0) & 31)) ALPHA[e] = s;
-                    const float nmx = fmaxf(mx, s);
-                    const float scale = (mx == -INFINITY) ? 0.f : expf(mx - nmx);
-                    const float p = expf(s - nmx);
-                    den = fmaf(den, scale, p);
-#pragma unroll
-                    for (int v = 0; v < MAXV; ++v) {
-                        phi[v] = fmaf(phi[v], scale, p * (vj[v] + ep[v]));
-                        kj[v] = kn[v]; vj[v] = vn[v]; ep[v] = en[v];
-                    }
-                    mx = nmx;
-                }
-            } else
-            for (int e = r0; e < r1; ++e) {
-                const int64_t j = esrc[e];
-                float kj[MAXV], vj[MAXV], ep[MAXV];
-#pragma unroll
-                for (int v = 0; v < MAXV; ++v) {
-                    const int d = lane + 32 * v;
-                    const bool in = d < D;
-                    kj[v] = in ? QKVA[(size_t)j * ld + D + d] : 0.f;
-                    vj[v] = in ? QKVA[(size_t)j * ld + 2 * D + d] : 0.f;
-                    ep[v] = in ? EP[(size_t)e * D + d] : 0.f;
-                }
-                float part = 0.f;
-#pragma unroll
-                for (int v = 0; v < MAXV; ++v) part = fmaf(q[v], kj[v] + ep[v], part);
-                const float s = warp_sum(part) * inv_sqrt_d;
-                if (ALPHA && lane == ((e - r0) & 31)) ALPHA[e] = s;
-                const float nmx = fmaxf(mx, s);
-                const float scale = (mx == -INFINITY) ? 0.f : expf(mx - nmx);
-                const float p = expf(s - nmx);
-                den = fmaf(den, scale, p);
-#pragma unroll
-                for (int v = 0; v < MAXV; ++v) phi[v] = fmaf(phi[v], scale, p * (vj[v] + ep[v]));
-                mx = nmx;
-            }
+            edge_partial<MAXV>(QKVA, EP, esrc, D, ld, lane, q, r0, r1, 1, r0, ALPHA, inv_sqrt_d, mx, den, phi);
             const float inv = 1.f / (den + 1e-16f);
 #pragma unroll
             for (int v = 0; v < MAXV; ++v) phi[v] *= inv;
@@ -201,31 +215,88 @@ __global__ void edge_fwd_kernel(const float* __restrict__ QKVA, const float* __r
 #pragma unroll
         for (int v = 0; v < MAXV; ++v) {
             const int d = lane + 32 * v;
-            if (d < D) {
-                const float h = QKVA[(size_t)i * ld + 3 * D + d] + phi[v];
-                const float th = tanhf(h);
-                if (TH) TH[(size_t)i * D + d] = th;
-                const float xn = fmaf(eps, th, Xin[(size_t)i * D + d]);
-                Xout[(size_t)i * D + d] = xn;
-                if (Zout) Zout[(size_t)i * D + d] = tanhf(xn);
-            }
+            if (d < D) edge_finish(QKVA, Xin, eps, Xout, TH, Zout, D, i, d, phi[v]);
         }
     }
 }
 
+template <int MAXV>
+__global__ void __launch_bounds__(32 * EF_WARPS)
+edge_fwd_hub_kernel(const float* __restrict__ QKVA, const float* __restrict__ EP, const int32_t* __restrict__ rowptr,
+                    const int64_t* __restrict__ esrc, int D, const float* __restrict__ Xin, float eps,
+                    float* __restrict__ Xout, float* __restrict__ TH, float* __restrict__ ALPHA,
+                    float* __restrict__ Zout, float inv_sqrt_d, int* __restrict__ hub, int hub_cap) {
+    __shared__ float s_mx[EF_WARPS], s_den[EF_WARPS];
+    __shared__ float s_phi[EF_WARPS][MAXV * 32];
+    __shared__ int s_nh;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int ld = 4 * D;
+    if (threadIdx.x == 0) s_nh = min(hub[0], hub_cap);
+    __syncthreads();
+    const int nh = s_nh;
+    for (int hidx = blockIdx.x; hidx < nh; hidx += gridDim.x) {
+        const int i = hub[2 + hidx];
+        const int r0 = rowptr[i], r1 = rowptr[i + 1];
+        float q[MAXV], phi[MAXV];
+#pragma unroll
+        for (int v = 0; v < MAXV; ++v) {
+            const int d = lane + 32 * v;
+            q[v] = d < D ? QKVA[(size_t)i * ld + d] : 0.f;
+            phi[v] = 0.f;
+        }
+        float mx = -INFINITY, den = 0.f;
+        edge_partial<MAXV>(QKVA, EP, esrc, D, ld, lane, q, r0 + wib, r1, EF_WARPS, r0, ALPHA, inv_sqrt_d, mx, den, phi);
+#pragma unroll
+        for (int v = 0; v < MAXV; ++v) s_phi[wib][lane + 32 * v] = phi[v];
+        if (lane == 0) { s_mx[wib] = mx; s_den[wib] = den; }
+        __syncthreads();
+        float M = s_mx[0];
+#pragma unroll
+        for (int w = 1; w < EF_WARPS; ++w) M = fmaxf(M, s_mx[w]);
+        float sc[EF_WARPS], dsum = 0.f;
+#pragma unroll
+        for (int w = 0; w < EF_WARPS; ++w) {                            // fixed merge order: deterministic
+            sc[w] = s_mx[w] == -INFINITY ? 0.f : expf(s_mx[w] - M);
+            dsum = fmaf(s_den[w], sc[w], dsum);
+        }
+        const float inv = 1.f / (dsum + 1e-16f);
+        for (int d = threadIdx.x; d < D; d += 32 * EF_WARPS) {
+            float p = 0.f;
+#pragma unroll
+            for (int w = 0; w < EF_WARPS; ++w) p = fmaf(s_phi[w][d], sc[w], p);
+            edge_finish(QKVA, Xin, eps, Xout, TH, Zout, D, i, d, p * inv);
+        }
+        if (ALPHA)                                                      // raw scores were written by other warps of this CTA
+            for (int e = r0 + threadIdx.x; e < r1; e += 32 * EF_WARPS) ALPHA[e] = expf(ALPHA[e] - M) * inv;
+        __syncthreads();
+    }
+    // the last CTA to finish clears the list for the next launch (every CTA has read hub[0] before its ticket)
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(hub + 1, 1) == (int)gridDim.x - 1) { hub[0] = 0; hub[1] = 0; }
+    }
+}
+
+// hub_ws: optional int32 workspace of 2 + hub_cap entries, [0] and [1] ZERO before the first call (the call leaves
+// them zero again); NULL = every row on the plain path.
 extern "C" int ctan_edge_fwd(const float* QKVA, const float* EP, const int32_t* rowptr, const int64_t* esrc, int N,
                              const int* N_dev, int D, const float* Xin, float eps, float* Xout, float* TH,
-                             float* ALPHA, float* Zout, cudaStream_t stream) {
+                             float* ALPHA, float* Zout, int32_t* hub_ws, int hub_cap, cudaStream_t stream) {
     if (N <= 0) return 0;
     if (D > 512) return CTAN_ERR_UNSUPPORTED;
+    if (hub_ws && hub_cap <= 0) hub_ws = nullptr;
     const int grid = ctan_grid((long long)N * 32, 256);
     const float isd = 1.0f / sqrtf((float)D);
-#define LAUNCH2(V, P) edge_fwd_kernel<V, P><<<grid, 256, 0, stream>>>(QKVA, EP, rowptr, esrc, N, N_dev, D, Xin, eps, \
-                                                                       Xout, TH, ALPHA, Zout, isd)
-#define LAUNCH(V) LAUNCH2(V, true)
+    const int hgrid = 2 * CTAN_SM_COUNT;
+#define LAUNCH(V) do {                                                                                                 \
+        edge_fwd_kernel<V><<<grid, 256, 0, stream>>>(QKVA, EP, rowptr, esrc, N, N_dev, D, Xin, eps, Xout, TH, ALPHA,   \
+                                                     Zout, isd, hub_ws, hub_cap);                                      \
+        if (hub_ws)                                                                                                    \
+            edge_fwd_hub_kernel<V><<<hgrid, 32 * EF_WARPS, 0, stream>>>(QKVA, EP, rowptr, esrc, D, Xin, eps, Xout, TH, \
+                                                                        ALPHA, Zout, isd, hub_ws, hub_cap);            \
+    } while (0)
     if (D <= 32) LAUNCH(1); else if (D <= 64) LAUNCH(2); else if (D <= 128) LAUNCH(4);
-    else if (D <= 256) LAUNCH(8); else LAUNCH2(16, false);
-#undef LAUNCH2
+    else if (D <= 256) LAUNCH(8); else LAUNCH(16);
 #undef LAUNCH
     CTAN_CHECK_LAUNCH();
     return 0;

@@ -156,6 +156,8 @@ class StepEngine:
         w["z0"] = torch.zeros((N, D + self.Fn), **f32)
         w["X"] = torch.zeros((K + 1, N, D), **f32)
         w["EP"] = torch.zeros((E, D), **f32)
+        self.hub_cap = min(N, 16384)                      # rows of degree > 8 deferred to the block-cooperative kernel
+        w["hub"] = torch.zeros(2 + self.hub_cap, dtype=torch.int32, device=dev)
         w["A"] = torch.zeros((D, D), **f32)
         self.use_tc = _lib.use_tensor_cores(D)
         w["Wcat_hi"], w["Wcat_lo"] = torch.zeros((4 * D, D), **f32), torch.zeros((4 * D, D), **f32)
@@ -286,7 +288,7 @@ class StepEngine:
             last = k == K - 1
             call("ctan_edge_fwd", ptr(qk), ptr(w["EP"]), ptr(w["rowptr"]), ptr(w["esrc"]), N, Nd, D, ptr(xi), eps,
                  ptr(xo), ptr(w["TH"][k]) if train else None, ptr(w["ALPHA"][k]) if train else None,
-                 ptr(w["Z"]) if (last and self.final_tanh) else None)
+                 ptr(w["Z"]) if (last and self.final_tanh) else None, ptr(w["hub"]) if S > 8 else None, self.hub_cap)
         xk = w["X"][K] if train else w["X"][K & 1]
         z = w["Z"] if self.final_tanh else xk
         self._z = z

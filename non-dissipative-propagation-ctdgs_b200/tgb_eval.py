@@ -110,6 +110,8 @@ class TGBEvalEngine:
         w["rel"] = torch.zeros(E, **f32)
         w["X"] = torch.zeros((2, N, D), **f32)
         w["EP"] = torch.zeros((E, D), **f32)
+        self.hub_cap = min(N, 16384)                      # rows of degree > 8 deferred to the block-cooperative kernel
+        w["hub"] = torch.zeros(2 + self.hub_cap, dtype=torch.int32, device=dev)
         w["A"] = torch.zeros((D, D), **f32)
         self.use_tc = _lib.use_tensor_cores(D)
         # tensor-core enc_x (dense gathered rows + packed weights) and node-projection readout
@@ -223,7 +225,8 @@ class TGBEvalEngine:
                      ptr(ph.lin_value.bias), ptr(a.bias), ptr(w["QKVA"]))
                 last = k == K - 1
                 call("ctan_edge_fwd", ptr(w["QKVA"]), ptr(w["EP"]), ptr(w["rowptr"]), ptr(w["esrc"]), N, Nd, D,
-                     ptr(xi), eps, ptr(xo), None, None, ptr(w["Z"]) if (last and self.final_tanh) else None)
+                     ptr(xi), eps, ptr(xo), None, None, ptr(w["Z"]) if (last and self.final_tanh) else None,
+                     ptr(w["hub"]) if self.S > 8 else None, self.hub_cap)
             z = w["Z"] if self.final_tanh else w["X"][K & 1]
             if self.use_tc_ro:
                 # project every NODE once (tensor cores), then a scored pair only gathers two rows
