@@ -170,36 +170,44 @@ extern "C" int ctan_mrr(const float* pos, const float* neg, int Q, int n_neg, fl
 // stage_eval: this rank owns queries [q0,q1) of the batch.  Writes the whole batch's (src,dst,t) for the
 // state update, the rank's seed list, and its scored pairs in per-query order [pos, neg_1..neg_n].
 // ------------------------------------------------------------------------------------------
+// Several CTAs: every CTA reads the cursor counters[0] first; the LAST one to finish (ticket in counters[5])
+// advances it, so no CTA can observe the cursor of the next batch.  counters[1] (batch start) and counters[3]
+// (step count) are only read by later kernels of the batch and are written by CTA 0.
 __global__ void stage_eval_kernel(const int64_t* __restrict__ src_all, const int64_t* __restrict__ dst_all,
                                   const int64_t* __restrict__ t_all, const int64_t* __restrict__ neg_all, int n_neg,
                                   int B, int q0, int q1, int64_t* __restrict__ counters, int64_t* __restrict__ b_src,
                                   int64_t* __restrict__ b_dst, int64_t* __restrict__ b_t, int64_t* __restrict__ seeds,
                                   int64_t* __restrict__ pair_src, int64_t* __restrict__ pair_dst) {
-    __shared__ int64_t s_off;
-    if (threadIdx.x == 0) {
-        const int64_t cur = counters[0];
-        counters[0] = cur + B;
-        counters[1] = cur;
+    const int64_t off = *reinterpret_cast<volatile const int64_t*>(counters);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        counters[1] = off;
         counters[3] += 1;
-        s_off = cur;
     }
-    __syncthreads();
-    const int64_t off = s_off;
     const int Q = q1 - q0, L = 1 + n_neg;
-    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    for (int i = tid; i < B; i += nt) {
         b_src[i] = src_all[off + i]; b_dst[i] = dst_all[off + i]; b_t[i] = t_all[off + i];
     }
-    for (int i = threadIdx.x; i < Q; i += blockDim.x) {
+    for (int i = tid; i < Q; i += nt) {
         const int64_t s = src_all[off + q0 + i], d = dst_all[off + q0 + i];
         seeds[i] = s; seeds[Q + i] = d;
         pair_src[(size_t)i * L] = s; pair_dst[(size_t)i * L] = d;
     }
-    for (int i = threadIdx.x; i < Q * n_neg; i += blockDim.x) {
+    for (int i = tid; i < Q * n_neg; i += nt) {
         const int q = i / n_neg, j = i % n_neg;
         const int64_t ng = neg_all[(off + q0 + q) * n_neg + j];
         seeds[2 * Q + i] = ng;
         pair_src[(size_t)q * L + 1 + j] = src_all[off + q0 + q];
         pair_dst[(size_t)q * L + 1 + j] = ng;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long tk = atomicAdd(reinterpret_cast<unsigned long long*>(counters + 5), 1ull);
+        if (tk == (unsigned long long)gridDim.x - 1) {
+            counters[5] = 0;
+            counters[0] = off + B;
+        }
     }
 }
 
@@ -208,8 +216,12 @@ extern "C" int ctan_stage_eval(const int64_t* src_all, const int64_t* dst_all, c
                                int64_t* b_src, int64_t* b_dst, int64_t* b_t, int64_t* seeds, int64_t* pair_src,
                                int64_t* pair_dst, cudaStream_t stream) {
     if (B <= 0 || n_neg < 1 || q0 < 0 || q1 > B || q1 < q0) return CTAN_ERR_BAD_ARG;
-    stage_eval_kernel<<<1, 512, 0, stream>>>(src_all, dst_all, t_all, neg_all, n_neg, B, q0, q1, counters, b_src, b_dst,
-                                             b_t, seeds, pair_src, pair_dst);
+    const long long work = (long long)(q1 - q0) * n_neg + B;
+    int grid = (int)((work + 255) / 256);
+    if (grid < 1) grid = 1;
+    if (grid > 64) grid = 64;
+    stage_eval_kernel<<<grid, 256, 0, stream>>>(src_all, dst_all, t_all, neg_all, n_neg, B, q0, q1, counters, b_src, b_dst,
+                                               b_t, seeds, pair_src, pair_dst);
     CTAN_CHECK_LAUNCH();
     return 0;
 }
