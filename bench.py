@@ -42,6 +42,14 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured sustained bf16 (MEASURED_PEAKS.json)"
+    return 1400.0, "fallback sustained (B200_PROFILING.md)"
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -373,6 +381,16 @@ def main():
     if alg_bytes:
         ach = alg_bytes / (top_us * 1e-6) / 1e9
         roof.update(achieved=ach, frac=ach / peak, algorithmic_bytes=alg_bytes)
+    # a tcgen05 contraction is bounded by the tensor pipe, not HBM: report useful flops against the measured dense peak
+    tc_flops = {"ctan_dx_tc": 2.0 * N_last * 4 * D * D, "ctan_qkva_fwd_tc": 2.0 * N_last * D * 4 * D}.get(top_name)
+    if tc_flops:
+        tpeak, tsrc = load_tensor_peak()
+        ach = tc_flops / (top_us * 1e-6) / 1e12
+        roof.update(bound="tensor", unit="TFLOP/s", achieved=ach, peak=tpeak, frac=ach / tpeak, peak_source=tsrc,
+                    algorithmic_flops=tc_flops, hbm_view={"algorithmic_bytes": alg_bytes,
+                                                          "achieved_gbs": alg_bytes / (top_us * 1e-6) / 1e9},
+                    precision="3xTF32 (three tf32 MMAs per useful product; the peak is the measured dense bf16 figure, "
+                              "tf32 runs at half of it)")
     # whole-step algorithmic bytes (SURVEY.md S8d formula)
     U = 2 * B
     Pw = eng.n_params
