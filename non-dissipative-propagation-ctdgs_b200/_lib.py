@@ -93,6 +93,7 @@ SIGNATURES.update({
     "ctan_enc_prep": [P, I, P, I, P, I, P, P, P, P],
     "ctan_head_gather": [P, I, P, P, P, I, P, P, P],
     "ctan_head_pack": [P, I, P, I, P, P, P, I, I, P, P, P],
+    "ctan_set_pdl": [I],
     "ctan_delta_t_stats_ws_bytes": [L, P],
     "ctan_delta_t_stats": [P, P, P, L, L, P, L, P],
     "ctan_qkva_fwd_tc": [P, I, P, I, P, P, P, P, P, P, P, I],
@@ -138,7 +139,7 @@ def ptr(t, dtype=None):
 
 
 # kernels launched by each C entry point (for launch accounting; ctan_nbr_lookup adds one per hop)
-LAUNCHES = {"ctan_delta_t_stats_ws_bytes": 0, "ctan_delta_t_stats": 9, "ctan_nbr_insert": 2, "ctan_nbr_lookup": 1, "ctan_readout_fwd": 2, "ctan_readout_bwd": 2,
+LAUNCHES = {"ctan_set_pdl": 0, "ctan_delta_t_stats_ws_bytes": 0, "ctan_delta_t_stats": 9, "ctan_nbr_insert": 2, "ctan_nbr_lookup": 1, "ctan_readout_fwd": 2, "ctan_readout_bwd": 2,
             "ctan_qkva_bwd": 2, "ctan_eproj_bwd": 2}
 
 # Optional instrumentation (bench.py): TRACE = list -> every call appends (name, start_event, end_event)

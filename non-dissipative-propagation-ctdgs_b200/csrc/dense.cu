@@ -58,6 +58,7 @@ extern "C" int ctan_qkva_fwd(const float* X, int N, const int* N_dev, int D, con
 __global__ void head_fwd_kernel(const float* __restrict__ H, int P_host, const int* __restrict__ P_dev, int Hd, int O,
                                 const float* __restrict__ Wfin, const float* __restrict__ bfin,
                                 float* __restrict__ OUT) {
+    ctan_pdl_begin();
     const int P = P_dev ? *P_dev : P_host;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -104,7 +105,7 @@ extern "C" int ctan_readout_fwd(const float* Z, int D, const int64_t* src, const
     }
     if (rc) return rc;
     if (!OUT) return 0;                 // hidden layer only (the caller fuses the head with the loss)
-    head_fwd_kernel<<<ctan_grid((long long)P * 32, 256), 256, 0, stream>>>(H, P, P_dev, Hd, O, Wfin, bfin, OUT);
+    CTAN_LAUNCH((head_fwd_kernel), ctan_grid((long long)P * 32, 256), 256, 0, stream, H, P, P_dev, Hd, O, Wfin, bfin, OUT);
     CTAN_CHECK_LAUNCH();
     return 0;
 }
@@ -119,6 +120,7 @@ __global__ void head_loss_kernel(const float* __restrict__ H, int P, int Hd, con
                                  const float* __restrict__ bfin, int n_pos, float* __restrict__ OUT,
                                  float* __restrict__ dOUT, float* __restrict__ dHid, float* __restrict__ loss_hist,
                                  int hist_cap, const int64_t* __restrict__ counters) {
+    ctan_pdl_begin();
     __shared__ float s_loss[8];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int p = blockIdx.x * (blockDim.x >> 5) + wib;
@@ -156,7 +158,7 @@ extern "C" int ctan_head_loss(const float* H, int P, int Hd, const float* Wfin, 
                               float* OUT, float* dOUT, float* dHid, float* loss_hist, int hist_cap,
                               const int64_t* counters, cudaStream_t stream) {
     if (P <= 0 || n_pos <= 0 || n_pos >= P || hist_cap <= 0) return CTAN_ERR_BAD_ARG;
-    head_loss_kernel<<<ctan_div_up(P, 8), 256, 0, stream>>>(H, P, Hd, Wfin, bfin, n_pos, OUT, dOUT, dHid, loss_hist,
+    CTAN_LAUNCH((head_loss_kernel), ctan_div_up(P, 8), 256, 0, stream, H, P, Hd, Wfin, bfin, n_pos, OUT, dOUT, dHid, loss_hist,
                                                             hist_cap, counters);
     CTAN_CHECK_LAUNCH();
     return 0;
@@ -186,6 +188,7 @@ struct EpiScatterAtomic2 {         // n<D: C[row(idx1[m])][n] += v ; else C[row(
 __global__ void head_bwd_kernel(const float* __restrict__ dOUT, const float* __restrict__ H, int P_host,
                                 const int* __restrict__ P_dev, int Hd, int O, const float* __restrict__ Wfin,
                                 float* __restrict__ dHid) {
+    ctan_pdl_begin();
     const int P = P_dev ? *P_dev : P_host;
     const long long n = (long long)P * Hd;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -224,7 +227,7 @@ extern "C" int ctan_readout_bwd(const float* dOUT, const float* H, const float* 
     int rc;
     if (dZ) {
         if (!dhid_ready) {              // (ctan_head_loss already produced dHid in the fused training step)
-            head_bwd_kernel<<<ctan_grid((long long)P * Hd, 256), 256, 0, stream>>>(dOUT, H, P, P_dev, Hd, O, Wfin,
+            CTAN_LAUNCH((head_bwd_kernel), ctan_grid((long long)P * Hd, 256), 256, 0, stream, dOUT, H, P, P_dev, Hd, O, Wfin,
                                                                                   dHid);
             CTAN_CHECK_LAUNCH();
         }

@@ -20,6 +20,7 @@ __global__ void edge_rel_kernel(const int64_t* __restrict__ last_update, const i
                                 const int64_t* __restrict__ edge_src, const int64_t* __restrict__ t_tab,
                                 const int64_t* __restrict__ eidx, int E_host, const int* __restrict__ E_dev,
                                 float mean, float stdv, float* __restrict__ rel) {
+    ctan_pdl_begin();
     const int E = E_dev ? *E_dev : E_host;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
         const int64_t lu = last_update[n_id ? n_id[edge_src[e]] : edge_src[e]];
@@ -34,7 +35,7 @@ extern "C" int ctan_edge_rel(const int64_t* last_update, const int64_t* n_id, co
                              const int64_t* t_tab, const int64_t* eidx, int E, const int* E_dev, float mean,
                              float stdv, float* rel, cudaStream_t stream) {
     if (E <= 0) return 0;
-    edge_rel_kernel<<<ctan_grid(E, 256), 256, 0, stream>>>(last_update, n_id, edge_src, t_tab, eidx, E, E_dev, mean,
+    CTAN_LAUNCH((edge_rel_kernel), ctan_grid(E, 256), 256, 0, stream, last_update, n_id, edge_src, t_tab, eidx, E, E_dev, mean,
                                                           stdv, rel);
     CTAN_CHECK_LAUNCH();
     return 0;
@@ -44,6 +45,7 @@ extern "C" int ctan_edge_rel(const int64_t* last_update, const int64_t* n_id, co
 __global__ void gather_rows2_kernel(const float* __restrict__ t1, int K1, const float* __restrict__ t2, int K2,
                                     const int64_t* __restrict__ idx, int N_host, const int* __restrict__ N_dev,
                                     float* __restrict__ out) {
+    ctan_pdl_begin();
     const int N = N_dev ? *N_dev : N_host;
     const int ld = K1 + K2;
     const int lane = threadIdx.x & 31;
@@ -58,32 +60,34 @@ __global__ void gather_rows2_kernel(const float* __restrict__ t1, int K1, const 
 extern "C" int ctan_gather_rows2(const float* t1, int K1, const float* t2, int K2, const int64_t* idx, int N,
                                  const int* N_dev, float* out, cudaStream_t stream) {
     if (N <= 0) return 0;
-    gather_rows2_kernel<<<ctan_grid((long long)N * 32, 256), 256, 0, stream>>>(t1, K1, t2, K2, idx, N, N_dev, out);
+    CTAN_LAUNCH((gather_rows2_kernel), ctan_grid((long long)N * 32, 256), 256, 0, stream, t1, K1, t2, K2, idx, N, N_dev, out);
     CTAN_CHECK_LAUNCH();
     return 0;
 }
 
 // A = W - W^T - gamma*I   (AntiSymmetricConv.forward, first line)
 __global__ void antisym_prep_kernel(const float* __restrict__ W, float gamma, int D, float* __restrict__ A) {
+    ctan_pdl_begin();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D * D; i += gridDim.x * blockDim.x) {
         const int a = i / D, b = i % D;
         A[i] = W[i] - W[b * D + a] - (a == b ? gamma : 0.f);
     }
 }
 extern "C" int ctan_antisym_prep(const float* W, float gamma, int D, float* A, cudaStream_t stream) {
-    antisym_prep_kernel<<<ctan_grid(D * D, 256), 256, 0, stream>>>(W, gamma, D, A);
+    CTAN_LAUNCH((antisym_prep_kernel), ctan_grid(D * D, 256), 256, 0, stream, W, gamma, D, A);
     CTAN_CHECK_LAUNCH();
     return 0;
 }
 // dW = dA - dA^T
 __global__ void antisym_bwd_kernel(const float* __restrict__ dA, int D, float* __restrict__ dW) {
+    ctan_pdl_begin();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D * D; i += gridDim.x * blockDim.x) {
         const int a = i / D, b = i % D;
         dW[i] = dA[i] - dA[b * D + a];
     }
 }
 extern "C" int ctan_antisym_bwd(const float* dA, int D, float* dW, cudaStream_t stream) {
-    antisym_bwd_kernel<<<ctan_grid(D * D, 256), 256, 0, stream>>>(dA, D, dW);
+    CTAN_LAUNCH((antisym_bwd_kernel), ctan_grid(D * D, 256), 256, 0, stream, dA, D, dW);
     CTAN_CHECK_LAUNCH();
     return 0;
 }
@@ -177,6 +181,7 @@ edge_fwd_kernel(const float* __restrict__ QKVA, const float* __restrict__ EP,
                                 const int* __restrict__ N_dev, int D, const float* __restrict__ Xin, float eps,
                                 float* __restrict__ Xout, float* __restrict__ TH, float* __restrict__ ALPHA,
                                 float* __restrict__ Zout, float inv_sqrt_d, int* __restrict__ hub, int hub_cap) {
+    ctan_pdl_begin();
     const int N = N_dev ? *N_dev : N_host;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -226,6 +231,7 @@ edge_fwd_hub_kernel(const float* __restrict__ QKVA, const float* __restrict__ EP
                     const int64_t* __restrict__ esrc, int D, const float* __restrict__ Xin, float eps,
                     float* __restrict__ Xout, float* __restrict__ TH, float* __restrict__ ALPHA,
                     float* __restrict__ Zout, float inv_sqrt_d, int* __restrict__ hub, int hub_cap) {
+    ctan_pdl_begin();
     __shared__ float s_mx[EF_WARPS], s_den[EF_WARPS];
     __shared__ float s_phi[EF_WARPS][MAXV * 32];
     __shared__ int s_nh;
@@ -289,10 +295,10 @@ extern "C" int ctan_edge_fwd(const float* QKVA, const float* EP, const int32_t* 
     const float isd = 1.0f / sqrtf((float)D);
     const int hgrid = 2 * CTAN_SM_COUNT;
 #define LAUNCH(V) do {                                                                                                 \
-        edge_fwd_kernel<V><<<grid, 256, 0, stream>>>(QKVA, EP, rowptr, esrc, N, N_dev, D, Xin, eps, Xout, TH, ALPHA,   \
+        CTAN_LAUNCH((edge_fwd_kernel<V>), grid, 256, 0, stream, QKVA, EP, rowptr, esrc, N, N_dev, D, Xin, eps, Xout, TH, ALPHA,   \
                                                      Zout, isd, hub_ws, hub_cap);                                      \
         if (hub_ws)                                                                                                    \
-            edge_fwd_hub_kernel<V><<<hgrid, 32 * EF_WARPS, 0, stream>>>(QKVA, EP, rowptr, esrc, D, Xin, eps, Xout, TH, \
+            CTAN_LAUNCH((edge_fwd_hub_kernel<V>), hgrid, 32 * EF_WARPS, 0, stream, QKVA, EP, rowptr, esrc, D, Xin, eps, Xout, TH, \
                                                                         ALPHA, Zout, isd, hub_ws, hub_cap);            \
     } while (0)
     if (D <= 32) LAUNCH(1); else if (D <= 64) LAUNCH(2); else if (D <= 128) LAUNCH(4);
@@ -318,6 +324,7 @@ __global__ void edge_bwd_kernel(const float* __restrict__ QKVA, const float* __r
                                 const float* __restrict__ TH, const float* __restrict__ ALPHA, float eps,
                                 float* __restrict__ DQKVA, float* __restrict__ DEP, int accumulate_dep,
                                 float* __restrict__ DS, float inv_sqrt_d) {
+    ctan_pdl_begin();
     const int N = N_dev ? *N_dev : N_host;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -409,7 +416,7 @@ extern "C" int ctan_edge_bwd(const float* QKVA, const float* EP, const int32_t* 
     if (D > 512) return CTAN_ERR_UNSUPPORTED;
     const int grid = ctan_grid((long long)N * 32, 256);
     const float isd = 1.0f / sqrtf((float)D);
-#define LAUNCH(V) edge_bwd_kernel<V><<<grid, 256, 0, stream>>>(QKVA, EP, rowptr, esrc, N, N_dev, D, G, TH, ALPHA, eps, \
+#define LAUNCH(V) CTAN_LAUNCH((edge_bwd_kernel<V>), grid, 256, 0, stream, QKVA, EP, rowptr, esrc, N, N_dev, D, G, TH, ALPHA, eps, \
                                                                 DQKVA, DEP, accumulate_dep, DS, isd)
     if (D <= 32) LAUNCH(1); else if (D <= 64) LAUNCH(2); else if (D <= 128) LAUNCH(4);
     else if (D <= 256) LAUNCH(8); else LAUNCH(16);
@@ -421,6 +428,7 @@ extern "C" int ctan_edge_bwd(const float* QKVA, const float* EP, const int32_t* 
 // dX = dZ * (1 - Z^2)     (final_act = tanh, ctdg_models.py:457-458)
 __global__ void tanh_bwd_kernel(const float* __restrict__ dZ, const float* __restrict__ Z, long long n_host,
                                 const int* __restrict__ rows_dev, int D, float* __restrict__ dX) {
+    ctan_pdl_begin();
     const long long n = rows_dev ? (long long)(*rows_dev) * D : n_host;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float z = Z[i];
@@ -430,7 +438,7 @@ __global__ void tanh_bwd_kernel(const float* __restrict__ dZ, const float* __res
 extern "C" int ctan_tanh_bwd(const float* dZ, const float* Z, int N, const int* N_dev, int D, float* dX,
                              cudaStream_t stream) {
     if (N <= 0) return 0;
-    tanh_bwd_kernel<<<ctan_grid((long long)N * D, 256), 256, 0, stream>>>(dZ, Z, (long long)N * D, N_dev, D, dX);
+    CTAN_LAUNCH((tanh_bwd_kernel), ctan_grid((long long)N * D, 256), 256, 0, stream, dZ, Z, (long long)N * D, N_dev, D, dX);
     CTAN_CHECK_LAUNCH();
     return 0;
 }
@@ -440,6 +448,7 @@ extern "C" int ctan_tanh_bwd(const float* dZ, const float* Z, int N, const int* 
 __global__ void tenc_bwd_kernel(const float* __restrict__ dTenc, const float* __restrict__ rel,
                                 const float* __restrict__ tw, const float* __restrict__ tb, int E_host,
                                 const int* __restrict__ E_dev, int T, float* __restrict__ dtw, float* __restrict__ dtb) {
+    ctan_pdl_begin();
     // block = 256 threads = G groups x Tc columns; a block reduces a slab of 128 edges
     __shared__ float s_w[256], s_b[256];
     const int E = E_dev ? *E_dev : E_host;
@@ -474,7 +483,7 @@ __global__ void tenc_bwd_kernel(const float* __restrict__ dTenc, const float* __
 extern "C" int ctan_tenc_bwd(const float* dTenc, const float* rel, const float* tw, const float* tb, int E,
                              const int* E_dev, int T, float* dtw, float* dtb, cudaStream_t stream) {
     if (E <= 0 || T <= 0) return 0;
-    tenc_bwd_kernel<<<ctan_div_up(E, 128), 256, 0, stream>>>(dTenc, rel, tw, tb, E, E_dev, T, dtw, dtb);
+    CTAN_LAUNCH((tenc_bwd_kernel), ctan_div_up(E, 128), 256, 0, stream, dTenc, rel, tw, tb, E, E_dev, T, dtw, dtb);
     CTAN_CHECK_LAUNCH();
     return 0;
 }
@@ -482,6 +491,7 @@ extern "C" int ctan_tenc_bwd(const float* dTenc, const float* rel, const float* 
 // rowptr from a destination-sorted edge list that did not come from our loader.  flag[0] |= 1 if unsorted.
 __global__ void csr_from_sorted_kernel(const int64_t* __restrict__ edst, int E, int N, int32_t* __restrict__ rowptr,
                                        int* __restrict__ flag) {
+    ctan_pdl_begin();
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e <= E; e += gridDim.x * blockDim.x) {
         const long long prev = e > 0 ? edst[e - 1] : -1;
         const long long cur = e < E ? edst[e] : (long long)N;
@@ -492,7 +502,7 @@ __global__ void csr_from_sorted_kernel(const int64_t* __restrict__ edst, int E, 
 extern "C" int ctan_csr_from_sorted(const int64_t* edst, int E, int N, int32_t* rowptr, int* flag,
                                     cudaStream_t stream) {
     if (N < 0 || E < 0) return CTAN_ERR_BAD_ARG;
-    csr_from_sorted_kernel<<<ctan_grid(E + 1, 256), 256, 0, stream>>>(edst, E, N, rowptr, flag);
+    CTAN_LAUNCH((csr_from_sorted_kernel), ctan_grid(E + 1, 256), 256, 0, stream, edst, E, N, rowptr, flag);
     CTAN_CHECK_LAUNCH();
     return 0;
 }
@@ -504,6 +514,7 @@ extern "C" int ctan_csr_from_sorted(const int64_t* edst, int E, int N, int32_t* 
 __global__ void enc_prep_kernel(const float* __restrict__ mem, int D, const float* __restrict__ xfeat, int Fn,
                                 const int64_t* __restrict__ n_id, int N_host, const int* __restrict__ N_dev,
                                 const float* __restrict__ Wenc, float* __restrict__ zmain, float* __restrict__ tail) {
+    ctan_pdl_begin();
     const int N = N_dev ? *N_dev : N_host;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -521,7 +532,7 @@ __global__ void enc_prep_kernel(const float* __restrict__ mem, int D, const floa
 extern "C" int ctan_enc_prep(const float* mem, int D, const float* xfeat, int Fn, const int64_t* n_id, int N,
                              const int* N_dev, const float* Wenc, float* zmain, float* tail, cudaStream_t stream) {
     if (N <= 0) return 0;
-    enc_prep_kernel<<<ctan_grid((long long)N * 32, 256), 256, 0, stream>>>(mem, D, xfeat, Fn, n_id, N, N_dev, Wenc,
+    CTAN_LAUNCH((enc_prep_kernel), ctan_grid((long long)N * 32, 256), 256, 0, stream, mem, D, xfeat, Fn, n_id, N, N_dev, Wenc,
                                                                            zmain, tail);
     CTAN_CHECK_LAUNCH();
     return 0;
@@ -534,6 +545,7 @@ __global__ void eproj_prep_kernel(const float* __restrict__ msg, int Fe, const i
                                   const float* __restrict__ rel, const float* __restrict__ tw,
                                   const float* __restrict__ tb, int T, int E_host, const int* __restrict__ E_dev,
                                   int Kpad, float* __restrict__ A) {
+    ctan_pdl_begin();
     const int E = E_dev ? *E_dev : E_host;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -554,7 +566,7 @@ extern "C" int ctan_eproj_prep(const float* msg, int Fe, const int64_t* eid, con
                                cudaStream_t stream) {
     if (E <= 0) return 0;
     if (Kpad < Fe + T || Kpad % 32 != 0) return CTAN_ERR_BAD_ARG;
-    eproj_prep_kernel<<<ctan_grid((long long)E * 32, 256), 256, 0, stream>>>(msg, Fe, eid, rel, tw, tb, T, E, E_dev,
+    CTAN_LAUNCH((eproj_prep_kernel), ctan_grid((long long)E * 32, 256), 256, 0, stream, msg, Fe, eid, rel, tw, tb, T, E, E_dev,
                                                                            Kpad, A);
     CTAN_CHECK_LAUNCH();
     return 0;
@@ -567,6 +579,7 @@ __global__ void head_gather_kernel(const float* __restrict__ Y, int Hd, const in
                                    const int64_t* __restrict__ dst, const int64_t* __restrict__ map, int P,
                                    const float* __restrict__ Wfin, const float* __restrict__ bfin,
                                    float* __restrict__ OUT) {
+    ctan_pdl_begin();
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     for (int p = warp; p < P; p += nw) {
@@ -583,7 +596,7 @@ __global__ void head_gather_kernel(const float* __restrict__ Y, int Hd, const in
 extern "C" int ctan_head_gather(const float* Y, int Hd, const int64_t* src, const int64_t* dst, const int64_t* map,
                                 int P, const float* Wfin, const float* bfin, float* OUT, cudaStream_t stream) {
     if (P <= 0) return 0;
-    head_gather_kernel<<<ctan_grid((long long)P * 32, 256), 256, 0, stream>>>(Y, Hd, src, dst, map, P, Wfin, bfin, OUT);
+    CTAN_LAUNCH((head_gather_kernel), ctan_grid((long long)P * 32, 256), 256, 0, stream, Y, Hd, src, dst, map, P, Wfin, bfin, OUT);
     CTAN_CHECK_LAUNCH();
     return 0;
 }

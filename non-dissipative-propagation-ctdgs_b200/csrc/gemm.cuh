@@ -264,6 +264,7 @@ template <int BT, class AL, class BL, class EP>
 __global__ void __launch_bounds__((BT / 4) * (BT / 4))
 gemm_kernel(const AL A, const BL Bm, const EP epi, int M_host, const int* __restrict__ M_dev, int N, int K_host,
             const int* __restrict__ K_dev, int k_chunk) {
+    ctan_pdl_begin();
     constexpr int TPR = BT / 4, NT = TPR * TPR;         // threads per tile row, threads per CTA
     constexpr int VPT = (BT * BK / 4) / NT;             // operand vectors per thread per k-tile (1 or 2)
     __shared__ __align__(16) float As[2][BK][BT + PAD];
@@ -393,8 +394,8 @@ static inline int launch(const AL& A, const BL& B, const EP& epi, int M_max, con
         if (gy > cap) gy = cap > 1 ? cap : 1;
     }
     dim3 grid(gx, gy, splits);
-    if (use_big) gemm_kernel<64, AL, BL, EP><<<grid, 256, 0, stream>>>(A, B, epi, M_max, M_dev, N, K_max, K_dev, k_chunk);
-    else         gemm_kernel<32, AL, BL, EP><<<grid, 64, 0, stream>>>(A, B, epi, M_max, M_dev, N, K_max, K_dev, k_chunk);
+    if (use_big) CTAN_LAUNCH((gemm_kernel<64, AL, BL, EP>), grid, 256, 0, stream, A, B, epi, M_max, M_dev, N, K_max, K_dev, k_chunk);
+    else         CTAN_LAUNCH((gemm_kernel<32, AL, BL, EP>), grid, 64, 0, stream, A, B, epi, M_max, M_dev, N, K_max, K_dev, k_chunk);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }

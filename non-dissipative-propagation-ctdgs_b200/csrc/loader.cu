@@ -18,6 +18,7 @@
 // ------------------------------------------------------------------------------------------
 __global__ void nbr_reset_kernel(int64_t* __restrict__ nbr, int64_t* __restrict__ eid,
                                  int32_t* __restrict__ deg, long long rows, int S) {
+    ctan_pdl_begin();
     const long long n = rows * S;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -30,7 +31,7 @@ __global__ void nbr_reset_kernel(int64_t* __restrict__ nbr, int64_t* __restrict_
 extern "C" int ctan_nbr_reset(int64_t* nbr, int64_t* eid, int32_t* deg, int64_t num_nodes, int S,
                               cudaStream_t stream) {
     if (num_nodes <= 0 || S <= 0) return CTAN_ERR_BAD_ARG;
-    nbr_reset_kernel<<<ctan_grid(num_nodes * S, 256 * 4), 256, 0, stream>>>(nbr, eid, deg, num_nodes, S);
+    CTAN_LAUNCH((nbr_reset_kernel), ctan_grid(num_nodes * S, 256 * 4), 256, 0, stream, nbr, eid, deg, num_nodes, S);
     CTAN_CHECK_LAUNCH();
     return 0;
 }
@@ -55,6 +56,7 @@ __global__ void nbr_insert_rank_shift_kernel(int64_t* __restrict__ nbr, int64_t*
                                              int32_t* __restrict__ deg, const int64_t* __restrict__ src,
                                              const int64_t* __restrict__ dst, int B, int S,
                                              int2* __restrict__ rc) {
+    ctan_pdl_begin();
     const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
     const int n = 2 * B;
     for (int p = blockIdx.x * wpb + (threadIdx.x >> 5); p < n; p += gridDim.x * wpb) {
@@ -96,6 +98,7 @@ __global__ void nbr_insert_write_kernel(int64_t* __restrict__ nbr, int64_t* __re
                                         const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
                                         int B, int S, int64_t cur_host, const int64_t* __restrict__ cur_dev,
                                         const int2* __restrict__ rc) {
+    ctan_pdl_begin();
     const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
     const int n = 2 * B;
     const int64_t cur = cur_dev ? *cur_dev : cur_host;
@@ -130,9 +133,9 @@ extern "C" int ctan_nbr_insert(int64_t* nbr, int64_t* eid, int32_t* deg, const i
     if (B == 0) return 0;
     const int wpb = 8;
     const int grid = ctan_grid(2LL * B, wpb);
-    nbr_insert_rank_shift_kernel<<<grid, wpb * 32, 0, stream>>>(nbr, eid, deg, src, dst, B, S, (int2*)ws);
+    CTAN_LAUNCH((nbr_insert_rank_shift_kernel), grid, wpb * 32, 0, stream, nbr, eid, deg, src, dst, B, S, (int2*)ws);
     CTAN_CHECK_LAUNCH();
-    nbr_insert_write_kernel<<<grid, wpb * 32, 0, stream>>>(nbr, eid, src, dst, B, S, cur_e_id, cur_e_id_dev,
+    CTAN_LAUNCH((nbr_insert_write_kernel), grid, wpb * 32, 0, stream, nbr, eid, src, dst, B, S, cur_e_id, cur_e_id_dev,
                                                           (const int2*)ws);
     CTAN_CHECK_LAUNCH();
     return 0;
@@ -154,6 +157,7 @@ __global__ void lk_expand_kernel(const int64_t* __restrict__ list, int n_host, c
                                  uint32_t* __restrict__ bitmap, uint32_t* __restrict__ cbitmap,
                                  int64_t* __restrict__ next, int* __restrict__ next_cnt, int next_cap,
                                  int* __restrict__ err) {
+    ctan_pdl_begin();
     const int end = min(n_dev ? *n_dev : n_host, list_cap);
     const int gpw = 32 / lpi;
     const int lane = threadIdx.x & 31, g = lane / lpi, gl = lane % lpi;
@@ -191,6 +195,7 @@ lk_scan_kernel(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__
                const int32_t* __restrict__ deg, int n_words, int64_t* __restrict__ n_id_out,
                int64_t* __restrict__ assoc, int32_t* __restrict__ rowptr, int32_t* __restrict__ counts,
                int n_cap, int e_cap, int* __restrict__ frontier_cnt, int n_frontier_cnt) {
+    ctan_pdl_begin();
     __shared__ int s_n[32], s_e[32], s_c[32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int chunk = (n_words + 1023) / 1024;
@@ -275,6 +280,7 @@ __global__ void lk_fill_kernel(const int64_t* __restrict__ nbr, const int64_t* _
                                uint32_t* __restrict__ cbitmap, const int64_t* __restrict__ last_update,
                                const int64_t* __restrict__ t_tab, float mean, float stdv,
                                float* __restrict__ rel) {
+    ctan_pdl_begin();
     const int N = n_dev ? *n_dev : n_host;
     const int gpw = 32 / lpi;
     const int lane = threadIdx.x & 31, g = lane / lpi, gl = lane % lpi;
@@ -344,6 +350,7 @@ __device__ __forceinline__ void block_scan2(int a, int b, int& ea, int& eb, int&
 __global__ void __launch_bounds__(256)
 lk_scan_partial_kernel(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ cbitmap,
                        const int32_t* __restrict__ deg, int n_words, int* __restrict__ partials) {
+    ctan_pdl_begin();
     __shared__ int s_a[8], s_b[8], s_c[8];
     const int chunk = (n_words + SCAN_CTAS - 1) / SCAN_CTAS;
     const int c0 = min(n_words, (int)blockIdx.x * chunk), c1 = min(n_words, c0 + chunk);
@@ -367,6 +374,7 @@ lk_scan_emit_kernel(const uint32_t* __restrict__ bitmap, const uint32_t* __restr
                     int64_t* __restrict__ n_id_out, int64_t* __restrict__ assoc, int32_t* __restrict__ rowptr,
                     int32_t* __restrict__ counts, int n_cap, int e_cap, int* __restrict__ frontier_cnt,
                     int n_frontier_cnt) {
+    ctan_pdl_begin();
     __shared__ int s_a[8], s_b[8], s_base[5];
     if (threadIdx.x == 0) {
         int bn = 0, be = 0, tn = 0, te = 0, tcn = 0;
@@ -445,7 +453,7 @@ extern "C" int ctan_nbr_lookup(const int64_t* nbr, const int32_t* deg, int64_t n
         int* nxt_cnt = last ? nullptr : frontier_cnt + h;
         const long long items = (h == 0) ? n_seeds : frontier_cap;
         const int grid = ctan_grid(items * lpi, threads);
-        lk_expand_kernel<<<grid, threads, 0, stream>>>(cur_list, cur_n, cur_cnt_dev, h == 0 ? n_seeds : frontier_cap,
+        CTAN_LAUNCH((lk_expand_kernel), grid, threads, 0, stream, cur_list, cur_n, cur_cnt_dev, h == 0 ? n_seeds : frontier_cap,
                                                        nbr, deg, S, lpi, bitmap, cbitmap, nxt, nxt_cnt, frontier_cap,
                                                        counts + 3);
         CTAN_CHECK_LAUNCH();
@@ -456,13 +464,13 @@ extern "C" int ctan_nbr_lookup(const int64_t* nbr, const int32_t* deg, int64_t n
     int* scan_partials = (frontier && (size_t)frontier_cap * sizeof(int64_t) >= SCAN_CTAS * 3 * sizeof(int))
                              ? reinterpret_cast<int*>(frontier) : nullptr;
     if (n_words <= 4096 || !scan_partials) {
-        lk_scan_kernel<<<1, 1024, 0, stream>>>(bitmap, cbitmap, deg, n_words, n_id_out, assoc, rowptr, counts, n_cap,
+        CTAN_LAUNCH((lk_scan_kernel), 1, 1024, 0, stream, bitmap, cbitmap, deg, n_words, n_id_out, assoc, rowptr, counts, n_cap,
                                                e_cap, frontier_cnt, num_hops > 1 ? num_hops - 1 : 0);
     } else {
         // large id spaces (e.g. 994k nodes = 31k bitmap words): two-level scan over SCAN_CTAS CTAs
-        lk_scan_partial_kernel<<<SCAN_CTAS, 256, 0, stream>>>(bitmap, cbitmap, deg, n_words, scan_partials);
+        CTAN_LAUNCH((lk_scan_partial_kernel), SCAN_CTAS, 256, 0, stream, bitmap, cbitmap, deg, n_words, scan_partials);
         CTAN_CHECK_LAUNCH();
-        lk_scan_emit_kernel<<<SCAN_CTAS, 256, 0, stream>>>(bitmap, cbitmap, deg, n_words, scan_partials, n_id_out, assoc,
+        CTAN_LAUNCH((lk_scan_emit_kernel), SCAN_CTAS, 256, 0, stream, bitmap, cbitmap, deg, n_words, scan_partials, n_id_out, assoc,
                                                          rowptr, counts, n_cap, e_cap, frontier_cnt,
                                                          num_hops > 1 ? num_hops - 1 : 0);
     }
@@ -478,7 +486,7 @@ extern "C" int ctan_nbr_fill(const int64_t* nbr, const int64_t* eid, int S, cons
                              uint32_t* cbitmap, cudaStream_t stream) {
     if (n <= 0) return 0;
     const int lpi = lanes_per_item(S);
-    lk_fill_kernel<<<ctan_grid((long long)n * lpi, 256), 256, 0, stream>>>(nbr, eid, S, lpi, n_id, rowptr, assoc, n,
+    CTAN_LAUNCH((lk_fill_kernel), ctan_grid((long long)n * lpi, 256), 256, 0, stream, nbr, eid, S, lpi, n_id, rowptr, assoc, n,
                                                                            n_dev, edge_src, edge_dst, e_id_out,
                                                                            bitmap, cbitmap, nullptr, nullptr, 0.f, 1.f,
                                                                            nullptr);
@@ -495,7 +503,7 @@ extern "C" int ctan_nbr_fill_rel(const int64_t* nbr, const int64_t* eid, int S, 
                                  float stdv, float* rel, cudaStream_t stream) {
     if (n <= 0) return 0;
     const int lpi = lanes_per_item(S);
-    lk_fill_kernel<<<ctan_grid((long long)n * lpi, 256), 256, 0, stream>>>(nbr, eid, S, lpi, n_id, rowptr, assoc, n,
+    CTAN_LAUNCH((lk_fill_kernel), ctan_grid((long long)n * lpi, 256), 256, 0, stream, nbr, eid, S, lpi, n_id, rowptr, assoc, n,
                                                                            n_dev, edge_src, edge_dst, e_id_out,
                                                                            bitmap, cbitmap, last_update, t_tab, mean,
                                                                            stdv, rel);
@@ -515,6 +523,7 @@ __global__ void mem_update_kernel(float* __restrict__ mem, int64_t* __restrict__
                                   const int64_t* __restrict__ t, int B, const float* __restrict__ emb_src,
                                   const float* __restrict__ emb_dst, int emb_ld, const float* __restrict__ z,
                                   const int64_t* __restrict__ assoc) {
+    ctan_pdl_begin();
     const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
     const int n = 2 * B;
     for (int p = blockIdx.x * wpb + (threadIdx.x >> 5); p < n; p += gridDim.x * wpb) {
@@ -550,7 +559,7 @@ extern "C" int ctan_mem_update(float* mem, int64_t* last_update, int D, const in
     if (B == 0) return 0;
     if (!z && (!emb_src || !emb_dst)) return CTAN_ERR_BAD_ARG;
     const int wpb = 4;
-    mem_update_kernel<<<ctan_grid(2LL * B, wpb), wpb * 32, 0, stream>>>(mem, last_update, D, src, dst, t, B, emb_src,
+    CTAN_LAUNCH((mem_update_kernel), ctan_grid(2LL * B, wpb), wpb * 32, 0, stream, mem, last_update, D, src, dst, t, B, emb_src,
                                                                        emb_dst, emb_ld > 0 ? emb_ld : D, z, assoc);
     CTAN_CHECK_LAUNCH();
     return 0;
@@ -558,6 +567,7 @@ extern "C" int ctan_mem_update(float* mem, int64_t* last_update, int D, const in
 
 __global__ void mem_reset_kernel(float* __restrict__ mem, int64_t* __restrict__ last_update, long long rows, int D,
                                  int64_t init_time) {
+    ctan_pdl_begin();
     const long long n = rows * D;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) mem[i] = 0.f;
@@ -569,7 +579,7 @@ __global__ void mem_reset_kernel(float* __restrict__ mem, int64_t* __restrict__ 
 extern "C" int ctan_mem_reset(float* mem, int64_t* last_update, int64_t num_nodes, int D, int64_t init_time,
                               cudaStream_t stream) {
     if (num_nodes <= 0 || D <= 0) return CTAN_ERR_BAD_ARG;
-    mem_reset_kernel<<<ctan_grid(num_nodes * D, 256 * 4), 256, 0, stream>>>(mem, last_update, num_nodes, D, init_time);
+    CTAN_LAUNCH((mem_reset_kernel), ctan_grid(num_nodes * D, 256 * 4), 256, 0, stream, mem, last_update, num_nodes, D, init_time);
     CTAN_CHECK_LAUNCH();
     return 0;
 }

@@ -17,6 +17,7 @@ __global__ void stage_batch_kernel(const int64_t* __restrict__ src_all, const in
                                    int64_t* __restrict__ b_t, int64_t* __restrict__ seeds,
                                    int64_t* __restrict__ pair_src, int64_t* __restrict__ pair_dst,
                                    float* __restrict__ loss_hist, int hist_cap) {
+    ctan_pdl_begin();
     // single block; negatives are laid out [event][n_neg]
     __shared__ int64_t s_off;
     if (threadIdx.x == 0) {
@@ -53,7 +54,7 @@ extern "C" int ctan_stage_batch(const int64_t* src_all, const int64_t* dst_all, 
                                 int64_t* b_src, int64_t* b_dst, int64_t* b_t, int64_t* seeds, int64_t* pair_src,
                                 int64_t* pair_dst, float* loss_hist, int hist_cap, cudaStream_t stream) {
     if (B <= 0 || n_neg < 0) return CTAN_ERR_BAD_ARG;
-    stage_batch_kernel<<<1, 256, 0, stream>>>(src_all, dst_all, t_all, neg_all, n_neg, B, counters, use_cursor, b_src,
+    CTAN_LAUNCH((stage_batch_kernel), 1, 256, 0, stream, src_all, dst_all, t_all, neg_all, n_neg, B, counters, use_cursor, b_src,
                                               b_dst, b_t, seeds, pair_src, pair_dst, loss_hist,
                                               hist_cap > 0 ? hist_cap : 1);
     CTAN_CHECK_LAUNCH();
@@ -66,6 +67,7 @@ __device__ __forceinline__ float softplus_stable(float x) { return fmaxf(x, 0.f)
 
 __global__ void bce_loss_kernel(const float* __restrict__ OUT, int n_pos, int n_negs, float* __restrict__ dOUT,
                                 float* __restrict__ loss_hist, int hist_cap, const int64_t* __restrict__ counters) {
+    ctan_pdl_begin();
     __shared__ float red[32];
     const int n = n_pos + n_negs;
     float acc = 0.f;
@@ -96,7 +98,7 @@ __global__ void bce_loss_kernel(const float* __restrict__ OUT, int n_pos, int n_
 extern "C" int ctan_bce_loss(const float* OUT, int n_pos, int n_negs, float* dOUT, float* loss_hist, int hist_cap,
                              const int64_t* counters, cudaStream_t stream) {
     if (n_pos <= 0 || n_negs <= 0 || hist_cap <= 0) return CTAN_ERR_BAD_ARG;
-    bce_loss_kernel<<<1, 512, 0, stream>>>(OUT, n_pos, n_negs, dOUT, loss_hist, hist_cap, counters);
+    CTAN_LAUNCH((bce_loss_kernel), 1, 512, 0, stream, OUT, n_pos, n_negs, dOUT, loss_hist, hist_cap, counters);
     CTAN_CHECK_LAUNCH();
     return 0;
 }
@@ -107,6 +109,7 @@ extern "C" int ctan_bce_loss(const float* OUT, int n_pos, int n_negs, float* dOU
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int n, float lr, float beta1, float beta2, float eps, float wd,
                             int64_t step_host, const int64_t* __restrict__ counters) {
+    ctan_pdl_begin();
     __shared__ float s_step_size, s_bc2_sqrt;
     if (threadIdx.x == 0) {
         const int64_t step = counters ? counters[2] : step_host;
@@ -132,7 +135,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 extern "C" int ctan_adam_step(float* p, const float* g, float* m, float* v, int n, float lr, float beta1, float beta2,
                               float eps, float wd, int64_t step, const int64_t* counters, cudaStream_t stream) {
     if (n <= 0) return 0;
-    adam_kernel<<<ctan_grid(n, 1024, 1), 1024, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, step, counters);
+    CTAN_LAUNCH((adam_kernel), ctan_grid(n, 1024, 1), 1024, 0, stream, p, g, m, v, n, lr, beta1, beta2, eps, wd, step, counters);
     CTAN_CHECK_LAUNCH();
     return 0;
 }
@@ -141,6 +144,7 @@ extern "C" int ctan_adam_step(float* p, const float* g, float* m, float* v, int 
 // rank = 0.5*(#neg >= pos + #neg > pos) + 1; rr[q] = 1/rank (fp32)   -- TGB evaluate.py:109-120
 __global__ void mrr_kernel(const float* __restrict__ pos, const float* __restrict__ neg, int Q, int n_neg,
                            float* __restrict__ rr) {
+    ctan_pdl_begin();
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     for (int q = warp; q < Q; q += nw) {
@@ -158,7 +162,7 @@ __global__ void mrr_kernel(const float* __restrict__ pos, const float* __restric
 
 extern "C" int ctan_mrr(const float* pos, const float* neg, int Q, int n_neg, float* rr, cudaStream_t stream) {
     if (Q <= 0) return 0;
-    mrr_kernel<<<ctan_grid((long long)Q * 32, 256), 256, 0, stream>>>(pos, neg, Q, n_neg, rr);
+    CTAN_LAUNCH((mrr_kernel), ctan_grid((long long)Q * 32, 256), 256, 0, stream, pos, neg, Q, n_neg, rr);
     CTAN_CHECK_LAUNCH();
     return 0;
 }
@@ -178,6 +182,7 @@ __global__ void stage_eval_kernel(const int64_t* __restrict__ src_all, const int
                                   int B, int q0, int q1, int64_t* __restrict__ counters, int64_t* __restrict__ b_src,
                                   int64_t* __restrict__ b_dst, int64_t* __restrict__ b_t, int64_t* __restrict__ seeds,
                                   int64_t* __restrict__ pair_src, int64_t* __restrict__ pair_dst) {
+    ctan_pdl_begin();
     const int64_t off = *reinterpret_cast<volatile const int64_t*>(counters);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         counters[1] = off;
@@ -220,7 +225,7 @@ extern "C" int ctan_stage_eval(const int64_t* src_all, const int64_t* dst_all, c
     int grid = (int)((work + 255) / 256);
     if (grid < 1) grid = 1;
     if (grid > 64) grid = 64;
-    stage_eval_kernel<<<grid, 256, 0, stream>>>(src_all, dst_all, t_all, neg_all, n_neg, B, q0, q1, counters, b_src, b_dst,
+    CTAN_LAUNCH((stage_eval_kernel), grid, 256, 0, stream, src_all, dst_all, t_all, neg_all, n_neg, B, q0, q1, counters, b_src, b_dst,
                                                b_t, seeds, pair_src, pair_dst);
     CTAN_CHECK_LAUNCH();
     return 0;
@@ -232,6 +237,7 @@ __global__ void pack_eval_kernel(const float* __restrict__ OUT, const float* __r
                                  const int64_t* __restrict__ assoc, const int64_t* __restrict__ pair_src,
                                  const int64_t* __restrict__ pair_dst, int Q, int n_neg, int D,
                                  float* __restrict__ rows) {
+    ctan_pdl_begin();
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     const int L = 1 + n_neg, W = 1 + L + 2 * D;
@@ -260,7 +266,7 @@ __global__ void pack_eval_kernel(const float* __restrict__ OUT, const float* __r
 extern "C" int ctan_pack_eval(const float* OUT, const float* z, const int64_t* assoc, const int64_t* pair_src,
                               const int64_t* pair_dst, int Q, int n_neg, int D, float* rows, cudaStream_t stream) {
     if (Q <= 0) return 0;
-    pack_eval_kernel<<<ctan_grid((long long)Q * 32, 128), 128, 0, stream>>>(OUT, z, assoc, pair_src, pair_dst, Q, n_neg,
+    CTAN_LAUNCH((pack_eval_kernel), ctan_grid((long long)Q * 32, 128), 128, 0, stream, OUT, z, assoc, pair_src, pair_dst, Q, n_neg,
                                                                             D, rows);
     CTAN_CHECK_LAUNCH();
     return 0;
@@ -275,6 +281,7 @@ __global__ void head_pack_kernel(const float* __restrict__ Y, int Hd, const floa
                                  const int64_t* __restrict__ pair_dst, int Q, int n_neg,
                                  const float* __restrict__ Wfin, const float* __restrict__ bfin,
                                  float* __restrict__ rows) {
+    ctan_pdl_begin();
     extern __shared__ float sc[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int L = 1 + n_neg, W = 1 + L + 2 * D;
@@ -320,7 +327,7 @@ extern "C" int ctan_head_pack(const float* Y, int Hd, const float* z, int D, con
     const int grid = Q < 4 * CTAN_SM_COUNT ? Q : 4 * CTAN_SM_COUNT;
     // one warp per candidate when they fit (each is a chain of dependent gathers: pair -> row id -> projected rows)
     const int warps = (1 + n_neg) < 32 ? (1 + n_neg) : 32;
-    head_pack_kernel<<<grid, 32 * warps, (1 + n_neg) * sizeof(float), stream>>>(Y, Hd, z, D, assoc, pair_src, pair_dst, Q,
+    CTAN_LAUNCH((head_pack_kernel), grid, 32 * warps, (1 + n_neg) * sizeof(float), stream, Y, Hd, z, D, assoc, pair_src, pair_dst, Q,
                                                                          n_neg, Wfin, bfin, rows);
     CTAN_CHECK_LAUNCH();
     return 0;
@@ -328,6 +335,7 @@ extern "C" int ctan_head_pack(const float* Y, int Hd, const float* z, int D, con
 
 // acc[0] += sum_r rows[r*ld + col]; acc[1] += R    (running sum of reciprocal ranks and query count)
 __global__ void accum_col_kernel(const float* __restrict__ rows, int R, int ld, int col, double* __restrict__ acc) {
+    ctan_pdl_begin();
     __shared__ float red[32];
     float s = 0.f;
     for (int r = threadIdx.x; r < R; r += blockDim.x) s += rows[(size_t)r * ld + col];
@@ -343,8 +351,17 @@ __global__ void accum_col_kernel(const float* __restrict__ rows, int R, int ld, 
 
 extern "C" int ctan_accum_col(const float* rows, int R, int ld, int col, double* acc, cudaStream_t stream) {
     if (R <= 0) return 0;
-    accum_col_kernel<<<1, 256, 0, stream>>>(rows, R, ld, col, acc);
+    CTAN_LAUNCH((accum_col_kernel), 1, 256, 0, stream, rows, R, ld, col, acc);
     CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+// Switch programmatic dependent launch on/off for the launches that follow on this host thread (common.cuh).  Host
+// state only: under stream capture the choice is baked into the captured edges.
+int g_ctan_pdl = 1;
+extern "C" int ctan_set_pdl(int on, cudaStream_t stream) {
+    (void)stream;
+    g_ctan_pdl = on;
     return 0;
 }
 

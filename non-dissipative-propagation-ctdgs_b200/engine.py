@@ -258,6 +258,10 @@ class StepEngine:
             w["H"].zero_()
             if train:
                 self.zero_buf.zero_()
+        # Programmatic dependent launch (csrc/common.cuh) shortens the single-chain no-grad step (80 -> 75 us) but
+        # LENGTHENS the training step (118 -> 122..127 us, more the further into the DAG it is enabled): dependents
+        # scheduled early hold SM slots that the step's parallel branches need.  So: inference on, training off.
+        _lib.lib().ctan_set_pdl(0 if train else 1, None)
         call("ctan_stage_batch", ptr(self.src), ptr(self.dst), ptr(self.t), ptr(self.neg), self.n_neg, B,
              ptr(w["counters"]), 0 if self.host_staged else 1, ptr(w["b_src"]), ptr(w["b_dst"]), ptr(w["b_t"]),
              ptr(w["seeds"]), ptr(w["pair_src"]), ptr(w["pair_dst"]), ptr(w["loss_hist"]), self.hist_cap)
@@ -306,6 +310,7 @@ class StepEngine:
                  B, 0, cur1, S, ptr(w["ins_ws"]))
         if not train:
             state_update()
+            _lib.lib().ctan_set_pdl(1, None)
             return
         with self._fork(1):                                  # side 1 (after the z0 gather): state write-back
             state_update()
@@ -351,6 +356,7 @@ class StepEngine:
         self._join(3)
         call("ctan_adam_step", ptr(self.flat_p), ptr(self.flat_g), ptr(self.adam_m), ptr(self.adam_v),
              self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 0, ptr(w["counters"]))
+        _lib.lib().ctan_set_pdl(1, None)
 
     # ------------------------------------------------------------------ public stepping API
     def _graph(self, train: bool):
