@@ -300,6 +300,10 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        if world > 1 or args.gpus > 1:                  # the multi-GPU metric is TGB evaluation: time the same on the CPU
+            from bench_tgb import run_tgb_eval_reference
+            run_tgb_eval_reference(args)
+            return
         n_steps = min(args.steps, 300)
         st, mean, std = make_workload((W + n_steps + 2) * B)
         cores = os.cpu_count() or 1

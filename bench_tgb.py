@@ -105,3 +105,57 @@ def run_tgb_eval_bench(args, rank, world, quiet=False):
     if world > 1:
         dist.destroy_process_group()
     return out
+
+
+def run_tgb_eval_reference(args, quiet=False):
+    """`--impl reference` for the multi-GPU metric: the reference's own per-query evaluation loop (tgb_test
+    'val', train_link.py:111-201; oracle port) on the host cores, same stream / model / negatives / warm state, on
+    a bounded sample of batches."""
+    from oracle import ctan_oracle as O
+    from ctan_b200 import synth
+    cfg = COMMENT
+    B = cfg["B"]
+    n_b = max(1, min(args.steps, 6))
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    warm = WARM_EVENTS
+    n_events = warm + (n_b + 4) * B
+    st = synth.make_stream("comment", n_events=n_events, seed=0, tgb=True)
+    g = torch.Generator().manual_seed(1)
+    neg = torch.randint(st["min_dst"], st["max_dst"] + 1, (n_events, cfg["n_neg"]), generator=g)
+    mean, std = synth.delta_t_stats(st, 20000)
+    torch.manual_seed(0)
+    om = O.OracleCTAN(num_nodes=st["num_nodes"], edge_dim=st["msg"].size(1), memory_dim=cfg["D"], time_dim=cfg["T"],
+                      node_dim=1, num_iters=cfg["K"], epsilon=cfg["eps"], gamma=cfg["gamma"], mean_delta_t=mean,
+                      std_delta_t=std, tgb=True)
+    loader = O.TorchNeighborLoader(st["num_nodes"], cfg["S"])
+    for lo in range(0, warm, 2000):
+        loader.insert(st["src"][lo:lo + 2000], st["dst"][lo:lo + 2000])
+    gen = torch.Generator(device="cpu").manual_seed(7)
+    touched = torch.unique(torch.cat([st["src"][:warm], st["dst"][:warm]]))
+    om.memory.memory[touched] = 0.1 * torch.randn(touched.numel(), cfg["D"], generator=gen)
+    om.memory.last_update[touched] = st["t"][warm - 1] // 2
+    helper = torch.zeros(st["num_nodes"], dtype=torch.long)
+    with torch.no_grad():
+        O.tgb_eval_batch_ref(om, loader, helper, st, warm, warm + B, [neg[q].tolist() for q in range(warm, warm + B)])
+        t0 = time.perf_counter()
+        mrrs = []
+        for it in range(1, 1 + n_b):
+            lo, hi = warm + it * B, warm + (it + 1) * B
+            m, _, _ = O.tgb_eval_batch_ref(om, loader, helper, st, lo, hi, [neg[q].tolist() for q in range(lo, hi)])
+            mrrs += m
+        dt = time.perf_counter() - t0
+    v = n_b * B / dt
+    out = {"impl": "reference", "metric": "tgb_eval_queries_per_sec", "value": v, "unit": "queries/s",
+           "n_gpus": args.gpus, "steps": n_b, "warmup": 1, "ms_per_step": dt / n_b * 1e3, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "tgbl-comment-shaped TGB one-vs-many eval: 994790 nodes, 2-d msgs, 200 queries/batch "
+                                  "x 20 negatives, CTAN_tgb D=T=256 S=32 K=1; the reference's per-query loop on the host "
+                                  f"cores after a {WARM_EVENTS}-event warm insert"},
+           "mrr": float(np.mean(mrrs)),
+           "cpu_baseline": {"value": v, "unit": "queries/s", "cores": cores, "kind": "port",
+                            "sample": f"{n_b} consecutive 200-query batches (oracle port of train_link.py:111-201)"},
+           "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if not quiet:
+        print(json.dumps(out))
+    return out

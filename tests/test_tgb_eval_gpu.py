@@ -119,3 +119,13 @@ def test_full_size_comment_shape_engine_vs_module_api():
         assert float((sc - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-6, it
     eng.check()
     assert 0.0 < eng.mrr() <= 1.0
+
+
+def test_full_size_mrr_matches_reference_loop():
+    """BASELINE config C5 at full size against the reference's per-query evaluation loop (oracle port of
+    train_link.py:111-201) run on the host: same stream, model, negatives and 1M-event warm state; per-batch MRR of
+    3 consecutive batches, neighbour tables bit-exact, memory within 1e-4 (scripts/check_eval_vs_cpu.py)."""
+    import runpy
+    import os
+    runpy.run_path(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts",
+                                "check_eval_vs_cpu.py"), run_name="__main__")
