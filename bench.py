@@ -108,15 +108,22 @@ def model_kwargs(st, K, mean, std, cfg=WIKI):
 
 
 # ------------------------------------------------------------------------------------------ baselines
-def oracle_train_rate(st, K, mean, std, device, n_steps, warmup, threads=None):
-    """events/sec of the restated reference training loop (oracle) on `device`."""
+def oracle_train_rate(st, K, mean, std, device, n_steps, warmup, threads=None, drop_in=False):
+    """events/sec of the restated reference training loop (oracle) on `device`.  drop_in=True: the SAME loop body
+    (train_link.py:237-282: unique -> loader(n_id) x K -> model(...) -> loss -> update/insert -> backward ->
+    torch.optim.Adam) driving OUR modules through the reference API -- what a user gets by only swapping imports."""
     from oracle import ctan_oracle as O
     if threads:
         torch.set_num_threads(threads)
     cfg = WIKI
     torch.manual_seed(0)
-    om = O.OracleCTAN(**model_kwargs(st, K, mean, std)).to(device)
-    ld = O.TorchNeighborLoader(st["num_nodes"], cfg["S"], device=device)
+    if drop_in:
+        from ctan_b200.models import CTAN, LastNeighborLoader
+        om = CTAN(**model_kwargs(st, K, mean, std)).to(device)
+        ld = LastNeighborLoader(st["num_nodes"], cfg["S"], device=device)
+    else:
+        om = O.OracleCTAN(**model_kwargs(st, K, mean, std)).to(device)
+        ld = O.TorchNeighborLoader(st["num_nodes"], cfg["S"], device=device)
     h = torch.zeros(st["num_nodes"], dtype=torch.long, device=device)
     opt = torch.optim.Adam(om.parameters(), lr=cfg["lr"])
     g = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in st.items()}
@@ -419,6 +426,20 @@ def main():
         if tr:
             sat["traffic"] = tr["traffic_bytes"]
     out["roofline_saturating"] = sat
+    # the scatter side (edge backward: atomic accumulation into source rows) at the same shape
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import sat_edge_bwd
+    sb = sat_edge_bwd.run(dev=dev)
+    sb = {"kernel": sb["kernel"], "shape": {"N": sb["N"], "E": sb["E"], "D": sb["D"]}, "ms_per_launch": sb["ms_per_launch"],
+          "algorithmic_bytes": sb["algorithmic_bytes"], "achieved": sb["achieved_gbs"], "bound": "hbm", "peak": peak,
+          "unit": "GB/s", "frac": sb["achieved_gbs"] / peak, "traffic": None,
+          "note": "atomics counted as read-modify-write (16*D bytes per edge)"}
+    if os.path.exists(tpath):
+        tr = json.load(open(tpath)).get("edge_bwd_kernel@saturating(N=100000,E=1600000,D=256)")
+        if tr:
+            sb["traffic"] = tr["traffic_bytes"]
+    out["roofline_saturating_scatter"] = sb
+    torch.cuda.empty_cache()
 
     # ---- end to end with host buffers
     e2e_v, h2d, d2h, last_loss = run_e2e(st, K, mean, std, dev, min(args.steps, 400), W)
@@ -429,6 +450,10 @@ def main():
         gv, gms = oracle_train_rate(st, K, mean, std, "cuda:0", 100, 10)
         out["torch_gpu_baseline"] = {"value": gv, "unit": "events/s", "ms_per_step": gms,
                                      "what": "restated reference loop, eager PyTorch ops on the same B200 (fp32)"}
+        dv, dms = oracle_train_rate(st, K, mean, std, "cuda:0", 200, 20, drop_in=True)
+        out["drop_in_api"] = {"value": dv, "unit": "events/s", "ms_per_step": dms,
+                              "what": "the reference's loop body unchanged (train_link.py:237-282, torch.optim.Adam, one "
+                                      "host sync per loader call) on ctan_b200.models through the C-ABI kernels"}
         cores = os.cpu_count() or 1
         cv, cms = oracle_train_rate(st, K, mean, std, "cpu", 120, 5, threads=cores)
         out["cpu_baseline"] = {"value": cv, "unit": "events/s", "cores": cores, "kind": "port",

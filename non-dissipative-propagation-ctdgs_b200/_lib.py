@@ -122,7 +122,9 @@ TC_MODE = int(os.environ.get("CTAN_TC_MODE", "0"))
 
 
 def stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    # the raw-stream query is ~30x cheaper than torch.cuda.current_stream().cuda_stream (which builds a Stream
+    # object per call); the strict-API path makes ~20 C-ABI calls per step
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def ptr(t, dtype=None):

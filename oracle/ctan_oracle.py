@@ -410,7 +410,7 @@ def train_step_ref(model: OracleCTAN, loader, helper: Tensor, optimizer, stream:
     seeds = torch.cat([src, dst, neg_dst]).unique()
     n_id, edge_index, e_id = khop_lookup(loader, seeds, model.num_gnn_layers)
     helper[n_id] = torch.arange(n_id.numel(), device=n_id.device)
-    if model.tgb:
+    if getattr(model, "tgb", type(model).__name__ == "CTAN_tgb"):      # also drives any model with the reference API
         batch = Batch(src=torch.cat([src, src]), dst=torch.cat([dst, neg_dst]), n_neg=neg_dst.numel(), x=stream.get("x"))
     else:
         batch = Batch(src=src, dst=dst, neg_dst=neg_dst, x=stream.get("x"))
@@ -431,7 +431,7 @@ def infer_step_ref(model: OracleCTAN, loader, helper: Tensor, stream: dict, lo: 
     seeds = torch.cat([src, dst, neg_dst]).unique()
     n_id, edge_index, e_id = khop_lookup(loader, seeds, model.num_gnn_layers)
     helper[n_id] = torch.arange(n_id.numel(), device=n_id.device)
-    if model.tgb:
+    if getattr(model, "tgb", type(model).__name__ == "CTAN_tgb"):      # also drives any model with the reference API
         batch = Batch(src=torch.cat([src, src]), dst=torch.cat([dst, neg_dst]), n_neg=neg_dst.numel(), x=stream.get("x"))
     else:
         batch = Batch(src=src, dst=dst, neg_dst=neg_dst, x=stream.get("x"))
