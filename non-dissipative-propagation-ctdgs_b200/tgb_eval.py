@@ -97,15 +97,25 @@ class TGBEvalEngine:
         i64 = dict(device=dev, dtype=torch.long)
         w = {}
         w["counters"] = torch.zeros(8, **i64)
-        w["b_src"], w["b_dst"], w["b_t"] = (torch.zeros(B, **i64) for _ in range(3))
-        w["seeds"] = torch.zeros(self.n_seeds, **i64)
-        w["pair_src"], w["pair_dst"] = torch.zeros(P, **i64), torch.zeros(P, **i64)
         w["frontier"] = torch.zeros(max(K - 1, 1) * N, **i64)
         w["frontier_cnt"] = torch.zeros(8, device=dev, dtype=torch.int32)
-        w["counts"] = torch.zeros(8, device=dev, dtype=torch.int32)
-        w["n_id"] = torch.zeros(N, **i64)
-        w["rowptr"] = torch.zeros(N + 1, device=dev, dtype=torch.int32)
-        w["esrc"], w["edst"], w["eid"] = (torch.zeros(E, **i64) for _ in range(3))
+        # Front-end outputs (staged batch, seeds, scored pairs, sorted node set, CSR edge list, global->local map)
+        # are double-buffered: the stage/lookup/fill of batch j+1 depends only on the neighbour tables (final once
+        # batch j's insert is done), so it runs as a side branch WHILE batch j is scored -- off the critical path.
+        self.fe = []
+        for par in range(2):
+            f = {}
+            f["b_src"], f["b_dst"], f["b_t"] = (torch.zeros(B, **i64) for _ in range(3))
+            f["seeds"] = torch.zeros(self.n_seeds, **i64)
+            f["pair_src"], f["pair_dst"] = torch.zeros(P, **i64), torch.zeros(P, **i64)
+            f["counts"] = torch.zeros(8, device=dev, dtype=torch.int32)
+            f["n_id"] = torch.zeros(N, **i64)
+            f["rowptr"] = torch.zeros(N + 1, device=dev, dtype=torch.int32)
+            f["esrc"], f["edst"], f["eid"] = (torch.zeros(E, **i64) for _ in range(3))
+            f["assoc"] = self.loader._assoc if par == 0 else torch.zeros_like(self.loader._assoc)
+            f["Nd"], f["Ed"] = f["counts"][0:1], f["counts"][1:2]
+            self.fe.append(f)
+        w["counts"] = self.fe[0]["counts"]                 # (diagnostics: sizes of an even batch's subgraph)
         w["ins_ws"] = torch.zeros(4 * B, device=dev, dtype=torch.int32)
         w["rel"] = torch.zeros(E, **f32)
         w["X"] = torch.zeros((2, N, D), **f32)
@@ -138,7 +148,6 @@ class TGBEvalEngine:
         w["rows"] = torch.zeros((B, self.row), **f32) if self.world > 1 else w["send"]
         w["acc"] = torch.zeros(2, device=dev, dtype=torch.float64)   # [sum of 1/rank, #queries]
         self.w = w
-        self._Nd, self._Ed = w["counts"][0:1], w["counts"][1:2]
 
     # ------------------------------------------------------------------ state
     def set_cursor(self, event_index: int):
@@ -154,63 +163,83 @@ class TGBEvalEngine:
 
     # ------------------------------------------------------------------ one batch
     def _launch(self, dry: bool = False):
-        self._compute(dry)
+        self._frontend(0)
+        self._batch(0, False, dry)
         self._exchange()
-        self._update(dry)
+        self._update(0, dry)
 
-    def _insert_branch(self, dry: bool):
-        """The neighbour-table insert of the batch needs only the staged (src, dst) and must follow this batch's
-        lookup/fill (the last readers of the tables): it runs as a parallel branch beside the whole forward and
-        the exchange instead of at the tail of the batch."""
-        w, ld = self.w, self.loader
-        self._side2.wait_stream(torch.cuda.current_stream())
+    def _frontend(self, par: int):
+        """stage -> K-hop lookup -> edge list of the batch at the cursor, into buffer set `par`.  Reads the neighbour
+        tables only (not the memory): may run before the previous batch's memory write-back."""
+        w, ld, f = self.w, self.loader, self.fe[par]
+        B, K, S, Q = self.B, self.K, self.S, self.Q
+        N, E = self.n_cap, self.e_cap
+        call("ctan_stage_eval", ptr(self.src), ptr(self.dst), ptr(self.t), ptr(self.neg), self.n_neg, B, self.q0,
+             self.q1, ptr(w["counters"]), ptr(f["b_src"]), ptr(f["b_dst"]), ptr(f["b_t"]), ptr(f["seeds"]),
+             ptr(f["pair_src"]), ptr(f["pair_dst"]))
+        if Q > 0:
+            call("ctan_nbr_lookup", ptr(ld.neighbors), ptr(ld._deg), self.num_nodes, S, ptr(f["seeds"]),
+                 Q * (2 + self.n_neg), None, K, ptr(ld._bitmap), ptr(ld._cbitmap), ptr(w["frontier"]),
+                 ptr(w["frontier_cnt"]), N, ptr(f["n_id"]), N, ptr(f["assoc"]), ptr(f["rowptr"]), E, ptr(f["counts"]))
+            call("ctan_nbr_fill", ptr(ld.neighbors), ptr(ld.e_id), S, ptr(f["n_id"]), ptr(f["rowptr"]), ptr(f["assoc"]),
+                 N, ptr(f["Nd"]), ptr(f["esrc"]), ptr(f["edst"]), ptr(f["eid"]), ptr(ld._bitmap), ptr(ld._cbitmap))
+
+    def _insert(self, par: int, dry: bool):
+        """Neighbour-table insert of the batch in buffer set `par` (needs only the staged (src, dst); must follow that
+        batch's lookup/fill, the last readers of the tables)."""
+        w, ld, f = self.w, self.loader, self.fe[par]
+        if dry:
+            sm, sl, sn, se, sd = self._scratch
+            call("ctan_nbr_insert", ptr(sn), ptr(se), ptr(sd), ptr(sl), ptr(sl), 1, 0, None, self.S, ptr(w["ins_ws"]))
+        else:
+            call("ctan_nbr_insert", ptr(ld.neighbors), ptr(ld.e_id), ptr(ld._deg), ptr(f["b_src"]), ptr(f["b_dst"]),
+                 self.B, 0, ptr(w["counters"]) + 8, self.S, ptr(w["ins_ws"]))
+
+    def _batch(self, par: int, prefetch: bool, dry: bool = False):
+        """Score the batch whose front-end is in buffer set `par`; beside it (side branch): its neighbour insert and,
+        if `prefetch`, the front-end of the NEXT batch into the other buffer set."""
+        cur = torch.cuda.current_stream()
+        self._side2.wait_stream(cur)
         with torch.cuda.stream(self._side2):
-            if dry:
-                sm, sl, sn, se, sd = self._scratch
-                call("ctan_nbr_insert", ptr(sn), ptr(se), ptr(sd), ptr(sl), ptr(sl), 1, 0, None, self.S, ptr(w["ins_ws"]))
-            else:
-                call("ctan_nbr_insert", ptr(ld.neighbors), ptr(ld.e_id), ptr(ld._deg), ptr(w["b_src"]), ptr(w["b_dst"]),
-                     self.B, 0, ptr(w["counters"]) + 8, self.S, ptr(w["ins_ws"]))
+            self._insert(par, dry)            # reads counters[1] of this batch: before the next stage overwrites it
+            if prefetch:
+                self._frontend(par ^ 1)
+        self._forward(par)
+        cur.wait_stream(self._side2)
 
-    def _compute(self, dry: bool = False):
-        """stage -> lookup -> forward -> scores -> packed per-query rows of this rank's shard."""
-        w, m, ld = self.w, self.model, self.loader
+    def _forward(self, par: int):
+        """delta-t -> forward -> scores -> packed per-query rows of this rank's shard."""
+        w, m, f = self.w, self.model, self.fe[par]
         B, D, K, S, Fe, Fn, T, Hd, O, P, Q = self.B, self.D, self.K, self.S, self.Fe, self.Fn, self.T, self.Hd, self.O, self.P, self.Q
         N, E = self.n_cap, self.e_cap
-        Nd, Ed = ptr(self._Nd), ptr(self._Ed)
+        Nd, Ed = ptr(f["Nd"]), ptr(f["Ed"])
         g, a, r = m.gnn, m.gnn.aconv, m.readout
         ph = a.phi
         mem, lu = m.memory.memory, m.memory.last_update
         xf = ptr(self.x) if Fn else None
         eps = float(a.epsilon)
-        call("ctan_stage_eval", ptr(self.src), ptr(self.dst), ptr(self.t), ptr(self.neg), self.n_neg, B, self.q0,
-             self.q1, ptr(w["counters"]), ptr(w["b_src"]), ptr(w["b_dst"]), ptr(w["b_t"]), ptr(w["seeds"]),
-             ptr(w["pair_src"]), ptr(w["pair_dst"]))
         if Q > 0:
-            call("ctan_nbr_lookup", ptr(ld.neighbors), ptr(ld._deg), self.num_nodes, S, ptr(w["seeds"]),
-                 Q * (2 + self.n_neg), None, K, ptr(ld._bitmap), ptr(ld._cbitmap), ptr(w["frontier"]),
-                 ptr(w["frontier_cnt"]), N, ptr(w["n_id"]), N, ptr(ld._assoc), ptr(w["rowptr"]), E, ptr(w["counts"]))
-            call("ctan_nbr_fill_rel", ptr(ld.neighbors), ptr(ld.e_id), S, ptr(w["n_id"]), ptr(w["rowptr"]),
-                 ptr(ld._assoc), N, Nd, ptr(w["esrc"]), ptr(w["edst"]), ptr(w["eid"]), ptr(ld._bitmap),
-                 ptr(ld._cbitmap), ptr(lu), ptr(self.t), float(g.mean_delta_t), float(g.std_delta_t), ptr(w["rel"]))
             self._side.wait_stream(torch.cuda.current_stream())
-            self._insert_branch(dry)
             with torch.cuda.stream(self._side):
+                # delta-t reads last_update, i.e. the memory write-back of the previous batch: it belongs here, not
+                # to the (prefetched) front-end
+                call("ctan_edge_rel", ptr(lu), ptr(f["n_id"]), ptr(f["esrc"]), ptr(self.t), ptr(f["eid"]), E, Ed,
+                     float(g.mean_delta_t), float(g.std_delta_t), ptr(w["rel"]))
                 if self.use_tc_ep:
-                    call("ctan_eproj_prep", ptr(self.msg), Fe, ptr(w["eid"]), ptr(w["rel"]), ptr(g.time_enc.lin.weight),
+                    call("ctan_eproj_prep", ptr(self.msg), Fe, ptr(f["eid"]), ptr(w["rel"]), ptr(g.time_enc.lin.weight),
                          ptr(g.time_enc.lin.bias), T, E, Ed, self.Kep, ptr(w["Aep"]))
                     call("ctan_gemm_tc", ptr(w["Aep"]), E, Ed, self.Kep, ptr(w["Wep_hi"]), ptr(w["Wep_lo"]), D, None,
                          None, None, None, D, None, 0, ptr(w["EP"]), _lib.TC_MODE)
                 else:
-                    call("ctan_eproj_fwd", ptr(self.msg), Fe, ptr(w["eid"]), ptr(w["rel"]), ptr(g.time_enc.lin.weight),
+                    call("ctan_eproj_fwd", ptr(self.msg), Fe, ptr(f["eid"]), ptr(w["rel"]), ptr(g.time_enc.lin.weight),
                          ptr(g.time_enc.lin.bias), T, ptr(ph.lin_edge.weight), E, Ed, D, ptr(w["EP"]))
             if self.use_tc_enc:          # gather -> dense rows; enc_x on the tensor cores; node-feature columns as residual
-                call("ctan_enc_prep", ptr(mem), D, xf, Fn, ptr(w["n_id"]), N, Nd, ptr(g.enc_x.weight), ptr(w["zmain"]),
+                call("ctan_enc_prep", ptr(mem), D, xf, Fn, ptr(f["n_id"]), N, Nd, ptr(g.enc_x.weight), ptr(w["zmain"]),
                      ptr(w["ztail"]))
                 call("ctan_gemm_tc", ptr(w["zmain"]), N, Nd, D, ptr(w["Wenc_hi"]), ptr(w["Wenc_lo"]), D,
                      ptr(g.enc_x.bias), None, None, None, D, ptr(w["ztail"]), D, ptr(w["X"][0]), _lib.TC_MODE)
             else:
-                call("ctan_enc_fwd", ptr(mem), D, xf, Fn, ptr(w["n_id"]), None, N, Nd, ptr(g.enc_x.weight),
+                call("ctan_enc_fwd", ptr(mem), D, xf, Fn, ptr(f["n_id"]), None, N, Nd, ptr(g.enc_x.weight),
                      ptr(g.enc_x.bias), ptr(w["X"][0]))
             torch.cuda.current_stream().wait_stream(self._side)
             for k in range(K):
@@ -220,11 +249,11 @@ class TGBEvalEngine:
                          ptr(ph.lin_query.bias), ptr(ph.lin_key.bias), ptr(ph.lin_value.bias), ptr(a.bias),
                          ptr(w["QKVA"]), _lib.TC_MODE)
                 else:
-                  call("ctan_qkva_fwd", ptr(xi), N, Nd, D, ptr(ph.lin_query.weight), ptr(ph.lin_key.weight),
-                     ptr(ph.lin_value.weight), ptr(w["A"]), ptr(ph.lin_query.bias), ptr(ph.lin_key.bias),
-                     ptr(ph.lin_value.bias), ptr(a.bias), ptr(w["QKVA"]))
+                    call("ctan_qkva_fwd", ptr(xi), N, Nd, D, ptr(ph.lin_query.weight), ptr(ph.lin_key.weight),
+                         ptr(ph.lin_value.weight), ptr(w["A"]), ptr(ph.lin_query.bias), ptr(ph.lin_key.bias),
+                         ptr(ph.lin_value.bias), ptr(a.bias), ptr(w["QKVA"]))
                 last = k == K - 1
-                call("ctan_edge_fwd", ptr(w["QKVA"]), ptr(w["EP"]), ptr(w["rowptr"]), ptr(w["esrc"]), N, Nd, D,
+                call("ctan_edge_fwd", ptr(w["QKVA"]), ptr(w["EP"]), ptr(f["rowptr"]), ptr(f["esrc"]), N, Nd, D,
                      ptr(xi), eps, ptr(xo), None, None, ptr(w["Z"]) if (last and self.final_tanh) else None,
                      ptr(w["hub"]) if self.S > 8 else None, self.hub_cap)
             z = w["Z"] if self.final_tanh else w["X"][K & 1]
@@ -232,17 +261,14 @@ class TGBEvalEngine:
                 # project every NODE once (tensor cores), then a scored pair only gathers two rows
                 call("ctan_gemm_tc", ptr(z), N, Nd, D, ptr(w["Wro_hi"]), ptr(w["Wro_lo"]), 2 * Hd, ptr(r.lin_src.bias),
                      ptr(r.lin_dst.bias), None, None, Hd, None, 0, ptr(w["Y"]), _lib.TC_MODE)
-                call("ctan_head_pack", ptr(w["Y"]), Hd, ptr(z), D, ptr(ld._assoc), ptr(w["pair_src"]), ptr(w["pair_dst"]),
+                call("ctan_head_pack", ptr(w["Y"]), Hd, ptr(z), D, ptr(f["assoc"]), ptr(f["pair_src"]), ptr(f["pair_dst"]),
                      Q, self.n_neg, ptr(r.lin_final.weight), ptr(r.lin_final.bias), ptr(w["send"]))
             else:
-                call("ctan_readout_fwd", ptr(z), D, ptr(w["pair_src"]), ptr(w["pair_dst"]), ptr(ld._assoc), Q * self.L,
+                call("ctan_readout_fwd", ptr(z), D, ptr(f["pair_src"]), ptr(f["pair_dst"]), ptr(f["assoc"]), Q * self.L,
                      None, Hd, O, ptr(r.lin_src.weight), ptr(r.lin_src.bias), ptr(r.lin_dst.weight), ptr(r.lin_dst.bias),
                      ptr(r.lin_final.weight), ptr(r.lin_final.bias), ptr(w["H"]), ptr(w["OUT"]), 0)   # no split-K: scores must not depend on atomic order
-                call("ctan_pack_eval", ptr(w["OUT"]), ptr(z), ptr(ld._assoc), ptr(w["pair_src"]), ptr(w["pair_dst"]), Q,
+                call("ctan_pack_eval", ptr(w["OUT"]), ptr(z), ptr(f["assoc"]), ptr(f["pair_src"]), ptr(f["pair_dst"]), Q,
                      self.n_neg, D, ptr(w["send"]))
-        else:
-            self._insert_branch(dry)         # a rank without queries still applies the state update
-        torch.cuda.current_stream().wait_stream(self._side2)
 
     def _prep_weights(self):
         """Weight-only operands (A = W - W^T - gamma I, the packed / hi-lo split weight panels of the tensor-core
@@ -275,10 +301,10 @@ class TGBEvalEngine:
             w = self.w
             exchange_rows(w["send"], w["recv"], w["rows"], self.B, self.world, self.group)
 
-    def _update(self, dry: bool = False):
-        """metric accumulation + the identical ground-truth state update on every rank."""
-        w, m, ld = self.w, self.model, self.loader
-        B, D, S = self.B, self.D, self.S
+    def _update(self, par: int, dry: bool = False):
+        """metric accumulation + the identical ground-truth memory write-back on every rank."""
+        w, m, f = self.w, self.model, self.fe[par]
+        B, D = self.B, self.D
         mem, lu = m.memory.memory, m.memory.last_update
         rows = w["rows"] if self.world > 1 else w["send"]
         call("ctan_accum_col", ptr(rows), B, self.row, 0, ptr(w["acc"]))
@@ -288,7 +314,7 @@ class TGBEvalEngine:
             call("ctan_mem_update", ptr(sm), ptr(sl), D, ptr(sl), ptr(sl), ptr(sl), 1, emb, emb + 4 * D, self.row,
                  None, None)
             return
-        call("ctan_mem_update", ptr(mem), ptr(lu), D, ptr(w["b_src"]), ptr(w["b_dst"]), ptr(w["b_t"]), B, emb,
+        call("ctan_mem_update", ptr(mem), ptr(lu), D, ptr(f["b_src"]), ptr(f["b_dst"]), ptr(f["b_t"]), B, emb,
              emb + 4 * D, self.row, None, None)
 
     def warmup(self):
@@ -311,31 +337,54 @@ class TGBEvalEngine:
         self.w["counters"].copy_(cur)
         self.w["acc"].zero_()
 
+    def _graphs_for(self, par: int, prefetch: bool):
+        key = (par, prefetch)
+        if key not in self._graphs:
+            ga, gb = torch.cuda.CUDAGraph(), None
+            with torch.cuda.graph(ga):
+                self._batch(par, prefetch)
+                if self.world == 1:
+                    self._update(par)
+            if self.world > 1:
+                gb = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gb):
+                    self._update(par)
+            self._graphs[key] = (ga, gb)
+        return self._graphs[key]
+
     def run(self, n_batches: int):
+        """Evaluate the next n_batches batches.  Inside one call the front-end of batch j+1 is prefetched beside the
+        scoring of batch j; the state after the call is exactly that of a batch-by-batch run."""
         if self.loader.cur_e_id + n_batches * self.B > self.n_events:
             raise ValueError("stream exhausted")
+        if n_batches <= 0:
+            return
         self._prep_weights()          # once per run() call (a whole split), not per batch
         with torch.cuda.device(self.dev):
             if self.use_graph:
                 if self._graph is None:
-                    ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(ga):
-                        self._compute()
-                        if self.world == 1:
-                            self._update()
-                    if self.world > 1:
-                        with torch.cuda.graph(gb):
-                            self._update()
-                    self._graph = (ga, gb)
-                ga, gb = self._graph
-                for _ in range(n_batches):
+                    self._graphs = {}
+                    g0 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g0):
+                        self._frontend(0)
+                    self._graph = g0
+                self._graph.replay()                       # front-end of the first batch of this call
+                par = 0
+                for j in range(n_batches):
+                    ga, gb = self._graphs_for(par, j < n_batches - 1)
                     ga.replay()
                     if self.world > 1:
                         self._exchange()
                         gb.replay()
+                    par ^= 1
             else:
-                for _ in range(n_batches):
-                    self._launch()
+                self._frontend(0)
+                par = 0
+                for j in range(n_batches):
+                    self._batch(par, j < n_batches - 1)
+                    self._exchange()
+                    self._update(par)
+                    par ^= 1
         self.loader.cur_e_id += n_batches * self.B
 
     def scores(self) -> torch.Tensor:
@@ -344,6 +393,6 @@ class TGBEvalEngine:
         return rows[: self.B, 1:1 + self.L]
 
     def check(self):
-        err = int(self.w["counts"][3].item())
+        err = max(int(f["counts"][3].item()) for f in self.fe)
         if err:
             raise _lib.CtanLibraryError(f"neighbor lookup overflowed the engine workspace (code {err})")

@@ -13,7 +13,7 @@ g = torch.cuda.CUDAGraph()
 with torch.cuda.graph(g):
     _lib.lib().ctan_probe(ts.data_ptr(), 0, torch.cuda.current_stream().cuda_stream); names.append("start")
     _lib.PROBE = (ts, names, torch.cuda.current_stream().cuda_stream)
-    eng._compute(); eng._update()
+    eng._frontend(0); eng._batch(0, False); eng._update(0)
     _lib.PROBE = None
 acc = torch.zeros(len(names), dtype=torch.float64)
 R = 50
