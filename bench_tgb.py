@@ -77,7 +77,9 @@ def run_tgb_eval_bench(args, rank, world, quiet=False):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    h0 = time.perf_counter()
     eng.run(steps)
+    host_ms = (time.perf_counter() - h0) * 1e3 / steps       # host time to ISSUE a batch (no sync inside)
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -99,7 +101,7 @@ def run_tgb_eval_bench(args, rank, world, quiet=False):
                                   "insert (SURVEY.md S8d)",
                       "l2": "state tables (1.0 GB memory + 0.5 GB neighbour rows) exceed L2; no flush"},
            "clocks": clocks, "mrr": mrr, "rank0_subgraph": {"N": counts[0], "E": counts[1]},
-           "gpu_launches": steps * eng.launches_per_batch, "launches_per_step": eng.launches_per_batch}
+           "host_issue_ms_per_step": host_ms, "gpu_launches": steps * eng.launches_per_batch, "launches_per_step": eng.launches_per_batch}
     if rank == 0 and not quiet:
         print(json.dumps(out))
     if world > 1:
