@@ -165,14 +165,13 @@ def build_engine(st, K, mean, std, dev, host_staged=False):
 
 def time_steps(eng, n_steps, train, flush_buf):
     """Per-step CUDA events with an L2 flush (write of a >L2 buffer) between timed steps."""
-    g = eng._graph(train)
     evs = []
-    for _ in range(n_steps):
-        if flush_buf is not None:
+    for fn in eng.plan(n_steps, train):      # the engine's own replay sequence (a training step also issues the
+        if flush_buf is not None:            # next step's front-end beside its backward: that work is timed here)
             flush_buf.add_(1.0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        g.replay()
+        fn()
         e1.record()
         evs.append((e0, e1))
     torch.cuda.synchronize()

@@ -9,7 +9,7 @@
 #include "common.cuh"
 
 // counters (int64 [8], device): [0] next batch start (event index), [1] current batch start,
-// [2] Adam step (1-based, of the current step), [3] number of steps taken so far.
+// [2] optimizer steps COMPLETED (advanced by the Adam kernel), [3] number of steps staged so far, [5]/[6] tickets.
 __global__ void stage_batch_kernel(const int64_t* __restrict__ src_all, const int64_t* __restrict__ dst_all,
                                    const int64_t* __restrict__ t_all, const int64_t* __restrict__ neg_all,
                                    int n_neg, int B, int64_t* __restrict__ counters, int use_cursor,
@@ -24,8 +24,7 @@ __global__ void stage_batch_kernel(const int64_t* __restrict__ src_all, const in
         const int64_t cur = counters[0];              // event index of this batch's first event
         counters[0] = cur + B;
         counters[1] = cur;
-        counters[2] += 1;
-        counters[3] += 1;
+        counters[3] += 1;                             // (the optimizer step count, counters[2], is advanced by Adam itself)
         if (loss_hist) loss_hist[(counters[3] - 1) % hist_cap] = 0.f;   // slot the fused head+loss accumulates into
         s_off = use_cursor ? cur : 0;                 // 0: the arrays ARE the batch (host-staged buffers)
     }
@@ -112,7 +111,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     ctan_pdl_begin();
     __shared__ float s_step_size, s_bc2_sqrt;
     if (threadIdx.x == 0) {
-        const int64_t step = counters ? counters[2] : step_host;
+        const int64_t step = counters ? counters[2] + 1 : step_host;
         const double bc1 = 1.0 - pow((double)beta1, (double)step);
         const double bc2 = 1.0 - pow((double)beta2, (double)step);
         s_step_size = (float)((double)lr / bc1);
@@ -129,6 +128,20 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
         m[i] = mi; v[i] = vi;
         const float denom = sqrtf(vi) / bc2_sqrt + eps;
         p[i] = pi - step_size * (mi / denom);
+    }
+    // Every CTA has read the step count above; the last one to finish advances it (ticket in counters[6]).  The stage
+    // kernel cannot own it: the NEXT step's stage may already have run (prefetched beside this step's backward).
+    if (counters) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int64_t* c = const_cast<int64_t*>(counters);
+            __threadfence();
+            const unsigned long long tk = atomicAdd(reinterpret_cast<unsigned long long*>(c + 6), 1ull);
+            if (tk == (unsigned long long)gridDim.x - 1) {
+                c[6] = 0;
+                c[2] += 1;
+            }
+        }
     }
 }
 

@@ -142,17 +142,27 @@ class StepEngine:
         N, E, P = self.n_cap, self.e_cap, self.P
         w = {}
         w["counters"] = torch.zeros(8, **i64)
-        w["b_src"], w["b_dst"], w["b_t"] = (torch.zeros(B, **i64) for _ in range(3))
-        w["seeds"] = torch.zeros(n_seeds, **i64)
-        w["pair_src"], w["pair_dst"] = torch.zeros(P, **i64), torch.zeros(P, **i64)
         w["frontier"] = torch.zeros(max(K - 1, 1) * N, **i64)
         w["frontier_cnt"] = torch.zeros(8, device=dev, dtype=torch.int32)
-        w["counts"] = torch.zeros(8, device=dev, dtype=torch.int32)
-        w["n_id"] = torch.zeros(N, **i64)
-        w["rowptr"] = torch.zeros(N + 1, device=dev, dtype=torch.int32)
-        w["esrc"], w["edst"], w["eid"] = (torch.zeros(E, **i64) for _ in range(3))
+        # Front-end outputs (staged batch, seeds, scored pairs, sorted node set, CSR edge list, delta-t, global->local
+        # map) exist twice: the stage/lookup/fill of step j+1 needs only the state written by step j's write-back,
+        # which happens right after step j's forward, so it is issued beside step j's BACKWARD into the other set.
+        self.fe = []
+        for par in range(2):
+            f = {}
+            f["b_src"], f["b_dst"], f["b_t"] = (torch.zeros(B, **i64) for _ in range(3))
+            f["seeds"] = torch.zeros(n_seeds, **i64)
+            f["pair_src"], f["pair_dst"] = torch.zeros(P, **i64), torch.zeros(P, **i64)
+            f["counts"] = torch.zeros(8, device=dev, dtype=torch.int32)
+            f["n_id"] = torch.zeros(N, **i64)
+            f["rowptr"] = torch.zeros(N + 1, device=dev, dtype=torch.int32)
+            f["esrc"], f["edst"], f["eid"] = (torch.zeros(E, **i64) for _ in range(3))
+            f["rel"] = torch.zeros(E, **f32)
+            f["assoc"] = self.loader._assoc if par == 0 else torch.zeros_like(self.loader._assoc)
+            f["Nd"], f["Ed"] = f["counts"][0:1], f["counts"][1:2]
+            self.fe.append(f)
+        w["counts"] = self.fe[0]["counts"]                 # (diagnostics)
         w["ins_ws"] = torch.zeros(4 * B, device=dev, dtype=torch.int32)
-        w["rel"] = torch.zeros(E, **f32)
         w["z0"] = torch.zeros((N, D + self.Fn), **f32)
         w["X"] = torch.zeros((K + 1, N, D), **f32)
         w["EP"] = torch.zeros((E, D), **f32)
@@ -182,8 +192,7 @@ class StepEngine:
         w["dTenc"] = torch.zeros((E, max(self.T, 1)), **f32)
         w["dA"] = self._dA
         self.w = w
-        self._Nd = w["counts"][0:1]
-        self._Ed = w["counts"][1:2]
+        self.prefetch = (not self.host_staged) and os.environ.get("CTAN_TRAIN_PREFETCH", "1") == "1"
 
     # ------------------------------------------------------------------ state
     def reset(self, reset_optimizer: bool = False):
@@ -191,7 +200,8 @@ class StepEngine:
         self.model.reset_memory()
         self.loader.reset_state()
         self.w["counters"].zero_()
-        self.w["counts"].zero_()
+        for f in self.fe:
+            f["counts"].zero_()
         if self.host_staged:
             self._host_cursor = 0
         if reset_optimizer:
@@ -233,22 +243,35 @@ class StepEngine:
         if self.parallel:
             torch.cuda.current_stream().wait_stream(self._side[i])
 
-    def _launch(self, train: bool):
-        """Issue one step.  Work that is off the critical path (edge projection, weight gradients,
-        state write-back) goes to two side streams with fork/join edges; under graph capture these
-        become parallel branches of the captured DAG."""
-        w, m, ld = self.w, self.model, self.loader
-        B, D, K, S, Fe, Fn, T = self.B, self.D, self.K, self.S, self.Fe, self.Fn, self.T
-        Hd, O, P = self.Hd, self.O, self.P
+    def _frontend(self, par: int):
+        """stage -> K-hop lookup -> edge list + delta-t of the batch at the cursor, into buffer set `par`.  Reads the
+        neighbour tables and last_update: must follow the previous step's state write-back, nothing else."""
+        w, m, ld, f = self.w, self.model, self.loader, self.fe[par]
+        B, K, S = self.B, self.K, self.S
         N, E = self.n_cap, self.e_cap
-        Nd, Ed = ptr(self._Nd), ptr(self._Ed)
-        (Wenc, benc, Wq, bq, Wk, bk, Wv, bv, We, W, b, tw, tb, Wsrc, bsrc, Wdst, bdst, Wfin,
-         bfin) = (ptr(t) for t in self.p)
-        mem, lu = m.memory.memory, m.memory.last_update
-        cur1 = ptr(w["counters"]) + 8                       # &counters[1]: current batch start
-        xf = ptr(self.x) if Fn else None
-        eps = float(m.gnn.aconv.epsilon)
-        with self._fork(2):                                  # side 2: work with no dependence on the batch
+        call("ctan_stage_batch", ptr(self.src), ptr(self.dst), ptr(self.t), ptr(self.neg), self.n_neg, B,
+             ptr(w["counters"]), 0 if self.host_staged else 1, ptr(f["b_src"]), ptr(f["b_dst"]), ptr(f["b_t"]),
+             ptr(f["seeds"]), ptr(f["pair_src"]), ptr(f["pair_dst"]), ptr(w["loss_hist"]), self.hist_cap)
+        call("ctan_nbr_lookup", ptr(ld.neighbors), ptr(ld._deg), self.num_nodes, S, ptr(f["seeds"]), self.n_seeds,
+             None, K, ptr(ld._bitmap), ptr(ld._cbitmap), ptr(w["frontier"]), ptr(w["frontier_cnt"]), N,
+             ptr(f["n_id"]), N, ptr(f["assoc"]), ptr(f["rowptr"]), E, ptr(f["counts"]))
+        call("ctan_nbr_fill_rel", ptr(ld.neighbors), ptr(ld.e_id), S, ptr(f["n_id"]), ptr(f["rowptr"]),
+             ptr(f["assoc"]), N, ptr(f["Nd"]), ptr(f["esrc"]), ptr(f["edst"]), ptr(f["eid"]), ptr(ld._bitmap),
+             ptr(ld._cbitmap), ptr(m.memory.last_update), ptr(self.t_tab), float(m.gnn.mean_delta_t),
+             float(m.gnn.std_delta_t), ptr(f["rel"]))
+
+    def _launch(self, train: bool):
+        """One whole step, front-end inline (eager mode, warm-up, timeline scripts)."""
+        self._prep(train)
+        self._frontend(0)
+        self._step(train, 0, False, prep_done=True)
+
+    def _prep(self, train: bool):
+        """Side branch with no dependence on the batch (weight-only operands, memsets) + the launch mode of the step."""
+        w, m = self.w, self.model
+        D = self.D
+        Wq, Wk, Wv, W = (ptr(self.p[i]) for i in (2, 4, 6, 9))
+        with self._fork(2):
             if self.use_tc:      # A = W - W^T - gamma I, packed with q/k/v weights and split for 3xTF32
                 call("ctan_wcat_prep", Wq, Wk, Wv, W, float(m.gnn.aconv.gamma), D, ptr(w["Wcat_hi"]),
                      ptr(w["Wcat_lo"]), ptr(w["A"]), ptr(w["WcatT_hi"]) if (train and self.use_tc_dx) else None,
@@ -262,22 +285,33 @@ class StepEngine:
         # LENGTHENS the training step (118 -> 122..127 us, more the further into the DAG it is enabled): dependents
         # scheduled early hold SM slots that the step's parallel branches need.  So: inference on, training off.
         _lib.lib().ctan_set_pdl(0 if train else 1, None)
-        call("ctan_stage_batch", ptr(self.src), ptr(self.dst), ptr(self.t), ptr(self.neg), self.n_neg, B,
-             ptr(w["counters"]), 0 if self.host_staged else 1, ptr(w["b_src"]), ptr(w["b_dst"]), ptr(w["b_t"]),
-             ptr(w["seeds"]), ptr(w["pair_src"]), ptr(w["pair_dst"]), ptr(w["loss_hist"]), self.hist_cap)
-        call("ctan_nbr_lookup", ptr(ld.neighbors), ptr(ld._deg), self.num_nodes, S, ptr(w["seeds"]), self.n_seeds,
-             None, K, ptr(ld._bitmap), ptr(ld._cbitmap), ptr(w["frontier"]), ptr(w["frontier_cnt"]), N,
-             ptr(w["n_id"]), N, ptr(ld._assoc), ptr(w["rowptr"]), E, ptr(w["counts"]))
-        call("ctan_nbr_fill_rel", ptr(ld.neighbors), ptr(ld.e_id), S, ptr(w["n_id"]), ptr(w["rowptr"]),
-             ptr(ld._assoc), N, Nd, ptr(w["esrc"]), ptr(w["edst"]), ptr(w["eid"]), ptr(ld._bitmap), ptr(ld._cbitmap),
-             ptr(lu), ptr(self.t_tab), float(m.gnn.mean_delta_t), float(m.gnn.std_delta_t), ptr(w["rel"]))
+
+    def _step(self, train: bool, par: int, prefetch: bool, prep_done: bool = False):
+        """Issue one step whose front-end is already in buffer set `par`.  Work that is off the critical path (edge
+        projection, weight gradients, state write-back, and -- if `prefetch` -- the NEXT step's front-end into the
+        other buffer set) goes to side streams with fork/join edges; under graph capture these become parallel
+        branches of the captured DAG."""
+        w, m, ld, f = self.w, self.model, self.loader, self.fe[par]
+        B, D, K, S, Fe, Fn, T = self.B, self.D, self.K, self.S, self.Fe, self.Fn, self.T
+        Hd, O, P = self.Hd, self.O, self.P
+        N, E = self.n_cap, self.e_cap
+        Nd, Ed = ptr(f["Nd"]), ptr(f["Ed"])
+        assoc = f["assoc"]
+        (Wenc, benc, Wq, bq, Wk, bk, Wv, bv, We, W, b, tw, tb, Wsrc, bsrc, Wdst, bdst, Wfin,
+         bfin) = (ptr(t) for t in self.p)
+        mem, lu = m.memory.memory, m.memory.last_update
+        cur1 = ptr(w["counters"]) + 8                       # &counters[1]: current batch start
+        xf = ptr(self.x) if Fn else None
+        eps = float(m.gnn.aconv.epsilon)
+        if not prep_done:
+            self._prep(train)
         with self._fork(0):                                  # side 0: edge-attribute projection (|| enc_x)
-            call("ctan_eproj_fwd", ptr(self.msg), Fe, ptr(w["eid"]), ptr(w["rel"]), tw, tb, T, We, E, Ed, D,
+            call("ctan_eproj_fwd", ptr(self.msg), Fe, ptr(f["eid"]), ptr(f["rel"]), tw, tb, T, We, E, Ed, D,
                  ptr(w["EP"]))
         if train:
             with self._fork(1):                              # side 1: saved copy of the gathered input rows
-                call("ctan_gather_rows2", ptr(mem), D, xf, Fn, ptr(w["n_id"]), N, Nd, ptr(w["z0"]))
-        call("ctan_enc_fwd", ptr(mem), D, xf, Fn, ptr(w["n_id"]), None, N, Nd, Wenc, benc, ptr(w["X"][0]))
+                call("ctan_gather_rows2", ptr(mem), D, xf, Fn, ptr(f["n_id"]), N, Nd, ptr(w["z0"]))
+        call("ctan_enc_fwd", ptr(mem), D, xf, Fn, ptr(f["n_id"]), None, N, Nd, Wenc, benc, ptr(w["X"][0]))
         self._join(0)
         self._join(2)
         for k in range(K):
@@ -290,13 +324,13 @@ class StepEngine:
             else:
                 call("ctan_qkva_fwd", ptr(xi), N, Nd, D, Wq, Wk, Wv, ptr(w["A"]), bq, bk, bv, b, ptr(qk))
             last = k == K - 1
-            call("ctan_edge_fwd", ptr(qk), ptr(w["EP"]), ptr(w["rowptr"]), ptr(w["esrc"]), N, Nd, D, ptr(xi), eps,
+            call("ctan_edge_fwd", ptr(qk), ptr(w["EP"]), ptr(f["rowptr"]), ptr(f["esrc"]), N, Nd, D, ptr(xi), eps,
                  ptr(xo), ptr(w["TH"][k]) if train else None, ptr(w["ALPHA"][k]) if train else None,
                  ptr(w["Z"]) if (last and self.final_tanh) else None, ptr(w["hub"]) if S > 8 else None, self.hub_cap)
         xk = w["X"][K] if train else w["X"][K & 1]
         z = w["Z"] if self.final_tanh else xk
         self._z = z
-        call("ctan_readout_fwd", ptr(z), D, ptr(w["pair_src"]), ptr(w["pair_dst"]), ptr(ld._assoc), P, None, Hd, O,
+        call("ctan_readout_fwd", ptr(z), D, ptr(f["pair_src"]), ptr(f["pair_dst"]), ptr(assoc), P, None, Hd, O,
              Wsrc, bsrc, Wdst, bdst, Wfin, bfin, ptr(w["H"]), None, 1)
         # head + BCE loss + dOUT + dHid in one launch (the loss slot was cleared by the stage kernel)
         call("ctan_head_loss", ptr(w["H"]), P, Hd, Wfin, bfin, B, ptr(w["OUT"]), ptr(w["dOUT"]) if train else None,
@@ -304,19 +338,21 @@ class StepEngine:
 
         def state_update():
             # ground-truth state update (train_link.py:276-277)
-            call("ctan_mem_update", ptr(mem), ptr(lu), D, ptr(w["b_src"]), ptr(w["b_dst"]), ptr(w["b_t"]), B, None,
-                 None, 0, ptr(z), ptr(ld._assoc))
-            call("ctan_nbr_insert", ptr(ld.neighbors), ptr(ld.e_id), ptr(ld._deg), ptr(w["b_src"]), ptr(w["b_dst"]),
+            call("ctan_mem_update", ptr(mem), ptr(lu), D, ptr(f["b_src"]), ptr(f["b_dst"]), ptr(f["b_t"]), B, None,
+                 None, 0, ptr(z), ptr(assoc))
+            call("ctan_nbr_insert", ptr(ld.neighbors), ptr(ld.e_id), ptr(ld._deg), ptr(f["b_src"]), ptr(f["b_dst"]),
                  B, 0, cur1, S, ptr(w["ins_ws"]))
         if not train:
             state_update()
             _lib.lib().ctan_set_pdl(1, None)
             return
-        with self._fork(1):                                  # side 1 (after the z0 gather): state write-back
+        with self._fork(1):                                  # side 1 (after the z0 gather): state write-back ...
             state_update()
+            if prefetch:                                     # ... then the NEXT step's front-end, beside this backward
+                self._frontend(par ^ 1)
         (gWenc, gbenc, gWq, gbq, gWk, gbk, gWv, gbv, gWe, gW, gb, gtw, gtb, gWsrc, gbsrc, gWdst, gbdst, gWfin,
          gbfin) = (ptr(t) for t in self.g)
-        rb_args = (ptr(w["dOUT"]), ptr(w["H"]), ptr(z), D, ptr(w["pair_src"]), ptr(w["pair_dst"]), ptr(ld._assoc), P,
+        rb_args = (ptr(w["dOUT"]), ptr(w["H"]), ptr(z), D, ptr(f["pair_src"]), ptr(f["pair_dst"]), ptr(assoc), P,
                    None, Hd, O, Wsrc, Wdst, Wfin, ptr(w["dHid"]))
         call("ctan_readout_bwd", *rb_args, ptr(w["dZ"]), None, None, None, None, None, None, 1)
         with self._fork(2):                                  # side 2: readout weight gradients
@@ -329,7 +365,7 @@ class StepEngine:
             if k != K - 1:
                 self._join(0)                                # the previous iteration's dW contraction reads DQKVA
                 w["DQKVA"].zero_()
-            call("ctan_edge_bwd", ptr(w["QKVA"][k]), ptr(w["EP"]), ptr(w["rowptr"]), ptr(w["esrc"]), N, Nd, D, ptr(g),
+            call("ctan_edge_bwd", ptr(w["QKVA"][k]), ptr(w["EP"]), ptr(f["rowptr"]), ptr(f["esrc"]), N, Nd, D, ptr(g),
                  ptr(w["TH"][k]), ptr(w["ALPHA"][k]), eps, ptr(w["DQKVA"]), ptr(w["dEP"]), int(k != K - 1),
                  ptr(w["DS"]))
             qb = (ptr(w["DQKVA"]), ptr(w["X"][k]), ptr(g), N, Nd, D, Wq, Wk, Wv, ptr(w["A"]))
@@ -339,9 +375,9 @@ class StepEngine:
                     call("ctan_antisym_bwd", ptr(w["dA"]), D, gW)
             if k == 0:
                 with self._fork(3):                          # side 3: lin_edge / time-encoder gradients
-                    call("ctan_eproj_bwd", ptr(w["dEP"]), ptr(self.msg), Fe, ptr(w["eid"]), ptr(w["rel"]), tw, tb, T,
+                    call("ctan_eproj_bwd", ptr(w["dEP"]), ptr(self.msg), Fe, ptr(f["eid"]), ptr(f["rel"]), tw, tb, T,
                          We, E, Ed, D, gWe, ptr(w["dTenc"]), self.e_typ)
-                    call("ctan_tenc_bwd", ptr(w["dTenc"]), ptr(w["rel"]), tw, tb, E, Ed, T, gtw, gtb)
+                    call("ctan_tenc_bwd", ptr(w["dTenc"]), ptr(f["rel"]), tw, tb, E, Ed, T, gtw, gtb)
             gn = self._DX[k]
             if self.use_tc_dx:   # dX = G + DQKVA Wcat on tcgen05 (plain stores)
                 call("ctan_dx_tc", ptr(w["DQKVA"]), ptr(g), N, Nd, D, ptr(w["WcatT_hi"]), ptr(w["WcatT_lo"]), ptr(gn),
@@ -359,12 +395,27 @@ class StepEngine:
         _lib.lib().ctan_set_pdl(1, None)
 
     # ------------------------------------------------------------------ public stepping API
-    def _graph(self, train: bool):
-        key = bool(train)
+    def _graph(self, train: bool, par: int = 0, prefetch: bool = False, inline: bool = True):
+        """Captured step.  inline: the front-end is part of the graph (one self-contained step; inference, host-staged
+        mode).  Otherwise the front-end of buffer set `par` is expected to be done already and, if `prefetch`, the
+        next step's front-end is a branch of this graph."""
+        key = (bool(train), par, bool(prefetch), bool(inline))
         if key not in self._graphs:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=self._main):
-                self._launch(train)
+                if inline:
+                    self._prep(train)
+                    self._frontend(par)
+                self._step(train, par, prefetch, prep_done=inline)
+            self._graphs[key] = g
+        return self._graphs[key]
+
+    def _graph_frontend(self, par: int = 0):
+        key = ("fe", par)
+        if key not in self._graphs:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self._main):
+                self._frontend(par)
             self._graphs[key] = g
         return self._graphs[key]
 
@@ -380,18 +431,33 @@ class StepEngine:
         self.reset(reset_optimizer=True)
         self.w["loss_hist"].zero_()
 
+    def plan(self, n_steps: int, train: bool = True):
+        """The replay sequence of n_steps steps as a list of callables (one per step; the first also issues the first
+        front-end).  Training steps prefetch the next step's front-end beside their backward, except the last of the
+        sequence: the state after the sequence is exactly that of n_steps self-contained steps."""
+        if not self.use_graph:
+            return [lambda: self._launch(train) for _ in range(n_steps)]
+        if not (train and self.prefetch):
+            g = self._graph(train)
+            return [g.replay for _ in range(n_steps)]
+        seq, par = [], 0
+        for j in range(n_steps):
+            g = self._graph(True, par, j < n_steps - 1, inline=False)
+            if j == 0:
+                fe = self._graph_frontend(0)
+                seq.append(lambda fe=fe, g=g: (fe.replay(), g.replay()))
+            else:
+                seq.append(g.replay)
+            par ^= 1
+        return seq
+
     def run(self, n_steps: int, train: bool = True):
         """Advance n_steps full batches from the cursor (no host synchronisation)."""
         if self.loader.cur_e_id + n_steps * self.B > self.n_events:
             raise ValueError(f"stream exhausted: cursor {self.loader.cur_e_id} + {n_steps}x{self.B} > {self.n_events}")
         with torch.cuda.device(self.dev):
-            if self.use_graph:
-                g = self._graph(train)
-                for _ in range(n_steps):
-                    g.replay()
-            else:
-                for _ in range(n_steps):
-                    self._launch(train)
+            for fn in self.plan(n_steps, train):
+                fn()
         self.loader.cur_e_id += n_steps * self.B
 
     def losses(self, n: int) -> torch.Tensor:
@@ -402,6 +468,6 @@ class StepEngine:
 
     def check(self):
         """Raise if any lookup overflowed its workspace during the run (device flag, one sync)."""
-        err = int(self.w["counts"][3].item())
+        err = max(int(f["counts"][3].item()) for f in self.fe)
         if err:
             raise _lib.CtanLibraryError(f"neighbor lookup overflowed the engine workspace (code {err})")
