@@ -75,7 +75,7 @@ OPTIONAL_SIGNATURES = {}
 
 SIGNATURES.update({
     # step.cu
-    "ctan_stage_batch": [P, P, P, P, I, I, P, I, P, P, P, P, P, P, P, I],
+    "ctan_stage_batch": [P, P, P, P, I, I, P, I, P, P, P, P, P, P, P, I, P],
     "ctan_bce_loss": [P, I, I, P, P, I, P],
     "ctan_adam_step": [P, P, P, P, I, F, F, F, F, F, L, P],
     "ctan_mrr": [P, P, I, I, P],

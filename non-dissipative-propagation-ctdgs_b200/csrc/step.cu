@@ -16,7 +16,7 @@ __global__ void stage_batch_kernel(const int64_t* __restrict__ src_all, const in
                                    int64_t* __restrict__ b_src, int64_t* __restrict__ b_dst,
                                    int64_t* __restrict__ b_t, int64_t* __restrict__ seeds,
                                    int64_t* __restrict__ pair_src, int64_t* __restrict__ pair_dst,
-                                   float* __restrict__ loss_hist, int hist_cap) {
+                                   float* __restrict__ loss_hist, int hist_cap, int64_t* __restrict__ step_out) {
     ctan_pdl_begin();
     // single block; negatives are laid out [event][n_neg]
     __shared__ int64_t s_off;
@@ -26,6 +26,9 @@ __global__ void stage_batch_kernel(const int64_t* __restrict__ src_all, const in
         counters[1] = cur;
         counters[3] += 1;                             // (the optimizer step count, counters[2], is advanced by Adam itself)
         if (loss_hist) loss_hist[(counters[3] - 1) % hist_cap] = 0.f;   // slot the fused head+loss accumulates into
+        // the step number of THIS staged batch, for kernels that run after a later batch may have been staged
+        // (prefetched front-end): they read step_out[3] instead of counters[3]
+        if (step_out) step_out[3] = counters[3];
         s_off = use_cursor ? cur : 0;                 // 0: the arrays ARE the batch (host-staged buffers)
     }
     __syncthreads();
@@ -51,11 +54,12 @@ __global__ void stage_batch_kernel(const int64_t* __restrict__ src_all, const in
 extern "C" int ctan_stage_batch(const int64_t* src_all, const int64_t* dst_all, const int64_t* t_all,
                                 const int64_t* neg_all, int n_neg, int B, int64_t* counters, int use_cursor,
                                 int64_t* b_src, int64_t* b_dst, int64_t* b_t, int64_t* seeds, int64_t* pair_src,
-                                int64_t* pair_dst, float* loss_hist, int hist_cap, cudaStream_t stream) {
+                                int64_t* pair_dst, float* loss_hist, int hist_cap, int64_t* step_out,
+                                cudaStream_t stream) {
     if (B <= 0 || n_neg < 0) return CTAN_ERR_BAD_ARG;
     CTAN_LAUNCH((stage_batch_kernel), 1, 256, 0, stream, src_all, dst_all, t_all, neg_all, n_neg, B, counters, use_cursor, b_src,
                                               b_dst, b_t, seeds, pair_src, pair_dst, loss_hist,
-                                              hist_cap > 0 ? hist_cap : 1);
+                                              hist_cap > 0 ? hist_cap : 1, step_out);
     CTAN_CHECK_LAUNCH();
     return 0;
 }

@@ -160,6 +160,7 @@ class StepEngine:
             f["rel"] = torch.zeros(E, **f32)
             f["assoc"] = self.loader._assoc if par == 0 else torch.zeros_like(self.loader._assoc)
             f["Nd"], f["Ed"] = f["counts"][0:1], f["counts"][1:2]
+            f["ctr"] = torch.zeros(8, **i64)              # [3] = step number of the batch staged in this set
             self.fe.append(f)
         w["counts"] = self.fe[0]["counts"]                 # (diagnostics)
         w["ins_ws"] = torch.zeros(4 * B, device=dev, dtype=torch.int32)
@@ -243,22 +244,27 @@ class StepEngine:
         if self.parallel:
             torch.cuda.current_stream().wait_stream(self._side[i])
 
-    def _frontend(self, par: int):
-        """stage -> K-hop lookup -> edge list + delta-t of the batch at the cursor, into buffer set `par`.  Reads the
-        neighbour tables and last_update: must follow the previous step's state write-back, nothing else."""
+    def _frontend(self, par: int, with_rel: bool = True):
+        """stage -> K-hop lookup -> edge list (+ delta-t) of the batch at the cursor, into buffer set `par`.  Reads the
+        neighbour tables and, with_rel, last_update: must follow the previous step's neighbour insert (and, with_rel,
+        its memory write-back), nothing else."""
         w, m, ld, f = self.w, self.model, self.loader, self.fe[par]
         B, K, S = self.B, self.K, self.S
         N, E = self.n_cap, self.e_cap
         call("ctan_stage_batch", ptr(self.src), ptr(self.dst), ptr(self.t), ptr(self.neg), self.n_neg, B,
              ptr(w["counters"]), 0 if self.host_staged else 1, ptr(f["b_src"]), ptr(f["b_dst"]), ptr(f["b_t"]),
-             ptr(f["seeds"]), ptr(f["pair_src"]), ptr(f["pair_dst"]), ptr(w["loss_hist"]), self.hist_cap)
+             ptr(f["seeds"]), ptr(f["pair_src"]), ptr(f["pair_dst"]), ptr(w["loss_hist"]), self.hist_cap, ptr(f["ctr"]))
         call("ctan_nbr_lookup", ptr(ld.neighbors), ptr(ld._deg), self.num_nodes, S, ptr(f["seeds"]), self.n_seeds,
              None, K, ptr(ld._bitmap), ptr(ld._cbitmap), ptr(w["frontier"]), ptr(w["frontier_cnt"]), N,
              ptr(f["n_id"]), N, ptr(f["assoc"]), ptr(f["rowptr"]), E, ptr(f["counts"]))
-        call("ctan_nbr_fill_rel", ptr(ld.neighbors), ptr(ld.e_id), S, ptr(f["n_id"]), ptr(f["rowptr"]),
-             ptr(f["assoc"]), N, ptr(f["Nd"]), ptr(f["esrc"]), ptr(f["edst"]), ptr(f["eid"]), ptr(ld._bitmap),
-             ptr(ld._cbitmap), ptr(m.memory.last_update), ptr(self.t_tab), float(m.gnn.mean_delta_t),
-             float(m.gnn.std_delta_t), ptr(f["rel"]))
+        if with_rel:
+            call("ctan_nbr_fill_rel", ptr(ld.neighbors), ptr(ld.e_id), S, ptr(f["n_id"]), ptr(f["rowptr"]),
+                 ptr(f["assoc"]), N, ptr(f["Nd"]), ptr(f["esrc"]), ptr(f["edst"]), ptr(f["eid"]), ptr(ld._bitmap),
+                 ptr(ld._cbitmap), ptr(m.memory.last_update), ptr(self.t_tab), float(m.gnn.mean_delta_t),
+                 float(m.gnn.std_delta_t), ptr(f["rel"]))
+        else:
+            call("ctan_nbr_fill", ptr(ld.neighbors), ptr(ld.e_id), S, ptr(f["n_id"]), ptr(f["rowptr"]), ptr(f["assoc"]),
+                 N, ptr(f["Nd"]), ptr(f["esrc"]), ptr(f["edst"]), ptr(f["eid"]), ptr(ld._bitmap), ptr(ld._cbitmap))
 
     def _launch(self, train: bool):
         """One whole step, front-end inline (eager mode, warm-up, timeline scripts)."""
@@ -286,7 +292,7 @@ class StepEngine:
         # scheduled early hold SM slots that the step's parallel branches need.  So: inference on, training off.
         _lib.lib().ctan_set_pdl(0 if train else 1, None)
 
-    def _step(self, train: bool, par: int, prefetch: bool, prep_done: bool = False):
+    def _step(self, train: bool, par: int, prefetch: bool, prep_done: bool = False, early: bool = False):
         """Issue one step whose front-end is already in buffer set `par`.  Work that is off the critical path (edge
         projection, weight gradients, state write-back, and -- if `prefetch` -- the NEXT step's front-end into the
         other buffer set) goes to side streams with fork/join edges; under graph capture these become parallel
@@ -305,7 +311,20 @@ class StepEngine:
         eps = float(m.gnn.aconv.epsilon)
         if not prep_done:
             self._prep(train)
+        def insert():
+            call("ctan_nbr_insert", ptr(ld.neighbors), ptr(ld.e_id), ptr(ld._deg), ptr(f["b_src"]), ptr(f["b_dst"]),
+                 B, 0, cur1, S, ptr(w["ins_ws"]))
+        if early:
+            # no-grad pipelining: the neighbour insert needs only the staged batch, so it -- and then the NEXT step's
+            # front-end (without delta-t, which reads this step's memory write-back) -- run beside the whole forward
+            with self._fork(1):
+                insert()
+                if prefetch:
+                    self._frontend(par ^ 1, with_rel=False)
         with self._fork(0):                                  # side 0: edge-attribute projection (|| enc_x)
+            if early:                                        # delta-t of THIS step (its front-end was prefetched without)
+                call("ctan_edge_rel", ptr(lu), ptr(f["n_id"]), ptr(f["esrc"]), ptr(self.t_tab), ptr(f["eid"]), E, Ed,
+                     float(m.gnn.mean_delta_t), float(m.gnn.std_delta_t), ptr(f["rel"]))
             call("ctan_eproj_fwd", ptr(self.msg), Fe, ptr(f["eid"]), ptr(f["rel"]), tw, tb, T, We, E, Ed, D,
                  ptr(w["EP"]))
         if train:
@@ -334,16 +353,18 @@ class StepEngine:
              Wsrc, bsrc, Wdst, bdst, Wfin, bfin, ptr(w["H"]), None, 1)
         # head + BCE loss + dOUT + dHid in one launch (the loss slot was cleared by the stage kernel)
         call("ctan_head_loss", ptr(w["H"]), P, Hd, Wfin, bfin, B, ptr(w["OUT"]), ptr(w["dOUT"]) if train else None,
-             ptr(w["dHid"]) if train else None, ptr(w["loss_hist"]), self.hist_cap, ptr(w["counters"]))
+             ptr(w["dHid"]) if train else None, ptr(w["loss_hist"]), self.hist_cap, ptr(f["ctr"]))
 
         def state_update():
             # ground-truth state update (train_link.py:276-277)
             call("ctan_mem_update", ptr(mem), ptr(lu), D, ptr(f["b_src"]), ptr(f["b_dst"]), ptr(f["b_t"]), B, None,
                  None, 0, ptr(z), ptr(assoc))
-            call("ctan_nbr_insert", ptr(ld.neighbors), ptr(ld.e_id), ptr(ld._deg), ptr(f["b_src"]), ptr(f["b_dst"]),
-                 B, 0, cur1, S, ptr(w["ins_ws"]))
+            if not early:
+                insert()
         if not train:
             state_update()
+            if early:
+                self._join(1)
             _lib.lib().ctan_set_pdl(1, None)
             return
         with self._fork(1):                                  # side 1 (after the z0 gather): state write-back ...
@@ -395,27 +416,27 @@ class StepEngine:
         _lib.lib().ctan_set_pdl(1, None)
 
     # ------------------------------------------------------------------ public stepping API
-    def _graph(self, train: bool, par: int = 0, prefetch: bool = False, inline: bool = True):
+    def _graph(self, train: bool, par: int = 0, prefetch: bool = False, inline: bool = True, early: bool = False):
         """Captured step.  inline: the front-end is part of the graph (one self-contained step; inference, host-staged
         mode).  Otherwise the front-end of buffer set `par` is expected to be done already and, if `prefetch`, the
         next step's front-end is a branch of this graph."""
-        key = (bool(train), par, bool(prefetch), bool(inline))
+        key = (bool(train), par, bool(prefetch), bool(inline), bool(early))
         if key not in self._graphs:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=self._main):
                 if inline:
                     self._prep(train)
                     self._frontend(par)
-                self._step(train, par, prefetch, prep_done=inline)
+                self._step(train, par, prefetch, prep_done=inline, early=early)
             self._graphs[key] = g
         return self._graphs[key]
 
-    def _graph_frontend(self, par: int = 0):
-        key = ("fe", par)
+    def _graph_frontend(self, par: int = 0, with_rel: bool = True):
+        key = ("fe", par, with_rel)
         if key not in self._graphs:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=self._main):
-                self._frontend(par)
+                self._frontend(par, with_rel)
             self._graphs[key] = g
         return self._graphs[key]
 
@@ -433,18 +454,18 @@ class StepEngine:
 
     def plan(self, n_steps: int, train: bool = True):
         """The replay sequence of n_steps steps as a list of callables (one per step; the first also issues the first
-        front-end).  Training steps prefetch the next step's front-end beside their backward, except the last of the
-        sequence: the state after the sequence is exactly that of n_steps self-contained steps."""
+        front-end).  Training steps prefetch the next step's front-end beside their backward, no-grad steps beside their
+        forward, except the last of the sequence: the state after the sequence is exactly that of n_steps self-contained steps."""
         if not self.use_graph:
             return [lambda: self._launch(train) for _ in range(n_steps)]
-        if not (train and self.prefetch):
+        if not self.prefetch:
             g = self._graph(train)
             return [g.replay for _ in range(n_steps)]
         seq, par = [], 0
         for j in range(n_steps):
-            g = self._graph(True, par, j < n_steps - 1, inline=False)
+            g = self._graph(train, par, j < n_steps - 1, inline=False, early=not train)
             if j == 0:
-                fe = self._graph_frontend(0)
+                fe = self._graph_frontend(0, with_rel=train)
                 seq.append(lambda fe=fe, g=g: (fe.replay(), g.replay()))
             else:
                 seq.append(g.replay)
