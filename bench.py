@@ -260,25 +260,33 @@ def run_e2e(st, K, mean, std, dev, n_steps, warmup):
     B = eng.B
     pin = {k: st[k].pin_memory() for k in ("src", "dst", "t", "msg")}
     pin["neg"] = st["neg"].view(-1, 1).pin_memory()
-    loss_host = torch.zeros(1).pin_memory()
+    loss_host = torch.zeros(2).pin_memory()                  # two pinned slots: step i's loss is read while i+1 runs
+    done = [torch.cuda.Event(), torch.cuda.Event()]
     h2d = 0
 
-    def step(it):
+    def issue(it):
         nonlocal h2d
         lo, hi = it * B, (it + 1) * B
         h2d = eng.push_batch(pin["src"][lo:hi], pin["dst"][lo:hi], pin["t"][lo:hi], pin["neg"][lo:hi], pin["msg"][lo:hi])
         eng.run(1, train=True)
         slot = it % eng.hist_cap
-        loss_host.copy_(eng.w["loss_hist"][slot:slot + 1], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return float(loss_host[0])
+        loss_host[it & 1:(it & 1) + 1].copy_(eng.w["loss_hist"][slot:slot + 1], non_blocking=True)
+        done[it & 1].record()
+
+    def collect(it):                                         # host read of step `it`'s loss (blocks until it is there)
+        done[it & 1].synchronize()
+        return float(loss_host[it & 1])
     for it in range(warmup):
-        step(it)
+        issue(it)
+        collect(it)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     last = 0.0
     for it in range(warmup, warmup + n_steps):
-        last = step(it)
+        issue(it)                                            # H2D of this step's batch + the step + D2H of its loss
+        if it > warmup:
+            last = collect(it - 1)                           # every step's loss reaches the host, one step behind
+    last = collect(warmup + n_steps - 1)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     eng.check()
@@ -443,7 +451,8 @@ def main():
     # ---- end to end with host buffers
     e2e_v, h2d, d2h, last_loss = run_e2e(st, K, mean, std, dev, min(args.steps, 400), W)
     out["e2e"] = {"value": e2e_v, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                  "api": "StepEngine(host_staged=True).run(1) per batch: pinned-host batch -> device, one step, loss -> host"}
+                  "api": "StepEngine(host_staged=True): per batch pinned-host batch -> device, run(1), loss -> pinned host; the "
+                         "host reads step i's loss while step i+1 runs (every loss is read, one step behind)"}
 
     if not args.no_baselines:
         gv, gms = oracle_train_rate(st, K, mean, std, "cuda:0", 100, 10)
