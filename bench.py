@@ -264,10 +264,14 @@ def run_e2e(st, K, mean, std, dev, n_steps, warmup):
     done = [torch.cuda.Event(), torch.cuda.Event()]
     h2d = 0
 
+    nb = st["src"].numel() // B
+    ids_pin = torch.cat([st["src"][:nb * B].view(nb, B), st["dst"][:nb * B].view(nb, B), st["t"][:nb * B].view(nb, B),
+                         st["neg"][:nb * B].view(nb, B)], 1).contiguous().pin_memory()   # the loader's packed batches
+
     def issue(it):
         nonlocal h2d
         lo, hi = it * B, (it + 1) * B
-        h2d = eng.push_batch(pin["src"][lo:hi], pin["dst"][lo:hi], pin["t"][lo:hi], pin["neg"][lo:hi], pin["msg"][lo:hi])
+        h2d = eng.push_packed(ids_pin[it], pin["msg"][lo:hi])
         eng.run(1, train=True)
         slot = it % eng.hist_cap
         loss_host[it & 1:(it & 1) + 1].copy_(eng.w["loss_hist"][slot:slot + 1], non_blocking=True)
@@ -451,8 +455,9 @@ def main():
     # ---- end to end with host buffers
     e2e_v, h2d, d2h, last_loss = run_e2e(st, K, mean, std, dev, min(args.steps, 400), W)
     out["e2e"] = {"value": e2e_v, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                  "api": "StepEngine(host_staged=True): per batch pinned-host batch -> device, run(1), loss -> pinned host; the "
-                         "host reads step i's loss while step i+1 runs (every loss is read, one step behind)"}
+                  "api": "StepEngine(host_staged=True): per batch push_packed(pinned ids, pinned msg rows) -> device over a "
+                         "copy stream (double-buffered staging), run(1), loss -> pinned host; the host reads step i's "
+                         "loss while step i+1 runs (every loss is read, one step behind)"}
 
     if not args.no_baselines:
         gv, gms = oracle_train_rate(st, K, mean, std, "cuda:0", 100, 10)

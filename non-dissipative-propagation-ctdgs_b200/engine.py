@@ -59,8 +59,18 @@ class StepEngine:
         self.Fe = int(st["msg"].size(1))
         if host_staged:
             # batches arrive from the host: fixed device staging buffers + event tables filled as they come
-            self.src, self.dst, self.t = (torch.zeros(self.B, dtype=torch.long, device=dev) for _ in range(3))
-            self.neg = torch.zeros((self.B, self.n_neg), dtype=torch.long, device=dev)
+            # two staging sets: the copy of batch j+1 (on a copy stream) overlaps the step of batch j
+            self._stg = []
+            for _ in range(2):                             # one packed buffer per set: [src | dst | t | neg]
+                ids = torch.zeros((3 + self.n_neg) * self.B, dtype=torch.long, device=dev)
+                Bq = self.B
+                self._stg.append(dict(ids=ids, src=ids[:Bq], dst=ids[Bq:2 * Bq], t=ids[2 * Bq:3 * Bq],
+                                      neg=ids[3 * Bq:].view(Bq, self.n_neg)))
+            self.src, self.dst, self.t, self.neg = (self._stg[0][k] for k in ("src", "dst", "t", "neg"))
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._copied = [torch.cuda.Event(), torch.cuda.Event()]      # staging set filled
+            self._consumed = [None, None]                                 # step that read the staging set is done
+            self._push_par = self._run_par = 0
             self.t_tab = torch.zeros(self.n_events, dtype=torch.long, device=dev)
             self.msg = torch.zeros((self.n_events, self.Fe), device=dev)
             self._host_cursor = 0
@@ -205,6 +215,8 @@ class StepEngine:
             f["counts"].zero_()
         if self.host_staged:
             self._host_cursor = 0
+            self._push_par = self._run_par = 0
+            self._consumed = [None, None]
         if reset_optimizer:
             self.adam_m.zero_()
             self.adam_v.zero_()
@@ -214,12 +226,40 @@ class StepEngine:
         staging buffers the step reads, the message rows and times into the event tables."""
         lo = self._host_cursor
         hi = lo + self.B
-        self.src.copy_(src, non_blocking=True)
-        self.dst.copy_(dst, non_blocking=True)
-        self.t.copy_(t, non_blocking=True)
-        self.neg.copy_(neg.view(self.B, -1), non_blocking=True)
-        self.msg[lo:hi].copy_(msg, non_blocking=True)
-        self.t_tab[lo:hi].copy_(t, non_blocking=True)
+        par = self._push_par
+        stg = self._stg[par]
+        cs = self._copy_stream
+        if self._consumed[par] is not None:
+            cs.wait_event(self._consumed[par])               # the step that read this staging set has finished
+        with torch.cuda.stream(cs):
+            stg["src"].copy_(src, non_blocking=True)
+            stg["dst"].copy_(dst, non_blocking=True)
+            stg["t"].copy_(t, non_blocking=True)
+            stg["neg"].copy_(neg.view(self.B, -1), non_blocking=True)
+            self.msg[lo:hi].copy_(msg, non_blocking=True)
+            self.t_tab[lo:hi].copy_(t, non_blocking=True)
+            self._copied[par].record(cs)
+        self._push_par = par ^ 1
+        self._host_cursor = hi
+        return self.B * (8 * (3 + self.n_neg) + 4 * self.Fe)
+
+    def push_packed(self, ids, msg):
+        """push_batch with the ids pre-packed by the data loader: `ids` pinned int64 [(3+n_neg)*B] laid out
+        [src | dst | t | neg (event-major)], `msg` pinned [B,Fe].  Three copies instead of six (the host, not the GPU,
+        bounds the end-to-end loop)."""
+        lo = self._host_cursor
+        hi = lo + self.B
+        par = self._push_par
+        stg = self._stg[par]
+        cs = self._copy_stream
+        if self._consumed[par] is not None:
+            cs.wait_event(self._consumed[par])
+        with torch.cuda.stream(cs):
+            stg["ids"].copy_(ids, non_blocking=True)
+            self.msg[lo:hi].copy_(msg, non_blocking=True)
+            self.t_tab[lo:hi].copy_(stg["t"], non_blocking=True)
+            self._copied[par].record(cs)
+        self._push_par = par ^ 1
         self._host_cursor = hi
         return self.B * (8 * (3 + self.n_neg) + 4 * self.Fe)
 
@@ -251,7 +291,9 @@ class StepEngine:
         w, m, ld, f = self.w, self.model, self.loader, self.fe[par]
         B, K, S = self.B, self.K, self.S
         N, E = self.n_cap, self.e_cap
-        call("ctan_stage_batch", ptr(self.src), ptr(self.dst), ptr(self.t), ptr(self.neg), self.n_neg, B,
+        src, dst, t, neg = ((self._stg[par][k] for k in ("src", "dst", "t", "neg")) if self.host_staged
+                            else (self.src, self.dst, self.t, self.neg))
+        call("ctan_stage_batch", ptr(src), ptr(dst), ptr(t), ptr(neg), self.n_neg, B,
              ptr(w["counters"]), 0 if self.host_staged else 1, ptr(f["b_src"]), ptr(f["b_dst"]), ptr(f["b_t"]),
              ptr(f["seeds"]), ptr(f["pair_src"]), ptr(f["pair_dst"]), ptr(w["loss_hist"]), self.hist_cap, ptr(f["ctr"]))
         call("ctan_nbr_lookup", ptr(ld.neighbors), ptr(ld._deg), self.num_nodes, S, ptr(f["seeds"]), self.n_seeds,
@@ -456,6 +498,8 @@ class StepEngine:
         """The replay sequence of n_steps steps as a list of callables (one per step; the first also issues the first
         front-end).  Training steps prefetch the next step's front-end beside their backward, no-grad steps beside their
         forward, except the last of the sequence: the state after the sequence is exactly that of n_steps self-contained steps."""
+        if self.host_staged:
+            return [lambda: self._run_staged(train) for _ in range(n_steps)]
         if not self.use_graph:
             return [lambda: self._launch(train) for _ in range(n_steps)]
         if not self.prefetch:
@@ -471,6 +515,22 @@ class StepEngine:
                 seq.append(g.replay)
             par ^= 1
         return seq
+
+    def _run_staged(self, train: bool):
+        """host_staged mode: one step on the batch of the oldest un-consumed push_batch()."""
+        par = self._run_par
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._copied[par])
+        if self.use_graph:
+            self._graph(train, par).replay()
+        else:
+            self._prep(train)
+            self._frontend(par)
+            self._step(train, par, False, prep_done=True)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self._consumed[par] = ev
+        self._run_par = par ^ 1
 
     def run(self, n_steps: int, train: bool = True):
         """Advance n_steps full batches from the cursor (no host synchronisation)."""

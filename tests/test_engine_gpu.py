@@ -130,3 +130,51 @@ def test_bench_configuration_matches_oracle(K):
         if "lin_skip" not in k:
             d = float((p.detach().cpu() - po[k].detach()).abs().max())
             assert d <= 2e-3 * float(po[k].abs().max()) + 1e-6, (k, d)
+
+
+def test_host_staged_matches_device_resident(small_stream):
+    """The end-to-end mode (batches pushed from pinned host memory over a copy stream, double-buffered staging)
+    follows the same trajectory as the device-resident engine: identical losses, parameters and state."""
+    from ctan_b200.engine import StepEngine
+    from ctan_b200.models import CTAN, LastNeighborLoader
+    st = small_stream
+    dev = torch.device("cuda:0")
+    B, S, steps = 200, 5, 7
+    kw = dict(num_nodes=st["num_nodes"], edge_dim=st["msg"].size(1), memory_dim=32, time_dim=8, node_dim=1,
+              num_iters=1, epsilon=0.5, gamma=0.1, readout_hidden=16, mean_delta_t=np.float64(1234.5),
+              std_delta_t=np.float64(4567.8))
+    engs = []
+    for host in (False, True):
+        torch.manual_seed(0)
+        mm = CTAN(**kw).to(dev)
+        ld = LastNeighborLoader(st["num_nodes"], S, device=dev)
+        if host:
+            g = dict(st)
+        else:
+            g = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in st.items()}
+            g["neg"] = st["neg"].view(-1, 1).to(dev)
+        eng = StepEngine(mm, ld, g, batch_size=B, n_neg=1, lr=1e-3, host_staged=host)
+        eng.reset(reset_optimizer=True)
+        eng.warmup()
+        engs.append((eng, mm, ld))
+    (e_dev, m_dev, l_dev), (e_host, m_host, l_host) = engs
+    e_dev.run(steps, train=True)
+    pin = {k: st[k].pin_memory() for k in ("src", "dst", "t", "msg")}
+    pin["neg"] = st["neg"].view(-1, 1).pin_memory()
+    def push(it):
+        lo, hi = it * B, (it + 1) * B
+        e_host.push_batch(pin["src"][lo:hi], pin["dst"][lo:hi], pin["t"][lo:hi], pin["neg"][lo:hi], pin["msg"][lo:hi])
+    push(0)
+    for it in range(steps):
+        if it + 1 < steps:
+            push(it + 1)                              # one batch ahead: both staging sets are in flight
+        e_host.run(1, train=True)
+    torch.cuda.synchronize()
+    e_host.check()
+    assert torch.equal(l_host.e_id, l_dev.e_id)
+    assert torch.equal(m_host.memory.last_update, m_dev.memory.last_update)
+    assert torch.allclose(e_host.losses(steps), e_dev.losses(steps), rtol=1e-5, atol=1e-7)
+    for (k, a), (_, b) in zip(m_host.named_parameters(), m_dev.named_parameters()):
+        # (two engine instances differ by the order of their atomic accumulations, which Adam amplifies on
+        # near-zero gradients: same bound as against the oracle)
+        assert float((a.detach() - b.detach()).abs().max()) <= 2e-3 * float(b.detach().abs().max()) + 1e-6, k
