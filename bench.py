@@ -235,7 +235,7 @@ def saturating_edge_roofline(dev, N=100_000, S=16, D=256, iters=10):
 
     def fn():
         call("ctan_edge_fwd", ptr(QKVA), ptr(EP), ptr(rowptr), ptr(esrc), N, None, D, ptr(X), 0.5, ptr(Xo), None, None,
-             None, None, 0)
+             None, None, 0, 0)
     for _ in range(3):
         fn()
     torch.cuda.synchronize()

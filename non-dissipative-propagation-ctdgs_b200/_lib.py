@@ -28,7 +28,8 @@ SIGNATURES = {
     "ctan_gather_rows2": [P, I, P, I, P, I, P, P],
     "ctan_antisym_prep": [P, F, I, P],
     "ctan_antisym_bwd": [P, I, P],
-    "ctan_edge_fwd": [P, P, P, P, I, P, I, P, F, P, P, P, P, P, I],
+    "ctan_edge_fwd": [P, P, P, P, I, P, I, P, F, P, P, P, P, P, I, I],
+    "ctan_hub_list": [P, I, P, P, I],
     "ctan_edge_bwd": [P, P, P, P, I, P, I, P, P, P, F, P, P, I, P],
     "ctan_tanh_bwd": [P, P, I, P, I, P],
     "ctan_tenc_bwd": [P, P, P, P, I, P, I, P, P],
@@ -158,8 +159,8 @@ def call(name: str, *args):
     global N_LAUNCHES
     fn = getattr(lib(), name)
     N_LAUNCHES += LAUNCHES.get(name, 1) + (args[7] if name == "ctan_nbr_lookup" else 0)
-    if name == "ctan_edge_fwd" and args[13] is not None:
-        N_LAUNCHES += 1                                     # the hub-row kernel
+    if name == "ctan_edge_fwd" and args[13] is not None and args[15] == 0:
+        N_LAUNCHES += 1                                     # the hub-row kernel (modes 1 / 2 launch one kernel each)
     if PROBE is not None and name != "ctan_probe":
         ts, names, main = PROBE
         rc = fn(*args, stream_ptr())

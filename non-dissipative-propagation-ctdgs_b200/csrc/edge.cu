@@ -180,7 +180,7 @@ edge_fwd_kernel(const float* __restrict__ QKVA, const float* __restrict__ EP,
                                 const int32_t* __restrict__ rowptr, const int64_t* __restrict__ esrc, int N_host,
                                 const int* __restrict__ N_dev, int D, const float* __restrict__ Xin, float eps,
                                 float* __restrict__ Xout, float* __restrict__ TH, float* __restrict__ ALPHA,
-                                float* __restrict__ Zout, float inv_sqrt_d, int* __restrict__ hub, int hub_cap) {
+                                float* __restrict__ Zout, float inv_sqrt_d, int* __restrict__ hub, int hub_cap, int hub_mode) {
     ctan_pdl_begin();
     const int N = N_dev ? *N_dev : N_host;
     const int lane = threadIdx.x & 31;
@@ -190,6 +190,7 @@ edge_fwd_kernel(const float* __restrict__ QKVA, const float* __restrict__ EP,
     for (int i = warp; i < N; i += nw) {
         const int r0 = rowptr[i], r1 = rowptr[i + 1];
         if (defer && r1 - r0 > HUB_DEG) {
+            if (hub_mode == 1) continue;                                // listed by ctan_hub_list: the hub kernel's row
             int slot = 0;
             if (lane == 0) slot = atomicAdd(hub, 1);
             slot = __shfl_sync(0xffffffffu, slot, 0);
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(32 * EF_WARPS)
 edge_fwd_hub_kernel(const float* __restrict__ QKVA, const float* __restrict__ EP, const int32_t* __restrict__ rowptr,
                     const int64_t* __restrict__ esrc, int D, const float* __restrict__ Xin, float eps,
                     float* __restrict__ Xout, float* __restrict__ TH, float* __restrict__ ALPHA,
-                    float* __restrict__ Zout, float inv_sqrt_d, int* __restrict__ hub, int hub_cap) {
+                    float* __restrict__ Zout, float inv_sqrt_d, int* __restrict__ hub, int hub_cap, int cleanup) {
     ctan_pdl_begin();
     __shared__ float s_mx[EF_WARPS], s_den[EF_WARPS];
     __shared__ float s_phi[EF_WARPS][MAXV * 32];
@@ -277,17 +278,45 @@ edge_fwd_hub_kernel(const float* __restrict__ QKVA, const float* __restrict__ EP
         __syncthreads();
     }
     // the last CTA to finish clears the list for the next launch (every CTA has read hub[0] before its ticket)
-    if (threadIdx.x == 0) {
+    if (cleanup && threadIdx.x == 0) {
         __threadfence();
         if (atomicAdd(hub + 1, 1) == (int)gridDim.x - 1) { hub[0] = 0; hub[1] = 0; }
     }
 }
 
-// hub_ws: optional int32 workspace of 2 + hub_cap entries, [0] and [1] ZERO before the first call (the call leaves
-// them zero again); NULL = every row on the plain path.
+// The hub list straight from the CSR pointer (same rule as edge_fwd_kernel: N <= HUB_MAX_N, degree > HUB_DEG), so
+// that a caller can run the plain rows (hub_mode 1) and the hub rows (hub_mode 2) of ctan_edge_fwd CONCURRENTLY on two
+// streams instead of one after the other.  hub[0] must be zero on entry; row order in the list is irrelevant (one
+// CTA per row, results do not depend on it).
+__global__ void hub_list_kernel(const int32_t* __restrict__ rowptr, int N_host, const int* __restrict__ N_dev,
+                                int* __restrict__ hub, int hub_cap) {
+    ctan_pdl_begin();
+    const int N = N_dev ? *N_dev : N_host;
+    if (N > HUB_MAX_N) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        if (rowptr[i + 1] - rowptr[i] > HUB_DEG) {
+            const int slot = atomicAdd(hub, 1);
+            if (slot < hub_cap) hub[2 + slot] = i;
+        }
+    }
+}
+extern "C" int ctan_hub_list(const int32_t* rowptr, int N, const int* N_dev, int32_t* hub_ws, int hub_cap,
+                             cudaStream_t stream) {
+    if (N <= 0 || !hub_ws || hub_cap <= 0) return 0;
+    CTAN_LAUNCH((hub_list_kernel), ctan_grid(N, 256), 256, 0, stream, rowptr, N, N_dev, hub_ws, hub_cap);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+// hub_ws: optional int32 workspace of 2 + hub_cap entries; NULL = every row on the plain path.
+// hub_mode 0: self-contained -- the plain-row kernel builds the list, the hub kernel consumes and clears it ([0] and [1]
+//             must be zero before the first call; the call leaves them zero again);
+// hub_mode 1: plain rows only, rows listed by ctan_hub_list are skipped;  hub_mode 2: listed hub rows only.
+//             (1 and 2 touch disjoint rows: issue them on two streams.)
 extern "C" int ctan_edge_fwd(const float* QKVA, const float* EP, const int32_t* rowptr, const int64_t* esrc, int N,
                              const int* N_dev, int D, const float* Xin, float eps, float* Xout, float* TH,
-                             float* ALPHA, float* Zout, int32_t* hub_ws, int hub_cap, cudaStream_t stream) {
+                             float* ALPHA, float* Zout, int32_t* hub_ws, int hub_cap, int hub_mode,
+                             cudaStream_t stream) {
     if (N <= 0) return 0;
     if (D > 512) return CTAN_ERR_UNSUPPORTED;
     if (hub_ws && hub_cap <= 0) hub_ws = nullptr;
@@ -295,11 +324,12 @@ extern "C" int ctan_edge_fwd(const float* QKVA, const float* EP, const int32_t* 
     const float isd = 1.0f / sqrtf((float)D);
     const int hgrid = 2 * CTAN_SM_COUNT;
 #define LAUNCH(V) do {                                                                                                 \
-        CTAN_LAUNCH((edge_fwd_kernel<V>), grid, 256, 0, stream, QKVA, EP, rowptr, esrc, N, N_dev, D, Xin, eps, Xout, TH, ALPHA,   \
-                                                     Zout, isd, hub_ws, hub_cap);                                      \
-        if (hub_ws)                                                                                                    \
-            CTAN_LAUNCH((edge_fwd_hub_kernel<V>), hgrid, 32 * EF_WARPS, 0, stream, QKVA, EP, rowptr, esrc, D, Xin, eps, Xout, TH, \
-                                                                        ALPHA, Zout, isd, hub_ws, hub_cap);            \
+        if (hub_mode != 2)                                                                                             \
+            CTAN_LAUNCH((edge_fwd_kernel<V>), grid, 256, 0, stream, QKVA, EP, rowptr, esrc, N, N_dev, D, Xin, eps, Xout, \
+                        TH, ALPHA, Zout, isd, hub_ws, hub_cap, hub_mode);                                              \
+        if (hub_ws && hub_mode != 1)                                                                                   \
+            CTAN_LAUNCH((edge_fwd_hub_kernel<V>), hgrid, 32 * EF_WARPS, 0, stream, QKVA, EP, rowptr, esrc, D, Xin, eps,  \
+                        Xout, TH, ALPHA, Zout, isd, hub_ws, hub_cap, hub_mode == 0 ? 1 : 0);                           \
     } while (0)
     if (D <= 32) LAUNCH(1); else if (D <= 64) LAUNCH(2); else if (D <= 128) LAUNCH(4);
     else if (D <= 256) LAUNCH(8); else LAUNCH(16);

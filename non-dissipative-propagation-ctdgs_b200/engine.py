@@ -171,14 +171,14 @@ class StepEngine:
             f["assoc"] = self.loader._assoc if par == 0 else torch.zeros_like(self.loader._assoc)
             f["Nd"], f["Ed"] = f["counts"][0:1], f["counts"][1:2]
             f["ctr"] = torch.zeros(8, **i64)              # [3] = step number of the batch staged in this set
+            f["hub"] = torch.zeros(2 + min(N, 16384), dtype=torch.int32, device=dev)   # rows of degree > 8
             self.fe.append(f)
         w["counts"] = self.fe[0]["counts"]                 # (diagnostics)
         w["ins_ws"] = torch.zeros(4 * B, device=dev, dtype=torch.int32)
         w["z0"] = torch.zeros((N, D + self.Fn), **f32)
         w["X"] = torch.zeros((K + 1, N, D), **f32)
         w["EP"] = torch.zeros((E, D), **f32)
-        self.hub_cap = min(N, 16384)                      # rows of degree > 8 deferred to the block-cooperative kernel
-        w["hub"] = torch.zeros(2 + self.hub_cap, dtype=torch.int32, device=dev)
+        self.hub_cap = min(N, 16384)                      # rows of degree > 8 go to the block-cooperative kernel
         w["A"] = torch.zeros((D, D), **f32)
         self.use_tc = _lib.use_tensor_cores(D)
         w["Wcat_hi"], w["Wcat_lo"] = torch.zeros((4 * D, D), **f32), torch.zeros((4 * D, D), **f32)
@@ -307,6 +307,9 @@ class StepEngine:
         else:
             call("ctan_nbr_fill", ptr(ld.neighbors), ptr(ld.e_id), S, ptr(f["n_id"]), ptr(f["rowptr"]), ptr(f["assoc"]),
                  N, ptr(f["Nd"]), ptr(f["esrc"]), ptr(f["edst"]), ptr(f["eid"]), ptr(ld._bitmap), ptr(ld._cbitmap))
+        if S > 8:                        # work list of the high-degree rows (edge_fwd runs them beside the plain rows)
+            f["hub"][:2].zero_()
+            call("ctan_hub_list", ptr(f["rowptr"]), N, ptr(f["Nd"]), ptr(f["hub"]), self.hub_cap)
 
     def _launch(self, train: bool):
         """One whole step, front-end inline (eager mode, warm-up, timeline scripts)."""
@@ -385,9 +388,16 @@ class StepEngine:
             else:
                 call("ctan_qkva_fwd", ptr(xi), N, Nd, D, Wq, Wk, Wv, ptr(w["A"]), bq, bk, bv, b, ptr(qk))
             last = k == K - 1
-            call("ctan_edge_fwd", ptr(qk), ptr(w["EP"]), ptr(f["rowptr"]), ptr(f["esrc"]), N, Nd, D, ptr(xi), eps,
-                 ptr(xo), ptr(w["TH"][k]) if train else None, ptr(w["ALPHA"][k]) if train else None,
-                 ptr(w["Z"]) if (last and self.final_tanh) else None, ptr(w["hub"]) if S > 8 else None, self.hub_cap)
+            ef = (ptr(qk), ptr(w["EP"]), ptr(f["rowptr"]), ptr(f["esrc"]), N, Nd, D, ptr(xi), eps, ptr(xo),
+                  ptr(w["TH"][k]) if train else None, ptr(w["ALPHA"][k]) if train else None,
+                  ptr(w["Z"]) if (last and self.final_tanh) else None)
+            if S > 8:
+                with self._fork(0):
+                    call("ctan_edge_fwd", *ef, ptr(f["hub"]), self.hub_cap, 2)         # hub rows (one CTA per row)
+                call("ctan_edge_fwd", *ef, ptr(f["hub"]), self.hub_cap, 1)             # plain rows, concurrently
+                self._join(0)
+            else:
+                call("ctan_edge_fwd", *ef, None, 0, 0)
         xk = w["X"][K] if train else w["X"][K & 1]
         z = w["Z"] if self.final_tanh else xk
         self._z = z

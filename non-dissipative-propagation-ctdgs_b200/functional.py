@@ -66,7 +66,7 @@ class _EmbedFn(torch.autograd.Function):
                 last = k == K - 1
                 call("ctan_edge_fwd", ptr(qk), ptr(EP), ptr(rowptr, torch.int32), ptr(esrc), N, None, D, ptr(xi),
                      float(eps), ptr(xo), ptr(TH[k]) if need_grad else None, ptr(ALPHA[k]) if need_grad else None,
-                     ptr(Z) if (last and final_tanh) else None, None, 0)
+                     ptr(Z) if (last and final_tanh) else None, None, 0, 0)
             out = Z if final_tanh else (X[K] if need_grad else X[K & 1])
             if K == 0:
                 raise ValueError("num_iters must be >= 1")

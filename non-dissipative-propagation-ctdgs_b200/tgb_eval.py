@@ -117,6 +117,7 @@ class TGBEvalEngine:
             f["rowptr"] = torch.zeros(N + 1, device=dev, dtype=torch.int32)
             f["esrc"], f["edst"], f["eid"] = (torch.zeros(E, **i64) for _ in range(3))
             f["assoc"] = self.loader._assoc if par == 0 else torch.zeros_like(self.loader._assoc)
+            f["hub"] = torch.zeros(2 + min(N, 16384), dtype=torch.int32, device=dev)   # rows of degree > 8 (ctan_hub_list)
             f["Nd"], f["Ed"] = f["counts"][0:1], f["counts"][1:2]
             self.fe.append(f)
         w["counts"] = self.fe[0]["counts"]                 # (diagnostics: sizes of an even batch's subgraph)
@@ -124,8 +125,7 @@ class TGBEvalEngine:
         w["rel"] = torch.zeros(E, **f32)
         w["X"] = torch.zeros((2, N, D), **f32)
         w["EP"] = torch.zeros((E, D), **f32)
-        self.hub_cap = min(N, 16384)                      # rows of degree > 8 deferred to the block-cooperative kernel
-        w["hub"] = torch.zeros(2 + self.hub_cap, dtype=torch.int32, device=dev)
+        self.hub_cap = min(N, 16384)                      # rows of degree > 8 go to the block-cooperative kernel
         w["A"] = torch.zeros((D, D), **f32)
         self.use_tc = _lib.use_tensor_cores(D)
         # tensor-core enc_x (dense gathered rows + packed weights) and node-projection readout
@@ -187,6 +187,9 @@ class TGBEvalEngine:
                  ptr(w["frontier_cnt"]), N, ptr(f["n_id"]), N, ptr(f["assoc"]), ptr(f["rowptr"]), E, ptr(f["counts"]))
             call("ctan_nbr_fill", ptr(ld.neighbors), ptr(ld.e_id), S, ptr(f["n_id"]), ptr(f["rowptr"]), ptr(f["assoc"]),
                  N, ptr(f["Nd"]), ptr(f["esrc"]), ptr(f["edst"]), ptr(f["eid"]), ptr(ld._bitmap), ptr(ld._cbitmap))
+            if S > 8:                    # work list of the high-degree rows: plain and hub rows then run concurrently
+                f["hub"][:2].zero_()
+                call("ctan_hub_list", ptr(f["rowptr"]), N, ptr(f["Nd"]), ptr(f["hub"]), self.hub_cap)
 
     def _insert(self, par: int, dry: bool):
         """Neighbour-table insert of the batch in buffer set `par` (needs only the staged (src, dst); must follow that
@@ -257,9 +260,16 @@ class TGBEvalEngine:
                          ptr(ph.lin_value.weight), ptr(w["A"]), ptr(ph.lin_query.bias), ptr(ph.lin_key.bias),
                          ptr(ph.lin_value.bias), ptr(a.bias), ptr(w["QKVA"]))
                 last = k == K - 1
-                call("ctan_edge_fwd", ptr(w["QKVA"]), ptr(w["EP"]), ptr(f["rowptr"]), ptr(f["esrc"]), N, Nd, D,
-                     ptr(xi), eps, ptr(xo), None, None, ptr(w["Z"]) if (last and self.final_tanh) else None,
-                     ptr(w["hub"]) if self.S > 8 else None, self.hub_cap)
+                ef = (ptr(w["QKVA"]), ptr(w["EP"]), ptr(f["rowptr"]), ptr(f["esrc"]), N, Nd, D, ptr(xi), eps, ptr(xo), None,
+                      None, ptr(w["Z"]) if (last and self.final_tanh) else None)
+                if self.S > 8:
+                    self._side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(self._side):
+                        call("ctan_edge_fwd", *ef, ptr(f["hub"]), self.hub_cap, 2)     # hub rows (one CTA per row)
+                    call("ctan_edge_fwd", *ef, ptr(f["hub"]), self.hub_cap, 1)         # plain rows, concurrently
+                    torch.cuda.current_stream().wait_stream(self._side)
+                else:
+                    call("ctan_edge_fwd", *ef, None, 0, 0)
             z = w["Z"] if self.final_tanh else w["X"][K & 1]
             if self.use_tc_ro:
                 # project every NODE once (tensor cores), then a scored pair only gathers two rows

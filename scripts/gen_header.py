@@ -50,6 +50,7 @@ REF = {
     "ctan_delta_t_stats_ws_bytes": "(workspace size of ctan_delta_t_stats; host-side query)",
     "ctan_delta_t_stats": "compute_stats: mean/std of per-node inter-event times -- utils.py:46-92",
     "ctan_set_pdl": "(host-side switch for programmatic dependent launch; no reference counterpart)",
+    "ctan_hub_list": "(work list of high-degree destination rows for ctan_edge_fwd; no reference counterpart)",
     "ctan_dx_tc": "gradient of the projections w.r.t. the node state (autograd in the reference) on tcgen05",
     "ctan_qkva_fwd_tc": "TransformerConv lin_query/lin_key/lin_value + x @ A^T + bias on tcgen05 tensor cores -- PyG 2.3.1 (SURVEY.md App. A.5)",
 }

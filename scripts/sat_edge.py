@@ -21,7 +21,7 @@ def run(N=100_000, S=16, D=256, iters=10, dev=torch.device("cuda:0")):
     rowptr = (torch.arange(N + 1, dtype=torch.int32) * S).to(dev)
     esrc = torch.randint(0, N, (E,), generator=g).to(dev)
     fn = lambda: call("ctan_edge_fwd", ptr(QKVA), ptr(EP), ptr(rowptr), ptr(esrc), N, None, D, ptr(X), 0.5, ptr(Xo),
-                      None, None, None, None, 0)
+                      None, None, None, None, 0, 0)
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
