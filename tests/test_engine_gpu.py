@@ -178,3 +178,36 @@ def test_host_staged_matches_device_resident(small_stream):
         # (two engine instances differ by the order of their atomic accumulations, which Adam amplifies on
         # near-zero gradients: same bound as against the oracle)
         assert float((a.detach() - b.detach()).abs().max()) <= 2e-3 * float(b.detach().abs().max()) + 1e-6, k
+
+
+def test_mixed_train_infer_calls_match_oracle(small_stream):
+    """run() calls of different modes and lengths back to back (each call prefetches inside itself only): the buffer
+    parity and cursor hand-over between calls must leave exactly the oracle's trajectory."""
+    from oracle import ctan_oracle as O
+    st = small_stream
+    B, S = 200, 5
+    om, mm, ld, eng = _setup(st, False, 1, 32, 8, 16, None, S, B, True)
+    lo_ref = O.TorchNeighborLoader(st["num_nodes"], S)
+    h = torch.zeros(st["num_nodes"], dtype=torch.long)
+    opt = torch.optim.Adam(om.parameters(), lr=1e-3)
+    crit = torch.nn.BCEWithLogitsLoss()
+    plan = [(True, 3), (False, 2), (True, 1), (False, 1), (True, 2)]
+    ref, it = [], 0
+    for train, n in plan:
+        for _ in range(n):
+            ng = st["neg"][it * B:(it + 1) * B]
+            if train:
+                ref.append(float(O.train_step_ref(om, lo_ref, h, opt, st, it * B, (it + 1) * B, ng)[0]))
+            else:
+                po, no = O.infer_step_ref(om, lo_ref, h, st, it * B, (it + 1) * B, ng)
+                ref.append(float(crit(po, torch.ones_like(po)) + crit(no, torch.zeros_like(no))))
+            it += 1
+        eng.run(n, train=train)
+    torch.cuda.synchronize()
+    eng.check()
+    mine = eng.losses(it).cpu().tolist()
+    for a, b in zip(mine, ref):
+        assert abs(a - b) <= 2e-4 * abs(b) + 1e-6, (mine, ref)
+    assert eng.cursor == it * B and ld.cur_e_id == it * B
+    assert torch.equal(ld.e_id.cpu(), lo_ref.e_id)
+    assert torch.equal(mm.memory.last_update.cpu(), om.memory.last_update)

@@ -129,3 +129,36 @@ def test_full_size_mrr_matches_reference_loop():
     import os
     runpy.run_path(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts",
                                 "check_eval_vs_cpu.py"), run_name="__main__")
+
+
+def test_one_call_equals_batch_by_batch(small_stream):
+    """run(6) (front-ends prefetched inside the call) against six run(1) calls (no prefetch): identical scores of the
+    last batch, MRR and state -- bitwise, both are the same kernels in the same order per batch."""
+    from ctan_b200.models import CTAN_tgb, LastNeighborLoader
+    from ctan_b200.tgb_eval import TGBEvalEngine
+    st = small_stream
+    dev = torch.device("cuda:0")
+    B, S, n_neg, D = 50, 8, 20, 128
+    neg = _neg_table(st, n_neg)
+    kw = dict(num_nodes=st["num_nodes"], edge_dim=st["msg"].size(1), memory_dim=D, time_dim=8, node_dim=1, num_iters=1,
+              epsilon=0.5, gamma=0.1, mean_delta_t=np.float64(1234.5), std_delta_t=np.float64(4567.8))
+    outs = []
+    for chunks in ([6], [1] * 6, [2, 4]):
+        torch.manual_seed(0)
+        mm = CTAN_tgb(**kw).to(dev)
+        ld = LastNeighborLoader(st["num_nodes"], S, device=dev)
+        g = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in st.items()}
+        g["neg"] = neg.to(dev)
+        eng = TGBEvalEngine(mm, ld, g, batch_size=B, n_neg=n_neg)
+        eng.warmup()
+        for s in range(0, 400, B):                       # some state first (inserts + memory) so hubs and edges exist
+            ld.insert(g["src"][s:s + B], g["dst"][s:s + B])
+        mm.memory.memory.copy_(torch.randn(mm.memory.memory.shape, generator=torch.Generator().manual_seed(3)).to(dev) * 0.1)
+        eng.set_cursor(400)
+        for c in chunks:
+            eng.run(c)
+        eng.check()
+        outs.append((eng.scores().clone(), eng.mrr(), mm.memory.memory.clone(), mm.memory.last_update.clone(), ld.e_id.clone()))
+    for o in outs[1:]:
+        assert torch.equal(o[0], outs[0][0]) and o[1] == outs[0][1]
+        assert torch.equal(o[2], outs[0][2]) and torch.equal(o[3], outs[0][3]) and torch.equal(o[4], outs[0][4])
