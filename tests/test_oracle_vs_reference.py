@@ -106,3 +106,52 @@ def test_same_seed_init_of_cuda_modules_matches_reference(ref):
         for k in sa:
             if not k.endswith("_assoc"):
                 assert torch.equal(sa[k], sb[k]), k
+
+
+@pytest.mark.parametrize("predict_dst", [False, True])
+def test_multiclass_and_sequence_heads(ref, predict_dst):
+    """C4 (Pascal-VOC: no negatives, 21 classes, CrossEntropy, train_link.py:297-343) and C1's SequencePredictor head:
+    same-seed init, logits, loss and every gradient of the reference model against the oracle."""
+    g = torch.Generator().manual_seed(4)
+    num_nodes, n, B, D, Fn, out = 300, 512, 128, 37, 14, (1 if predict_dst else 21)
+    src = torch.randint(0, num_nodes, (n,), generator=g)
+    dst = torch.randint(0, num_nodes, (n,), generator=g)
+    t = torch.sort(torch.randint(0, 5000, (n,), generator=g)).values
+    msg = torch.randn(n, 1, generator=g)
+    x = torch.randn(num_nodes, Fn, generator=g)
+    y = torch.randint(0, 21, (n,), generator=g)
+    kw = dict(num_nodes=num_nodes, edge_dim=1, memory_dim=D, time_dim=1, node_dim=Fn, num_iters=3, epsilon=0.1,
+              gamma=0.1, readout_hidden=D // 2, readout_out=out, mean_delta_t=30.0, std_delta_t=50.0,
+              predict_dst=predict_dst)
+    torch.manual_seed(1)
+    rm = ref.CTAN(**kw)
+    torch.manual_seed(1)
+    om = O.OracleCTAN(**kw)
+    for (ka, a), (kb, b) in zip(rm.state_dict().items(), om.state_dict().items()):
+        assert ka == kb and (ka.endswith("_assoc") or torch.equal(a, b)), ka
+    with pyg_shim.stable_sort():
+        lr_, lo_ = ref.LastNeighborLoader(num_nodes, 5), O.TorchNeighborLoader(num_nodes, 5)
+        hr, ho = torch.zeros(num_nodes, dtype=torch.long), torch.zeros(num_nodes, dtype=torch.long)
+        for it in range(3):
+            a, b = it * B, (it + 1) * B
+            res = []
+            for model, loader, helper in ((rm, lr_, hr), (om, lo_, ho)):
+                model.zero_grad()
+                n_id = torch.cat([src[a:b], dst[a:b]]).unique()
+                for _ in range(model.num_gnn_layers):
+                    n_id, ei, eid = loader(n_id)
+                helper[n_id] = torch.arange(n_id.numel())
+                pos, neg, se, de = model(O.Batch(src=src[a:b], dst=dst[a:b], x=x), n_id, msg[eid], t[eid], ei, helper)
+                assert neg is None
+                loss = (torch.nn.BCEWithLogitsLoss()(pos.view(-1), (y[a:b] % 2).float()) if predict_dst
+                        else torch.nn.CrossEntropyLoss()(pos, y[a:b]))
+                model.update(src[a:b], dst[a:b], t[a:b], msg[a:b], se, de)
+                loader.insert(src[a:b], dst[a:b])
+                loss.backward()
+                res.append((pos.detach(), loss.detach(), {k: p.grad.clone() for k, p in model.named_parameters()
+                                                          if p.grad is not None}))
+            (p_r, l_r, g_r), (p_o, l_o, g_o) = res
+            assert torch.allclose(p_r, p_o, rtol=1e-5, atol=1e-6) and torch.allclose(l_r, l_o, rtol=1e-6)
+            assert set(g_r) == set(g_o)
+            for k in g_r:
+                assert torch.allclose(g_r[k], g_o[k], rtol=1e-4, atol=1e-6), k
