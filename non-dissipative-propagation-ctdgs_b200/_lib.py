@@ -145,6 +145,10 @@ def ptr(t, dtype=None):
 LAUNCHES = {"ctan_set_pdl": 0, "ctan_delta_t_stats_ws_bytes": 0, "ctan_delta_t_stats": 9, "ctan_nbr_insert": 2, "ctan_nbr_lookup": 1, "ctan_readout_fwd": 2, "ctan_readout_bwd": 2,
             "ctan_qkva_bwd": 2, "ctan_eproj_bwd": 2}
 
+# Bumped by every writer of model weights that bypasses torch's tensor versioning (StepEngine's Adam kernel updates
+# the flat parameter buffer through raw pointers); readers of derived weight operands compare it with their last prep.
+WEIGHTS_EPOCH = 0
+
 # Optional instrumentation (bench.py): TRACE = list -> every call appends (name, start_event, end_event)
 TRACE = None
 N_LAUNCHES = 0

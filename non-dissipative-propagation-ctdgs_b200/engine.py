@@ -546,6 +546,8 @@ class StepEngine:
         """Advance n_steps full batches from the cursor (no host synchronisation)."""
         if self.loader.cur_e_id + n_steps * self.B > self.n_events:
             raise ValueError(f"stream exhausted: cursor {self.loader.cur_e_id} + {n_steps}x{self.B} > {self.n_events}")
+        if train:
+            _lib.WEIGHTS_EPOCH += 1                          # (see _lib.WEIGHTS_EPOCH)
         with torch.cuda.device(self.dev):
             for fn in self.plan(n_steps, train):
                 fn()

@@ -287,7 +287,8 @@ class TGBEvalEngine:
     def _prep_weights(self):
         """Weight-only operands (A = W - W^T - gamma I, the packed / hi-lo split weight panels of the tensor-core
         contractions).  Evaluation runs with frozen weights (tgb_test is @torch.no_grad, train_link.py:111),
-        so they are formed at the start of every run() call, not once per batch."""
+        so they are formed when the weights have changed since the last run() call (torch tensor versions +
+        _lib.WEIGHTS_EPOCH for raw-pointer writers; `refresh_weights()` forces it), never once per batch."""
         w, m = self.w, self.model
         D, Fn, Hd = self.D, self.Fn, self.Hd
         g, a, r = m.gnn, m.gnn.aconv, m.readout
@@ -307,6 +308,10 @@ class TGBEvalEngine:
             if self.use_tc_ep:
                 call("ctan_pack_split_pad", ptr(ph.lin_edge.weight), D, self.Fe + self.T, self.Fe + self.T, self.Kep,
                      ptr(w["Wep_hi"]), ptr(w["Wep_lo"]))
+
+    def refresh_weights(self):
+        """Force the weight-only operands to be re-formed at the next run() (after writing weights behind torch's back)."""
+        self._w_ver = None
 
     def _exchange(self):
         """The one collective of the batch (kept OUT of CUDA-graph capture: torch's NCCL process group and
@@ -375,7 +380,10 @@ class TGBEvalEngine:
             raise ValueError("stream exhausted")
         if n_batches <= 0:
             return
-        self._prep_weights()          # once per run() call (a whole split), not per batch
+        ver = (_lib.WEIGHTS_EPOCH,) + tuple((p.data_ptr(), p._version) for p in self.model.parameters())
+        if ver != getattr(self, "_w_ver", None):      # weight-only operands: re-formed only when the weights changed
+            self._prep_weights()
+            self._w_ver = ver
         with torch.cuda.device(self.dev):
             if self.use_graph:
                 if self._graph is None:

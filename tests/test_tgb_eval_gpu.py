@@ -162,3 +162,42 @@ def test_one_call_equals_batch_by_batch(small_stream):
     for o in outs[1:]:
         assert torch.equal(o[0], outs[0][0]) and o[1] == outs[0][1]
         assert torch.equal(o[2], outs[0][2]) and torch.equal(o[3], outs[0][3]) and torch.equal(o[4], outs[0][4])
+
+
+def test_weight_change_between_calls_is_seen(small_stream):
+    """The tensor-core weight panels are cached across run() calls: an in-place weight change between two calls must
+    re-form them (torch tensor versions), giving exactly the scores of an engine that had the new weights all along."""
+    from ctan_b200.models import CTAN_tgb, LastNeighborLoader
+    from ctan_b200.tgb_eval import TGBEvalEngine
+    st = small_stream
+    dev = torch.device("cuda:0")
+    B, S, n_neg, D = 50, 8, 20, 128
+    neg = _neg_table(st, n_neg)
+    kw = dict(num_nodes=st["num_nodes"], edge_dim=st["msg"].size(1), memory_dim=D, time_dim=8, node_dim=1, num_iters=1,
+              epsilon=0.5, gamma=0.1, mean_delta_t=np.float64(1234.5), std_delta_t=np.float64(4567.8))
+    res = []
+    for change_first in (False, True):
+        torch.manual_seed(0)
+        mm = CTAN_tgb(**kw).to(dev)
+        ld = LastNeighborLoader(st["num_nodes"], S, device=dev)
+        g = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in st.items()}
+        g["neg"] = neg.to(dev)
+        eng = TGBEvalEngine(mm, ld, g, batch_size=B, n_neg=n_neg)
+        eng.warmup()
+        for s in range(0, 400, B):
+            ld.insert(g["src"][s:s + B], g["dst"][s:s + B])
+        eng.set_cursor(400)
+
+        def change():
+            with torch.no_grad():                      # readout weights do not influence the state update
+                mm.readout.lin_src.weight.mul_(-0.5)
+                mm.readout.lin_dst.weight.add_(0.01)
+        if change_first:
+            change()
+            eng.run(2)
+        else:
+            eng.run(1)
+            change()
+            eng.run(1)
+        res.append(eng.scores().clone())
+    assert torch.equal(res[0], res[1])
