@@ -406,6 +406,13 @@ def main():
     # a tcgen05 contraction is bounded by the tensor pipe, not HBM: report useful flops against the measured dense peak
     tc_flops = {"ctan_dx_tc": 2.0 * N_last * 4 * D * D, "ctan_qkva_fwd_tc": 2.0 * N_last * D * 4 * D}.get(top_name)
     if tc_flops:
+        tkey = {"ctan_dx_tc": "qkva_tc_kernel@wiki_dx(N=710,K=512,Nout=128,split4)",
+                "ctan_qkva_fwd_tc": "qkva_tc_kernel@wiki_qkva(N=710,K=128,Nout=512)"}[top_name]
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if K == 1 and os.path.exists(tp):
+            tr = json.load(open(tp)).get(tkey)
+            if tr:
+                roof["traffic"] = tr["traffic_bytes"]
         tpeak, tsrc = load_tensor_peak()
         ach = tc_flops / (top_us * 1e-6) / 1e12
         roof.update(bound="tensor", unit="TFLOP/s", achieved=ach, peak=tpeak, frac=ach / tpeak, peak_source=tsrc,

@@ -454,7 +454,7 @@ class StepEngine:
             gn = self._DX[k]
             if self.use_tc_dx:   # dX = G + DQKVA Wcat on tcgen05 (plain stores)
                 call("ctan_dx_tc", ptr(w["DQKVA"]), ptr(g), N, Nd, D, ptr(w["WcatT_hi"]), ptr(w["WcatT_lo"]), ptr(gn),
-                     _lib.TC_MODE, 4 if self.n_typ <= 4096 else 1)     # gn lives in the zeroed buffer
+                     _lib.TC_MODE, 2 if self.n_typ <= 4096 else 1)     # (split sweep 1/2/4/8/16: 110.5/109.8/112.5/112.9/112.8 us per step)
             else:
                 call("ctan_qkva_bwd", *qb, ptr(gn), None, None, None, None, None, None, None, None, self.n_typ)
             g = gn
