@@ -108,22 +108,58 @@ def model_kwargs(st, K, mean, std, cfg=WIKI):
 
 
 # ------------------------------------------------------------------------------------------ baselines
-def oracle_train_rate(st, K, mean, std, device, n_steps, warmup, threads=None, drop_in=False):
-    """events/sec of the restated reference training loop (oracle) on `device`.  drop_in=True: the SAME loop body
-    (train_link.py:237-282: unique -> loader(n_id) x K -> model(...) -> loss -> update/insert -> backward ->
-    torch.optim.Adam) driving OUR modules through the reference API -- what a user gets by only swapping imports."""
+def dropin_train_rate(st, K, mean, std, device, n_steps, warmup):
+    """events/sec of OUR modules driven through the reference API by the reference's own loop body, written out here
+    (train_link.py:237-282: unique -> loader(n_id) x K -> helper[n_id] = arange -> model(...) -> BCE on pos/neg ->
+    update + insert -> backward -> torch.optim.Adam): what a user gets by only swapping the imports."""
+    import types
+    from ctan_b200.models import CTAN, LastNeighborLoader
+    cfg = WIKI
+    torch.manual_seed(0)
+    model = CTAN(**model_kwargs(st, K, mean, std)).to(device)
+    loader = LastNeighborLoader(st["num_nodes"], cfg["S"], device=device)
+    helper = torch.zeros(st["num_nodes"], dtype=torch.long, device=device)
+    opt = torch.optim.Adam(model.parameters(), lr=cfg["lr"])
+    crit = torch.nn.BCEWithLogitsLoss()
+    g = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in st.items()}
+    B = cfg["B"]
+
+    def step(it):
+        lo, hi = it * B, (it + 1) * B
+        src, dst, t, msg, neg = g["src"][lo:hi], g["dst"][lo:hi], g["t"][lo:hi], g["msg"][lo:hi], g["neg"][lo:hi]
+        opt.zero_grad()
+        n_id = torch.cat([src, dst, neg]).unique()
+        for _ in range(model.num_gnn_layers):
+            n_id, edge_index, e_id = loader(n_id)
+        helper[n_id] = torch.arange(n_id.size(0), device=device)
+        batch = types.SimpleNamespace(src=src, dst=dst, neg_dst=neg, x=g.get("x"))
+        pos, ngo, se, de = model(batch, n_id, g["msg"][e_id], g["t"][e_id], edge_index, helper)
+        loss = crit(pos, torch.ones_like(pos)) + crit(ngo, torch.zeros_like(ngo))
+        model.update(src, dst, t, msg, se, de)
+        loader.insert(src, dst)
+        loss.backward()
+        opt.step()
+        model.detach_memory()
+    for it in range(warmup):
+        step(it)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for it in range(warmup, warmup + n_steps):
+        step(it)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return n_steps * B / dt, dt / n_steps * 1e3
+
+
+def oracle_train_rate(st, K, mean, std, device, n_steps, warmup, threads=None):
+    """events/sec of the restated reference training loop (oracle port; BASELINE legs only) on `device`."""
     from oracle import ctan_oracle as O
     if threads:
         torch.set_num_threads(threads)
     cfg = WIKI
     torch.manual_seed(0)
-    if drop_in:
-        from ctan_b200.models import CTAN, LastNeighborLoader
-        om = CTAN(**model_kwargs(st, K, mean, std)).to(device)
-        ld = LastNeighborLoader(st["num_nodes"], cfg["S"], device=device)
-    else:
-        om = O.OracleCTAN(**model_kwargs(st, K, mean, std)).to(device)
-        ld = O.TorchNeighborLoader(st["num_nodes"], cfg["S"], device=device)
+    om = O.OracleCTAN(**model_kwargs(st, K, mean, std)).to(device)
+    ld = O.TorchNeighborLoader(st["num_nodes"], cfg["S"], device=device)
     h = torch.zeros(st["num_nodes"], dtype=torch.long, device=device)
     opt = torch.optim.Adam(om.parameters(), lr=cfg["lr"])
     g = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in st.items()}
@@ -470,7 +506,7 @@ def main():
         gv, gms = oracle_train_rate(st, K, mean, std, "cuda:0", 100, 10)
         out["torch_gpu_baseline"] = {"value": gv, "unit": "events/s", "ms_per_step": gms,
                                      "what": "restated reference loop, eager PyTorch ops on the same B200 (fp32)"}
-        dv, dms = oracle_train_rate(st, K, mean, std, "cuda:0", 200, 20, drop_in=True)
+        dv, dms = dropin_train_rate(st, K, mean, std, "cuda:0", 200, 20)
         out["drop_in_api"] = {"value": dv, "unit": "events/s", "ms_per_step": dms,
                               "what": "the reference's loop body unchanged (train_link.py:237-282, torch.optim.Adam, one "
                                       "host sync per loader call) on ctan_b200.models through the C-ABI kernels"}

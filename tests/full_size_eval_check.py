@@ -1,7 +1,7 @@
 """Full-size TGB evaluation: per-batch MRR of the GPU engine vs the reference's per-query loop (oracle port) on the
 CPU, same stream / model / negatives / 1M-event warm state, first 3 batches after the warm insert."""
 import os, sys, types
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # (test infrastructure: imports the oracle)
 sys.path.insert(0, ROOT)
 import numpy as np
 import torch

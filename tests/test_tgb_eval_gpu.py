@@ -124,11 +124,11 @@ def test_full_size_comment_shape_engine_vs_module_api():
 def test_full_size_mrr_matches_reference_loop():
     """BASELINE config C5 at full size against the reference's per-query evaluation loop (oracle port of
     train_link.py:111-201) run on the host: same stream, model, negatives and 1M-event warm state; per-batch MRR of
-    3 consecutive batches, neighbour tables bit-exact, memory within 1e-4 (scripts/check_eval_vs_cpu.py)."""
+    3 consecutive batches, neighbour tables bit-exact, memory within 1e-4 (tests/full_size_eval_check.py)."""
     import runpy
     import os
-    runpy.run_path(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts",
-                                "check_eval_vs_cpu.py"), run_name="__main__")
+    runpy.run_path(os.path.join(os.path.dirname(os.path.abspath(__file__)), "full_size_eval_check.py"),
+                   run_name="__main__")
 
 
 def test_one_call_equals_batch_by_batch(small_stream):
