@@ -14,7 +14,10 @@ so the oracle is pinned against outputs of the reference itself, produced in the
 container by running the reference's own `models/*.py` and `TGB/modules/*.py` unmodified
 (through `oracle/pyg_shim.py`): see `tests/golden/make_golden.py` (committed fixtures under
 `tests/golden/`) and `tests/test_oracle_vs_reference.py` (live cross-check when
-/root/reference is present).  The PyG `TransformerConv`/`AntiSymmetricConv`/`softmax`
+/root/reference is present).  The one fixture the reference does ship (`data/label_sequence.tar.xz`: the
+path-graph datasets and the known answers of `utils.compute_stats`) pins `delta_t_stats_ref` and, through the
+reference's own `train_sequence.train/eval`, the sequence loop (`tests/golden/make_sequence_golden.py`).
+The PyG `TransformerConv`/`AntiSymmetricConv`/`softmax`
 operators themselves are "parity unpinned": no PyG source or wheel is available offline, so
 both the shim and this file restate them from the same published description.
 """
