@@ -89,6 +89,7 @@ SIGNATURES.update({
     "ctan_dx_tc": [P, P, I, P, I, P, P, P, I, I],
     "ctan_pack_split": [P, I, I, I, P, P],
     "ctan_pack_split_pad": [P, I, I, I, I, P, P],
+    "ctan_pack_bf16": [P, I, I, I, I, P],
     "ctan_eproj_prep": [P, I, P, P, P, P, I, I, P, I, P],
     "ctan_gemm_tc": [P, I, P, I, P, P, I, P, P, P, P, I, P, I, P, I],
     "ctan_enc_prep": [P, I, P, I, P, I, P, P, P, P],

@@ -76,6 +76,22 @@ __device__ __forceinline__ void mma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, ui
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+// kind::f16 with BF16 operands (both from shared memory), fp32 accumulate, K-major, M=128, N=128
+__device__ __forceinline__ uint32_t instr_desc_bf16() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {        // low half = a (element k), high half = b (k+1)
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
@@ -113,8 +129,12 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 //              tcgen05.ld -> per-warp smem staging -> +bias/+residual -> full-line coalesced stores (or atomics)
 // Barriers: raw[s] TMA landed | ready[s] A of stage s is in TMEM (128 arrivals) | empty[s] MMAs of stage s retired
 //           done[b] accumulator b complete | accfree[b] accumulator b drained (128 arrivals)
-// mode 0: 3xTF32 (fp32 parity path); mode 1: single TF32 pass (1e-2 path; hi only).
-__global__ void __launch_bounds__(THREADS)
+// mode 0: 3xTF32 (fp32 parity path); mode 1: single TF32 pass (hi only);
+// mode 2: BF16 (the 1e-2 path): k-blocks of 64 elements in a 3-stage ring of [A raw k 0..31 | A raw k 32..63 | A bf16 | B bf16]
+//         tiles; the transform warps convert the fp32 activation tile to a BF16 tile in the canonical K-major 128-byte-
+//         swizzled layout (what TMA would have produced) and the MMA (kind::f16) reads both operands from shared memory;
+//         tmBhi is then the tensor map of a BF16 weight panel, tmBlo is unused.
+__global__ void __launch_bounds__(THREADS, 1)
 qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                const __grid_constant__ CUtensorMap tmBlo, Bias4 bias, float* __restrict__ C, int ldc, int M_host,
                const int* __restrict__ M_dev, int N, int K, int mode) {
@@ -148,10 +168,14 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_holder;
     // split-K over gridDim.z (atomic epilogue): thin problems (few row tiles, long K) get more CTAs
-    const int kb_per = (K / BKF + (int)gridDim.z - 1) / (int)gridDim.z;
+    const bool bf = mode == 2;
+    const int bke = bf ? 2 * BKF : BKF;                                 // elements of K per k-block
+    const int nst = bf ? 3 : STAGES;                                    // ring depth (bf16 stages are 64 KB)
+    const int stage_bytes = bf ? 4 * TILE_BYTES : STAGE_BYTES;
+    const int kb_per = (K / bke + (int)gridDim.z - 1) / (int)gridDim.z;
     const int kb0 = (int)blockIdx.z * kb_per;
-    const int n_kb = min(K / BKF - kb0, kb_per);
-    auto stage_ptr = [&](int s, int which) { return smem + s * STAGE_BYTES + which * TILE_BYTES; };
+    const int n_kb = min(K / bke - kb0, kb_per);
+    auto stage_ptr = [&](int s, int which) { return smem + s * stage_bytes + which * TILE_BYTES; };
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer
@@ -159,8 +183,15 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int it = 0;                                                 // k-blocks issued so far (all tiles)
             for (int m0 = blockIdx.y * BM; m0 < M; m0 += gridDim.y * BM)
             for (int kb = 0; kb < n_kb; ++kb, ++it) {
-                const int s = it % STAGES;
-                if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);
+                const int s = it % nst;
+                if (it >= nst) mbar_wait(&empty[s], ((it / nst) - 1) & 1);
+                if (bf) {
+                    mbar_expect_tx(&raw[s], 3 * TILE_BYTES);
+                    tma_load_2d(stage_ptr(s, 0), &tmA, &raw[s], (kb0 + kb) * bke, m0);
+                    tma_load_2d(stage_ptr(s, 1), &tmA, &raw[s], (kb0 + kb) * bke + BKF, m0);
+                    tma_load_2d(stage_ptr(s, 3), &tmBhi, &raw[s], (kb0 + kb) * bke, n0);
+                    continue;
+                }
                 mbar_expect_tx(&raw[s], (mode == 0 ? 3 : 2) * TILE_BYTES);
                 tma_load_2d(stage_ptr(s, 0), &tmA, &raw[s], (kb0 + kb) * BKF, m0);
                 tma_load_2d(stage_ptr(s, 1), &tmBhi, &raw[s], (kb0 + kb) * BKF, n0);
@@ -180,9 +211,19 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 const uint32_t acc = tmem_base + TM_ACC + (uint32_t)buf * BN;
                 for (int kb = 0; kb < n_kb; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait(&ready[s], (it / STAGES) & 1);
+                    const int s = it % nst;
+                    mbar_wait(&ready[s], (it / nst) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (bf) {
+                        const uint32_t idb = instr_desc_bf16();
+                        const uint32_t a_bf = smem_u32(stage_ptr(s, 2)), b_bf = smem_u32(stage_ptr(s, 3));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)                     // UMMA_K = 16 bf16 = 32 bytes inside the swizzle atom
+                            mma_bf16_ss(acc, smem_desc_sw128(a_bf + k * 32), smem_desc_sw128(b_bf + k * 32), idb,
+                                        (kb | k) ? 1u : 0u);
+                        mma_commit(&empty[s]);
+                        continue;
+                    }
                     const uint32_t a_hi = tmem_base + TM_A + (uint32_t)s * 64, a_lo = a_hi + 32;
                     const uint32_t b_hi = smem_u32(stage_ptr(s, 1)), b_lo = smem_u32(stage_ptr(s, 2));
 #pragma unroll
@@ -213,8 +254,25 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int m0 = blockIdx.y * BM; m0 < M; m0 += gridDim.y * BM)
         for (int kb = 0; kb < n_kb; ++kb, ++it) {
             if (it % TGROUPS != grp) continue;
-            const int s = it % STAGES;
-            mbar_wait(&raw[s], (it / STAGES) & 1);
+            const int s = it % nst;
+            mbar_wait(&raw[s], (it / nst) & 1);
+            if (bf) {
+                uint8_t* orow = stage_ptr(s, 2) + r * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {                           // output chunk j = elements k 8j .. 8j+7 of row r
+                    const uint8_t* irow = stage_ptr(s, j >> 2) + r * 128;
+                    const int c0 = (2 * j) & 7;
+                    const float4 v0 = *reinterpret_cast<const float4*>(irow + ((c0 ^ (r & 7)) << 4));
+                    const float4 v1 = *reinterpret_cast<const float4*>(irow + (((c0 + 1) ^ (r & 7)) << 4));
+                    uint4 o;
+                    o.x = pack_bf16x2(v0.x, v0.y); o.y = pack_bf16x2(v0.z, v0.w);
+                    o.z = pack_bf16x2(v1.x, v1.y); o.w = pack_bf16x2(v1.z, v1.w);
+                    *reinterpret_cast<uint4*>(orow + ((j ^ (r & 7)) << 4)) = o;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA
+                mbar_arrive(&ready[s]);
+                continue;
+            }
             const uint8_t* arow = stage_ptr(s, 0) + r * 128;
             const uint32_t t_hi = tmem_base + tlane + TM_A + (uint32_t)s * 64;
 #pragma unroll
@@ -333,6 +391,20 @@ static int make_map(CUtensorMap* m, const float* base, int rows, int K) {
     return r == CUDA_SUCCESS ? 0 : CTAN_ERR_BAD_ARG;
 }
 
+// row-major bf16 [rows, K] weight panel, box = 128 rows x 64 elements (128 bytes), 128-byte swizzle
+static int make_map_bf16(CUtensorMap* m, const void* base, int rows, int K) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return CTAN_ERR_UNSUPPORTED;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)(2 * BKF), (cuuint32_t)BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : CTAN_ERR_BAD_ARG;
+}
+
 // grid.y: a CTA holds ~212 KB of smem and all 512 TMEM columns, so exactly one is resident per SM; launch at most
 // one wave and let each CTA walk the remaining row tiles (that is also what overlaps epilogue and main loop)
 static int bounded_rows(int M_max, const int* M_dev, int gx) {
@@ -393,12 +465,14 @@ extern "C" int ctan_qkva_fwd_tc(const float* X, int N, const int* N_dev, int D, 
                                 const float* Wcat_lo, const float* bq, const float* bk, const float* bv,
                                 const float* b, float* QKVA, int mode, cudaStream_t stream) {
     if (N <= 0) return 0;
-    if (D % tc::BKF != 0 || ((4 * D) % tc::BN) != 0 || (((uintptr_t)X | (uintptr_t)Wcat_hi | (uintptr_t)Wcat_lo) & 15))
+    const bool bf = mode == 2;                // Wcat_hi is then a BF16 [4D, D] panel (ctan_pack_bf16), Wcat_lo unused
+    if (D % (bf ? 2 * tc::BKF : tc::BKF) != 0 || ((4 * D) % tc::BN) != 0 ||
+        (((uintptr_t)X | (uintptr_t)Wcat_hi | (bf ? 0 : (uintptr_t)Wcat_lo)) & 15))
         return CTAN_ERR_UNSUPPORTED;
     CUtensorMap tmA, tmBhi, tmBlo;
     int rc = tc::make_map(&tmA, X, N, D);
-    if (!rc) rc = tc::make_map(&tmBhi, Wcat_hi, 4 * D, D);
-    if (!rc) rc = tc::make_map(&tmBlo, Wcat_lo, 4 * D, D);
+    if (!rc) rc = bf ? tc::make_map_bf16(&tmBhi, Wcat_hi, 4 * D, D) : tc::make_map(&tmBhi, Wcat_hi, 4 * D, D);
+    if (!rc) rc = bf ? tc::make_map_bf16(&tmBlo, Wcat_hi, 4 * D, D) : tc::make_map(&tmBlo, Wcat_lo, 4 * D, D);
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
@@ -472,19 +546,41 @@ extern "C" int ctan_pack_split_pad(const float* src, int rows, int cols, int ld,
     return 0;
 }
 
+// BF16 weight panel of a row-major fp32 [rows, cols] block (leading dimension ld), rows zero-padded to ld_out elements
+// (K rounded up to the 64-element k-block of the BF16 path).
+__global__ void pack_bf16_kernel(const float* __restrict__ src, int rows, int cols, int ld, int ld_out,
+                                 unsigned short* __restrict__ dst) {
+    ctan_pdl_begin();
+    const int n = rows * ld_out;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int r = i / ld_out, c = i - r * ld_out;
+        const float x = c < cols ? src[(size_t)r * ld + c] : 0.f;
+        dst[i] = (unsigned short)(tc::pack_bf16x2(x, 0.f) & 0xFFFFu);
+    }
+}
+extern "C" int ctan_pack_bf16(const float* src, int rows, int cols, int ld, int ld_out, void* dst_bf16,
+                              cudaStream_t stream) {
+    if (rows <= 0 || cols <= 0 || ld_out < cols) return CTAN_ERR_BAD_ARG;
+    CTAN_LAUNCH((pack_bf16_kernel), ctan_grid((long long)rows * ld_out, 256), 256, 0, stream, src, rows, cols, ld, ld_out,
+                (unsigned short*)dst_bf16);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
 // Generic tensor-core linear layer: C[M,Nout] = A[M,K] B^T + bias_seg[n/seg][n%seg] + res[m][n]  (3xTF32 / TF32).
 // A row-major [M(max),K] dense, B = packed split weights [Nout,K].  K % 32 == 0, Nout % 128 == 0, seg % 16 == 0.
 extern "C" int ctan_gemm_tc(const float* A, int M, const int* M_dev, int K, const float* Bhi, const float* Blo, int Nout,
                             const float* b0, const float* b1, const float* b2, const float* b3, int seg,
                             const float* res, int ldr, float* C, int mode, cudaStream_t stream) {
     if (M <= 0) return 0;
-    if (K % tc::BKF != 0 || Nout % tc::BN != 0 || seg <= 0 || seg % 16 != 0 ||
-        (((uintptr_t)A | (uintptr_t)Bhi | (uintptr_t)Blo | (uintptr_t)C) & 15))
+    const bool bf = mode == 2;                // Bhi is then a BF16 [Nout, K] panel (ctan_pack_bf16), Blo unused
+    if (K % (bf ? 2 * tc::BKF : tc::BKF) != 0 || Nout % tc::BN != 0 || seg <= 0 || seg % 16 != 0 ||
+        (((uintptr_t)A | (uintptr_t)Bhi | (bf ? 0 : (uintptr_t)Blo) | (uintptr_t)C) & 15))
         return CTAN_ERR_UNSUPPORTED;
     CUtensorMap tmA, tmBhi, tmBlo;
     int rc = tc::make_map(&tmA, A, M, K);
-    if (!rc) rc = tc::make_map(&tmBhi, Bhi, Nout, K);
-    if (!rc) rc = tc::make_map(&tmBlo, Blo, Nout, K);
+    if (!rc) rc = bf ? tc::make_map_bf16(&tmBhi, Bhi, Nout, K) : tc::make_map(&tmBhi, Bhi, Nout, K);
+    if (!rc) rc = bf ? tc::make_map_bf16(&tmBlo, Bhi, Nout, K) : tc::make_map(&tmBlo, Blo, Nout, K);
     if (rc) return rc;
     cudaError_t e = cudaFuncSetAttribute(tc::qkva_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;

@@ -43,6 +43,7 @@ REF = {
     "ctan_pack_split": "(weight packing + TF32 split for the tensor-core path; no reference counterpart)",
     "ctan_pack_split_pad": "(same, rows zero-padded to the 32-float k-block; no reference counterpart)",
     "ctan_eproj_prep": "edge_attr = cat([msg, time_enc(rel)]) as a dense TMA operand -- models/gnn_layers.py:96-97, TGB/modules/time_enc.py:23-24",
+    "ctan_pack_bf16": "(BF16 weight panel for the 1e-2 tensor-core path; no reference counterpart)",
     "ctan_gemm_tc": "torch.nn.Linear on tcgen05 tensor cores (enc_x: models/gnn_layers.py:96; readout lin_src/lin_dst: models/predictors.py:16-17)",
     "ctan_enc_prep": "SimpleMemory.forward gather + node-feature columns of enc_x -- models/memory_layers.py:155-156, models/gnn_layers.py:96",
     "ctan_head_gather": "TGBLinkPredictor.forward on pre-projected node rows -- models/predictors.py:16-19",

@@ -114,3 +114,29 @@ def test_qkva_tc_persistent_row_loop():
     err = float((out[:n_true].double() - ref).abs().max()) / float(ref.abs().max())
     assert err < 5e-6, err
     assert bool((out[n_true:] == 7.0).all())
+
+
+@pytest.mark.parametrize("M,K,Nout", [(300, 64, 128), (1000, 256, 512), (4200, 320, 256)])
+def test_bf16_mode_matches_fp64_at_1e2(M, K, Nout):
+    """mode 2 (the north star's 1e-2 path): activations converted to BF16 in the kernel, BF16 weight panel, fp32
+    accumulation in TMEM; bias and residual epilogue as in the other modes; device-sized M."""
+    from ctan_b200._lib import call, ptr
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(M + K)
+    A = torch.randn(M + 37, K, generator=g).to(dev)
+    W = (torch.randn(Nout, K, generator=g) / K ** 0.5).to(dev)
+    b = torch.randn(Nout, generator=g).to(dev)
+    res = torch.randn(M + 37, Nout, generator=g).to(dev)
+    Wb = torch.zeros((Nout, K), dtype=torch.bfloat16, device=dev)
+    call("ctan_pack_bf16", ptr(W), Nout, K, K, K, ptr(Wb))
+    assert torch.equal(Wb, W.to(torch.bfloat16))
+    C = torch.full((M + 37, Nout), 7.0, device=dev)
+    Md = torch.tensor([M], dtype=torch.int32, device=dev)
+    call("ctan_gemm_tc", ptr(A), M + 37, ptr(Md), K, ptr(Wb), None, Nout, ptr(b), None, None, None, Nout, ptr(res), Nout,
+         ptr(C), 2)
+    ref = A[:M].double() @ W.double().t() + b.double() + res[:M].double()
+    err = float((C[:M].double() - ref).abs().max() / ref.abs().max())
+    assert 1e-5 < err < 1e-2, err
+    assert bool((C[M:] == 7.0).all())                       # rows past the true M untouched
+    exact = A[:M].to(torch.bfloat16).double() @ Wb.double().t() + b.double() + res[:M].double()
+    assert float((C[:M].double() - exact).abs().max() / ref.abs().max()) < 1e-5     # = bf16 inputs, fp32 accumulate
