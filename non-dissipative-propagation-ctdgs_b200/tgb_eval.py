@@ -128,21 +128,29 @@ class TGBEvalEngine:
         self.hub_cap = min(N, 16384)                      # rows of degree > 8 go to the block-cooperative kernel
         w["A"] = torch.zeros((D, D), **f32)
         self.use_tc = _lib.use_tensor_cores(D)
+        # precision of the tensor-core contractions: 0 = 3xTF32 (fp32 parity), 1 = TF32, 2 = BF16 (needs D % 64 == 0)
+        self.tc_mode = _lib.TC_MODE if (_lib.TC_MODE != 2 or D % 64 == 0) else 0
+        bf16 = dict(device=dev, dtype=torch.bfloat16)
         # tensor-core enc_x (dense gathered rows + packed weights) and node-projection readout
         self.use_tc_enc = self.use_tc and D % 128 == 0
         self.use_tc_ro = self.use_tc and (2 * self.Hd) % 128 == 0 and self.Hd % 16 == 0
         self.use_tc_ep = self.use_tc and D % 128 == 0
         if self.use_tc_ep:               # lin_edge on the tensor cores: dense [E, Kpad] edge_attr operand
-            self.Kep = ((self.Fe + self.T + 31) // 32) * 32
+            kq = 64 if self.tc_mode == 2 else 32
+            self.Kep = ((self.Fe + self.T + kq - 1) // kq) * kq
+            w["Wep_bf"] = torch.zeros((D, self.Kep), **bf16)
             w["Aep"] = torch.zeros((self.e_cap + 128, self.Kep), **f32)
             w["Wep_hi"], w["Wep_lo"] = torch.zeros((D, self.Kep), **f32), torch.zeros((D, self.Kep), **f32)
         if self.use_tc_enc:
             w["zmain"], w["ztail"] = torch.zeros((N, D), **f32), torch.zeros((N, D), **f32)
             w["Wenc_hi"], w["Wenc_lo"] = torch.zeros((D, D), **f32), torch.zeros((D, D), **f32)
+            w["Wenc_bf"] = torch.zeros((D, D), **bf16)
         if self.use_tc_ro:
             w["Wro_hi"], w["Wro_lo"] = torch.zeros((2 * self.Hd, D), **f32), torch.zeros((2 * self.Hd, D), **f32)
             w["Y"] = torch.zeros((N, 2 * self.Hd), **f32)
+            w["Wro_bf"] = torch.zeros((2 * self.Hd, D), **bf16)
         w["Wcat_hi"], w["Wcat_lo"] = torch.zeros((4 * D, D), **f32), torch.zeros((4 * D, D), **f32)
+        w["Wcat_bf"] = torch.zeros((4 * D, D), **bf16)
         w["QKVA"] = torch.zeros((N, 4 * D), **f32)
         w["Z"] = torch.zeros((N, D), **f32) if self.final_tanh else None
         w["H"] = torch.zeros((P, self.Hd), **f32)
@@ -214,6 +222,12 @@ class TGBEvalEngine:
         self._forward(par)
         cur.wait_stream(self._side2)
 
+    def _panel(self, name: str):
+        """(B_hi, B_lo) pointers of a weight panel for the current precision mode (BF16: one panel, no lo part)."""
+        if self.tc_mode == 2:
+            return self.w[name + "_bf"].data_ptr(), None
+        return ptr(self.w[name + "_hi"]), ptr(self.w[name + "_lo"])
+
     def _forward(self, par: int):
         """delta-t -> forward -> scores -> packed per-query rows of this rank's shard."""
         w, m, f = self.w, self.model, self.fe[par]
@@ -235,16 +249,16 @@ class TGBEvalEngine:
                 if self.use_tc_ep:
                     call("ctan_eproj_prep", ptr(self.msg), Fe, ptr(f["eid"]), ptr(w["rel"]), ptr(g.time_enc.lin.weight),
                          ptr(g.time_enc.lin.bias), T, E, Ed, self.Kep, ptr(w["Aep"]))
-                    call("ctan_gemm_tc", ptr(w["Aep"]), E, Ed, self.Kep, ptr(w["Wep_hi"]), ptr(w["Wep_lo"]), D, None,
-                         None, None, None, D, None, 0, ptr(w["EP"]), _lib.TC_MODE)
+                    call("ctan_gemm_tc", ptr(w["Aep"]), E, Ed, self.Kep, *self._panel("Wep"), D, None,
+                         None, None, None, D, None, 0, ptr(w["EP"]), self.tc_mode)
                 else:
                     call("ctan_eproj_fwd", ptr(self.msg), Fe, ptr(f["eid"]), ptr(w["rel"]), ptr(g.time_enc.lin.weight),
                          ptr(g.time_enc.lin.bias), T, ptr(ph.lin_edge.weight), E, Ed, D, ptr(w["EP"]))
             if self.use_tc_enc:          # gather -> dense rows; enc_x on the tensor cores; node-feature columns as residual
                 call("ctan_enc_prep", ptr(mem), D, xf, Fn, ptr(f["n_id"]), N, Nd, ptr(g.enc_x.weight), ptr(w["zmain"]),
                      ptr(w["ztail"]))
-                call("ctan_gemm_tc", ptr(w["zmain"]), N, Nd, D, ptr(w["Wenc_hi"]), ptr(w["Wenc_lo"]), D,
-                     ptr(g.enc_x.bias), None, None, None, D, ptr(w["ztail"]), D, ptr(w["X"][0]), _lib.TC_MODE)
+                call("ctan_gemm_tc", ptr(w["zmain"]), N, Nd, D, *self._panel("Wenc"), D,
+                     ptr(g.enc_x.bias), None, None, None, D, ptr(w["ztail"]), D, ptr(w["X"][0]), self.tc_mode)
             else:
                 call("ctan_enc_fwd", ptr(mem), D, xf, Fn, ptr(f["n_id"]), None, N, Nd, ptr(g.enc_x.weight),
                      ptr(g.enc_x.bias), ptr(w["X"][0]))
@@ -252,9 +266,9 @@ class TGBEvalEngine:
             for k in range(K):
                 xi, xo = w["X"][k & 1], w["X"][(k + 1) & 1]
                 if self.use_tc:
-                    call("ctan_qkva_fwd_tc", ptr(xi), N, Nd, D, ptr(w["Wcat_hi"]), ptr(w["Wcat_lo"]),
+                    call("ctan_qkva_fwd_tc", ptr(xi), N, Nd, D, *self._panel("Wcat"),
                          ptr(ph.lin_query.bias), ptr(ph.lin_key.bias), ptr(ph.lin_value.bias), ptr(a.bias),
-                         ptr(w["QKVA"]), _lib.TC_MODE)
+                         ptr(w["QKVA"]), self.tc_mode)
                 else:
                     call("ctan_qkva_fwd", ptr(xi), N, Nd, D, ptr(ph.lin_query.weight), ptr(ph.lin_key.weight),
                          ptr(ph.lin_value.weight), ptr(w["A"]), ptr(ph.lin_query.bias), ptr(ph.lin_key.bias),
@@ -273,8 +287,8 @@ class TGBEvalEngine:
             z = w["Z"] if self.final_tanh else w["X"][K & 1]
             if self.use_tc_ro:
                 # project every NODE once (tensor cores), then a scored pair only gathers two rows
-                call("ctan_gemm_tc", ptr(z), N, Nd, D, ptr(w["Wro_hi"]), ptr(w["Wro_lo"]), 2 * Hd, ptr(r.lin_src.bias),
-                     ptr(r.lin_dst.bias), None, None, Hd, None, 0, ptr(w["Y"]), _lib.TC_MODE)
+                call("ctan_gemm_tc", ptr(z), N, Nd, D, *self._panel("Wro"), 2 * Hd, ptr(r.lin_src.bias),
+                     ptr(r.lin_dst.bias), None, None, Hd, None, 0, ptr(w["Y"]), self.tc_mode)
                 call("ctan_head_pack", ptr(w["Y"]), Hd, ptr(z), D, ptr(f["assoc"]), ptr(f["pair_src"]), ptr(f["pair_dst"]),
                      Q, self.n_neg, ptr(r.lin_final.weight), ptr(r.lin_final.bias), ptr(w["send"]))
             else:
@@ -308,6 +322,18 @@ class TGBEvalEngine:
             if self.use_tc_ep:
                 call("ctan_pack_split_pad", ptr(ph.lin_edge.weight), D, self.Fe + self.T, self.Fe + self.T, self.Kep,
                      ptr(w["Wep_hi"]), ptr(w["Wep_lo"]))
+            if self.tc_mode == 2:                    # BF16 panels of the same weights (A = W - W^T - gamma I from above)
+                bp = w["Wcat_bf"].data_ptr()
+                for i, src in enumerate((ph.lin_query.weight, ph.lin_key.weight, ph.lin_value.weight, w["A"])):
+                    call("ctan_pack_bf16", ptr(src), D, D, D, D, bp + 2 * i * D * D)
+                if self.use_tc_enc:
+                    call("ctan_pack_bf16", ptr(g.enc_x.weight), D, D, D + Fn, D, w["Wenc_bf"].data_ptr())
+                if self.use_tc_ro:
+                    call("ctan_pack_bf16", ptr(r.lin_src.weight), Hd, D, D, D, w["Wro_bf"].data_ptr())
+                    call("ctan_pack_bf16", ptr(r.lin_dst.weight), Hd, D, D, D, w["Wro_bf"].data_ptr() + 2 * Hd * D)
+                if self.use_tc_ep:
+                    call("ctan_pack_bf16", ptr(ph.lin_edge.weight), D, self.Fe + self.T, self.Fe + self.T, self.Kep,
+                         w["Wep_bf"].data_ptr())
 
     def refresh_weights(self):
         """Force the weight-only operands to be re-formed at the next run() (after writing weights behind torch's back)."""

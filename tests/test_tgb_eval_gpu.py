@@ -201,3 +201,41 @@ def test_weight_change_between_calls_is_seen(small_stream):
             eng.run(1)
         res.append(eng.scores().clone())
     assert torch.equal(res[0], res[1])
+
+
+def test_bf16_mode_scores_within_1e2(small_stream, monkeypatch):
+    """The 1e-2 path (BF16 tensor-core contractions, CTAN_TC_MODE=2) against the fp32-parity path (3xTF32) on the same
+    state: scores within 1e-2 of the score scale, identical neighbour tables and last_update, MRR close."""
+    from ctan_b200 import _lib
+    from ctan_b200.models import CTAN_tgb, LastNeighborLoader
+    from ctan_b200.tgb_eval import TGBEvalEngine
+    st = small_stream
+    dev = torch.device("cuda:0")
+    B, S, n_neg, D = 50, 8, 20, 128
+    neg = _neg_table(st, n_neg)
+    kw = dict(num_nodes=st["num_nodes"], edge_dim=st["msg"].size(1), memory_dim=D, time_dim=8, node_dim=1, num_iters=1,
+              epsilon=0.5, gamma=0.1, mean_delta_t=np.float64(1234.5), std_delta_t=np.float64(4567.8))
+    outs = []
+    for mode in (0, 2):
+        monkeypatch.setattr(_lib, "TC_MODE", mode)
+        torch.manual_seed(0)
+        mm = CTAN_tgb(**kw).to(dev)
+        ld = LastNeighborLoader(st["num_nodes"], S, device=dev)
+        g = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in st.items()}
+        g["neg"] = neg.to(dev)
+        eng = TGBEvalEngine(mm, ld, g, batch_size=B, n_neg=n_neg)
+        assert eng.tc_mode == mode
+        eng.warmup()
+        for s in range(0, 400, B):
+            ld.insert(g["src"][s:s + B], g["dst"][s:s + B])
+        mm.memory.memory.copy_(torch.randn(mm.memory.memory.shape, generator=torch.Generator().manual_seed(3)).to(dev) * 0.1)
+        eng.set_cursor(400)
+        eng.run(4)
+        eng.check()
+        outs.append((eng.scores().clone(), eng.mrr(), mm.memory.last_update.clone(), ld.e_id.clone(), mm.memory.memory.clone()))
+    (s0, m0, lu0, e0, mem0), (s2, m2, lu2, e2, mem2) = outs
+    scale = float(s0.abs().max())
+    assert 0 < float((s2 - s0).abs().max()) < 1e-2 * scale + 1e-3
+    assert torch.equal(lu0, lu2) and torch.equal(e0, e2)
+    assert float((mem2 - mem0).abs().max()) < 1e-2 * float(mem0.abs().max())
+    assert abs(m0 - m2) < 0.05
