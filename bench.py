@@ -91,12 +91,12 @@ class ClockSampler:
         return out
 
 
-def make_workload(n_events, seed=0):
+def make_workload(n_events, seed=0, shape="wiki"):
     import ctan_b200  # noqa: F401
     from ctan_b200 import synth
-    st = synth.make_stream("wiki", n_events=n_events, seed=seed)
+    st = synth.make_stream(shape, n_events=n_events, seed=seed)
     st["neg"] = synth.draw_negatives(st)[:, 0]
-    n_train = int(0.7 * n_events)
+    n_train = int(0.7 * st["src"].numel())
     mean, std = synth.delta_t_stats(st, min(n_train, 20000))
     return st, mean, std
 
@@ -108,57 +108,54 @@ def model_kwargs(st, K, mean, std, cfg=WIKI):
 
 
 # ------------------------------------------------------------------------------------------ baselines
-def dropin_train_rate(st, K, mean, std, device, n_steps, warmup):
-    """events/sec of OUR modules driven through the reference API by the reference's own loop body, written out here
-    (train_link.py:237-282: unique -> loader(n_id) x K -> helper[n_id] = arange -> model(...) -> BCE on pos/neg ->
-    update + insert -> backward -> torch.optim.Adam): what a user gets by only swapping the imports."""
-    import types
-    from ctan_b200.models import CTAN, LastNeighborLoader
-    cfg = WIKI
-    torch.manual_seed(0)
-    model = CTAN(**model_kwargs(st, K, mean, std)).to(device)
-    loader = LastNeighborLoader(st["num_nodes"], cfg["S"], device=device)
-    helper = torch.zeros(st["num_nodes"], dtype=torch.long, device=device)
-    opt = torch.optim.Adam(model.parameters(), lr=cfg["lr"])
-    crit = torch.nn.BCEWithLogitsLoss()
-    g = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in st.items()}
+def reference_train_rate(st, K, mean, std, device, n_steps, warmup, threads=None, ours=False, cfg=None):
+    """events/sec of the reference's OWN `train_link.train` (train_link.py:287-345), imported UNMODIFIED through
+    oracle/ref_loops.py (PyG operators from oracle/pyg_shim.py; the files come from /root/reference or its git-ignored
+    mirror baseline/_ref/), on `device`, fed the same pre-drawn negatives as every other implementation.  The loop
+    function is called once on W+K batches; a timestamping loader wrapper isolates the last K.
+    ours=True: the same call with ctan_b200.models swapped in for the reference's classes -- what a user gets from
+    the two-line import change of INTEGRATION.md.  Returns (events/s, ms/step, kind)."""
+    from oracle import ref_loops
+    cfg = cfg or WIKI
     B = cfg["B"]
+    if not ref_loops.available():
+        if ours:
+            raise RuntimeError("baseline/_ref/ is missing: run `python __graft_entry__.py build` where /root/reference exists")
+        v, ms = oracle_train_rate(st, K, mean, std, device, n_steps, warmup, threads, cfg)
+        return v, ms, "port"
+    R = ref_loops.load()
+    if threads:
+        torch.set_num_threads(threads)
+    n = (warmup + n_steps) * B
+    data = R.TemporalData(src=st["src"][:n].to(device), dst=st["dst"][:n].to(device), t=st["t"][:n].to(device),
+                          msg=st["msg"][:n].to(device))
+    data.x = st["x"].to(device)
+    torch.manual_seed(0)
+    if ours:
+        from ctan_b200.models import CTAN, LastNeighborLoader
+        model = CTAN(**model_kwargs(st, K, mean, std, cfg)).to(device)
+        loader = LastNeighborLoader(st["num_nodes"], cfg["S"], device=device)
+    else:
+        model = R.ns.CTAN(**model_kwargs(st, K, mean, std, cfg)).to(device)
+        loader = R.ns.LastNeighborLoader(st["num_nodes"], size=cfg["S"], device=device)
+    helper = torch.empty(st["num_nodes"], dtype=torch.long, device=device)
+    opt = torch.optim.Adam(model.parameters(), lr=cfg["lr"])
+    sync = torch.cuda.synchronize if str(device) != "cpu" else None
+    tl = ref_loops.TimedLoader(R.TemporalDataLoader(data, batch_size=B), skip=warmup, sync=sync)
+    R.train_link.train(data, model, opt, tl, torch.nn.BCEWithLogitsLoss(), loader, helper,
+                       train_neg_sampler=ref_loops.FixedNegatives(st["neg"].view(-1)), device=device)
+    return tl.n_timed * B / tl.seconds, tl.seconds / tl.n_timed * 1e3, "reference"
 
-    def step(it):
-        lo, hi = it * B, (it + 1) * B
-        src, dst, t, msg, neg = g["src"][lo:hi], g["dst"][lo:hi], g["t"][lo:hi], g["msg"][lo:hi], g["neg"][lo:hi]
-        opt.zero_grad()
-        n_id = torch.cat([src, dst, neg]).unique()
-        for _ in range(model.num_gnn_layers):
-            n_id, edge_index, e_id = loader(n_id)
-        helper[n_id] = torch.arange(n_id.size(0), device=device)
-        batch = types.SimpleNamespace(src=src, dst=dst, neg_dst=neg, x=g.get("x"))
-        pos, ngo, se, de = model(batch, n_id, g["msg"][e_id], g["t"][e_id], edge_index, helper)
-        loss = crit(pos, torch.ones_like(pos)) + crit(ngo, torch.zeros_like(ngo))
-        model.update(src, dst, t, msg, se, de)
-        loader.insert(src, dst)
-        loss.backward()
-        opt.step()
-        model.detach_memory()
-    for it in range(warmup):
-        step(it)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for it in range(warmup, warmup + n_steps):
-        step(it)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    return n_steps * B / dt, dt / n_steps * 1e3
 
-
-def oracle_train_rate(st, K, mean, std, device, n_steps, warmup, threads=None):
-    """events/sec of the restated reference training loop (oracle port; BASELINE legs only) on `device`."""
+def oracle_train_rate(st, K, mean, std, device, n_steps, warmup, threads=None, cfg=None):
+    """events/sec of the restated reference training loop (oracle port; used only when the reference's own files are
+    not available on the box) on `device`."""
     from oracle import ctan_oracle as O
     if threads:
         torch.set_num_threads(threads)
-    cfg = WIKI
+    cfg = cfg or WIKI
     torch.manual_seed(0)
-    om = O.OracleCTAN(**model_kwargs(st, K, mean, std)).to(device)
+    om = O.OracleCTAN(**model_kwargs(st, K, mean, std, cfg)).to(device)
     ld = O.TorchNeighborLoader(st["num_nodes"], cfg["S"], device=device)
     h = torch.zeros(st["num_nodes"], dtype=torch.long, device=device)
     opt = torch.optim.Adam(om.parameters(), lr=cfg["lr"])
@@ -180,11 +177,11 @@ def oracle_train_rate(st, K, mean, std, device, n_steps, warmup, threads=None):
 
 
 # ------------------------------------------------------------------------------------------ ours, N=1
-def build_engine(st, K, mean, std, dev, host_staged=False):
+def build_engine(st, K, mean, std, dev, host_staged=False, cfg=None):
     import ctan_b200  # noqa: F401
     from ctan_b200.engine import StepEngine
     from ctan_b200.models import CTAN, LastNeighborLoader
-    cfg = WIKI
+    cfg = cfg or WIKI
     torch.manual_seed(0)
     model = CTAN(**model_kwargs(st, K, mean, std)).to(dev)
     loader = LastNeighborLoader(st["num_nodes"], cfg["S"], device=dev)
@@ -333,6 +330,92 @@ def run_e2e(st, K, mean, std, dev, n_steps, warmup):
     return n_steps * B / dt, h2d, 4, last
 
 
+def other_configs(dev, W, flush):
+    """Short engine runs on the other single-GPU BASELINE.json shapes: C3 (Reddit-shaped, 10 984 nodes / 672 447
+    events) and C2 with K=3.  Same per-step CUDA-event timing with the L2 flush."""
+    res = {}
+    B = WIKI["B"]
+    for name, shape, K in (("reddit_K1", "reddit", 1), ("wiki_K3", "wiki", 3), ("wiki_K5", "wiki", 5)):
+        n_steps = 100
+        st, mean, std = make_workload(None if shape == "reddit" else 157474, shape=shape)
+        eng = build_engine(st, K, mean, std, dev)
+        eng.run(W, train=True)
+        torch.cuda.synchronize()
+        tr = sum(time_steps(eng, n_steps, True, flush))
+        eng.check()
+        eng.reset()
+        eng.run(W, train=False)
+        inf = sum(time_steps(eng, n_steps, False, flush))
+        eng.check()
+        c = eng.w["counts"].cpu().tolist()
+        res[name] = {"train_events_per_sec": n_steps * B / (tr * 1e-3), "infer_events_per_sec": n_steps * B / (inf * 1e-3),
+                     "train_ms_per_step": tr / n_steps, "steps": n_steps, "N": c[0], "E": c[1],
+                     "events_in_stream": int(st["src"].numel()), "nodes": int(st["num_nodes"])}
+        del eng, st
+        torch.cuda.empty_cache()
+    return res
+
+
+def dropin_engine_rate(st, K, mean, std, dev, n_steps):
+    """events/sec of `ctan_b200.train_link.train` -- the reference's loop SIGNATURE (train_link.py:287) on the engine:
+    same arguments, same return value (per-batch losses), one call."""
+    from ctan_b200 import train_link as TL
+    from ctan_b200.models import CTAN, LastNeighborLoader
+    from oracle import ref_loops
+    cfg = WIKI
+    B = cfg["B"]
+    n = n_steps * B
+    torch.manual_seed(0)
+    model = CTAN(**model_kwargs(st, K, mean, std)).to(dev)
+    loader = LastNeighborLoader(st["num_nodes"], cfg["S"], device=dev)
+    helper = torch.empty(st["num_nodes"], dtype=torch.long, device=dev)
+    opt = torch.optim.Adam(model.parameters(), lr=cfg["lr"])
+    data = TL.TemporalData(src=st["src"][:n].to(dev), dst=st["dst"][:n].to(dev), t=st["t"][:n].to(dev),
+                           msg=st["msg"][:n].to(dev))
+    data.x = st["x"].to(dev)
+    tl = TL.TemporalDataLoader(data, batch_size=B)
+    sampler = ref_loops.FixedNegatives(st["neg"].view(-1))
+    crit = torch.nn.BCEWithLogitsLoss()
+    TL.train(data, model, opt, tl, crit, loader, helper, train_neg_sampler=sampler, device=dev)   # builds + warms the engine
+    sampler.reset()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    losses = TL.train(data, model, opt, tl, crit, loader, helper, train_neg_sampler=sampler, device=dev)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "events/s", "ms_per_step": dt / n_steps * 1e3, "batches": n_steps,
+            "last_loss": float(losses[-1]),
+            "what": "ctan_b200.train_link.train(data, model, optimizer, train_loader, criterion, neighbor_loader, helper, "
+                    "train_neg_sampler, device): the reference's signature and return value, StepEngine underneath; "
+                    "wall clock of one whole call (one epoch of the sample), negatives drawn by the sampler per batch"}
+
+
+def pick_metric(args, world):
+    """Which of BASELINE.json's two metrics is this run's `value`?
+    * train events/sec (configs[1], one B200): the headline of a single-GPU run -- the training step does not shard.
+    * TGB-eval queries/sec (configs[4]): the metric that scales over GPUs.  It is the `value` of every run of a SCALING
+      series -- N > 1, any run under torchrun, and also the N=1 point taken on a multi-GPU box -- so that the 1/2/4/8
+      curve is ONE metric; each line carries the other metric as an extra key.  `--metric` overrides."""
+    if args.metric != "auto":
+        return args.metric
+    if world > 1 or args.gpus > 1 or "WORLD_SIZE" in os.environ:
+        return "tgb_eval"
+    try:
+        if torch.cuda.device_count() > 1 or _visible_gpus() > 1:
+            return "tgb_eval"
+    except Exception:
+        pass
+    return "train"
+
+
+def _visible_gpus():
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=20).stdout
+        return sum(1 for ln in out.splitlines() if ln.startswith("GPU "))
+    except Exception:
+        return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -340,6 +423,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--iters", type=int, default=1, help="CTAN num_iters (K)")
+    ap.add_argument("--metric", default="auto", choices=["auto", "train", "tgb_eval"])
     ap.add_argument("--no-baselines", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -347,34 +431,41 @@ def main():
     W = max(args.warmup, 3)
     K = args.iters
     B = WIKI["B"]
+    metric = pick_metric(args, world)
     cfg_desc = {"workload": "wiki-shaped synthetic link prediction: 9227 nodes, 157474 events, 172-d msgs, batch 200; "
                             f"CTAN D=128 T=16 S=5 K={K} H=64, 1 negative/positive, full train step incl. Adam",
-                "l2": "flushed between timed steps (256 MiB write), per-step CUDA events summed"}
+                "l2": "flushed between timed steps (256 MiB write), per-step CUDA events summed",
+                "metric_rule": "single-GPU box: train events/s (this line); scaling series (multi-GPU box, any N): "
+                               "TGB-eval queries/s, so the N=1 point of a scaling run differs from this line BY DESIGN"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        if world > 1 or args.gpus > 1:                  # the multi-GPU metric is TGB evaluation: time the same on the CPU
+        if metric == "tgb_eval":                        # the scaling metric is TGB evaluation: time the same on the CPU
             from bench_tgb import run_tgb_eval_reference
             run_tgb_eval_reference(args)
             return
-        n_steps = min(args.steps, 300)
-        st, mean, std = make_workload((W + n_steps + 2) * B)
+        n_steps = args.steps
+        st, mean, std = make_workload(max(157474, (W + n_steps + 64) * B))
+        if st["src"].numel() != 157474:
+            cfg_desc["workload"] += f" (stream lengthened to {st['src'].numel()} events to fit --steps)"
         cores = os.cpu_count() or 1
-        v, ms = oracle_train_rate(st, K, mean, std, "cpu", n_steps, W, threads=cores)
+        v, ms, kind = reference_train_rate(st, K, mean, std, "cpu", n_steps, W, threads=cores)
+        what = ("the reference's own train_link.train (train_link.py:287-345) imported unmodified, PyG operators from "
+                "oracle/pyg_shim.py" if kind == "reference" else "oracle port of train_link.py:287-345")
         print(json.dumps({"impl": "reference", "metric": "train_events_per_sec", "value": v, "unit": "events/s",
                           "n_gpus": args.gpus, "steps": n_steps, "warmup": W, "ms_per_step": ms,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                           "data": "synthetic", "config": cfg_desc,
-                          "cpu_baseline": {"value": v, "unit": "events/s", "cores": cores, "kind": "port",
+                          "cpu_baseline": {"value": v, "unit": "events/s", "cores": cores, "kind": kind,
                                            "sample": f"{n_steps} consecutive 200-event training batches of the same "
-                                                     "stream after warm-up (oracle port of train_link.py:237-282)"},
+                                                     f"stream after {W} warm-up batches ({what})"},
                           "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
-    if world > 1 or args.gpus > 1:
-        from bench_tgb import run_tgb_eval_bench        # multi-GPU path: sharded TGB evaluation
-        run_tgb_eval_bench(args, rank, world)
+    if metric == "tgb_eval":
+        from bench_tgb import run_tgb_eval_bench        # scaling series: sharded TGB evaluation
+        run_tgb_eval_bench(args, rank, world, extras=not args.no_baselines)
         return
 
     dev = torch.device("cuda:0")
@@ -503,25 +594,43 @@ def main():
                          "loss while step i+1 runs (every loss is read, one step behind)"}
 
     if not args.no_baselines:
-        gv, gms = oracle_train_rate(st, K, mean, std, "cuda:0", 100, 10)
-        out["torch_gpu_baseline"] = {"value": gv, "unit": "events/s", "ms_per_step": gms,
-                                     "what": "restated reference loop, eager PyTorch ops on the same B200 (fp32)"}
-        dv, dms = dropin_train_rate(st, K, mean, std, "cuda:0", 200, 20)
-        out["drop_in_api"] = {"value": dv, "unit": "events/s", "ms_per_step": dms,
-                              "what": "the reference's loop body unchanged (train_link.py:237-282, torch.optim.Adam, one "
-                                      "host sync per loader call) on ctan_b200.models through the C-ABI kernels"}
-        cores = os.cpu_count() or 1
-        cv, cms = oracle_train_rate(st, K, mean, std, "cpu", 120, 5, threads=cores)
-        out["cpu_baseline"] = {"value": cv, "unit": "events/s", "cores": cores, "kind": "port",
-                               "sample": "120 consecutive 200-event training batches of the same stream (oracle port)"}
-        # single-GPU point of the TGB-eval scaling curve (the N>1 runs report this metric as `value`)
-        import types
-        from bench_tgb import run_tgb_eval_bench
         del eng
         torch.cuda.empty_cache()
-        r = run_tgb_eval_bench(types.SimpleNamespace(steps=min(args.steps, 100), warmup=5), 0, 1, quiet=True)
+        # ---- other BASELINE.json shapes of the same path, short runs (extra keys; same engine, same timing rule)
+        out["other_configs"] = other_configs(dev, W, flush)
+        # ---- the GPU-PyTorch baseline north_star's ">= 20x" is quoted against: the reference's own loop on this B200
+        gst, gmean, gstd = (st, mean, std) if st["src"].numel() >= 520 * B else make_workload(520 * B)
+        gv, gms, gkind = reference_train_rate(gst, K, gmean, gstd, "cuda:0", 500, 20)
+        out["torch_gpu_baseline"] = {"value": gv, "unit": "events/s", "ms_per_step": gms, "kind": gkind, "batches": 500,
+                                     "what": "the reference's own train_link.train (unmodified, PyG operators from the "
+                                             "shim) in eager PyTorch on the same B200, fp32, 500 batches after 20"
+                                             if gkind == "reference" else "oracle port, eager PyTorch on the same B200"}
+        out["speedup_vs_torch_gpu"] = {"device_timed": value / gv, "e2e": e2e_v / gv}
+        try:
+            dv, dms, _ = reference_train_rate(gst, K, gmean, gstd, "cuda:0", 300, 20, ours=True)
+            out["drop_in_api"] = {"value": dv, "unit": "events/s", "ms_per_step": dms,
+                                  "what": "the reference's own train_link.train, UNMODIFIED, on ctan_b200.models (CTAN + "
+                                          "LastNeighborLoader swapped in, torch.optim.Adam, loss.item() per step)"}
+        except RuntimeError as e:
+            out["drop_in_api"] = {"unavailable": str(e)}
+        try:
+            out["drop_in_engine_loop"] = dropin_engine_rate(gst, K, gmean, gstd, dev, 300)
+        except Exception as e:                                   # pragma: no cover
+            out["drop_in_engine_loop"] = {"unavailable": f"{type(e).__name__}: {e}"}
+        cores = os.cpu_count() or 1
+        cv, cms, ckind = reference_train_rate(st, K, mean, std, "cpu", 120, 5, threads=cores)
+        out["cpu_baseline"] = {"value": cv, "unit": "events/s", "cores": cores, "kind": ckind,
+                               "sample": "120 consecutive 200-event training batches of the same stream after 5 warm-up "
+                                         "batches (the reference's own train_link.train)" if ckind == "reference" else
+                                         "120 consecutive 200-event training batches of the same stream (oracle port)"}
+        # single-GPU point of the TGB-eval scaling curve (scaling runs report this metric as `value`)
+        import types
+        from bench_tgb import run_tgb_eval_bench
+        torch.cuda.empty_cache()
+        r = run_tgb_eval_bench(types.SimpleNamespace(steps=max(args.steps, 100), warmup=W, gpus=1), 0, 1, quiet=True,
+                               extras=False)
         out["tgb_eval"] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "mrr", "rank0_subgraph", "e2e",
-                                             "launches_per_step")}
+                                             "launches_per_step", "steps")}
     print(json.dumps(out))
 
 

@@ -78,7 +78,9 @@ SIGNATURES.update({
     # step.cu
     "ctan_stage_batch": [P, P, P, P, I, I, P, I, P, P, P, P, P, P, P, I, P],
     "ctan_bce_loss": [P, I, I, P, P, I, P],
-    "ctan_adam_step": [P, P, P, P, I, F, F, F, F, F, L, P],
+    "ctan_adam_step": [P, P, P, P, I, F, F, F, F, F, L, P, P],
+    "ctan_loss_generic": [P, I, I, I, P, F, P, P, I, P],
+    "ctan_record_rows": [P, I, P, I, P],
     "ctan_mrr": [P, P, I, I, P],
     "ctan_stage_eval": [P, P, P, P, I, I, I, I, P, P, P, P, P, P, P],
     "ctan_pack_eval": [P, P, P, P, P, I, I, I, P],

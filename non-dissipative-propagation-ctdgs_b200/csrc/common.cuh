@@ -40,7 +40,7 @@ __device__ __forceinline__ void ctan_pdl_begin() {
 }
 // host-side switch (ctan_set_pdl): the engines turn PDL off for the stretches of the step DAG where parallel
 // branches compete for the SMs (early-scheduled dependents would sit on their slots while they wait)
-extern int g_ctan_pdl;
+extern thread_local int g_ctan_pdl;      // per host thread: two engines on two threads do not see each other's choice
 static inline bool ctan_pdl_enabled() {
     static const bool on = [] { const char* e = getenv("CTAN_PDL"); return !(e && e[0] == '0'); }();
     return on && g_ctan_pdl != 0;

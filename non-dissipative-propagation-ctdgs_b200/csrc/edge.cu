@@ -303,6 +303,9 @@ __global__ void hub_list_kernel(const int32_t* __restrict__ rowptr, int N_host, 
 extern "C" int ctan_hub_list(const int32_t* rowptr, int N, const int* N_dev, int32_t* hub_ws, int hub_cap,
                              cudaStream_t stream) {
     if (N <= 0 || !hub_ws || hub_cap <= 0) return 0;
+    // every row of degree > HUB_DEG must fit the list: ctan_edge_fwd's hub_mode 1 skips them all, so a dropped row
+    // would be computed by neither kernel
+    if (hub_cap < (N < HUB_MAX_N ? N : HUB_MAX_N)) return CTAN_ERR_BAD_ARG;
     CTAN_LAUNCH((hub_list_kernel), ctan_grid(N, 256), 256, 0, stream, rowptr, N, N_dev, hub_ws, hub_cap);
     CTAN_CHECK_LAUNCH();
     return 0;
@@ -320,6 +323,7 @@ extern "C" int ctan_edge_fwd(const float* QKVA, const float* EP, const int32_t* 
     if (N <= 0) return 0;
     if (D > 512) return CTAN_ERR_UNSUPPORTED;
     if (hub_ws && hub_cap <= 0) hub_ws = nullptr;
+    if (hub_mode != 0 && (!hub_ws || hub_cap < (N < HUB_MAX_N ? N : HUB_MAX_N))) return CTAN_ERR_BAD_ARG;   // (see ctan_hub_list)
     const int grid = ctan_grid((long long)N * 32, 256);
     const float isd = 1.0f / sqrtf((float)D);
     const int hgrid = 2 * CTAN_SM_COUNT;

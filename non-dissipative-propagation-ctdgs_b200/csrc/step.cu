@@ -28,7 +28,7 @@ __global__ void stage_batch_kernel(const int64_t* __restrict__ src_all, const in
         if (loss_hist) loss_hist[(counters[3] - 1) % hist_cap] = 0.f;   // slot the fused head+loss accumulates into
         // the step number of THIS staged batch, for kernels that run after a later batch may have been staged
         // (prefetched front-end): they read step_out[3] instead of counters[3]
-        if (step_out) step_out[3] = counters[3];
+        if (step_out) { step_out[3] = counters[3]; step_out[1] = cur; }   // [1]: first event of THIS staged batch
         s_off = use_cursor ? cur : 0;                 // 0: the arrays ARE the batch (host-staged buffers)
     }
     __syncthreads();
@@ -106,14 +106,99 @@ extern "C" int ctan_bce_loss(const float* OUT, int n_pos, int n_negs, float* dOU
     return 0;
 }
 
+// Loss + dOUT of the heads that are not the fused binary link head (dense.cu::ctan_head_loss):
+//   mode 1  CrossEntropyLoss, mean over P rows: OUT [P,O] logits, y int64 [.,1] class ids   (train_link.py:708-709, :329)
+//   mode 2  MSELoss  (mean over P*O), y fp32 [.,O]        (utils.py:36 REGRESSION_SCORES, train_link.py:706)
+//   mode 3  L1Loss   (mean over P*O), y fp32 [.,O]
+//   mode 4  BCEWithLogitsLoss with fp32 targets y [.,O], mean over P*O          (train_sequence.py:57)
+// The batch's labels are rows [y_row0, y_row0+P) of the label table, y_row0 = ctr[1] (the staged batch's first event,
+// written by ctan_stage_batch) or 0 when ctr is NULL.  dOUT (optional) is multiplied by `scale` (gradient accumulation
+// over several steps whose losses are averaged).  The loss goes to loss_hist[(ctr[3]-1) % hist_cap].  One CTA.
+__global__ void loss_generic_kernel(const float* __restrict__ OUT, int P, int O, int mode, const void* __restrict__ y,
+                                    float scale, float* __restrict__ dOUT, float* __restrict__ loss_hist, int hist_cap,
+                                    const int64_t* __restrict__ ctr) {
+    ctan_pdl_begin();
+    __shared__ float red[32];
+    const int64_t row0 = ctr ? ctr[1] : 0;
+    float acc = 0.f;
+    if (mode == 1) {
+        const int64_t* yl = reinterpret_cast<const int64_t*>(y) + row0;
+        for (int p = threadIdx.x; p < P; p += blockDim.x) {
+            const float* o = OUT + (size_t)p * O;
+            float mx = -INFINITY;
+            for (int c = 0; c < O; ++c) mx = fmaxf(mx, o[c]);
+            float den = 0.f;
+            for (int c = 0; c < O; ++c) den += expf(o[c] - mx);
+            const int64_t t = yl[p];
+            const float lse = mx + logf(den);
+            acc += (lse - o[t]) / (float)P;
+            if (dOUT)
+                for (int c = 0; c < O; ++c)
+                    dOUT[(size_t)p * O + c] = scale * (expf(o[c] - lse) - (c == t ? 1.f : 0.f)) / (float)P;
+        }
+    } else {
+        const float* yf = reinterpret_cast<const float*>(y) + row0 * O;
+        const int n = P * O;
+        const float inv = 1.f / (float)n;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const float x = OUT[i], t = yf[i];
+            float l, d;
+            if (mode == 2) { l = (x - t) * (x - t); d = 2.f * (x - t); }
+            else if (mode == 3) { l = fabsf(x - t); d = x > t ? 1.f : (x < t ? -1.f : 0.f); }
+            else { l = fmaxf(x, 0.f) - x * t + log1pf(expf(-fabsf(x))); d = 1.f / (1.f + expf(-x)) - t; }
+            acc += l * inv;
+            if (dOUT) dOUT[i] = scale * d * inv;
+        }
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) {
+            long long slot = ctr ? (long long)ctr[3] - 1 : 0;
+            if (slot < 0) slot = 0;
+            loss_hist[slot % hist_cap] = v;
+        }
+    }
+}
+
+extern "C" int ctan_loss_generic(const float* OUT, int P, int O, int mode, const void* y, float scale, float* dOUT,
+                                 float* loss_hist, int hist_cap, const int64_t* ctr, cudaStream_t stream) {
+    if (P <= 0 || O <= 0 || mode < 1 || mode > 4 || !y || hist_cap <= 0) return CTAN_ERR_BAD_ARG;
+    CTAN_LAUNCH((loss_generic_kernel), 1, 256, 0, stream, OUT, P, O, mode, y, scale, dOUT, loss_hist, hist_cap, ctr);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+// hist[((ctr[3]-1) % cap) * n + i] = src[i]: keeps every step's scores for the callers that need them after the run
+// (eval: train_link.py:383-395 collects y_pred of every batch).
+__global__ void record_rows_kernel(const float* __restrict__ src, int n, float* __restrict__ hist, int cap,
+                                   const int64_t* __restrict__ ctr) {
+    ctan_pdl_begin();
+    long long slot = ctr ? (long long)ctr[3] - 1 : 0;
+    if (slot < 0) slot = 0;
+    float* dst = hist + (size_t)(slot % cap) * n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+extern "C" int ctan_record_rows(const float* src, int n, float* hist, int cap, const int64_t* ctr, cudaStream_t stream) {
+    if (n <= 0 || cap <= 0) return CTAN_ERR_BAD_ARG;
+    CTAN_LAUNCH((record_rows_kernel), ctan_grid(n, 256, 1), 256, 0, stream, src, n, hist, cap, ctr);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
 // torch.optim.Adam (amsgrad=False, maximize=False) on a flat parameter vector.  The bias corrections
 // need double-precision pow(): one thread per block computes them (FP64 is slow on this part, and every
 // thread doing it cost more than the update itself).
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int n, float lr, float beta1, float beta2, float eps, float wd,
-                            int64_t step_host, const int64_t* __restrict__ counters) {
+                            int64_t step_host, const int64_t* __restrict__ counters, const float* __restrict__ hyper) {
     ctan_pdl_begin();
     __shared__ float s_step_size, s_bc2_sqrt;
+    // hyper (device, optional): [lr, beta1, beta2, eps, weight_decay] -- lets a captured graph follow an lr scheduler
+    if (hyper) { lr = hyper[0]; beta1 = hyper[1]; beta2 = hyper[2]; eps = hyper[3]; wd = hyper[4]; }
     if (threadIdx.x == 0) {
         const int64_t step = counters ? counters[2] + 1 : step_host;
         const double bc1 = 1.0 - pow((double)beta1, (double)step);
@@ -150,9 +235,10 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }
 
 extern "C" int ctan_adam_step(float* p, const float* g, float* m, float* v, int n, float lr, float beta1, float beta2,
-                              float eps, float wd, int64_t step, const int64_t* counters, cudaStream_t stream) {
+                              float eps, float wd, int64_t step, const int64_t* counters, const float* hyper,
+                              cudaStream_t stream) {
     if (n <= 0) return 0;
-    CTAN_LAUNCH((adam_kernel), ctan_grid(n, 1024, 1), 1024, 0, stream, p, g, m, v, n, lr, beta1, beta2, eps, wd, step, counters);
+    CTAN_LAUNCH((adam_kernel), ctan_grid(n, 1024, 1), 1024, 0, stream, p, g, m, v, n, lr, beta1, beta2, eps, wd, step, counters, hyper);
     CTAN_CHECK_LAUNCH();
     return 0;
 }
@@ -373,9 +459,10 @@ extern "C" int ctan_accum_col(const float* rows, int R, int ld, int col, double*
     return 0;
 }
 
-// Switch programmatic dependent launch on/off for the launches that follow on this host thread (common.cuh).  Host
-// state only: under stream capture the choice is baked into the captured edges.
-int g_ctan_pdl = 1;
+// Switch programmatic dependent launch on/off for the launches that follow on THIS host thread (common.cuh).  Host
+// state only, thread-local (no cross-thread coupling); under stream capture the choice is baked into the captured
+// edges.  Callers restore the default (on) in a finally block.
+thread_local int g_ctan_pdl = 1;
 extern "C" int ctan_set_pdl(int on, cudaStream_t stream) {
     (void)stream;
     g_ctan_pdl = on;

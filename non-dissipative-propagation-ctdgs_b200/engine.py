@@ -25,20 +25,36 @@ from .neighbor_loader import LastNeighborLoader
 
 
 def _param_list(model):
+    """The 19 parameter slots the step uses, in the engine's fixed order (None where the head has no such tensor:
+    SequencePredictor has a single input projection `lin`, models/predictors.py:37-48)."""
     g, a, r = model.gnn, model.gnn.aconv, model.readout
     p = a.phi
+    if model.predict_dst:
+        head = [None, None, r.lin.weight, r.lin.bias, r.lin_final.weight, r.lin_final.bias]
+    else:
+        head = [r.lin_src.weight, r.lin_src.bias, r.lin_dst.weight, r.lin_dst.bias, r.lin_final.weight, r.lin_final.bias]
     return [g.enc_x.weight, g.enc_x.bias, p.lin_query.weight, p.lin_query.bias, p.lin_key.weight, p.lin_key.bias,
             p.lin_value.weight, p.lin_value.bias, p.lin_edge.weight, a.W, a.bias, g.time_enc.lin.weight,
-            g.time_enc.lin.bias, r.lin_src.weight, r.lin_src.bias, r.lin_dst.weight, r.lin_dst.bias,
-            r.lin_final.weight, r.lin_final.bias]
+            g.time_enc.lin.bias] + head
+
+
+LOSS_MODES = {"CrossEntropyLoss": 1, "MSELoss": 2, "L1Loss": 3, "BCEWithLogitsLoss": 4}
 
 
 class StepEngine:
     def __init__(self, model: CTAN, loader: LastNeighborLoader, stream: dict, batch_size: int, n_neg: int = 1,
                  lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
-                 use_graph: bool = True, hist_cap: int = 1 << 16, host_staged: bool = False):
-        if model.predict_dst:
-            raise NotImplementedError("StepEngine covers the link-prediction heads")
+                 use_graph: bool = True, hist_cap: int = 1 << 16, host_staged: bool = False, criterion=None,
+                 out_cap: int = 0, neg_base: int = 0, y_base: int = 0):
+        """Heads (chosen from the model and `n_neg`):
+          * link head with negatives (n_neg >= 1): pairs (src,dst) + (src,neg), fused BCE on pos/neg
+            (train_link.py:269-270, 335-336) -- `criterion` must be None or BCEWithLogitsLoss(mean);
+          * labelled head (n_neg == 0): pairs (src,dst) scored by LinkPredictor (readout_out >= 1) or, with
+            predict_dst, z[dst] by SequencePredictor; loss = criterion(out, y) with y = stream["y"] rows of the batch:
+            CrossEntropyLoss (int64 class ids; multiclass, train_link.py:708-709), MSELoss / L1Loss (regression,
+            :706), BCEWithLogitsLoss (fp32 targets; train_sequence.py:57).
+        out_cap > 0 keeps the scores of the last out_cap steps (`outputs(n)`); neg_base / y_base: event index of row 0
+        of stream["neg"] / stream["y"] when those tables cover only a suffix of the event stream."""
         dev = model.memory.memory.device
         if dev.type != "cuda":
             raise _lib.CtanLibraryError("StepEngine needs the model on a CUDA device")
@@ -46,9 +62,14 @@ class StepEngine:
         self.model, self.loader, self.dev = model, loader, dev
         self.tgb = isinstance(model, CTAN_tgb)
         self.B, self.n_neg = int(batch_size), int(n_neg)
+        self.predict_dst = bool(model.predict_dst)
+        self.labelled = self.n_neg == 0
+        if self.predict_dst and not self.labelled:
+            raise ValueError("predict_dst heads take no negatives (n_neg must be 0)")
         self.lr, self.betas = float(lr), (float(betas[0]), float(betas[1]))
         self.eps, self.wd = float(eps), float(weight_decay)
         self.use_graph, self.hist_cap, self.host_staged = use_graph, int(hist_cap), host_staged
+        self.out_cap, self.neg_base, self.y_base = int(out_cap), int(neg_base), int(y_base)
         self.K = model.num_gnn_layers
         self.D = model.memory.memory_dim
         self.S = loader.size
@@ -57,6 +78,21 @@ class StepEngine:
         st = stream
         self.n_events = int(st["src"].numel())
         self.Fe = int(st["msg"].size(1))
+        cname = type(criterion).__name__ if criterion is not None else None
+        if self.labelled:
+            if cname not in LOSS_MODES:
+                raise NotImplementedError(f"labelled head: criterion must be one of {sorted(LOSS_MODES)}, got {cname}")
+            if getattr(criterion, "reduction", "mean") != "mean" or getattr(criterion, "weight", None) is not None \
+                    or getattr(criterion, "pos_weight", None) is not None or getattr(criterion, "label_smoothing", 0.0):
+                raise NotImplementedError("labelled head: plain mean-reduced criteria only")
+            self.loss_mode = LOSS_MODES[cname]
+            if host_staged:
+                raise NotImplementedError("host_staged mode covers the link head with negatives")
+        else:
+            if criterion is not None and (cname != "BCEWithLogitsLoss" or criterion.reduction != "mean"
+                                          or criterion.pos_weight is not None or criterion.weight is not None):
+                raise NotImplementedError("link head: criterion must be BCEWithLogitsLoss() (mean)")
+            self.loss_mode = 0
         if host_staged:
             # batches arrive from the host: fixed device staging buffers + event tables filled as they come
             # two staging sets: the copy of batch j+1 (on a copy stream) overlaps the step of batch j
@@ -75,23 +111,38 @@ class StepEngine:
             self.msg = torch.zeros((self.n_events, self.Fe), device=dev)
             self._host_cursor = 0
         else:
-            for k in ("src", "dst", "t", "msg", "neg"):
+            for k in ("src", "dst", "t", "msg") + (() if self.labelled else ("neg",)):
                 if not st[k].is_cuda:
                     raise _lib.CtanLibraryError(f"stream['{k}'] must be device resident")
             self.src, self.dst, self.t = st["src"].contiguous(), st["dst"].contiguous(), st["t"].contiguous()
             self.t_tab = self.t
             self.msg = st["msg"].float().contiguous()
-            self.neg = st["neg"].contiguous().view(self.n_events, -1)
-            assert self.neg.size(1) == self.n_neg
+            if self.labelled:
+                self.neg = None
+            else:
+                self.neg = st["neg"].contiguous().view(-1, self.n_neg)
         self.x = st.get("x")
         if self.x is not None:
             self.x = (self.x.squeeze(0) if self.x.dim() == 3 else self.x).to(dev).float().contiguous()
         self.Fn = self.x.size(1) if self.x is not None else 0
         self.T = model.gnn.time_enc.lin.bias.numel()
-        self.Hd = model.readout.lin_src.weight.size(0)
-        self.O = model.readout.lin_final.weight.size(0)
-        if self.O != 1:
-            raise NotImplementedError("StepEngine's fused loss is binary (readout_out=1)")
+        r = model.readout
+        self.Hd = (r.lin if self.predict_dst else r.lin_src).weight.size(0)
+        self.O = r.lin_final.weight.size(0)
+        if not self.labelled and self.O != 1:
+            raise NotImplementedError("the link head with negatives is binary (readout_out=1)")
+        self.y = None
+        if self.labelled:
+            y = st["y"]
+            if not y.is_cuda:
+                raise _lib.CtanLibraryError("stream['y'] must be device resident")
+            if self.loss_mode == 1:
+                self.y = y.reshape(-1).to(torch.long).contiguous()
+            else:
+                self.y = y.reshape(y.size(0), -1).float().contiguous()
+                if self.y.size(1) != self.O:
+                    raise ValueError(f"targets have {self.y.size(1)} columns, the head {self.O}")
+        self.grad_scale = 1.0
         self.P = self.B * (1 + self.n_neg)
         self.n_seeds = self.B * (2 + self.n_neg)
         self.n_cap = min(self.num_nodes, self.n_seeds * (self.S + 1) ** self.K)
@@ -110,9 +161,21 @@ class StepEngine:
 
     # ------------------------------------------------------------------ parameters in one flat buffer
     def _flatten_params(self):
-        plist = _param_list(self.model)
+        self._slots = _param_list(self.model)
+        plist = [p for p in self._slots if p is not None]
+        self._plist = plist
         n = sum(p.numel() for p in plist)
-        self.flat_p = torch.empty(n, device=self.dev)
+        # ONE flat parameter buffer per model, shared by every engine built on it (a second engine must not re-home
+        # the parameters under the first one's feet)
+        shared = self.model.__dict__.get("_ctan_flat")
+        reuse = False
+        if shared is not None and shared.numel() == n and shared.device == self.dev:
+            o, reuse = 0, True
+            for p in plist:
+                reuse = reuse and p.data.data_ptr() == shared.data_ptr() + 4 * o
+                o += p.numel()
+        self.flat_p = shared if reuse else torch.empty(n, device=self.dev)
+        self.model.__dict__["_ctan_flat"] = self.flat_p
         # everything the backward accumulates into lives in ONE buffer so a single memset clears it
         N, D = self.n_cap, self.D
         K = self.K
@@ -133,15 +196,101 @@ class StepEngine:
         self.adam_v = torch.zeros(n, device=self.dev)
         self.p, self.g = [], []
         o = 0
-        for p in plist:
+        for p in self._slots:
+            if p is None:                                  # slot absent in this head (NULL pointer at the C ABI)
+                self.p.append(None)
+                self.g.append(None)
+                continue
             k = p.numel()
-            self.flat_p[o:o + k].copy_(p.data.reshape(-1))
-            p.data = self.flat_p[o:o + k].view(p.shape)
+            if not reuse:
+                self.flat_p[o:o + k].copy_(p.data.reshape(-1))
+                p.data = self.flat_p[o:o + k].view(p.shape)
             p.grad = self.flat_g[o:o + k].view(p.shape)
             self.p.append(p.data)
             self.g.append(p.grad)
             o += k
         self.n_params = n
+        # optimizer hyper-parameters live on the device so that a captured graph follows an lr scheduler
+        self.hyper = torch.tensor([self.lr, self.betas[0], self.betas[1], self.eps, self.wd], device=self.dev)
+        self._opt = None
+        self._opt_steps = 0
+
+    def set_hyper(self, lr=None, betas=None, eps=None, weight_decay=None):
+        if lr is not None:
+            self.lr = float(lr)
+        if betas is not None:
+            self.betas = (float(betas[0]), float(betas[1]))
+        if eps is not None:
+            self.eps = float(eps)
+        if weight_decay is not None:
+            self.wd = float(weight_decay)
+        self.hyper.copy_(torch.tensor([self.lr, self.betas[0], self.betas[1], self.eps, self.wd]))
+
+    # ------------------------------------------------------------------ torch.optim.Adam bridge
+    def attach_optimizer(self, opt):
+        """Make `opt` (torch.optim.Adam over model.parameters()) and the engine share ONE optimizer state: the
+        engine's flat moment buffers become the optimizer's `exp_avg` / `exp_avg_sq` tensors (views), hyper-parameters
+        are read from its param group, and the step count is kept in sync by pull_optimizer() / push_optimizer().
+        So `optimizer.state_dict()` / `load_state_dict()` checkpoint and resume an engine-trained run exactly like
+        the reference does (train_link.py:497-511, 587-603), and `optimizer.step()` on the module path continues the
+        same moments."""
+        if type(opt).__name__ != "Adam":
+            raise NotImplementedError("StepEngine implements torch.optim.Adam")
+        if len(opt.param_groups) != 1:
+            raise NotImplementedError("one parameter group expected (torch.optim.Adam(model.parameters(), ...))")
+        g = opt.param_groups[0]
+        if g.get("amsgrad") or g.get("maximize") or g.get("capturable") or g.get("fused") or g.get("decoupled_weight_decay"):
+            raise NotImplementedError("StepEngine's Adam kernel: amsgrad / maximize / capturable / fused must be off")
+        self._opt = opt
+        o = 0
+        for p in self._plist:
+            k = p.numel()
+            st = opt.state.get(p) or {}
+            if "exp_avg" in st:                              # adopt what the optimizer already holds (resumed run)
+                self.adam_m[o:o + k].copy_(st["exp_avg"].reshape(-1))
+                self.adam_v[o:o + k].copy_(st["exp_avg_sq"].reshape(-1))
+            step = st.get("step", torch.tensor(0.0))
+            opt.state[p] = {"step": step.detach().clone().float().cpu() if torch.is_tensor(step) else torch.tensor(float(step)),
+                            "exp_avg": self.adam_m[o:o + k].view(p.shape),
+                            "exp_avg_sq": self.adam_v[o:o + k].view(p.shape)}
+            o += k
+        self.pull_optimizer()
+
+    def pull_optimizer(self):
+        """optimizer -> engine: hyper-parameters (an lr scheduler may have changed them), step count, and moments that
+        `load_state_dict` may have replaced."""
+        opt = self._opt
+        if opt is None:
+            return
+        g = opt.param_groups[0]
+        self.set_hyper(g["lr"], g["betas"], g["eps"], g["weight_decay"])
+        o, steps = 0, 0
+        for p in self._plist:
+            k = p.numel()
+            st = opt.state.get(p)
+            if st is None or "exp_avg" not in st:
+                opt.state[p] = st = {"step": torch.tensor(0.0), "exp_avg": self.adam_m[o:o + k].view(p.shape),
+                                     "exp_avg_sq": self.adam_v[o:o + k].view(p.shape)}
+            elif st["exp_avg"].data_ptr() != self.adam_m.data_ptr() + 4 * o:     # load_state_dict made new tensors
+                self.adam_m[o:o + k].copy_(st["exp_avg"].reshape(-1))
+                self.adam_v[o:o + k].copy_(st["exp_avg_sq"].reshape(-1))
+                st["exp_avg"] = self.adam_m[o:o + k].view(p.shape)
+                st["exp_avg_sq"] = self.adam_v[o:o + k].view(p.shape)
+            steps = max(steps, int(st["step"]))
+            o += k
+        self._opt_steps = steps
+        self.w["counters"][2] = steps
+
+    def push_optimizer(self):
+        """engine -> optimizer: the step count after run(); the moments are shared storage already."""
+        if self._opt is None:
+            return
+        for p in self._plist:
+            st = self._opt.state[p]
+            if torch.is_tensor(st["step"]):
+                st["step"].fill_(float(self._opt_steps))
+            else:
+                st["step"] = torch.tensor(float(self._opt_steps))
 
     # ------------------------------------------------------------------ workspaces (upper bounds)
     def _alloc(self):
@@ -193,6 +342,7 @@ class StepEngine:
         w["OUT"] = torch.zeros((P, self.O), **f32)
         w["dOUT"] = torch.zeros((P, self.O), **f32)
         w["loss_hist"] = torch.zeros(self.hist_cap, **f32)
+        w["out_hist"] = torch.zeros((self.out_cap, P * self.O), **f32) if self.out_cap else None
         # backward
         w["dHid"] = torch.zeros((P, self.Hd), **f32)
         w["dZ"] = self._dZ
@@ -210,7 +360,12 @@ class StepEngine:
         """Fresh memory + empty graph + cursor at event 0 (train_link.py:226-227)."""
         self.model.reset_memory()
         self.loader.reset_state()
+        # cursor / batch start / staged-step count / tickets restart; counters[2] is the optimizer's step count, which
+        # torch.optim.Adam keeps across epochs (the reference resets only memory and graph, train_link.py:226-227)
+        steps_done = self.w["counters"][2].clone()
         self.w["counters"].zero_()
+        if not reset_optimizer:
+            self.w["counters"][2] = steps_done
         for f in self.fe:
             f["counts"].zero_()
         if self.host_staged:
@@ -220,6 +375,7 @@ class StepEngine:
         if reset_optimizer:
             self.adam_m.zero_()
             self.adam_v.zero_()
+            self._opt_steps = 0
 
     def push_batch(self, src, dst, t, neg, msg):
         """host_staged mode: copy one batch (pinned host tensors) to the device -- the ids/times into the
@@ -293,7 +449,8 @@ class StepEngine:
         N, E = self.n_cap, self.e_cap
         src, dst, t, neg = ((self._stg[par][k] for k in ("src", "dst", "t", "neg")) if self.host_staged
                             else (self.src, self.dst, self.t, self.neg))
-        call("ctan_stage_batch", ptr(src), ptr(dst), ptr(t), ptr(neg), self.n_neg, B,
+        neg_p = None if neg is None else ptr(neg) - (0 if self.host_staged else 8 * self.n_neg * self.neg_base)
+        call("ctan_stage_batch", ptr(src), ptr(dst), ptr(t), neg_p, self.n_neg, B,
              ptr(w["counters"]), 0 if self.host_staged else 1, ptr(f["b_src"]), ptr(f["b_dst"]), ptr(f["b_t"]),
              ptr(f["seeds"]), ptr(f["pair_src"]), ptr(f["pair_dst"]), ptr(w["loss_hist"]), self.hist_cap, ptr(f["ctr"]))
         call("ctan_nbr_lookup", ptr(ld.neighbors), ptr(ld._deg), self.num_nodes, S, ptr(f["seeds"]), self.n_seeds,
@@ -313,9 +470,12 @@ class StepEngine:
 
     def _launch(self, train: bool):
         """One whole step, front-end inline (eager mode, warm-up, timeline scripts)."""
-        self._prep(train)
-        self._frontend(0)
-        self._step(train, 0, False, prep_done=True)
+        try:
+            self._prep(train)
+            self._frontend(0)
+            self._step(train, 0, False, prep_done=True)
+        finally:
+            _lib.lib().ctan_set_pdl(1, None)               # the launch-mode switch is thread-local host state: never leak it
 
     def _prep(self, train: bool):
         """Side branch with no dependence on the batch (weight-only operands, memsets) + the launch mode of the step."""
@@ -401,11 +561,21 @@ class StepEngine:
         xk = w["X"][K] if train else w["X"][K & 1]
         z = w["Z"] if self.final_tanh else xk
         self._z = z
-        call("ctan_readout_fwd", ptr(z), D, ptr(f["pair_src"]), ptr(f["pair_dst"]), ptr(assoc), P, None, Hd, O,
-             Wsrc, bsrc, Wdst, bdst, Wfin, bfin, ptr(w["H"]), None, 1)
-        # head + BCE loss + dOUT + dHid in one launch (the loss slot was cleared by the stage kernel)
-        call("ctan_head_loss", ptr(w["H"]), P, Hd, Wfin, bfin, B, ptr(w["OUT"]), ptr(w["dOUT"]) if train else None,
-             ptr(w["dHid"]) if train else None, ptr(w["loss_hist"]), self.hist_cap, ptr(f["ctr"]))
+        if not self.labelled:
+            call("ctan_readout_fwd", ptr(z), D, ptr(f["pair_src"]), ptr(f["pair_dst"]), ptr(assoc), P, None, Hd, O,
+                 Wsrc, bsrc, Wdst, bdst, Wfin, bfin, ptr(w["H"]), None, 1)
+            # head + BCE loss + dOUT + dHid in one launch (the loss slot was cleared by the stage kernel)
+            call("ctan_head_loss", ptr(w["H"]), P, Hd, Wfin, bfin, B, ptr(w["OUT"]), ptr(w["dOUT"]) if train else None,
+                 ptr(w["dHid"]) if train else None, ptr(w["loss_hist"]), self.hist_cap, ptr(f["ctr"]))
+        else:
+            # labelled heads (multi-class / regression / sequence): hidden + head, then loss(out, y) and dOUT
+            call("ctan_readout_fwd", ptr(z), D, ptr(f["pair_src"]), ptr(f["pair_dst"]), ptr(assoc), P, None, Hd, O,
+                 Wsrc, bsrc, Wdst, bdst, Wfin, bfin, ptr(w["H"]), ptr(w["OUT"]), 1)
+            y_p = self.y.data_ptr() - self.y_base * (8 if self.loss_mode == 1 else 4 * O)
+            call("ctan_loss_generic", ptr(w["OUT"]), P, O, self.loss_mode, y_p, float(self.grad_scale),
+                 ptr(w["dOUT"]) if train else None, ptr(w["loss_hist"]), self.hist_cap, ptr(f["ctr"]))
+        if w["out_hist"] is not None:
+            call("ctan_record_rows", ptr(w["OUT"]), P * O, ptr(w["out_hist"]), self.out_cap, ptr(f["ctr"]))
 
         def state_update():
             # ground-truth state update (train_link.py:276-277)
@@ -427,7 +597,8 @@ class StepEngine:
          gbfin) = (ptr(t) for t in self.g)
         rb_args = (ptr(w["dOUT"]), ptr(w["H"]), ptr(z), D, ptr(f["pair_src"]), ptr(f["pair_dst"]), ptr(assoc), P,
                    None, Hd, O, Wsrc, Wdst, Wfin, ptr(w["dHid"]))
-        call("ctan_readout_bwd", *rb_args, ptr(w["dZ"]), None, None, None, None, None, None, 1)
+        ready = 0 if self.labelled else 1                    # (the fused binary head already produced dHid)
+        call("ctan_readout_bwd", *rb_args, ptr(w["dZ"]), None, None, None, None, None, None, ready)
         with self._fork(2):                                  # side 2: readout weight gradients
             call("ctan_readout_bwd", *rb_args, None, gWsrc, gbsrc, gWdst, gbdst, gWfin, gbfin, 1)
         g = w["dZ"]
@@ -464,7 +635,8 @@ class StepEngine:
         self._join(2)
         self._join(3)
         call("ctan_adam_step", ptr(self.flat_p), ptr(self.flat_g), ptr(self.adam_m), ptr(self.adam_v),
-             self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 0, ptr(w["counters"]))
+             self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 0, ptr(w["counters"]),
+             ptr(self.hyper))
         _lib.lib().ctan_set_pdl(1, None)
 
     # ------------------------------------------------------------------ public stepping API
@@ -475,11 +647,14 @@ class StepEngine:
         key = (bool(train), par, bool(prefetch), bool(inline), bool(early))
         if key not in self._graphs:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=self._main):
-                if inline:
-                    self._prep(train)
-                    self._frontend(par)
-                self._step(train, par, prefetch, prep_done=inline, early=early)
+            try:
+                with torch.cuda.graph(g, stream=self._main):
+                    if inline:
+                        self._prep(train)
+                        self._frontend(par)
+                    self._step(train, par, prefetch, prep_done=inline, early=early)
+            finally:
+                _lib.lib().ctan_set_pdl(1, None)
             self._graphs[key] = g
         return self._graphs[key]
 
@@ -503,6 +678,25 @@ class StepEngine:
         self.flat_p.copy_(keep)
         self.reset(reset_optimizer=True)
         self.w["loss_hist"].zero_()
+        self.capture_all()
+
+    def capture_all(self, train=(True, False)):
+        """Capture every graph variant plan() can return, so that no capture ever lands in a caller's timed window."""
+        if not self.use_graph:
+            return
+        with torch.cuda.device(self.dev):
+            for tr in train:
+                if self.host_staged:
+                    for par in (0, 1):
+                        self._graph(tr, par)
+                elif not self.prefetch:
+                    self._graph(tr)
+                else:
+                    self._graph_frontend(0, with_rel=tr)
+                    for par in (0, 1):
+                        for pf in (True, False):
+                            self._graph(tr, par, pf, inline=False, early=not tr)
+        torch.cuda.synchronize(self.dev)
 
     def plan(self, n_steps: int, train: bool = True):
         """The replay sequence of n_steps steps as a list of callables (one per step; the first also issues the first
@@ -552,6 +746,17 @@ class StepEngine:
             for fn in self.plan(n_steps, train):
                 fn()
         self.loader.cur_e_id += n_steps * self.B
+        if train:
+            self._opt_steps += n_steps
+
+    def outputs(self, n: int) -> torch.Tensor:
+        """[n, P, O] scores of the last n steps (needs out_cap >= n; device tensor, reading synchronises).  Link head:
+        rows [0,B) are the positives, [B, B(1+n_neg)) the negatives grouped by event."""
+        if self.w["out_hist"] is None or n > self.out_cap:
+            raise ValueError("construct the engine with out_cap >= n to keep per-step scores")
+        steps = int(self.w["counters"][3].item())
+        idx = torch.arange(steps - n, steps, device=self.dev) % self.out_cap
+        return self.w["out_hist"][idx].view(n, self.P, self.O)
 
     def losses(self, n: int) -> torch.Tensor:
         """Last n recorded per-step losses (device tensor; reading it synchronises)."""

@@ -164,10 +164,10 @@ class SimpleMemory(torch.nn.Module):
             return
         se = src_emb.detach().float().contiguous()
         de = pos_dst_emb.detach().float().contiguous()
+        sc, dc, tc = src.contiguous(), pos_dst.contiguous(), t.contiguous()     # alive across the launch
         with torch.cuda.device(self.memory.device):
             call("ctan_mem_update", ptr(self.memory), ptr(self.last_update), self.memory_dim,
-                 ptr(src.contiguous(), torch.long), ptr(pos_dst.contiguous(), torch.long),
-                 ptr(t.contiguous(), torch.long), B, ptr(se), ptr(de), 0, None, None)
+                 ptr(sc, torch.long), ptr(dc, torch.long), ptr(tc, torch.long), B, ptr(se), ptr(de), 0, None, None)
 
     def reset_state(self):
         _require_cuda(self.memory, "SimpleMemory.reset_state")

@@ -48,7 +48,9 @@ def exchange_rows(send: torch.Tensor, recv: torch.Tensor, rows: torch.Tensor, B:
 
 class TGBEvalEngine:
     def __init__(self, model: CTAN_tgb, loader: LastNeighborLoader, stream: dict, batch_size: int, n_neg: int,
-                 rank: int = 0, world: int = 1, group=None, use_graph: bool = True):
+                 rank: int = 0, world: int = 1, group=None, use_graph: bool = True, neg_base: int = 0):
+        """neg_base: event index of row 0 of stream["neg"] when the negatives cover only a suffix of the event stream
+        (a validation / test split: train_link.py:117 queries them per split)."""
         dev = model.memory.memory.device
         if dev.type != "cuda":
             raise _lib.CtanLibraryError("TGBEvalEngine needs the model on a CUDA device")
@@ -69,7 +71,10 @@ class TGBEvalEngine:
         self.src, self.dst, self.t = st["src"].contiguous(), st["dst"].contiguous(), st["t"].contiguous()
         self.msg = st["msg"].float().contiguous()
         self.n_events = self.src.numel()
-        self.neg = st["neg"].contiguous().view(self.n_events, self.n_neg)
+        self.neg = st["neg"].contiguous().view(-1, self.n_neg)
+        self.neg_base = int(neg_base)
+        if self.neg.size(0) + self.neg_base < self.n_events and self.neg_base == 0:
+            raise ValueError("stream['neg'] must cover every event (or pass neg_base)")
         self.x = st.get("x")
         if self.x is not None:
             self.x = (self.x.squeeze(0) if self.x.dim() == 3 else self.x).to(dev).float().contiguous()
@@ -93,6 +98,7 @@ class TGBEvalEngine:
         self.prefetch = os.environ.get("CTAN_EVAL_PREFETCH", "1" if world == 1 else "0") == "1"
         self._side = torch.cuda.Stream(device=dev)
         self._side2 = torch.cuda.Stream(device=dev)
+        self.exchange_kind = "none (1 rank)" if world == 1 else "NCCL all_gather_into_tensor between two CUDA graphs"
 
     def _alloc(self):
         dev, B, K, D = self.dev, self.B, self.K, self.D
@@ -186,7 +192,8 @@ class TGBEvalEngine:
         w, ld, f = self.w, self.loader, self.fe[par]
         B, K, S, Q = self.B, self.K, self.S, self.Q
         N, E = self.n_cap, self.e_cap
-        call("ctan_stage_eval", ptr(self.src), ptr(self.dst), ptr(self.t), ptr(self.neg), self.n_neg, B, self.q0,
+        call("ctan_stage_eval", ptr(self.src), ptr(self.dst), ptr(self.t),
+             ptr(self.neg) - 8 * self.n_neg * self.neg_base, self.n_neg, B, self.q0,
              self.q1, ptr(w["counters"]), ptr(f["b_src"]), ptr(f["b_dst"]), ptr(f["b_t"]), ptr(f["seeds"]),
              ptr(f["pair_src"]), ptr(f["pair_dst"]))
         if Q > 0:
@@ -381,6 +388,27 @@ class TGBEvalEngine:
         self.launches_per_batch = _lib.N_LAUNCHES - n0      # our kernels per batch (the collective is NCCL's)
         self.w["counters"].copy_(cur)
         self.w["acc"].zero_()
+        if self.use_graph:
+            self._capture_all()
+
+    def _capture_all(self):
+        """Capture EVERY graph variant run() can replay (first front-end; per buffer set, with and without the
+        prefetch branch) up front, so that no capture can ever land inside a caller's timed window.  Capturing
+        launches nothing: the state is untouched."""
+        with torch.cuda.device(self.dev):
+            if self._graph is None:
+                self._graphs = {}
+                g0 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g0):
+                    self._frontend(0)
+                self._graph = g0
+            if self.prefetch:
+                for par in (0, 1):
+                    for pf in (True, False):
+                        self._graphs_for(par, pf)
+            else:
+                self._graphs_for(0, False)
+        torch.cuda.synchronize(self.dev)
 
     def _graphs_for(self, par: int, prefetch: bool):
         key = (par, prefetch)
@@ -413,11 +441,7 @@ class TGBEvalEngine:
         with torch.cuda.device(self.dev):
             if self.use_graph:
                 if self._graph is None:
-                    self._graphs = {}
-                    g0 = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g0):
-                        self._frontend(0)
-                    self._graph = g0
+                    self._capture_all()
                 if self.prefetch:
                     self._graph.replay()                   # front-end of the first batch of this call
                 par = 0
