@@ -81,6 +81,8 @@ SIGNATURES.update({
     "ctan_adam_step": [P, P, P, P, I, F, F, F, F, F, L, P, P],
     "ctan_loss_generic": [P, I, I, I, P, F, P, P, I, P],
     "ctan_record_rows": [P, I, P, I, P],
+    # sampler.cu
+    "ctan_neg_sample": [P, L, P, L, P, I, ctypes.c_uint64, ctypes.c_uint64, I, P, P],
     "ctan_mrr": [P, P, I, I, P],
     "ctan_stage_eval": [P, P, P, P, I, I, I, I, P, P, P, P, P, P, P],
     "ctan_pack_eval": [P, P, P, P, P, I, I, I, P],

@@ -34,6 +34,7 @@ REF = {
     "ctan_adam_step": "torch.optim.Adam.step -- train_link.py:281",
     "ctan_loss_generic": "criterion(pos_out, batch.y): CrossEntropyLoss / MSELoss / L1Loss (train_link.py:329,706-709) and BCEWithLogitsLoss on labels (train_sequence.py:57), with its gradient",
     "ctan_record_rows": "y_pred_confidence_list.append(...) -- per-batch scores kept for the end-of-pass metrics, train_link.py:383-395",
+    "ctan_neg_sample": "NegativeSampler.sample -- negative_sampler.py:27-40",
     "ctan_mrr": "TGB Evaluator._eval_hits_and_mrr (numpy branch) -- TGB/tgb/linkproppred/evaluate.py:109-120",
     "ctan_stage_eval": "per-query batch assembly of tgb_test -- train_link.py:111-142",
     "ctan_pack_eval": "per-query MRR + src/pos_dst embeddings kept for the state update -- train_link.py:150-158",
@@ -84,7 +85,7 @@ extern "C" {
 #endif
 ''']
 names = []
-for f in ("loader.cu", "edge.cu", "dense.cu", "step.cu", "tc_gemm.cu", "stats.cu"):
+for f in ("loader.cu", "edge.cu", "dense.cu", "step.cu", "tc_gemm.cu", "stats.cu", "sampler.cu"):
     src = open(os.path.join(CSRC, f)).read()
     out.append(f"/* ---------------------------------------------------------------- {f} */")
     for m in re.finditer(r'((?:^//[^\n]*\n)*)extern "C" int (\w+)\(([^{]*?)\)\s*\{', src, re.M):

@@ -53,3 +53,31 @@ def test_ragged_and_errors():
         PackedNegatives.from_eval_set(bad, src, dst, t)
     with pytest.raises(ValueError):
         PackedNegatives.from_eval_set(None, src, dst, t)
+
+
+def test_packed_matches_the_reference_sampler_itself():
+    """Against the reference's own NegativeEdgeSampler.query_batch (TGB/tgb/linkproppred/negative_sampler.py:83-138,
+    imported unmodified): same lists for every batch, same ValueError for an edge missing from the set."""
+    from oracle import ref_loops
+    if not ref_loops.available():
+        pytest.skip("reference files not present (neither /root/reference nor baseline/_ref/)")
+    R = ref_loops.load()
+    for ragged in (False, True):
+        ev, src, dst, t = _make(ragged=ragged, seed=11)
+        smp = R.NegativeEdgeSampler(dataset_name="tgbl-wiki", strategy="hist_rnd")
+        smp.eval_set["val"] = ev
+        pk = PackedNegatives.from_eval_set(ev, src, dst, t)
+        for lo in range(0, 500, 200):
+            hi = min(lo + 200, 500)
+            assert pk.query_batch(lo, hi) == smp.query_batch(src[lo:hi], dst[lo:hi], t[lo:hi], split_mode="val")
+        if not ragged:
+            want = torch.tensor(smp.query_batch(src, dst, t, split_mode="val"))
+            assert torch.equal(pk.dense(), want)
+    bad = dict(ev)
+    k = (int(src[0]), int(dst[0]), int(t[0]))
+    bad.pop(k)
+    smp.eval_set["val"] = bad
+    with pytest.raises(ValueError):
+        smp.query_batch(src[:1], dst[:1], t[:1], split_mode="val")
+    with pytest.raises(ValueError):
+        PackedNegatives.from_eval_set(bad, src, dst, t)
