@@ -151,6 +151,7 @@ def run_tgb_eval_bench(args, rank, world, quiet=False, extras=True):
            "clocks": clocks, "mrr": mrr, "rank0_subgraph": {"N": counts[0], "E": counts[1]},
            "host_issue_ms_per_step": host_ms, "e2e": e2e, "gpu_launches": steps * eng.launches_per_batch,
            "launches_per_step": eng.launches_per_batch}
+    eng.close()
     del eng
     torch.cuda.empty_cache()
     if extras:
@@ -179,6 +180,7 @@ def run_variant(cfg, rank, world, dev, steps, W):
          "workload": f"tgbl-wiki-shaped: {st['num_nodes']} nodes, 172-d msgs, 200 queries/batch x {cfg['n_neg']} negatives, "
                      f"CTAN_tgb D=T={cfg['D']} S={cfg['S']} K={cfg['K']} (conf_tgb_link_prediction.py:5-16), after a "
                      f"{cfg['warm']}-event warm insert", "launches_per_step": eng.launches_per_batch}
+    eng.close()
     del eng
     torch.cuda.empty_cache()
     return r

@@ -81,6 +81,11 @@ SIGNATURES.update({
     "ctan_adam_step": [P, P, P, P, I, F, F, F, F, F, L, P, P],
     "ctan_loss_generic": [P, I, I, I, P, F, P, P, I, P],
     "ctan_record_rows": [P, I, P, I, P],
+    # sym.cu (the host-side ctan_sym_* / ctan_ipc_* setup calls take no stream: bound in sym.py)
+    "ctan_xchg_push": [P, I, I, I, I, P, I, I, I, ctypes.c_size_t, P, P],
+    "ctan_xchg_wait": [P, I, P, P],
+    # mma_gemm.cu
+    "ctan_gemm_mma": [P, I, P, I, P, I, P, P, P, P, I, I, I, I, P, P, P, P, I, P, I, P, I, P, I, P, I, I, I],
     # sampler.cu
     "ctan_neg_sample": [P, L, P, L, P, I, ctypes.c_uint64, ctypes.c_uint64, I, P, P],
     "ctan_mrr": [P, P, I, I, P],
@@ -113,8 +118,11 @@ def _optional_signatures(dll):
         fn.restype = c_int
 
 
+HOST_ONLY = ["ctan_sym_alloc", "ctan_sym_free", "ctan_ipc_export", "ctan_ipc_import", "ctan_ipc_close"]
+
+
 def exported_symbols():
-    return list(SIGNATURES) + list(OPTIONAL_SIGNATURES)
+    return list(SIGNATURES) + list(OPTIONAL_SIGNATURES) + HOST_ONLY
 
 
 def use_tensor_cores(D: int) -> bool:

@@ -48,7 +48,8 @@ def exchange_rows(send: torch.Tensor, recv: torch.Tensor, rows: torch.Tensor, B:
 
 class TGBEvalEngine:
     def __init__(self, model: CTAN_tgb, loader: LastNeighborLoader, stream: dict, batch_size: int, n_neg: int,
-                 rank: int = 0, world: int = 1, group=None, use_graph: bool = True, neg_base: int = 0):
+                 rank: int = 0, world: int = 1, group=None, use_graph: bool = True, neg_base: int = 0,
+                 exchange: str = "auto"):
         """neg_base: event index of row 0 of stream["neg"] when the negatives cover only a suffix of the event stream
         (a validation / test split: train_link.py:117 queries them per split)."""
         dev = model.memory.memory.device
@@ -98,7 +99,18 @@ class TGBEvalEngine:
         self.prefetch = os.environ.get("CTAN_EVAL_PREFETCH", "1" if world == 1 else "0") == "1"
         self._side = torch.cuda.Stream(device=dev)
         self._side2 = torch.cuda.Stream(device=dev)
-        self.exchange_kind = "none (1 rank)" if world == 1 else "NCCL all_gather_into_tensor between two CUDA graphs"
+        # the per-batch exchange: "peer" = our kernels store the packed rows into every peer's symmetric buffer over
+        # NVLink from INSIDE the captured graph (csrc/sym.cu); "nccl" = torch's all_gather_into_tensor between two graphs
+        import os as _os
+        if exchange == "auto":
+            exchange = _os.environ.get("CTAN_EVAL_EXCHANGE", "peer")
+        self.exchange = exchange if world > 1 else "none"
+        self.sym = None
+        if self.exchange == "peer":
+            from .sym import SymmetricExchange
+            self.sym = SymmetricExchange(self.B, self.row, rank, world, dev, group)
+        self.exchange_kind = {"none": "none (1 rank)", "nccl": "NCCL all_gather_into_tensor between two CUDA graphs",
+                              "peer": "in-graph peer-memory stores over NVLink (ctan_xchg_push / ctan_xchg_wait)"}[self.exchange]
 
     def _alloc(self):
         dev, B, K, D = self.dev, self.B, self.K, self.D
@@ -183,8 +195,8 @@ class TGBEvalEngine:
     def _launch(self, dry: bool = False):
         self._frontend(0)
         self._batch(0, False, dry)
-        self._exchange()
-        self._update(0, dry)
+        xpar = self._exchange()
+        self._update(0, dry, xpar)
 
     def _frontend(self, par: int):
         """stage -> K-hop lookup -> edge list of the batch at the cursor, into buffer set `par`.  Reads the neighbour
@@ -347,18 +359,35 @@ class TGBEvalEngine:
         self._w_ver = None
 
     def _exchange(self):
-        """The one collective of the batch (kept OUT of CUDA-graph capture: torch's NCCL process group and
-        stream capture do not mix reliably; it is still stream-ordered and needs no host sync)."""
+        """The one exchange of the batch, issued eagerly.  peer mode: push + wait kernels (returns the buffer parity
+        used); nccl mode: torch's collective (kept OUT of CUDA-graph capture: torch's NCCL process group and stream
+        capture do not mix reliably; it is still stream-ordered and needs no host sync)."""
+        if self.exchange == "peer":
+            xpar = self.sym.count & 1
+            self._exchange_peer(xpar)
+            self.sym.count += 1
+            return xpar
         if self.world > 1:
             w = self.w
             exchange_rows(w["send"], w["recv"], w["rows"], self.B, self.world, self.group)
+        return 0
 
-    def _update(self, par: int, dry: bool = False):
+    def _exchange_peer(self, xpar: int):
+        """(capturable) store this rank's packed rows into every rank's parity-`xpar` buffer, then wait for all."""
+        self.sym.push(self.w["send"], self.Q, self.q0, xpar)
+        self.sym.wait(xpar)
+
+    def _rows(self, xpar: int = 0):
+        if self.exchange == "peer":
+            return self.sym.rows(xpar)
+        return self.w["rows"] if self.world > 1 else self.w["send"]
+
+    def _update(self, par: int, dry: bool = False, xpar: int = 0):
         """metric accumulation + the identical ground-truth memory write-back on every rank."""
         w, m, f = self.w, self.model, self.fe[par]
         B, D = self.B, self.D
         mem, lu = m.memory.memory, m.memory.last_update
-        rows = w["rows"] if self.world > 1 else w["send"]
+        rows = self._rows(xpar)
         call("ctan_accum_col", ptr(rows), B, self.row, 0, ptr(w["acc"]))
         emb = ptr(rows) + 4 * (1 + self.L)
         if dry:      # warm-up: same kernels, but the state update goes to scratch tables
@@ -402,25 +431,32 @@ class TGBEvalEngine:
                 with torch.cuda.graph(g0):
                     self._frontend(0)
                 self._graph = g0
-            if self.prefetch:
-                for par in (0, 1):
-                    for pf in (True, False):
-                        self._graphs_for(par, pf)
-            else:
-                self._graphs_for(0, False)
+            xpars = (0, 1) if self.exchange == "peer" else (0,)
+            for xpar in xpars:
+                if self.prefetch:
+                    for par in (0, 1):
+                        for pf in (True, False):
+                            self._graphs_for(par, pf, xpar)
+                else:
+                    self._graphs_for(0, False, xpar)
         torch.cuda.synchronize(self.dev)
 
-    def _graphs_for(self, par: int, prefetch: bool):
-        key = (par, prefetch)
+    def _graphs_for(self, par: int, prefetch: bool, xpar: int = 0):
+        """One batch as a captured graph.  1 rank / peer exchange: ONE graph (front-end | scoring | exchange kernels |
+        update); NCCL exchange: two graphs around the host-issued collective."""
+        key = (par, prefetch, xpar)
         if key not in self._graphs:
             ga, gb = torch.cuda.CUDAGraph(), None
+            one = self.exchange != "nccl"
             with torch.cuda.graph(ga):
                 if not self.prefetch:
                     self._frontend(par)                    # inline front-end: one graph per batch, no prefetch
                 self._batch(par, prefetch)
-                if self.world == 1:
-                    self._update(par)
-            if self.world > 1:
+                if self.exchange == "peer":
+                    self._exchange_peer(xpar)
+                if one:
+                    self._update(par, False, xpar)
+            if not one:
                 gb = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gb):
                     self._update(par)
@@ -446,9 +482,12 @@ class TGBEvalEngine:
                     self._graph.replay()                   # front-end of the first batch of this call
                 par = 0
                 for j in range(n_batches):
-                    ga, gb = self._graphs_for(par, self.prefetch and j < n_batches - 1)
+                    xpar = (self.sym.count & 1) if self.sym is not None else 0
+                    ga, gb = self._graphs_for(par, self.prefetch and j < n_batches - 1, xpar)
                     ga.replay()
-                    if self.world > 1:
+                    if self.sym is not None:
+                        self.sym.count += 1
+                    if gb is not None:
                         self._exchange()
                         gb.replay()
                     if self.prefetch:
@@ -459,16 +498,23 @@ class TGBEvalEngine:
                     if not self.prefetch or j == 0:
                         self._frontend(par)
                     self._batch(par, self.prefetch and j < n_batches - 1)
-                    self._exchange()
-                    self._update(par)
+                    xpar = self._exchange()
+                    self._update(par, False, xpar)
                     if self.prefetch:
                         par ^= 1
         self.loader.cur_e_id += n_batches * self.B
 
     def scores(self) -> torch.Tensor:
         """[B, 1+n_neg] scores of the last batch (column 0 = positive), batch order."""
-        rows = self.w["rows"] if self.world > 1 else self.w["send"]
+        rows = self._rows((self.sym.count - 1) & 1 if self.sym is not None else 0)
         return rows[: self.B, 1:1 + self.L]
+
+    def close(self):
+        """Release the symmetric peer memory (collective: every rank must call it)."""
+        if self.sym is not None:
+            self._graphs, self._graph = {}, None
+            self.sym.close()
+            self.sym = None
 
     def check(self):
         err = max(int(f["counts"][3].item()) for f in self.fe)

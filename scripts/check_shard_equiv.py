@@ -28,5 +28,6 @@ flags = [None] * world
 dist.all_gather_object(flags, bool(ok))
 if rank == 0:
     print("shard-equivalence", "OK" if all(flags) else "MISMATCH", flags, "mrr", mrr_s, ref.mrr(), "graph", eng._graph is not None, "mem", torch.equal(mem_s, ref.model.memory.memory), "lu", torch.equal(lu_s, ref.model.memory.last_update), "eid", torch.equal(eid_s, ref.loader.e_id), flush=True)
+eng.close()
 dist.destroy_process_group()
 sys.exit(0 if all(flags) else 1)

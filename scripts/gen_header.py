@@ -35,6 +35,14 @@ REF = {
     "ctan_loss_generic": "criterion(pos_out, batch.y): CrossEntropyLoss / MSELoss / L1Loss (train_link.py:329,706-709) and BCEWithLogitsLoss on labels (train_sequence.py:57), with its gradient",
     "ctan_record_rows": "y_pred_confidence_list.append(...) -- per-batch scores kept for the end-of-pass metrics, train_link.py:383-395",
     "ctan_neg_sample": "NegativeSampler.sample -- negative_sampler.py:27-40",
+    "ctan_sym_alloc": "(symmetric peer-memory block of the sharded evaluation; host-side, no reference counterpart)",
+    "ctan_sym_free": "(host-side, no reference counterpart)",
+    "ctan_ipc_export": "(CUDA IPC handle of the block; host-side, no reference counterpart)",
+    "ctan_ipc_import": "(map a peer's block; host-side, no reference counterpart)",
+    "ctan_ipc_close": "(host-side, no reference counterpart)",
+    "ctan_xchg_push": "the exchange step of the sharded tgb_test loop (per-query scores + embeddings for the identical update at train_link.py:198): stores into every peer's buffer over NVLink",
+    "ctan_xchg_wait": "consumer side of the exchange: wait until every rank's rows of the batch have arrived",
+    "ctan_gemm_mma": "enc_x / lin_query / lin_key / lin_value / x @ A^T and their input gradients at batch-sized M on warp-level tensor-core MMAs -- models/gnn_layers.py:96, PyG TransformerConv / AntiSymmetricConv (SURVEY.md App. A.5)",
     "ctan_mrr": "TGB Evaluator._eval_hits_and_mrr (numpy branch) -- TGB/tgb/linkproppred/evaluate.py:109-120",
     "ctan_stage_eval": "per-query batch assembly of tgb_test -- train_link.py:111-142",
     "ctan_pack_eval": "per-query MRR + src/pos_dst embeddings kept for the state update -- train_link.py:150-158",
@@ -85,7 +93,7 @@ extern "C" {
 #endif
 ''']
 names = []
-for f in ("loader.cu", "edge.cu", "dense.cu", "step.cu", "tc_gemm.cu", "stats.cu", "sampler.cu"):
+for f in ("loader.cu", "edge.cu", "dense.cu", "step.cu", "tc_gemm.cu", "stats.cu", "sampler.cu", "sym.cu", "mma_gemm.cu"):
     src = open(os.path.join(CSRC, f)).read()
     out.append(f"/* ---------------------------------------------------------------- {f} */")
     for m in re.finditer(r'((?:^//[^\n]*\n)*)extern "C" int (\w+)\(([^{]*?)\)\s*\{', src, re.M):
