@@ -84,8 +84,6 @@ SIGNATURES.update({
     # sym.cu (the host-side ctan_sym_* / ctan_ipc_* setup calls take no stream: bound in sym.py)
     "ctan_xchg_push": [P, I, I, I, I, P, I, I, I, ctypes.c_size_t, P, P],
     "ctan_xchg_wait": [P, I, P, P],
-    # mma_gemm.cu
-    "ctan_gemm_mma": [P, I, P, I, P, I, P, P, P, P, I, I, I, I, P, P, P, P, I, P, I, P, I, P, I, P, I, I, I],
     # sampler.cu
     "ctan_neg_sample": [P, L, P, L, P, I, ctypes.c_uint64, ctypes.c_uint64, I, P, P],
     "ctan_mrr": [P, P, I, I, P],

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libctan_sm100.so")
-SOURCES = ["loader.cu", "edge.cu", "dense.cu", "step.cu", "tc_gemm.cu", "stats.cu", "sampler.cu", "sym.cu", "mma_gemm.cu"]
+SOURCES = ["loader.cu", "edge.cu", "dense.cu", "step.cu", "tc_gemm.cu", "stats.cu", "sampler.cu", "sym.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--use_fast_math=false"]
 

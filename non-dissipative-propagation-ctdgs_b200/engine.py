@@ -330,11 +330,6 @@ class StepEngine:
         self.hub_cap = min(N, 16384)                      # rows of degree > 8 go to the block-cooperative kernel
         w["A"] = torch.zeros((D, D), **f32)
         self.use_tc = _lib.use_tensor_cores(D)
-        # Batch-sized contractions (enc_x, q/k/v/x.A^T, dX) on warp-level MMAs (csrc/mma_gemm.cu): no per-launch set-up,
-        # ~5 us instead of the 12-24 us of the tcgen05 / CUDA-core kernels at ~700 rows.  Larger node sets keep tcgen05.
-        self.use_mma = (D % 32 == 0 and self.n_typ <= int(os.environ.get("CTAN_MMA_MAX_ROWS", "4096"))
-                        and os.environ.get("CTAN_MMA", "1") == "1" and os.environ.get("CTAN_NO_TC", "0") != "1")
-        self.mma_mode = 0 if _lib.TC_MODE == 0 else 1        # 3xTF32 (fp32 parity) | single-pass TF32 (the 1e-2 tier)
         w["Wcat_hi"], w["Wcat_lo"] = torch.zeros((4 * D, D), **f32), torch.zeros((4 * D, D), **f32)
         self.use_tc_dx = (self.use_tc and D % 128 == 0          # dX contraction on tcgen05 needs 128-wide output tiles
                           and os.environ.get("CTAN_TC_DX", "1") == "1")
@@ -488,7 +483,7 @@ class StepEngine:
         D = self.D
         Wq, Wk, Wv, W = (ptr(self.p[i]) for i in (2, 4, 6, 9))
         with self._fork(2):
-            if self.use_tc and not self.use_mma:   # A = W - W^T - gamma I, packed with q/k/v weights and split for 3xTF32
+            if self.use_tc:      # A = W - W^T - gamma I, packed with q/k/v weights and split for 3xTF32
                 call("ctan_wcat_prep", Wq, Wk, Wv, W, float(m.gnn.aconv.gamma), D, ptr(w["Wcat_hi"]),
                      ptr(w["Wcat_lo"]), ptr(w["A"]), ptr(w["WcatT_hi"]) if (train and self.use_tc_dx) else None,
                      ptr(w["WcatT_lo"]) if (train and self.use_tc_dx) else None)
@@ -540,22 +535,14 @@ class StepEngine:
         if train:
             with self._fork(1):                              # side 1: saved copy of the gathered input rows
                 call("ctan_gather_rows2", ptr(mem), D, xf, Fn, ptr(f["n_id"]), N, Nd, ptr(w["z0"]))
-        if self.use_mma:         # enc_x on gathered memory rows; the node-feature columns enter as a rank-Fn tail
-            call("ctan_gemm_mma", ptr(mem), D, ptr(f["n_id"]), N, Nd, D, Wenc, None, None, None, D + Fn, D, 0, D,
-                 benc, None, None, None, D, None, 0, xf, Fn, (Wenc + 4 * D) if Fn else None, D + Fn, ptr(w["X"][0]), D,
-                 1, self.mma_mode)
-        else:
-            call("ctan_enc_fwd", ptr(mem), D, xf, Fn, ptr(f["n_id"]), None, N, Nd, Wenc, benc, ptr(w["X"][0]))
+        call("ctan_enc_fwd", ptr(mem), D, xf, Fn, ptr(f["n_id"]), None, N, Nd, Wenc, benc, ptr(w["X"][0]))
         self._join(0)
         self._join(2)
         for k in range(K):
             xi = w["X"][k] if train else w["X"][k & 1]
             xo = w["X"][k + 1] if train else w["X"][(k + 1) & 1]
             qk = w["QKVA"][k] if train else w["QKVA"][0]
-            if self.use_mma:     # [q|k|v|x.A^T] = x [Wq;Wk;Wv;A]^T + [bq;bk;bv;b] on warp-level MMAs
-                call("ctan_gemm_mma", ptr(xi), D, None, N, Nd, D, Wq, Wk, Wv, ptr(w["A"]), D, D, 0, 4 * D, bq, bk, bv, b,
-                     D, None, 0, None, 0, None, 0, ptr(qk), 4 * D, 1, self.mma_mode)
-            elif self.use_tc:    # tcgen05 + TMA projection
+            if self.use_tc:      # tcgen05 + TMA projection
                 call("ctan_qkva_fwd_tc", ptr(xi), N, Nd, D, ptr(w["Wcat_hi"]), ptr(w["Wcat_lo"]), bq, bk, bv, b,
                      ptr(qk), _lib.TC_MODE)
             else:
@@ -636,11 +623,7 @@ class StepEngine:
                          We, E, Ed, D, gWe, ptr(w["dTenc"]), self.e_typ)
                     call("ctan_tenc_bwd", ptr(w["dTenc"]), ptr(f["rel"]), tw, tb, E, Ed, T, gtw, gtb)
             gn = self._DX[k]
-            if self.use_mma:     # dX = G + DQKVA [Wq;Wk;Wv;A] (weights N-contiguous), K = 4D split over 4 CTAs per tile
-                call("ctan_gemm_mma", ptr(w["DQKVA"]), 4 * D, None, N, Nd, 4 * D, Wq, Wk, Wv, ptr(w["A"]), D, D, 1, D,
-                     None, None, None, None, 0, ptr(g), D, None, 0, None, 0, ptr(gn), D,
-                     int(os.environ.get("CTAN_MMA_DX_SPLIT", "4")), self.mma_mode)
-            elif self.use_tc_dx: # dX = G + DQKVA Wcat on tcgen05 (plain stores)
+            if self.use_tc_dx:   # dX = G + DQKVA Wcat on tcgen05 (plain stores)
                 call("ctan_dx_tc", ptr(w["DQKVA"]), ptr(g), N, Nd, D, ptr(w["WcatT_hi"]), ptr(w["WcatT_lo"]), ptr(gn),
                      _lib.TC_MODE, 2 if self.n_typ <= 4096 else 1)     # (split sweep 1/2/4/8/16: 110.5/109.8/112.5/112.9/112.8 us per step)
             else:
@@ -688,8 +671,13 @@ class StepEngine:
         """Run one throw-away training + inference step eagerly (loads every kernel before graph
         capture) and restore the fresh state.  Call on a freshly reset engine only."""
         keep = self.flat_p.clone()
+        base = max(self.neg_base, self.y_base)
+        if int(self.w["counters"][0]) < base:                # the throw-away batch must lie inside the neg / label tables
+            self.w["counters"][0] = base
         with torch.cuda.device(self.dev):
             self._launch(True)
+            if base:
+                self.w["counters"][0] = base
             self._launch(False)
         torch.cuda.synchronize(self.dev)
         self.flat_p.copy_(keep)

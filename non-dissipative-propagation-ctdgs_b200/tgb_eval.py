@@ -408,6 +408,8 @@ class TGBEvalEngine:
                          torch.full((2, self.S), -1, dtype=torch.long, device=dev),
                          torch.zeros(2, dtype=torch.int32, device=dev))
         cur = self.w["counters"].clone()
+        if int(cur[0]) < self.neg_base:                      # the dry batch must lie inside the negative table
+            self.w["counters"][0] = self.neg_base
         from . import _lib
         self._prep_weights()
         n0 = _lib.N_LAUNCHES

@@ -42,7 +42,6 @@ REF = {
     "ctan_ipc_close": "(host-side, no reference counterpart)",
     "ctan_xchg_push": "the exchange step of the sharded tgb_test loop (per-query scores + embeddings for the identical update at train_link.py:198): stores into every peer's buffer over NVLink",
     "ctan_xchg_wait": "consumer side of the exchange: wait until every rank's rows of the batch have arrived",
-    "ctan_gemm_mma": "enc_x / lin_query / lin_key / lin_value / x @ A^T and their input gradients at batch-sized M on warp-level tensor-core MMAs -- models/gnn_layers.py:96, PyG TransformerConv / AntiSymmetricConv (SURVEY.md App. A.5)",
     "ctan_mrr": "TGB Evaluator._eval_hits_and_mrr (numpy branch) -- TGB/tgb/linkproppred/evaluate.py:109-120",
     "ctan_stage_eval": "per-query batch assembly of tgb_test -- train_link.py:111-142",
     "ctan_pack_eval": "per-query MRR + src/pos_dst embeddings kept for the state update -- train_link.py:150-158",
@@ -93,7 +92,7 @@ extern "C" {
 #endif
 ''']
 names = []
-for f in ("loader.cu", "edge.cu", "dense.cu", "step.cu", "tc_gemm.cu", "stats.cu", "sampler.cu", "sym.cu", "mma_gemm.cu"):
+for f in ("loader.cu", "edge.cu", "dense.cu", "step.cu", "tc_gemm.cu", "stats.cu", "sampler.cu", "sym.cu"):
     src = open(os.path.join(CSRC, f)).read()
     out.append(f"/* ---------------------------------------------------------------- {f} */")
     for m in re.finditer(r'((?:^//[^\n]*\n)*)extern "C" int (\w+)\(([^{]*?)\)\s*\{', src, re.M):
