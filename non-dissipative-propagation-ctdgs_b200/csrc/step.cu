@@ -8,8 +8,10 @@
 //   TGB Evaluator MRR, numpy branch                                TGB/tgb/linkproppred/evaluate.py:109-120
 #include "common.cuh"
 
-// counters (int64 [8], device): [0] next batch start (event index), [1] current batch start,
-// [2] optimizer steps COMPLETED (advanced by the Adam kernel), [3] number of steps staged so far, [5]/[6] tickets.
+// counters (int64 [8], device): [0] next batch start (event index), [1] event id of the current batch's first event
+// (= batch start + [7]; read by the neighbour insert), [2] optimizer steps COMPLETED (advanced by the Adam kernel),
+// [3] number of steps staged so far, [5]/[6] tickets, [7] event-id offset of the stream (loader.cur_e_id - stream position:
+// non-zero when the stream buffers hold a window that does not start at event 0, e.g. one pass of train_sequence).
 __global__ void stage_batch_kernel(const int64_t* __restrict__ src_all, const int64_t* __restrict__ dst_all,
                                    const int64_t* __restrict__ t_all, const int64_t* __restrict__ neg_all,
                                    int n_neg, int B, int64_t* __restrict__ counters, int use_cursor,
@@ -23,7 +25,7 @@ __global__ void stage_batch_kernel(const int64_t* __restrict__ src_all, const in
     if (threadIdx.x == 0) {
         const int64_t cur = counters[0];              // event index of this batch's first event
         counters[0] = cur + B;
-        counters[1] = cur;
+        counters[1] = cur + counters[7];
         counters[3] += 1;                             // (the optimizer step count, counters[2], is advanced by Adam itself)
         if (loss_hist) loss_hist[(counters[3] - 1) % hist_cap] = 0.f;   // slot the fused head+loss accumulates into
         // the step number of THIS staged batch, for kernels that run after a later batch may have been staged
@@ -112,13 +114,14 @@ extern "C" int ctan_bce_loss(const float* OUT, int n_pos, int n_negs, float* dOU
 //   mode 3  L1Loss   (mean over P*O), y fp32 [.,O]
 //   mode 4  BCEWithLogitsLoss with fp32 targets y [.,O], mean over P*O          (train_sequence.py:57)
 // The batch's labels are rows [y_row0, y_row0+P) of the label table, y_row0 = ctr[1] (the staged batch's first event,
-// written by ctan_stage_batch) or 0 when ctr is NULL.  dOUT (optional) is multiplied by `scale` (gradient accumulation
-// over several steps whose losses are averaged).  The loss goes to loss_hist[(ctr[3]-1) % hist_cap].  One CTA.
+// written by ctan_stage_batch) or 0 when ctr is NULL.  dOUT (optional) is multiplied by `scale` and, when given, by the
+// device scalar *scale_dev (gradient accumulation over several steps whose losses are averaged: train_sequence.py:57).  The loss goes to loss_hist[(ctr[3]-1) % hist_cap].  One CTA.
 __global__ void loss_generic_kernel(const float* __restrict__ OUT, int P, int O, int mode, const void* __restrict__ y,
-                                    float scale, float* __restrict__ dOUT, float* __restrict__ loss_hist, int hist_cap,
-                                    const int64_t* __restrict__ ctr) {
+                                    float scale, const float* __restrict__ scale_dev, float* __restrict__ dOUT,
+                                    float* __restrict__ loss_hist, int hist_cap, const int64_t* __restrict__ ctr) {
     ctan_pdl_begin();
     __shared__ float red[32];
+    if (scale_dev) scale *= *scale_dev;
     const int64_t row0 = ctr ? ctr[1] : 0;
     float acc = 0.f;
     if (mode == 1) {
@@ -164,10 +167,30 @@ __global__ void loss_generic_kernel(const float* __restrict__ OUT, int P, int O,
     }
 }
 
-extern "C" int ctan_loss_generic(const float* OUT, int P, int O, int mode, const void* y, float scale, float* dOUT,
-                                 float* loss_hist, int hist_cap, const int64_t* ctr, cudaStream_t stream) {
+extern "C" int ctan_loss_generic(const float* OUT, int P, int O, int mode, const void* y, float scale,
+                                 const float* scale_dev, float* dOUT, float* loss_hist, int hist_cap, const int64_t* ctr,
+                                 cudaStream_t stream) {
     if (P <= 0 || O <= 0 || mode < 1 || mode > 4 || !y || hist_cap <= 0) return CTAN_ERR_BAD_ARG;
-    CTAN_LAUNCH((loss_generic_kernel), 1, 256, 0, stream, OUT, P, O, mode, y, scale, dOUT, loss_hist, hist_cap, ctr);
+    CTAN_LAUNCH((loss_generic_kernel), 1, 256, 0, stream, OUT, P, O, mode, y, scale, scale_dev, dOUT, loss_hist, hist_cap, ctr);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+// Sequence mode (train_sequence.py:38-41: `e_id = e_id % data.msg.shape[0]` after every loader call): the loader's event
+// ids count over the whole pass, the message / time tables of a sequence hold `mod` rows.  With the pass laid out as one
+// stream (sequence after sequence, `mod` rows each) the table row of an edge is base + e_id % mod, where base is the
+// first row of the sequence the staged event belongs to: (ctr[1] / mod) * mod.
+__global__ void eid_mod_kernel(int64_t* __restrict__ eid, int E_host, const int* __restrict__ E_dev, int mod,
+                               const int64_t* __restrict__ ctr) {
+    ctan_pdl_begin();
+    const int E = E_dev ? *E_dev : E_host;
+    const int64_t base = (ctr[1] / mod) * mod;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < E; i += gridDim.x * blockDim.x) eid[i] = base + eid[i] % mod;
+}
+extern "C" int ctan_eid_mod(int64_t* eid, int E, const int* E_dev, int mod, const int64_t* ctr, cudaStream_t stream) {
+    if (E <= 0) return 0;
+    if (mod <= 0 || !ctr) return CTAN_ERR_BAD_ARG;
+    CTAN_LAUNCH((eid_mod_kernel), ctan_grid(E, 256, 1), 256, 0, stream, eid, E, E_dev, mod, ctr);
     CTAN_CHECK_LAUNCH();
     return 0;
 }

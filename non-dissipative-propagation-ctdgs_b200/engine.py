@@ -45,7 +45,7 @@ class StepEngine:
     def __init__(self, model: CTAN, loader: LastNeighborLoader, stream: dict, batch_size: int, n_neg: int = 1,
                  lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
                  use_graph: bool = True, hist_cap: int = 1 << 16, host_staged: bool = False, criterion=None,
-                 out_cap: int = 0, neg_base: int = 0, y_base: int = 0):
+                 out_cap: int = 0, neg_base: int = 0, y_base: int = 0, seq_mod: int = 0):
         """Heads (chosen from the model and `n_neg`):
           * link head with negatives (n_neg >= 1): pairs (src,dst) + (src,neg), fused BCE on pos/neg
             (train_link.py:269-270, 335-336) -- `criterion` must be None or BCEWithLogitsLoss(mean);
@@ -54,7 +54,11 @@ class StepEngine:
             CrossEntropyLoss (int64 class ids; multiclass, train_link.py:708-709), MSELoss / L1Loss (regression,
             :706), BCEWithLogitsLoss (fp32 targets; train_sequence.py:57).
         out_cap > 0 keeps the scores of the last out_cap steps (`outputs(n)`); neg_base / y_base: event index of row 0
-        of stream["neg"] / stream["y"] when those tables cover only a suffix of the event stream."""
+        of stream["neg"] / stream["y"] when those tables cover only a suffix of the event stream.
+        seq_mod > 0: sequence mode (train_sequence.py): the stream is a pass over sequences of seq_mod events each; an
+        edge's message / time row is (first row of the current sequence) + e_id % seq_mod (train_sequence.py:41); steps
+        are issued one by one with `step(kind)`: "infer" | "grad" (accumulate gradients, scaled by set_grad_scale) |
+        `adam()` (optimizer step on the accumulated gradients, then clear them)."""
         dev = model.memory.memory.device
         if dev.type != "cuda":
             raise _lib.CtanLibraryError("StepEngine needs the model on a CUDA device")
@@ -70,6 +74,7 @@ class StepEngine:
         self.eps, self.wd = float(eps), float(weight_decay)
         self.use_graph, self.hist_cap, self.host_staged = use_graph, int(hist_cap), host_staged
         self.out_cap, self.neg_base, self.y_base = int(out_cap), int(neg_base), int(y_base)
+        self.seq_mod = int(seq_mod)
         self.K = model.num_gnn_layers
         self.D = model.memory.memory_dim
         self.S = loader.size
@@ -184,6 +189,8 @@ class StepEngine:
             return (v + 63) // 64 * 64
         o_dA = pad(n)
         o_dZ = o_dA + pad(D * D)
+        self._o_ws = o_dZ                                      # [0, _o_ws): parameter gradients + dA; beyond: per-step scratch
+        self._accumulate = False
         o_DQ = o_dZ + pad(N * D)
         o_DX = o_DQ + pad(N * 4 * D)
         self.zero_buf = torch.zeros(o_DX + K * N * D, device=self.dev)
@@ -211,7 +218,7 @@ class StepEngine:
             o += k
         self.n_params = n
         # optimizer hyper-parameters live on the device so that a captured graph follows an lr scheduler
-        self.hyper = torch.tensor([self.lr, self.betas[0], self.betas[1], self.eps, self.wd], device=self.dev)
+        self.hyper = torch.tensor([self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 1.0], device=self.dev)
         self._opt = None
         self._opt_steps = 0
 
@@ -224,7 +231,12 @@ class StepEngine:
             self.eps = float(eps)
         if weight_decay is not None:
             self.wd = float(weight_decay)
-        self.hyper.copy_(torch.tensor([self.lr, self.betas[0], self.betas[1], self.eps, self.wd]))
+        self.hyper[:5].copy_(torch.tensor([self.lr, self.betas[0], self.betas[1], self.eps, self.wd]))
+
+    def set_grad_scale(self, scale: float):
+        """Device-side factor on dL/d(out) of the labelled heads (read by the captured loss kernel): 1/n when the losses
+        of n steps are averaged before one optimizer step (train_sequence.py:57-60)."""
+        self.hyper[5:6].copy_(torch.tensor([float(scale)]))
 
     # ------------------------------------------------------------------ torch.optim.Adam bridge
     def attach_optimizer(self, opt):
@@ -353,7 +365,7 @@ class StepEngine:
         w["dTenc"] = torch.zeros((E, max(self.T, 1)), **f32)
         w["dA"] = self._dA
         self.w = w
-        self.prefetch = (not self.host_staged) and os.environ.get("CTAN_TRAIN_PREFETCH", "1") == "1"
+        self.prefetch = (not self.host_staged) and not self.seq_mod and os.environ.get("CTAN_TRAIN_PREFETCH", "1") == "1"
 
     # ------------------------------------------------------------------ state
     def reset(self, reset_optimizer: bool = False):
@@ -363,7 +375,7 @@ class StepEngine:
         # cursor / batch start / staged-step count / tickets restart; counters[2] is the optimizer's step count, which
         # torch.optim.Adam keeps across epochs (the reference resets only memory and graph, train_link.py:226-227)
         steps_done = self.w["counters"][2].clone()
-        self.w["counters"].zero_()
+        self.w["counters"].zero_()                           # (incl. [7], the event-id offset: the loader restarts at 0)
         if not reset_optimizer:
             self.w["counters"][2] = steps_done
         for f in self.fe:
@@ -456,7 +468,7 @@ class StepEngine:
         call("ctan_nbr_lookup", ptr(ld.neighbors), ptr(ld._deg), self.num_nodes, S, ptr(f["seeds"]), self.n_seeds,
              None, K, ptr(ld._bitmap), ptr(ld._cbitmap), ptr(w["frontier"]), ptr(w["frontier_cnt"]), N,
              ptr(f["n_id"]), N, ptr(f["assoc"]), ptr(f["rowptr"]), E, ptr(f["counts"]))
-        if with_rel:
+        if with_rel and not self.seq_mod:
             call("ctan_nbr_fill_rel", ptr(ld.neighbors), ptr(ld.e_id), S, ptr(f["n_id"]), ptr(f["rowptr"]),
                  ptr(f["assoc"]), N, ptr(f["Nd"]), ptr(f["esrc"]), ptr(f["edst"]), ptr(f["eid"]), ptr(ld._bitmap),
                  ptr(ld._cbitmap), ptr(m.memory.last_update), ptr(self.t_tab), float(m.gnn.mean_delta_t),
@@ -464,6 +476,8 @@ class StepEngine:
         else:
             call("ctan_nbr_fill", ptr(ld.neighbors), ptr(ld.e_id), S, ptr(f["n_id"]), ptr(f["rowptr"]), ptr(f["assoc"]),
                  N, ptr(f["Nd"]), ptr(f["esrc"]), ptr(f["edst"]), ptr(f["eid"]), ptr(ld._bitmap), ptr(ld._cbitmap))
+        if self.seq_mod:                 # event id -> row of the current sequence's message / time table
+            call("ctan_eid_mod", ptr(f["eid"]), E, ptr(f["Ed"]), self.seq_mod, ptr(f["ctr"]))
         if S > 8:                        # work list of the high-degree rows (edge_fwd runs them beside the plain rows)
             f["hub"][:2].zero_()
             call("ctan_hub_list", ptr(f["rowptr"]), N, ptr(f["Nd"]), ptr(f["hub"]), self.hub_cap)
@@ -491,7 +505,10 @@ class StepEngine:
                 call("ctan_antisym_prep", W, float(m.gnn.aconv.gamma), D, ptr(w["A"]))
             w["H"].zero_()
             if train:
-                self.zero_buf.zero_()
+                if self._accumulate:                         # keep flat_g and dA (they accumulate over several steps)
+                    self.zero_buf[self._o_ws:].zero_()
+                else:
+                    self.zero_buf.zero_()
         # Programmatic dependent launch (csrc/common.cuh) shortens the single-chain no-grad step (80 -> 75 us) but
         # LENGTHENS the training step (118 -> 122..127 us, more the further into the DAG it is enabled): dependents
         # scheduled early hold SM slots that the step's parallel branches need.  So: inference on, training off.
@@ -527,7 +544,7 @@ class StepEngine:
                 if prefetch:
                     self._frontend(par ^ 1, with_rel=False)
         with self._fork(0):                                  # side 0: edge-attribute projection (|| enc_x)
-            if early:                                        # delta-t of THIS step (its front-end was prefetched without)
+            if early or self.seq_mod:                        # delta-t of THIS step (the front-end left it out)
                 call("ctan_edge_rel", ptr(lu), ptr(f["n_id"]), ptr(f["esrc"]), ptr(self.t_tab), ptr(f["eid"]), E, Ed,
                      float(m.gnn.mean_delta_t), float(m.gnn.std_delta_t), ptr(f["rel"]))
             call("ctan_eproj_fwd", ptr(self.msg), Fe, ptr(f["eid"]), ptr(f["rel"]), tw, tb, T, We, E, Ed, D,
@@ -573,7 +590,7 @@ class StepEngine:
                  Wsrc, bsrc, Wdst, bdst, Wfin, bfin, ptr(w["H"]), ptr(w["OUT"]), 1)
             y_p = self.y.data_ptr() - self.y_base * (8 if self.loss_mode == 1 else 4 * O)
             call("ctan_loss_generic", ptr(w["OUT"]), P, O, self.loss_mode, y_p, float(self.grad_scale),
-                 ptr(w["dOUT"]) if train else None, ptr(w["loss_hist"]), self.hist_cap, ptr(f["ctr"]))
+                 ptr(self.hyper) + 20, ptr(w["dOUT"]) if train else None, ptr(w["loss_hist"]), self.hist_cap, ptr(f["ctr"]))
         if w["out_hist"] is not None:
             call("ctan_record_rows", ptr(w["OUT"]), P * O, ptr(w["out_hist"]), self.out_cap, ptr(f["ctr"]))
 
@@ -634,10 +651,71 @@ class StepEngine:
         self._join(0)
         self._join(2)
         self._join(3)
-        call("ctan_adam_step", ptr(self.flat_p), ptr(self.flat_g), ptr(self.adam_m), ptr(self.adam_v),
-             self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 0, ptr(w["counters"]),
-             ptr(self.hyper))
+        if not self._accumulate:
+            self._adam()
         _lib.lib().ctan_set_pdl(1, None)
+
+    def _adam(self):
+        call("ctan_adam_step", ptr(self.flat_p), ptr(self.flat_g), ptr(self.adam_m), ptr(self.adam_v),
+             self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 0, ptr(self.w["counters"]),
+             ptr(self.hyper))
+
+    # ------------------------------------------------------------------ sequence mode: one step at a time
+    def step(self, kind: str):
+        """Sequence mode: one event.  "infer": no-grad step; "grad": forward + backward, gradients ACCUMULATED into the
+        parameter gradients (scaled by set_grad_scale), no optimizer step."""
+        key = ("seq", kind)
+        g = self._graphs.get(key)
+        if g is None:
+            train = kind == "grad"
+            self._accumulate = train
+            try:
+                if self.use_graph:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=self._main):
+                        self._prep(train)
+                        self._frontend(0)
+                        self._step(train, 0, False, prep_done=True)
+                    g = g.replay
+                else:
+                    def g(train=train):
+                        self._accumulate = train
+                        try:
+                            self._launch(train)
+                        finally:
+                            self._accumulate = False
+            finally:
+                self._accumulate = False
+                _lib.lib().ctan_set_pdl(1, None)
+            self._graphs[key] = g
+        with torch.cuda.device(self.dev):
+            g()
+        self.loader.cur_e_id += self.B
+
+    def adam(self):
+        """Sequence mode: optimizer step on the accumulated gradients, then clear them (optimizer.zero_grad())."""
+        g = self._graphs.get(("seq", "adam"))
+        if g is None:
+            def body():
+                self._adam()
+                self.zero_buf[:self._o_ws].zero_()
+            if self.use_graph:
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, stream=self._main):
+                    body()
+                g = gr.replay
+            else:
+                g = body
+            self._graphs[("seq", "adam")] = g
+        _lib.WEIGHTS_EPOCH += 1
+        with torch.cuda.device(self.dev):
+            g()
+        self._opt_steps += 1
+
+    def set_eid_offset(self, offset: int):
+        """Event id of stream row 0 (loader.cur_e_id at the start of a pass minus the cursor): the neighbour insert
+        numbers the events of the pass from there."""
+        self.w["counters"][7] = int(offset)
 
     # ------------------------------------------------------------------ public stepping API
     def _graph(self, train: bool, par: int = 0, prefetch: bool = False, inline: bool = True, early: bool = False):
@@ -683,7 +761,8 @@ class StepEngine:
         self.flat_p.copy_(keep)
         self.reset(reset_optimizer=True)
         self.w["loss_hist"].zero_()
-        self.capture_all()
+        if not self.seq_mod:
+            self.capture_all()
 
     def capture_all(self, train=(True, False)):
         """Capture every graph variant plan() can return, so that no capture ever lands in a caller's timed window."""
