@@ -353,7 +353,80 @@ def other_configs(dev, W, flush):
                      "events_in_stream": int(st["src"].numel()), "nodes": int(st["num_nodes"])}
         del eng, st
         torch.cuda.empty_cache()
+    res["pascal_shaped_multiclass_K3"] = pascal_shaped(dev, W, flush)
+    res["path_graph_sequence_L20_K3"] = path_graph_sequence(dev)
     return res
+
+
+def pascal_shaped(dev, W, flush, n_steps=100):
+    """BASELINE.json configs[3] (C4, Temporal Pascal-VOC shape: conf_pascal.py:136-175, run_pascal.py:31): 256-event
+    batches over 1e5 nodes, 1-d messages, 14-d node features, 21-class head with CrossEntropy and NO negatives, CTAN D=74
+    T=16 S=5 K=3 H=37 -- the engine's labelled head.  Same timing rule as the headline (per-step events, L2 flushed)."""
+    import ctan_b200  # noqa: F401
+    from ctan_b200 import synth
+    from ctan_b200.engine import StepEngine
+    from ctan_b200.models import CTAN, LastNeighborLoader
+    B, K = 256, 3
+    st = synth.make_stream("comment", n_events=(W + n_steps + 8) * B, seed=0, msg_dim=1, n_nodes_scale=100_000 / 994_790)
+    g0 = torch.Generator().manual_seed(0)
+    x = torch.randn(st["num_nodes"], 14, generator=g0)
+    y = torch.randint(0, 21, (st["src"].numel(),), generator=g0)
+    mean, std = synth.delta_t_stats(st, 20000)
+    torch.manual_seed(0)
+    model = CTAN(num_nodes=st["num_nodes"], edge_dim=1, memory_dim=74, time_dim=16, node_dim=14, num_iters=K, epsilon=0.1,
+                 gamma=0.1, readout_hidden=37, readout_out=21, mean_delta_t=mean, std_delta_t=std).to(dev)
+    loader = LastNeighborLoader(st["num_nodes"], 5, device=dev)
+    g = {k: st[k].to(dev) for k in ("src", "dst", "t", "msg")}
+    g["x"], g["y"] = x.to(dev), y.to(dev)
+    eng = StepEngine(model, loader, g, batch_size=B, n_neg=0, lr=1e-4, weight_decay=1e-6, criterion=torch.nn.CrossEntropyLoss())
+    eng.reset(reset_optimizer=True)
+    eng.warmup()
+    eng.run(W, train=True)
+    torch.cuda.synchronize()
+    tr = sum(time_steps(eng, n_steps, True, flush))
+    eng.check()
+    c = eng.w["counts"].cpu().tolist()
+    return {"train_events_per_sec": n_steps * B / (tr * 1e-3), "train_ms_per_step": tr / n_steps, "steps": n_steps, "batch": B,
+            "N": c[0], "E": c[1], "nodes": int(st["num_nodes"]), "last_loss": float(eng.losses(1)[0]),
+            "contractions": "CUDA-core fp32 (D=74 is not a multiple of 32)"}
+
+
+def path_graph_sequence(dev, n_seq=200, L=20):
+    """BASELINE.json configs[0] (C1, Temporal Path Graph: datasets/label_prediction_sequence.py:27-57, conf_sequence.py:
+    134-170): sequences of L-1 one-event steps, SequencePredictor head, CTAN D=53 K=3, meta-batches of 16 sequences, through
+    ctan_b200.train_sequence.train (the reference's signature; engine sequence mode).  Wall clock of one whole pass."""
+    import ctan_b200  # noqa: F401
+    from ctan_b200 import train_link as TL
+    from ctan_b200 import train_sequence as TS
+    from ctan_b200.models import CTAN, LastNeighborLoader
+    g0 = torch.Generator().manual_seed(0)
+    num_nodes = n_seq * L
+    x = (torch.rand(1, num_nodes, 1, generator=g0) * 2 - 1).to(dev)
+    data = []
+    for i in range(n_seq):
+        s = torch.arange(i * L, i * L + L - 1)
+        data.append(TL.TemporalData(src=s.to(dev), dst=(s + 1).to(dev), t=torch.arange(L - 1).to(dev),
+                                    msg=(torch.rand(L - 1, 1, generator=g0) * 2 - 1).to(dev),
+                                    y=torch.tensor([float(i % 2)]).to(dev), x=x))
+    torch.manual_seed(0)
+    model = CTAN(num_nodes=num_nodes, edge_dim=1, memory_dim=53, time_dim=1, node_dim=1, num_iters=3, epsilon=0.5, gamma=0.1,
+                 readout_hidden=26, readout_out=1, mean_delta_t=1.0, std_delta_t=1.0, final_act="tanh", predict_dst=True).to(dev)
+    loader = LastNeighborLoader(num_nodes, 5, device=dev)
+    helper = torch.empty(num_nodes, dtype=torch.long, device=dev)
+    opt = torch.optim.Adam(model.parameters(), lr=3e-3, weight_decay=1e-5)
+    crit = torch.nn.BCEWithLogitsLoss()
+    meta = [torch.arange(i, min(i + 16, n_seq)) for i in range(0, n_seq, 16)]
+    loaders = [TL.TemporalDataLoader(d, batch_size=1) for d in data]
+    TS.train(data, model, opt, meta, loaders, crit, loader, helper, device=dev)          # builds + warms the engine
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    TS.train(data, model, opt, meta, loaders, crit, loader, helper, device=dev)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    n_ev = n_seq * (L - 1)
+    return {"train_events_per_sec": n_ev / dt, "us_per_event": dt / n_ev * 1e6, "sequences": n_seq, "events": n_ev,
+            "what": "wall clock of one ctan_b200.train_sequence.train pass (one graph replay per event, optimizer step "
+                    "per 16 sequences)"}
 
 
 def dropin_engine_rate(st, K, mean, std, dev, n_steps):
