@@ -407,8 +407,13 @@ static int make_map_bf16(CUtensorMap* m, const void* base, int rows, int K) {
 
 // grid.y: a CTA holds ~212 KB of smem and all 512 TMEM columns, so exactly one is resident per SM; launch at most
 // one wave and let each CTA walk the remaining row tiles (that is also what overlaps epilogue and main loop)
-static int bounded_rows(int M_max, const int* M_dev, int gx) {
+// m_typ (optional, > 0): the caller's estimate of the TRUE row count when M_max is only a workspace bound.  Every CTA of
+// this kernel needs a whole SM (213 KB of shared memory, all of TMEM), idle ones included, so a grid sized by a loose
+// bound makes the launch wait for dozens of SMs to drain of the step's concurrent branches.  The kernel strides over
+// row tiles, so a smaller grid is always correct.
+static int bounded_rows(int M_max, const int* M_dev, int gx, int m_typ = 0) {
     (void)M_dev;
+    if (m_typ > 0 && m_typ < M_max) M_max = m_typ;
     int gy = (M_max + BM - 1) / BM;
     const int cap = CTAN_SM_COUNT / gx;
     if (gy > cap) gy = cap > 1 ? cap : 1;
@@ -461,10 +466,14 @@ extern "C" int ctan_wcat_prep(const float* Wq, const float* Wk, const float* Wv,
 // QKVA[N,4D] = X Wcat^T + [bq;bk;bv;b] on tcgen05 (3xTF32).  Requirements: D % 32 == 0, X has at least
 // ceil(N/128)*128 addressable rows or N rows (TMA zero-fills out-of-bounds rows), 16-byte aligned bases.
 // Returns CTAN_ERR_UNSUPPORTED when the shape does not qualify (the caller then uses ctan_qkva_fwd).
+// mode: bits 0-7 = precision (0 3xTF32, 1 TF32, 2 BF16); bits 8+ = optional estimate of the true row count when N is only
+// a workspace bound (sizes the persistent grid; 0 = unknown).
 extern "C" int ctan_qkva_fwd_tc(const float* X, int N, const int* N_dev, int D, const float* Wcat_hi,
                                 const float* Wcat_lo, const float* bq, const float* bk, const float* bv,
                                 const float* b, float* QKVA, int mode, cudaStream_t stream) {
     if (N <= 0) return 0;
+    const int m_typ = mode >> 8;              // bits 8+: expected row count (0 = unknown), sizes the persistent grid only
+    mode &= 0xFF;
     const bool bf = mode == 2;                // Wcat_hi is then a BF16 [4D, D] panel (ctan_pack_bf16), Wcat_lo unused
     if (D % (bf ? 2 * tc::BKF : tc::BKF) != 0 || ((4 * D) % tc::BN) != 0 ||
         (((uintptr_t)X | (uintptr_t)Wcat_hi | (bf ? 0 : (uintptr_t)Wcat_lo)) & 15))
@@ -483,7 +492,7 @@ extern "C" int ctan_qkva_fwd_tc(const float* X, int N, const int* N_dev, int D, 
     }
     const uintptr_t ball = (uintptr_t)bq | (uintptr_t)bk | (uintptr_t)bv | (uintptr_t)b | (uintptr_t)QKVA;
     tc::Bias4 bias{{bq, bk, bv, b}, D, (ball & 15) == 0 ? 1 : 0, nullptr, 0};
-    dim3 grid((4 * D) / tc::BN, tc::bounded_rows(N, N_dev, (4 * D) / tc::BN));
+    dim3 grid((4 * D) / tc::BN, tc::bounded_rows(N, N_dev, (4 * D) / tc::BN, m_typ));
     tc::qkva_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, bias, QKVA, 4 * D, N, N_dev, 4 * D, D,
                                                               mode);
     CTAN_CHECK_LAUNCH();
@@ -497,6 +506,8 @@ extern "C" int ctan_qkva_fwd_tc(const float* X, int N, const int* N_dev, int D, 
 extern "C" int ctan_dx_tc(const float* DQKVA, const float* G, int N, const int* N_dev, int D, const float* WcatT_hi,
                           const float* WcatT_lo, float* dXin, int mode, int n_split, cudaStream_t stream) {
     if (N <= 0) return 0;
+    const int m_typ = mode >> 8;              // (see ctan_qkva_fwd_tc)
+    mode &= 0xFF;
     if (D % tc::BN != 0 || (((uintptr_t)DQKVA | (uintptr_t)WcatT_hi | (uintptr_t)WcatT_lo | (uintptr_t)G | (uintptr_t)dXin) & 15))
         return CTAN_ERR_UNSUPPORTED;
     CUtensorMap tmA, tmBhi, tmBlo;
@@ -511,7 +522,7 @@ extern "C" int ctan_dx_tc(const float* DQKVA, const float* G, int N, const int* 
     const int n_kb = (4 * D) / tc::BKF;
     int splits = n_split < 1 ? 1 : n_split;
     while (splits > 1 && (n_kb % splits != 0)) --splits;
-    dim3 grid(D / tc::BN, tc::bounded_rows(N, N_dev, (D / tc::BN) * splits), splits);
+    dim3 grid(D / tc::BN, tc::bounded_rows(N, N_dev, (D / tc::BN) * splits, m_typ), splits);
     tc::qkva_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, epi, dXin, D, N, N_dev, D, 4 * D, mode);
     CTAN_CHECK_LAUNCH();
     return 0;
@@ -573,6 +584,8 @@ extern "C" int ctan_gemm_tc(const float* A, int M, const int* M_dev, int K, cons
                             const float* b0, const float* b1, const float* b2, const float* b3, int seg,
                             const float* res, int ldr, float* C, int mode, cudaStream_t stream) {
     if (M <= 0) return 0;
+    const int m_typ = mode >> 8;              // (see ctan_qkva_fwd_tc)
+    mode &= 0xFF;
     const bool bf = mode == 2;                // Bhi is then a BF16 [Nout, K] panel (ctan_pack_bf16), Blo unused
     if (K % (bf ? 2 * tc::BKF : tc::BKF) != 0 || Nout % tc::BN != 0 || seg <= 0 || seg % 16 != 0 ||
         (((uintptr_t)A | (uintptr_t)Bhi | (bf ? 0 : (uintptr_t)Blo) | (uintptr_t)C) & 15))
@@ -587,7 +600,7 @@ extern "C" int ctan_gemm_tc(const float* A, int M, const int* M_dev, int K, cons
     const uintptr_t ball = (uintptr_t)b0 | (uintptr_t)b1 | (uintptr_t)b2 | (uintptr_t)b3 | (uintptr_t)res |
                            (uintptr_t)(ldr * 4);
     tc::Bias4 epi{{b0, b1, b2, b3}, seg, (ball & 15) == 0 ? 1 : 0, res, ldr};
-    dim3 grid(Nout / tc::BN, tc::bounded_rows(M, M_dev, Nout / tc::BN));
+    dim3 grid(Nout / tc::BN, tc::bounded_rows(M, M_dev, Nout / tc::BN, m_typ));
     tc::qkva_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, epi, C, Nout, M, M_dev, Nout, K, mode);
     CTAN_CHECK_LAUNCH();
     return 0;

@@ -342,6 +342,9 @@ class StepEngine:
         self.hub_cap = min(N, 16384)                      # rows of degree > 8 go to the block-cooperative kernel
         w["A"] = torch.zeros((D, D), **f32)
         self.use_tc = _lib.use_tensor_cores(D)
+        # expected row count of the node-side contractions, packed into the `mode` argument of the tcgen05 entry points:
+        # their CTAs need a whole SM each, so the persistent grid is sized by the typical N, not by the workspace bound
+        self._row_hint = (self.n_typ << 8) if os.environ.get("CTAN_TC_ROW_HINT", "1") == "1" else 0
         w["Wcat_hi"], w["Wcat_lo"] = torch.zeros((4 * D, D), **f32), torch.zeros((4 * D, D), **f32)
         self.use_tc_dx = (self.use_tc and D % 128 == 0          # dX contraction on tcgen05 needs 128-wide output tiles
                           and os.environ.get("CTAN_TC_DX", "1") == "1")
@@ -561,7 +564,7 @@ class StepEngine:
             qk = w["QKVA"][k] if train else w["QKVA"][0]
             if self.use_tc:      # tcgen05 + TMA projection
                 call("ctan_qkva_fwd_tc", ptr(xi), N, Nd, D, ptr(w["Wcat_hi"]), ptr(w["Wcat_lo"]), bq, bk, bv, b,
-                     ptr(qk), _lib.TC_MODE)
+                     ptr(qk), _lib.TC_MODE | self._row_hint)
             else:
                 call("ctan_qkva_fwd", ptr(xi), N, Nd, D, Wq, Wk, Wv, ptr(w["A"]), bq, bk, bv, b, ptr(qk))
             last = k == K - 1
@@ -642,7 +645,7 @@ class StepEngine:
             gn = self._DX[k]
             if self.use_tc_dx:   # dX = G + DQKVA Wcat on tcgen05 (plain stores)
                 call("ctan_dx_tc", ptr(w["DQKVA"]), ptr(g), N, Nd, D, ptr(w["WcatT_hi"]), ptr(w["WcatT_lo"]), ptr(gn),
-                     _lib.TC_MODE, 2 if self.n_typ <= 4096 else 1)     # (split sweep 1/2/4/8/16: 110.5/109.8/112.5/112.9/112.8 us per step)
+                     _lib.TC_MODE | self._row_hint, 2 if self.n_typ <= 4096 else 1)     # (split sweep 1/2/4/8/16: 110.5/109.8/112.5/112.9/112.8 us per step)
             else:
                 call("ctan_qkva_bwd", *qb, ptr(gn), None, None, None, None, None, None, None, None, self.n_typ)
             g = gn
@@ -711,6 +714,10 @@ class StepEngine:
         with torch.cuda.device(self.dev):
             g()
         self._opt_steps += 1
+
+    def zero_grads(self):
+        """optimizer.zero_grad() for the accumulating steps: clear the parameter gradients (and dA)."""
+        self.zero_buf[:self._o_ws].zero_()
 
     def set_eid_offset(self, offset: int):
         """Event id of stream row 0 (loader.cur_e_id at the start of a pass minus the cursor): the neighbour insert

@@ -156,6 +156,7 @@ def train(train_data, model, optimizer, train_meta_loader, train_loaders, criter
     eng.reset()
     order = [i for b in batches for i in b]
     _load_pass(eng, st, _stacked(model, train_data, device), order, L1)
+    eng.zero_grads()                                         # optimizer.zero_grad() (train_sequence.py:24); adam() re-clears
     for b in batches:
         eng.set_grad_scale(1.0 / len(b))
         for _ in b:
