@@ -17,8 +17,9 @@
 #include "common.cuh"
 
 
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+// flag store after ONE system-scope fence (a st.release.sys per peer would emit a MEMBAR.SYS each)
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
     unsigned long long v;
@@ -88,7 +89,7 @@ __global__ void xchg_push_kernel(const float* __restrict__ send, int n_rows, int
             __threadfence_system();
             const unsigned long long e = *epoch_ptr + 1;
             for (int p = 0; p < world; ++p)
-                st_release_sys(reinterpret_cast<unsigned long long*>(peers[p]) + (size_t)parity * world + my_rank, e);
+                st_relaxed_sys(reinterpret_cast<unsigned long long*>(peers[p]) + (size_t)parity * world + my_rank, e);
         }
     }
 }

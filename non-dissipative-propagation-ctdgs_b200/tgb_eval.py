@@ -148,6 +148,12 @@ class TGBEvalEngine:
         self.use_tc = _lib.use_tensor_cores(D)
         # precision of the tensor-core contractions: 0 = 3xTF32 (fp32 parity), 1 = TF32, 2 = BF16 (needs D % 64 == 0)
         self.tc_mode = _lib.TC_MODE if (_lib.TC_MODE != 2 or D % 64 == 0) else 0
+        # expected node / edge row counts, packed into bits 8+ of the tcgen05 entry points' `mode` argument (their CTAs
+        # need a whole SM each: the persistent grid is sized by the typical subgraph, not by the workspace bound)
+        import os as _os
+        hint = _os.environ.get("CTAN_TC_ROW_HINT", "1") == "1"
+        self._n_hint = (min(N, 2 * self.n_seeds) << 8) if hint else 0
+        self._e_hint = (min(E, 4 * self.n_seeds) << 8) if hint else 0
         bf16 = dict(device=dev, dtype=torch.bfloat16)
         # tensor-core enc_x (dense gathered rows + packed weights) and node-projection readout
         self.use_tc_enc = self.use_tc and D % 128 == 0
@@ -269,7 +275,7 @@ class TGBEvalEngine:
                     call("ctan_eproj_prep", ptr(self.msg), Fe, ptr(f["eid"]), ptr(w["rel"]), ptr(g.time_enc.lin.weight),
                          ptr(g.time_enc.lin.bias), T, E, Ed, self.Kep, ptr(w["Aep"]))
                     call("ctan_gemm_tc", ptr(w["Aep"]), E, Ed, self.Kep, *self._panel("Wep"), D, None,
-                         None, None, None, D, None, 0, ptr(w["EP"]), self.tc_mode)
+                         None, None, None, D, None, 0, ptr(w["EP"]), self.tc_mode | self._e_hint)
                 else:
                     call("ctan_eproj_fwd", ptr(self.msg), Fe, ptr(f["eid"]), ptr(w["rel"]), ptr(g.time_enc.lin.weight),
                          ptr(g.time_enc.lin.bias), T, ptr(ph.lin_edge.weight), E, Ed, D, ptr(w["EP"]))
@@ -277,7 +283,7 @@ class TGBEvalEngine:
                 call("ctan_enc_prep", ptr(mem), D, xf, Fn, ptr(f["n_id"]), N, Nd, ptr(g.enc_x.weight), ptr(w["zmain"]),
                      ptr(w["ztail"]))
                 call("ctan_gemm_tc", ptr(w["zmain"]), N, Nd, D, *self._panel("Wenc"), D,
-                     ptr(g.enc_x.bias), None, None, None, D, ptr(w["ztail"]), D, ptr(w["X"][0]), self.tc_mode)
+                     ptr(g.enc_x.bias), None, None, None, D, ptr(w["ztail"]), D, ptr(w["X"][0]), self.tc_mode | self._n_hint)
             else:
                 call("ctan_enc_fwd", ptr(mem), D, xf, Fn, ptr(f["n_id"]), None, N, Nd, ptr(g.enc_x.weight),
                      ptr(g.enc_x.bias), ptr(w["X"][0]))
@@ -287,7 +293,7 @@ class TGBEvalEngine:
                 if self.use_tc:
                     call("ctan_qkva_fwd_tc", ptr(xi), N, Nd, D, *self._panel("Wcat"),
                          ptr(ph.lin_query.bias), ptr(ph.lin_key.bias), ptr(ph.lin_value.bias), ptr(a.bias),
-                         ptr(w["QKVA"]), self.tc_mode)
+                         ptr(w["QKVA"]), self.tc_mode | self._n_hint)
                 else:
                     call("ctan_qkva_fwd", ptr(xi), N, Nd, D, ptr(ph.lin_query.weight), ptr(ph.lin_key.weight),
                          ptr(ph.lin_value.weight), ptr(w["A"]), ptr(ph.lin_query.bias), ptr(ph.lin_key.bias),
@@ -307,7 +313,7 @@ class TGBEvalEngine:
             if self.use_tc_ro:
                 # project every NODE once (tensor cores), then a scored pair only gathers two rows
                 call("ctan_gemm_tc", ptr(z), N, Nd, D, *self._panel("Wro"), 2 * Hd, ptr(r.lin_src.bias),
-                     ptr(r.lin_dst.bias), None, None, Hd, None, 0, ptr(w["Y"]), self.tc_mode)
+                     ptr(r.lin_dst.bias), None, None, Hd, None, 0, ptr(w["Y"]), self.tc_mode | self._n_hint)
                 call("ctan_head_pack", ptr(w["Y"]), Hd, ptr(z), D, ptr(f["assoc"]), ptr(f["pair_src"]), ptr(f["pair_dst"]),
                      Q, self.n_neg, ptr(r.lin_final.weight), ptr(r.lin_final.bias), ptr(w["send"]))
             else:

@@ -1,24 +1,30 @@
 #!/bin/bash
-# Multi-GPU session: bitwise shard equivalence, then the sharded-evaluation bench with the exchange variants.
-# usage: bash scripts/r2_multi_session.sh <N>
+# Multi-GPU session: bitwise shard equivalence at N ranks, then the scaling series 1..N of the sharded-evaluation bench
+# (peer-memory exchange), plus the NCCL exchange at N for comparison.   usage: bash scripts/r2_multi_session.sh <N>
 N=${1:-2}
 O=gpurun_out
 mkdir -p $O
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611"
-for ex in peer nccl; do
-  CTAN_EVAL_EXCHANGE=$ex timeout 600 $TR scripts/check_shard_equiv.py > $O/r2_equiv_${ex}_n$N.log 2>&1
-  echo "== equiv exchange=$ex N=$N rc=$?"; grep -E "shard-equivalence|Error|error" $O/r2_equiv_${ex}_n$N.log | head -5
-done
-for cfg in "peer 0" "peer 1" "nccl 0"; do
-  set -- $cfg
-  CTAN_EVAL_EXCHANGE=$1 CTAN_EVAL_PREFETCH=$2 timeout 900 $TR bench.py --gpus $N --steps 100 --warmup 10 > $O/r2_scale_$1_pf$2_n$N.json 2> $O/r2_scale_$1_pf$2_n$N.err
-  echo "== bench exchange=$1 prefetch=$2 N=$N rc=$?"
-  python - <<PY
+show() {
+python - <<PY
 import json
 try:
-    d = json.loads(open("$O/r2_scale_$1_pf$2_n$N.json").read().strip().splitlines()[-1])
-    print({k: d.get(k) for k in ("value", "ms_per_step", "mrr", "launches_per_step", "sharding")}, "e2e", d["e2e"]["value"], "wiki999", d.get("tgbl_wiki_999"))
+    d = json.loads(open("$1").read().strip().splitlines()[-1])
+    w = d.get("tgbl_wiki_999") or {}
+    print({k: d.get(k) for k in ("n_gpus", "value", "ms_per_step", "mrr", "launches_per_step")}, "e2e", d["e2e"]["value"],
+          "| wiki999", {k: w.get(k) for k in ("value", "ms_per_step", "mrr", "rank0_subgraph")})
 except Exception as e:
-    print("parse failed", e); print(open("$O/r2_scale_$1_pf$2_n$N.err").read()[-2500:])
+    print("parse failed", e); print(open("$1".replace(".json", ".err")).read()[-2500:])
 PY
+}
+TRN="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1 --master-port 29611"
+timeout 600 $TRN --nproc-per-node $N scripts/check_shard_equiv.py > $O/r2_equiv_peer_n$N.log 2>&1
+echo "== equiv exchange=peer N=$N rc=$?"; grep -E "shard-equivalence|Error|error" $O/r2_equiv_peer_n$N.log | head -5
+timeout 600 python bench.py --gpus 1 --metric tgb_eval --steps 100 --warmup 10 > $O/r2_scale_peer_n1.json 2> $O/r2_scale_peer_n1.err
+echo "== bench N=1 rc=$?"; show $O/r2_scale_peer_n1.json
+for n in 2 4 8; do
+  [ $n -le $N ] || continue
+  timeout 900 $TRN --nproc-per-node $n bench.py --gpus $n --steps 100 --warmup 10 > $O/r2_scale_peer_n$n.json 2> $O/r2_scale_peer_n$n.err
+  echo "== bench exchange=peer N=$n rc=$?"; show $O/r2_scale_peer_n$n.json
 done
+CTAN_EVAL_EXCHANGE=nccl timeout 900 $TRN --nproc-per-node $N bench.py --gpus $N --steps 100 --warmup 10 > $O/r2_scale_nccl_n$N.json 2> $O/r2_scale_nccl_n$N.err
+echo "== bench exchange=nccl N=$N rc=$?"; show $O/r2_scale_nccl_n$N.json
