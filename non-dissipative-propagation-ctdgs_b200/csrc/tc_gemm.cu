@@ -17,6 +17,28 @@
 #include "common.cuh"
 #include <cuda.h>
 
+// Phase timeline of the tcgen05 kernel (profiling builds only: -DCTAN_TC_TRACE; scripts/micro_tc3.py): one elected
+// thread per role stores %globaltimer at the phase boundaries of the first 64 CTAs.
+#ifdef CTAN_TC_TRACE
+__device__ unsigned long long g_tc_trace[64 * 32];
+#define TC_TRACE(slot)                                                                                         \
+    do {                                                                                                       \
+        const unsigned _cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);                   \
+        if (_cta < 64) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));         \
+                         g_tc_trace[_cta * 32 + (slot)] = _t; }                                                \
+    } while (0)
+extern "C" int ctan_tc_trace_read(unsigned long long* host_out, int clear) {
+    cudaError_t e = cudaMemcpyFromSymbol(host_out, g_tc_trace, sizeof(g_tc_trace));
+    if (e == cudaSuccess && clear) {
+        static unsigned long long z[64 * 32];
+        e = cudaMemcpyToSymbol(g_tc_trace, z, sizeof(z));
+    }
+    return (int)e;
+}
+#else
+#define TC_TRACE(slot) do {} while (0)
+#endif
+
 namespace tc {
 
 constexpr int BM = 128, BN = 128, BKF = 32, STAGES = 4;
@@ -143,6 +165,7 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int M = M_dev ? *M_dev : M_host;
     const int n0 = blockIdx.x * BN;
     if ((int)blockIdx.y * BM >= M) return;                            // uniform, before any allocation
+    if (threadIdx.x == 0) TC_TRACE(0);
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     float* epi = (float*)(smem + STAGES * STAGE_BYTES);
     uint64_t* raw = (uint64_t*)(smem + STAGES * STAGE_BYTES + EPI_BYTES);
@@ -167,6 +190,7 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_holder;
+    if (threadIdx.x == 0) TC_TRACE(1);
     // split-K over gridDim.z (atomic epilogue): thin problems (few row tiles, long K) get more CTAs
     const bool bf = mode == 2;
     const int bke = bf ? 2 * BKF : BKF;                                 // elements of K per k-block
@@ -196,6 +220,7 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tma_load_2d(stage_ptr(s, 0), &tmA, &raw[s], (kb0 + kb) * BKF, m0);
                 tma_load_2d(stage_ptr(s, 1), &tmBhi, &raw[s], (kb0 + kb) * BKF, n0);
                 if (mode == 0) tma_load_2d(stage_ptr(s, 2), &tmBlo, &raw[s], (kb0 + kb) * BKF, n0);
+                if (it == 0) TC_TRACE(2);
             }
         }
     } else if (warp == 1) {
@@ -214,6 +239,7 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int s = it % nst;
                     mbar_wait(&ready[s], (it / nst) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (it == 0) TC_TRACE(4);
                     if (bf) {
                         const uint32_t idb = instr_desc_bf16();
                         const uint32_t a_bf = smem_u32(stage_ptr(s, 2)), b_bf = smem_u32(stage_ptr(s, 3));
@@ -240,6 +266,7 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mma_commit(&empty[s]);                              // arrives when these MMAs have read stage s
                 }
                 mma_commit(&done[buf]);                                 // this tile's accumulator is complete
+                TC_TRACE(5);
             }
         }
     } else if (warp < 2 + 4 * TGROUPS) {
@@ -256,6 +283,7 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (it % TGROUPS != grp) continue;
             const int s = it % nst;
             mbar_wait(&raw[s], (it / nst) & 1);
+            if (warp == 2 && lane == 0 && it < 12) TC_TRACE(16 + it);
             if (bf) {
                 uint8_t* orow = stage_ptr(s, 2) + r * 128;
 #pragma unroll
@@ -304,6 +332,7 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int buf = tile & 1;
             mbar_wait(&done[buf], (tile >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (q == 0 && lane == 0) TC_TRACE(6);
             const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC + (uint32_t)buf * BN;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -351,11 +380,13 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 __syncwarp();
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (q == 0 && lane == 0) TC_TRACE(7);
             mbar_arrive(&accfree[buf]);                                 // TMEM reads of this tile are complete
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (threadIdx.x == 0) TC_TRACE(8);
     if (warp == 1)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
 }
