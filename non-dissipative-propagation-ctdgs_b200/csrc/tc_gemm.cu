@@ -135,7 +135,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-struct Bias4 { const float* p[4]; int D; int vec; const float* res; int ldr; };   // + optional residual res[m][n]
+struct Bias4 { const float* p[4]; int D; int vec; const float* res; int ldr; int cvec; };   // + optional residual res[m][n]; cvec: C rows 16-byte aligned
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -336,14 +336,10 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC + (uint32_t)buf * BN;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tacc + c0, v);
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(stg + lane * EPI_LD + j) =
-                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                    __uint_as_float(v[j + 3]));
-                __syncwarp();
+                // Everything this chunk needs from global memory (bias of the thread's 4 columns, the residual rows it will
+                // add) is REQUESTED FIRST, so the L2 round trips overlap the TMEM read and the staging pass instead of
+                // sitting between them and the stores (measured: a load -> add -> atomic chain per row made the residual
+                // epilogue of dX 10 us; the split-0 CTAs finished 6 us after the others).
                 const int n = n0 + c0 + sub_c;                          // 4 columns: inside one bias segment (D % 16 == 0)
                 float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (first && n < N) {
@@ -355,24 +351,39 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         else bv = make_float4(__ldg(bp), __ldg(bp + 1), __ldg(bp + 2), __ldg(bp + 3));
                     }
                 }
+                float4 rv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    rv[i] = bv;
+                    const int row = m0 + q * 32 + i * 4 + sub_r;
+                    if (first && bias.res && row < M && n < N) {
+                        const float* rp = bias.res + (size_t)row * bias.ldr + n;
+                        float4 r4;
+                        if (bias.vec) r4 = __ldg(reinterpret_cast<const float4*>(rp));
+                        else r4 = make_float4(__ldg(rp), __ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3));
+                        rv[i].x += r4.x; rv[i].y += r4.y; rv[i].z += r4.z; rv[i].w += r4.w;
+                    }
+                }
+                uint32_t v[32];
+                tmem_ld32(tacc + c0, v);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(stg + lane * EPI_LD + j) =
+                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                    __uint_as_float(v[j + 3]));
+                __syncwarp();
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {                           // 4 rows x 128 B per warp instruction
                     const int rr = i * 4 + sub_r;
                     const int row = m0 + q * 32 + rr;
                     if (row < M && n < N) {
                         float4 o = *reinterpret_cast<const float4*>(stg + rr * EPI_LD + sub_c);
-                        o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-                        if (first && bias.res) {
-                            const float* rp = bias.res + (size_t)row * bias.ldr + n;
-                            if (bias.vec) {
-                                const float4 rv = *reinterpret_cast<const float4*>(rp);
-                                o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
-                            } else { o.x += rp[0]; o.y += rp[1]; o.z += rp[2]; o.w += rp[3]; }
-                        }
+                        o.x += rv[i].x; o.y += rv[i].y; o.z += rv[i].z; o.w += rv[i].w;
                         float* out = C + (size_t)row * ldc + n;
                         if (gridDim.z > 1) {                            // split-K: accumulate into the zeroed output
-                            atomicAdd(out, o.x); atomicAdd(out + 1, o.y); atomicAdd(out + 2, o.z); atomicAdd(out + 3, o.w);
-                        } else if (bias.vec) {
+                            if (bias.cvec) atomicAdd(reinterpret_cast<float4*>(out), o);      // one 16-byte red
+                            else { atomicAdd(out, o.x); atomicAdd(out + 1, o.y); atomicAdd(out + 2, o.z); atomicAdd(out + 3, o.w); }
+                        } else if (bias.cvec) {
                             *reinterpret_cast<float4*>(out) = o;
                         } else { out[0] = o.x; out[1] = o.y; out[2] = o.z; out[3] = o.w; }
                     }
@@ -522,7 +533,7 @@ extern "C" int ctan_qkva_fwd_tc(const float* X, int N, const int* N_dev, int D, 
         attr_set = true;
     }
     const uintptr_t ball = (uintptr_t)bq | (uintptr_t)bk | (uintptr_t)bv | (uintptr_t)b | (uintptr_t)QKVA;
-    tc::Bias4 bias{{bq, bk, bv, b}, D, (ball & 15) == 0 ? 1 : 0, nullptr, 0};
+    tc::Bias4 bias{{bq, bk, bv, b}, D, (ball & 15) == 0 ? 1 : 0, nullptr, 0, ((uintptr_t)QKVA & 15) == 0 ? 1 : 0};
     dim3 grid((4 * D) / tc::BN, tc::bounded_rows(N, N_dev, (4 * D) / tc::BN, m_typ));
     tc::qkva_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, bias, QKVA, 4 * D, N, N_dev, 4 * D, D,
                                                               mode);
@@ -548,7 +559,7 @@ extern "C" int ctan_dx_tc(const float* DQKVA, const float* G, int N, const int* 
     if (rc) return rc;
     cudaError_t e = cudaFuncSetAttribute(tc::qkva_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    tc::Bias4 epi{{nullptr, nullptr, nullptr, nullptr}, D, 1, G, D};
+    tc::Bias4 epi{{nullptr, nullptr, nullptr, nullptr}, D, 1, G, D, 1};       // (every base was checked 16-byte aligned above)
     // K = 4D is long and there are few row tiles: split K when the caller provides a zeroed dXin (n_split > 1)
     const int n_kb = (4 * D) / tc::BKF;
     int splits = n_split < 1 ? 1 : n_split;
@@ -630,7 +641,7 @@ extern "C" int ctan_gemm_tc(const float* A, int M, const int* M_dev, int K, cons
     if (e != cudaSuccess) return (int)e;
     const uintptr_t ball = (uintptr_t)b0 | (uintptr_t)b1 | (uintptr_t)b2 | (uintptr_t)b3 | (uintptr_t)res |
                            (uintptr_t)(ldr * 4);
-    tc::Bias4 epi{{b0, b1, b2, b3}, seg, (ball & 15) == 0 ? 1 : 0, res, ldr};
+    tc::Bias4 epi{{b0, b1, b2, b3}, seg, (ball & 15) == 0 ? 1 : 0, res, ldr, 1};   // (C was checked 16-byte aligned above, Nout % 128 == 0)
     dim3 grid(Nout / tc::BN, tc::bounded_rows(M, M_dev, Nout / tc::BN, m_typ));
     tc::qkva_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, epi, C, Nout, M, M_dev, Nout, K, mode);
     CTAN_CHECK_LAUNCH();
