@@ -123,6 +123,16 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
                  ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                  : "memory");
 }
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* v) {      // caller waits (tcgen05.wait::ld)
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -334,43 +344,51 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (q == 0 && lane == 0) TC_TRACE(6);
             const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC + (uint32_t)buf * BN;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                // Everything this chunk needs from global memory (bias of the thread's 4 columns, the residual rows it will
-                // add) is REQUESTED FIRST, so the L2 round trips overlap the TMEM read and the staging pass instead of
-                // sitting between them and the stores (measured: a load -> add -> atomic chain per row made the residual
-                // epilogue of dX 10 us; the split-0 CTAs finished 6 us after the others).
+            // Software-pipelined over the four 32-column chunks: the TMEM read of chunk c+1 is in flight while chunk c is
+            // staged and stored, and everything a chunk needs from global memory (bias of the thread's 4 columns, the
+            // residual rows) is requested BEFORE its staging pass with unconditional, clamped addresses -- so the loads of a
+            // chunk are one batch of independent requests, not a load -> add -> store chain per row (measured: that chain
+            // made the residual epilogue of dX 10 us against 4 us without residual).
+            const bool has_res = first && bias.res != nullptr;
+            uint32_t v[2][32];
+            tmem_ld32_issue(tacc, v[0]);
+#pragma unroll
+            for (int ci = 0; ci < BN / 32; ++ci) {
+                const int c0 = ci * 32;
                 const int n = n0 + c0 + sub_c;                          // 4 columns: inside one bias segment (D % 16 == 0)
+                const int nc = n < N ? n : N - 4;                       // clamped (loads only; stores are predicated)
                 float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (first && n < N) {
-                    const int seg = n / bias.D;
+                if (first) {
+                    const int seg = nc / bias.D;
                     const float* bp = seg == 0 ? bias.p[0] : (seg == 1 ? bias.p[1] : (seg == 2 ? bias.p[2] : bias.p[3]));
                     if (bp) {
-                        bp += n - seg * bias.D;
+                        bp += nc - seg * bias.D;
                         if (bias.vec) bv = __ldg(reinterpret_cast<const float4*>(bp));
                         else bv = make_float4(__ldg(bp), __ldg(bp + 1), __ldg(bp + 2), __ldg(bp + 3));
                     }
                 }
                 float4 rv[8];
+                if (has_res) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    rv[i] = bv;
-                    const int row = m0 + q * 32 + i * 4 + sub_r;
-                    if (first && bias.res && row < M && n < N) {
-                        const float* rp = bias.res + (size_t)row * bias.ldr + n;
-                        float4 r4;
-                        if (bias.vec) r4 = __ldg(reinterpret_cast<const float4*>(rp));
-                        else r4 = make_float4(__ldg(rp), __ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3));
-                        rv[i].x += r4.x; rv[i].y += r4.y; rv[i].z += r4.z; rv[i].w += r4.w;
+                    for (int i = 0; i < 8; ++i) {
+                        int row = m0 + q * 32 + i * 4 + sub_r;
+                        row = row < M ? row : M - 1;
+                        const float* rp = bias.res + (size_t)row * bias.ldr + nc;
+                        if (bias.vec) rv[i] = __ldg(reinterpret_cast<const float4*>(rp));
+                        else rv[i] = make_float4(__ldg(rp), __ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3));
                     }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                uint32_t v[32];
-                tmem_ld32(tacc + c0, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");           // chunk ci is in registers
+                if (ci + 1 < BN / 32) tmem_ld32_issue(tacc + c0 + 32, v[(ci + 1) & 1]);  // next chunk's read overlaps this one
+                const uint32_t* vc = v[ci & 1];
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<float4*>(stg + lane * EPI_LD + j) =
-                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                    __uint_as_float(v[j + 3]));
+                        make_float4(__uint_as_float(vc[j]), __uint_as_float(vc[j + 1]), __uint_as_float(vc[j + 2]),
+                                    __uint_as_float(vc[j + 3]));
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {                           // 4 rows x 128 B per warp instruction
@@ -378,7 +396,7 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int row = m0 + q * 32 + rr;
                     if (row < M && n < N) {
                         float4 o = *reinterpret_cast<const float4*>(stg + rr * EPI_LD + sub_c);
-                        o.x += rv[i].x; o.y += rv[i].y; o.z += rv[i].z; o.w += rv[i].w;
+                        o.x += bv.x + rv[i].x; o.y += bv.y + rv[i].y; o.z += bv.z + rv[i].z; o.w += bv.w + rv[i].w;
                         float* out = C + (size_t)row * ldc + n;
                         if (gridDim.z > 1) {                            // split-K: accumulate into the zeroed output
                             if (bias.cvec) atomicAdd(reinterpret_cast<float4*>(out), o);      // one 16-byte red
