@@ -155,7 +155,7 @@ def ptr(t, dtype=None):
 
 # kernels launched by each C entry point (for launch accounting; ctan_nbr_lookup adds one per hop)
 LAUNCHES = {"ctan_set_pdl": 0, "ctan_delta_t_stats_ws_bytes": 0, "ctan_delta_t_stats": 9, "ctan_nbr_insert": 2, "ctan_nbr_lookup": 1, "ctan_readout_fwd": 2, "ctan_readout_bwd": 2,
-            "ctan_qkva_bwd": 2, "ctan_eproj_bwd": 2}
+            "ctan_qkva_bwd": 2, "ctan_eproj_bwd": 0, "ctan_sym_alloc": 0}
 
 # Bumped by every writer of model weights that bypasses torch's tensor versioning (StepEngine's Adam kernel updates
 # the flat parameter buffer through raw pointers); readers of derived weight operands compare it with their last prep.
@@ -175,6 +175,8 @@ def call(name: str, *args):
     global N_LAUNCHES
     fn = getattr(lib(), name)
     N_LAUNCHES += LAUNCHES.get(name, 1) + (args[7] if name == "ctan_nbr_lookup" else 0)
+    if name == "ctan_eproj_bwd":                            # one contraction per non-NULL output (dWe, dTenc)
+        N_LAUNCHES += (args[12] is not None) + (args[13] is not None)
     if name == "ctan_edge_fwd" and args[13] is not None and args[15] == 0:
         N_LAUNCHES += 1                                     # the hub-row kernel (modes 1 / 2 launch one kernel each)
     if PROBE is not None and name != "ctan_probe":

@@ -312,7 +312,8 @@ extern "C" int ctan_eproj_bwd(const float* dEP, const float* msg, int Fe, const 
     if (E <= 0) return 0;
     if (e_typ <= 0 || e_typ > E) e_typ = E;
     int rc;
-    {
+    if (dWe) {                          // either half may be skipped (NULL output): the two are independent and a caller
+                                        // can run them on different streams
         AColMajor A{dEP, D, v4(dEP, D)};
         BEdgeAttr B{msg, Fe, eidx, Fe, rel, tw, tb, v4(msg, Fe) || Fe == 0};
         EpiAtomic epi{dWe, Fe + T, nullptr, nullptr, 0};

@@ -638,14 +638,17 @@ class StepEngine:
                 if k == 0:
                     call("ctan_antisym_bwd", ptr(w["dA"]), D, gW)
             if k == 0:
-                with self._fork(3):                          # side 3: lin_edge / time-encoder gradients
-                    call("ctan_eproj_bwd", ptr(w["dEP"]), ptr(self.msg), Fe, ptr(f["eid"]), ptr(f["rel"]), tw, tb, T,
-                         We, E, Ed, D, gWe, ptr(w["dTenc"]), self.e_typ)
+                ep = (ptr(w["dEP"]), ptr(self.msg), Fe, ptr(f["eid"]), ptr(f["rel"]), tw, tb, T, We, E, Ed, D)
+                with self._fork(3):                          # side 3: lin_edge weight gradient
+                    call("ctan_eproj_bwd", *ep, gWe, None, self.e_typ)
+                with self._fork(2):                          # side 2 (readout gradients long done): time-encoder gradients
+                    call("ctan_eproj_bwd", *ep, None, ptr(w["dTenc"]), self.e_typ)
                     call("ctan_tenc_bwd", ptr(w["dTenc"]), ptr(f["rel"]), tw, tb, E, Ed, T, gtw, gtb)
             gn = self._DX[k]
             if self.use_tc_dx:   # dX = G + DQKVA Wcat on tcgen05 (plain stores)
                 call("ctan_dx_tc", ptr(w["DQKVA"]), ptr(g), N, Nd, D, ptr(w["WcatT_hi"]), ptr(w["WcatT_lo"]), ptr(gn),
-                     _lib.TC_MODE | self._row_hint, 2 if self.n_typ <= 4096 else 1)     # (split sweep 1/2/4/8/16: 110.5/109.8/112.5/112.9/112.8 us per step)
+                     _lib.TC_MODE | self._row_hint, int(os.environ.get("CTAN_DX_SPLIT", "4")) if self.n_typ <= 4096 else 1)
+                # (kernel body at N=640: 18 / 12 / 9 us with 1 / 2 / 4 splits, scripts/micro_tc3.py)
             else:
                 call("ctan_qkva_bwd", *qb, ptr(gn), None, None, None, None, None, None, None, None, self.n_typ)
             g = gn
