@@ -340,49 +340,57 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int tile = 0;
         for (int m0 = blockIdx.y * BM; m0 < M; m0 += gridDim.y * BM, ++tile) {
             const int buf = tile & 1;
+            // bias of this thread's 4 columns in each 32-column chunk: requested while the MMAs of the tile still run
+            float4 bvs[BN / 32];
+#pragma unroll
+            for (int ci = 0; ci < BN / 32; ++ci) {
+                bvs[ci] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int n = n0 + ci * 32 + sub_c;
+                if (first && n < N) {
+                    const int seg = n / bias.D;
+                    const float* bp = seg == 0 ? bias.p[0] : (seg == 1 ? bias.p[1] : (seg == 2 ? bias.p[2] : bias.p[3]));
+                    if (bp) {
+                        bp += n - seg * bias.D;
+                        if (bias.vec) bvs[ci] = __ldg(reinterpret_cast<const float4*>(bp));
+                        else bvs[ci] = make_float4(__ldg(bp), __ldg(bp + 1), __ldg(bp + 2), __ldg(bp + 3));
+                    }
+                }
+            }
             mbar_wait(&done[buf], (tile >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (q == 0 && lane == 0) TC_TRACE(6);
             const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC + (uint32_t)buf * BN;
-            // Software-pipelined over the four 32-column chunks: the TMEM read of chunk c+1 is in flight while chunk c is
-            // staged and stored, and everything a chunk needs from global memory (bias of the thread's 4 columns, the
-            // residual rows) is requested BEFORE its staging pass with unconditional, clamped addresses -- so the loads of a
-            // chunk are one batch of independent requests, not a load -> add -> store chain per row (measured: that chain
-            // made the residual epilogue of dX 10 us against 4 us without residual).
+            // Software-pipelined over the four 32-column chunks: the TMEM read AND the residual rows of chunk c+1 are in flight
+            // while chunk c is staged and stored (biases were requested before the accumulator was complete); residual
+            // addresses are clamped and unconditional, so a chunk's loads are one batch of independent requests, not a
+            // load -> add -> store chain per row (measured: that chain made the residual epilogue of dX 10 us against 4 us
+            // without residual; pipelined: 4.3 -> see scripts/micro_tc3.py).
             const bool has_res = first && bias.res != nullptr;
             uint32_t v[2][32];
+            float4 rv[2][8];
+            auto load_res = [&](int ci, float4 (&r)[8]) {               // residual rows of chunk ci (clamped, unconditional)
+                const int n = n0 + ci * 32 + sub_c;
+                const int nc = n < N ? n : N - 4;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    int row = m0 + q * 32 + i * 4 + sub_r;
+                    row = row < M ? row : M - 1;
+                    const float* rp = bias.res + (size_t)row * bias.ldr + nc;
+                    if (bias.vec) r[i] = __ldg(reinterpret_cast<const float4*>(rp));
+                    else r[i] = make_float4(__ldg(rp), __ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3));
+                }
+            };
+            if (has_res) load_res(0, rv[0]);
             tmem_ld32_issue(tacc, v[0]);
 #pragma unroll
             for (int ci = 0; ci < BN / 32; ++ci) {
                 const int c0 = ci * 32;
                 const int n = n0 + c0 + sub_c;                          // 4 columns: inside one bias segment (D % 16 == 0)
-                const int nc = n < N ? n : N - 4;                       // clamped (loads only; stores are predicated)
-                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (first) {
-                    const int seg = nc / bias.D;
-                    const float* bp = seg == 0 ? bias.p[0] : (seg == 1 ? bias.p[1] : (seg == 2 ? bias.p[2] : bias.p[3]));
-                    if (bp) {
-                        bp += nc - seg * bias.D;
-                        if (bias.vec) bv = __ldg(reinterpret_cast<const float4*>(bp));
-                        else bv = make_float4(__ldg(bp), __ldg(bp + 1), __ldg(bp + 2), __ldg(bp + 3));
-                    }
-                }
-                float4 rv[8];
-                if (has_res) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        int row = m0 + q * 32 + i * 4 + sub_r;
-                        row = row < M ? row : M - 1;
-                        const float* rp = bias.res + (size_t)row * bias.ldr + nc;
-                        if (bias.vec) rv[i] = __ldg(reinterpret_cast<const float4*>(rp));
-                        else rv[i] = make_float4(__ldg(rp), __ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3));
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");           // chunk ci is in registers
-                if (ci + 1 < BN / 32) tmem_ld32_issue(tacc + c0 + 32, v[(ci + 1) & 1]);  // next chunk's read overlaps this one
+                if (ci + 1 < BN / 32) {                                 // next chunk: TMEM read and residual rows in flight
+                    tmem_ld32_issue(tacc + c0 + 32, v[(ci + 1) & 1]);
+                    if (has_res) load_res(ci + 1, rv[(ci + 1) & 1]);
+                }
                 const uint32_t* vc = v[ci & 1];
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
@@ -390,13 +398,18 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         make_float4(__uint_as_float(vc[j]), __uint_as_float(vc[j + 1]), __uint_as_float(vc[j + 2]),
                                     __uint_as_float(vc[j + 3]));
                 __syncwarp();
+                const float4 bv = bvs[ci];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {                           // 4 rows x 128 B per warp instruction
                     const int rr = i * 4 + sub_r;
                     const int row = m0 + q * 32 + rr;
                     if (row < M && n < N) {
                         float4 o = *reinterpret_cast<const float4*>(stg + rr * EPI_LD + sub_c);
-                        o.x += bv.x + rv[i].x; o.y += bv.y + rv[i].y; o.z += bv.z + rv[i].z; o.w += bv.w + rv[i].w;
+                        o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                        if (has_res) {
+                            const float4 r4 = rv[ci & 1][i];
+                            o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+                        }
                         float* out = C + (size_t)row * ldc + n;
                         if (gridDim.z > 1) {                            // split-K: accumulate into the zeroed output
                             if (bias.cvec) atomicAdd(reinterpret_cast<float4*>(out), o);      // one 16-byte red
