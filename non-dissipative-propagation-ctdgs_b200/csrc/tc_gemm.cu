@@ -176,7 +176,9 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int n0 = blockIdx.x * BN;
     if ((int)blockIdx.y * BM >= M) return;                            // uniform, before any allocation
     if (threadIdx.x == 0) TC_TRACE(0);
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment as an OFFSET from the __shared__ array (not an integer round trip of the pointer): the
+    // compiler keeps the shared address space, so the staging / transform accesses compile to LDS/STS, not generic LD/ST
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float* epi = (float*)(smem + STAGES * STAGE_BYTES);
     uint64_t* raw = (uint64_t*)(smem + STAGES * STAGE_BYTES + EPI_BYTES);
     uint64_t* ready = raw + STAGES;
@@ -366,6 +368,7 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // load -> add -> store chain per row (measured: that chain made the residual epilogue of dX 10 us against 4 us
             // without residual; pipelined: 4.3 -> see scripts/micro_tc3.py).
             const bool has_res = first && bias.res != nullptr;
+            const int emode = (gridDim.z > 1 ? 2 : 0) + (bias.cvec ? 0 : 1);   // 0 store v4 | 1 store scalar | 2 red v4 | 3 red scalar
             uint32_t v[2][32];
             float4 rv[2][8];
             auto load_res = [&](int ci, float4 (&r)[8]) {               // residual rows of chunk ci (clamped, unconditional)
@@ -387,6 +390,7 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int c0 = ci * 32;
                 const int n = n0 + c0 + sub_c;                          // 4 columns: inside one bias segment (D % 16 == 0)
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");           // chunk ci is in registers
+                if (q == 0 && lane == 0 && ci < 2) TC_TRACE(9 + 3 * ci);
                 if (ci + 1 < BN / 32) {                                 // next chunk: TMEM read and residual rows in flight
                     tmem_ld32_issue(tacc + c0 + 32, v[(ci + 1) & 1]);
                     if (has_res) load_res(ci + 1, rv[(ci + 1) & 1]);
@@ -398,28 +402,43 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         make_float4(__uint_as_float(vc[j]), __uint_as_float(vc[j + 1]), __uint_as_float(vc[j + 2]),
                                     __uint_as_float(vc[j + 3]));
                 __syncwarp();
+                if (q == 0 && lane == 0 && ci < 2) TC_TRACE(10 + 3 * ci);
                 const float4 bv = bvs[ci];
+                // all eight staged vectors first (one batch of LDS), then the stores: no load -> store chain per row and no
+                // uniform-mode branches inside the row loop
+                float4 o[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {                           // 4 rows x 128 B per warp instruction
-                    const int rr = i * 4 + sub_r;
-                    const int row = m0 + q * 32 + rr;
-                    if (row < M && n < N) {
-                        float4 o = *reinterpret_cast<const float4*>(stg + rr * EPI_LD + sub_c);
-                        o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-                        if (has_res) {
-                            const float4 r4 = rv[ci & 1][i];
-                            o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
-                        }
-                        float* out = C + (size_t)row * ldc + n;
-                        if (gridDim.z > 1) {                            // split-K: accumulate into the zeroed output
-                            if (bias.cvec) atomicAdd(reinterpret_cast<float4*>(out), o);      // one 16-byte red
-                            else { atomicAdd(out, o.x); atomicAdd(out + 1, o.y); atomicAdd(out + 2, o.z); atomicAdd(out + 3, o.w); }
-                        } else if (bias.cvec) {
-                            *reinterpret_cast<float4*>(out) = o;
-                        } else { out[0] = o.x; out[1] = o.y; out[2] = o.z; out[3] = o.w; }
+                for (int i = 0; i < 8; ++i) {
+                    o[i] = *reinterpret_cast<const float4*>(stg + (i * 4 + sub_r) * EPI_LD + sub_c);
+                    o[i].x += bv.x; o[i].y += bv.y; o[i].z += bv.z; o[i].w += bv.w;
+                    if (has_res) {
+                        const float4 r4 = rv[ci & 1][i];
+                        o[i].x += r4.x; o[i].y += r4.y; o[i].z += r4.z; o[i].w += r4.w;
+                    }
+                }
+                float* outb = C + (size_t)(m0 + q * 32 + sub_r) * ldc + n;
+                const int rows_left = M - (m0 + q * 32 + sub_r);        // row i is valid iff 4*i < rows_left
+                if (n < N) {
+                    if (emode == 0) {                                   // plain 16-byte stores (full 128-byte lines per row)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (4 * i < rows_left) *reinterpret_cast<float4*>(outb + (size_t)(4 * i) * ldc) = o[i];
+                    } else if (emode == 2) {                            // split-K: one 16-byte red per vector
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (4 * i < rows_left) atomicAdd(reinterpret_cast<float4*>(outb + (size_t)(4 * i) * ldc), o[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (4 * i < rows_left) {
+                                float* out = outb + (size_t)(4 * i) * ldc;
+                                if (emode == 1) { out[0] = o[i].x; out[1] = o[i].y; out[2] = o[i].z; out[3] = o[i].w; }
+                                else { atomicAdd(out, o[i].x); atomicAdd(out + 1, o[i].y); atomicAdd(out + 2, o[i].z); atomicAdd(out + 3, o[i].w); }
+                            }
                     }
                 }
                 __syncwarp();
+                if (q == 0 && lane == 0 && ci < 2) TC_TRACE(11 + 3 * ci);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             if (q == 0 && lane == 0) TC_TRACE(7);

@@ -57,7 +57,8 @@ def dx(split):
                                   hint, split, st)
 
 
-NAMES = {0: "entry", 1: "setup", 2: "tma0", 4: "mma0", 5: "commit", 6: "acc", 7: "epi", 8: "end"}
+NAMES = {0: "entry", 1: "setup", 2: "tma0", 4: "mma0", 5: "commit", 6: "acc", 9: "c0_ld", 10: "c0_stg", 11: "c0_st", 12: "c1_ld",
+         13: "c1_stg", 14: "c1_st", 7: "epi", 8: "end"}
 flush = torch.zeros(64 * 1024 * 1024, device=dev)
 for name, fn in (("qkvA fwd [640,128]x[128,512]", qkva), ("dX split 1", dx(1)), ("dX split 2", dx(2)), ("dX split 4", dx(4))):
     for _ in range(5):
