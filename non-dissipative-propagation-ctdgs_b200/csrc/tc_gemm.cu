@@ -358,15 +358,6 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             }
-            mbar_wait(&done[buf], (tile >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (q == 0 && lane == 0) TC_TRACE(6);
-            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC + (uint32_t)buf * BN;
-            // Software-pipelined over the four 32-column chunks: the TMEM read AND the residual rows of chunk c+1 are in flight
-            // while chunk c is staged and stored (biases were requested before the accumulator was complete); residual
-            // addresses are clamped and unconditional, so a chunk's loads are one batch of independent requests, not a
-            // load -> add -> store chain per row (measured: that chain made the residual epilogue of dX 10 us against 4 us
-            // without residual; pipelined: 4.3 -> see scripts/micro_tc3.py).
             const bool has_res = first && bias.res != nullptr;
             const int emode = (gridDim.z > 1 ? 2 : 0) + (bias.cvec ? 0 : 1);   // 0 store v4 | 1 store scalar | 2 red v4 | 3 red scalar
             uint32_t v[2][32];
@@ -383,7 +374,16 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     else r[i] = make_float4(__ldg(rp), __ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3));
                 }
             };
-            if (has_res) load_res(0, rv[0]);
+            if (has_res) load_res(0, rv[0]);                         // first chunk's residual rows: requested while the MMAs run
+            mbar_wait(&done[buf], (tile >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (q == 0 && lane == 0) TC_TRACE(6);
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC + (uint32_t)buf * BN;
+            // Software-pipelined over the four 32-column chunks: the TMEM read AND the residual rows of chunk c+1 are in flight
+            // while chunk c is staged and stored (biases were requested before the accumulator was complete); residual
+            // addresses are clamped and unconditional, so a chunk's loads are one batch of independent requests, not a
+            // load -> add -> store chain per row (measured: that chain made the residual epilogue of dX 10 us against 4 us
+            // without residual; pipelined: 4.3 -> see scripts/micro_tc3.py).
             tmem_ld32_issue(tacc, v[0]);
 #pragma unroll
             for (int ci = 0; ci < BN / 32; ++ci) {
