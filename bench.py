@@ -606,13 +606,16 @@ def main():
     # a tcgen05 contraction is bounded by the tensor pipe, not HBM: report useful flops against the measured dense peak
     tc_flops = {"ctan_dx_tc": 2.0 * N_last * 4 * D * D, "ctan_qkva_fwd_tc": 2.0 * N_last * D * 4 * D}.get(top_name)
     if tc_flops:
-        tkey = {"ctan_dx_tc": "qkva_tc_kernel@wiki_dx(N=710,K=512,Nout=128,split4)",
-                "ctan_qkva_fwd_tc": "qkva_tc_kernel@wiki_qkva(N=710,K=128,Nout=512)"}[top_name]
-        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        # roofline.traffic = DRAM bytes of ONE launch of this kernel at this shape from the committed `ncu --set full`
+        # capture of the round (profiles/r02_ncu_tc_wiki.txt; DRAM counters need the profiler: they are not measured
+        # in this run, and the field says where they come from)
+        tkey = {"ctan_dx_tc": "qkva_tc_kernel@wiki_dx", "ctan_qkva_fwd_tc": "qkva_tc_kernel@wiki_qkva"}[top_name]
+        tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
         if K == 1 and os.path.exists(tp):
             tr = json.load(open(tp)).get(tkey)
             if tr:
                 roof["traffic"] = tr["traffic_bytes"]
+                roof["traffic_source"] = tr.get("source", "ncu --set full capture under profiles/")
         tpeak, tsrc = load_tensor_peak()
         ach = tc_flops / (top_us * 1e-6) / 1e12
         roof.update(bound="tensor", unit="TFLOP/s", achieved=ach, peak=tpeak, frac=ach / tpeak, peak_source=tsrc,
