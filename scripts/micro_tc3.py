@@ -24,7 +24,8 @@ lib = ctypes.CDLL(OUT)
 P, I = ctypes.c_void_p, ctypes.c_int
 dev = torch.device("cuda:0")
 torch.cuda.set_device(dev)
-N_true, N_cap, D = int(os.environ.get("N", 640)), 3600, 128
+N_true, D = int(os.environ.get("N", 640)), int(os.environ.get("D", 128))
+N_cap = max(3600, 2 * N_true)
 g = torch.Generator().manual_seed(0)
 X = torch.randn(N_cap, D, generator=g).to(dev)
 DQ = torch.randn(N_cap, 4 * D, generator=g).to(dev)
@@ -44,7 +45,7 @@ DX = torch.zeros(N_cap, D, device=dev)
 lib.ctan_qkva_fwd_tc.argtypes = [P, I, P, I, P, P, P, P, P, P, P, I, P]
 lib.ctan_dx_tc.argtypes = [P, P, I, P, I, P, P, P, I, I, P]
 lib.ctan_tc_trace_read.argtypes = [P, I]
-hint = (900 << 8)
+hint = (int(os.environ.get("HINT", 900)) << 8)
 
 
 def qkva():
