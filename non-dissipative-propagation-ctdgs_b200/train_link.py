@@ -75,6 +75,12 @@ class TemporalData:
                 self.__dict__[k] = v.to(device)
         return self
 
+    def train_val_test_split(self, val_ratio: float = 0.15, test_ratio: float = 0.15):
+        """Chronological split used by link_prediction_single (train_link.py:689): cuts at the quantiles of t."""
+        q = np.quantile(self.t.cpu().numpy(), [1.0 - val_ratio - test_ratio, 1.0 - test_ratio])
+        a, b = int((self.t <= q[0]).sum()), int((self.t <= q[1]).sum())
+        return self[:a], self[a:b], self[b:]
+
 
 class TemporalDataLoader:
     """Sequential mini-batches `data[i:i+batch_size]`, last one short (torch_geometric.loader.TemporalDataLoader)."""

@@ -260,6 +260,14 @@ class TemporalData:
                 setattr(self, k, v.to(device))
         return self
 
+    def train_val_test_split(self, val_ratio: float = 0.15, test_ratio: float = 0.15):
+        """PyG 2.3.1: chronological cut at the (1-val-test) and (1-test) quantiles of t (counts of t <= quantile)."""
+        import numpy as np
+        val_time, test_time = np.quantile(self.t.cpu().numpy(), [1.0 - val_ratio - test_ratio, 1.0 - test_ratio])
+        val_idx = int((self.t <= val_time).sum())
+        test_idx = int((self.t <= test_time).sum())
+        return self[:val_idx], self[val_idx:test_idx], self[test_idx:]
+
 
 class TemporalDataLoader:
     def __init__(self, data, batch_size=1, **kwargs):

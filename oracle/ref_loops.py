@@ -195,3 +195,23 @@ class TimedLoader:
     @property
     def seconds(self):
         return self.t1 - self.t0
+
+
+class legacy_torch_load:
+    """The reference targets torch 2.0.1, where `torch.load` un-pickles arbitrary objects; its drivers save numpy scalars
+    in their checkpoints (train_link.py:587-603) and re-load them with a bare `torch.load(path, map_location=...)`.
+    While one of its drivers runs under torch >= 2.6, restore that default (weights_only=False).  Nothing else changes."""
+
+    def __enter__(self):
+        import torch
+        self._torch, self._orig = torch, torch.load
+
+        def load(*a, **k):
+            k.setdefault("weights_only", False)
+            return self._orig(*a, **k)
+        torch.load = load
+        return self
+
+    def __exit__(self, *exc):
+        self._torch.load = self._orig
+        return False

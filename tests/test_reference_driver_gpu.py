@@ -1,0 +1,79 @@
+"""north_star: "drop-in for main.py".  The reference's OWN experiment driver `train_link.link_prediction_single`
+(train_link.py:677-918: split, samplers, epochs of train / eval / eval, checkpointing, final test pass), imported unmodified,
+is run three ways on the same synthetic dataset and seeds:
+  A. everything from the reference (its CTAN, PyG's LastNeighborLoader, its train / eval), on the CPU;
+  B. `ctan_b200.models.CTAN` + `ctan_b200` LastNeighborLoader, the reference's own train / eval loops (module path);
+  C. as B, plus `from ctan_b200.train_link import train, eval` (the engines).
+All three must report the same scores (AP / AUC / loss of the train, validation and test passes) and the same best epoch."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _conf(tmp, st):
+    return {
+        "wandb": False, "seed": 3, "exp_seed": 7, "data_dir": tmp, "data_name": "synthetic-wiki", "split": (0.15, 0.15),
+        "batch": 50, "sampler": {"size": 5}, "model": "CTAN", "regression": False, "multiclass": False,
+        "optim_params": {"lr": 1e-3, "wd": 0.0}, "lr_scheduler": False, "lr_scheduler_patience": 5, "strategy": "split",
+        "neg_sampler": "NegativeSampler", "no_check_link_existence": False, "ckpt_path": tmp, "conf_id": 0,
+        "overwrite_ckpt": True, "epochs": 2, "debug": False, "verbose": False, "reset_memory_eval": False, "metric": "ap",
+        "patience": 5, "use_all_strategies_eval": False, "log": True,
+        "model_params": dict(num_nodes=st["num_nodes"], edge_dim=st["msg"].size(1), memory_dim=32, time_dim=8, node_dim=1,
+                             num_iters=1, epsilon=0.5, gamma=0.1, readout_hidden=16, readout_out=1,
+                             mean_delta_t=np.float64(1234.5), std_delta_t=np.float64(4567.8), init_time=0),
+    }
+
+
+def test_reference_driver_three_ways(small_stream, monkeypatch):
+    from oracle import pyg_shim, ref_loops
+    if not ref_loops.available():
+        pytest.skip("reference loop files not present")
+    R = ref_loops.load()
+    import ctan_b200  # noqa: F401
+    from ctan_b200 import train_link as TL
+    from ctan_b200.models import CTAN, LastNeighborLoader
+    st, n = small_stream, 1130
+    tl = R.train_link
+
+    def get_dataset(root, name, seed):
+        d = R.TemporalData(src=st["src"][:n].clone(), dst=st["dst"][:n].clone(), t=st["t"][:n].clone(),
+                           msg=st["msg"][:n].clone())
+        d.x = st["x"].clone()
+        return d, st["num_nodes"], st["msg"].size(1), 1, 1, 0, None
+    monkeypatch.setattr(tl, "get_dataset", get_dataset)
+    ref_pieces = (tl.LastNeighborLoader, tl.train, tl.eval)
+    results = {}
+    for way in "ABC":
+        with tempfile.TemporaryDirectory() as tmp:
+            conf = _conf(tmp, st)
+            if way == "A":
+                monkeypatch.setattr(torch.cuda, "is_available", lambda: False)       # the reference run stays on the CPU
+                monkeypatch.setattr(tl, "LastNeighborLoader", ref_pieces[0])
+                model_cls = R.ns.CTAN
+            else:
+                monkeypatch.undo()
+                monkeypatch.setattr(tl, "get_dataset", get_dataset)
+                monkeypatch.setattr(tl, "LastNeighborLoader", LastNeighborLoader)
+                model_cls = CTAN
+            if way == "C":
+                monkeypatch.setattr(tl, "train", TL.train)
+                monkeypatch.setattr(tl, "eval", TL.eval)
+            with pyg_shim.stable_sort(), ref_loops.legacy_torch_load():
+                ts, vl, tr, epoch, _, history = tl.link_prediction_single(model_cls, conf)
+            results[way] = (ts["split"], vl["split"], tr["split"], epoch, history)
+    monkeypatch.undo()
+    a = results["A"]
+    for way in "BC":
+        b = results[way]
+        assert b[3] == a[3], (way, "best epoch", b[3], a[3])
+        for i, name in enumerate(("test", "val", "train")):
+            for k in ("ap", "auc", "loss", "accuracy"):
+                assert abs(float(b[i][k]) - float(a[i][k])) <= 5e-3, (way, name, k, b[i][k], a[i][k])
+        assert len(b[4]) == len(a[4]) == 2
+        for ha, hb in zip(a[4], b[4]):
+            assert abs(hb["val"]["ap"] - ha["val"]["ap"]) <= 5e-3
