@@ -225,7 +225,7 @@ def _module_epoch(data, model, optimizer, batches, criterion, neighbor_loader, h
             loss.backward()
             optimizer.step()
         model.detach_memory()
-        out.append((float(loss), pos_out.detach(), None if neg_out is None else neg_out.detach()))
+        out.append((loss.item(), pos_out.detach(), None if neg_out is None else neg_out.detach()))
     return out
 
 

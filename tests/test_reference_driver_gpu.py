@@ -77,3 +77,88 @@ def test_reference_driver_three_ways(small_stream, monkeypatch):
         assert len(b[4]) == len(a[4]) == 2
         for ha, hb in zip(a[4], b[4]):
             assert abs(hb["val"]["ap"] - ha["val"]["ap"]) <= 5e-3
+
+
+class _FakeTGBDataset:
+    """What `tgb_link_prediction_single` reads from PyGLinkPropPredDataset: the three masks, the metric name, the
+    negative sampler (the reference's own NegativeEdgeSampler with hand-filled evaluation sets) and the two loaders."""
+
+    def __init__(self, R, st, n, n_tr, n_va, n_neg=9):
+        idx = torch.arange(n)
+        self.train_mask, self.val_mask, self.test_mask = idx < n_tr, (idx >= n_tr) & (idx < n_tr + n_va), idx >= n_tr + n_va
+        self.eval_metric = "mrr"
+        negs = np.random.default_rng(11).integers(st["min_dst"], st["max_dst"] + 1, (n, n_neg))   # (not torch.randint: patched)
+        self.negative_sampler = R.NegativeEdgeSampler(dataset_name="tgbl-wiki", strategy="hist_rnd")
+        for name, mask in (("val", self.val_mask), ("test", self.test_mask)):
+            es = {}
+            for i in torch.nonzero(mask).view(-1).tolist():
+                es[(int(st["src"][i]), int(st["dst"][i]), int(st["t"][i]))] = negs[i]
+            self.negative_sampler.eval_set[name] = es
+
+    def load_val_ns(self):
+        pass
+
+    def load_test_ns(self):
+        pass
+
+
+def test_reference_tgb_driver_three_ways(small_stream, monkeypatch):
+    """Same for `main_tgb_ctan.py`'s driver, `tgb_link_prediction_single` (train_link.py:440-672): tgb_train epochs,
+    tgb_test on the 'train' / 'val_fast' / 'val' / 'test' splits, checkpoint + reload of the best epoch."""
+    from oracle import pyg_shim, ref_loops
+    if not ref_loops.available():
+        pytest.skip("reference loop files not present")
+    R = ref_loops.load()
+    import ctan_b200  # noqa: F401
+    from ctan_b200 import train_link as TL
+    from ctan_b200.models import CTAN_tgb, LastNeighborLoader
+    from test_train_link_gpu import fixed_randint
+    st, n, n_tr, n_va = small_stream, 900, 630, 130
+    tl = R.train_link
+
+    def get_dataset(root, name, seed):
+        d = R.TemporalData(src=st["src"][:n].clone(), dst=st["dst"][:n].clone(), t=st["t"][:n].clone(),
+                           msg=st["msg"][:n].clone())
+        return d, st["num_nodes"], st["msg"].size(1), 1, 1, 0, _FakeTGBDataset(R, st, n, n_tr, n_va)
+
+    class RefCTANtgb(R.ns.CTAN_tgb):                          # reference defects B2/B3: `separable` kwarg, `layernorm` attribute
+        def __init__(self, *a, separable=False, **k):
+            super().__init__(*a, **k)
+            self.layernorm = None
+
+    def conf_for(tmp):
+        c = _conf(tmp, st)
+        c.update(data_name="tgbl-wiki", epochs=3, validate_every=1, validation_subsample=5, validation_batched=False,
+                 metric="mrr")
+        c["model_params"] = dict(num_nodes=st["num_nodes"], edge_dim=st["msg"].size(1), memory_dim=32, time_dim=32,
+                                 node_dim=1, num_iters=1, epsilon=0.5, gamma=0.1, readout_hidden=32, readout_out=1,
+                                 mean_delta_t=np.float64(1234.5), std_delta_t=np.float64(4567.8), init_time=0,
+                                 final_act=None, separable=False)
+        return c
+    results = {}
+    for way in "ABC":
+        with tempfile.TemporaryDirectory() as tmp:
+            monkeypatch.undo()
+            monkeypatch.setattr(tl, "get_dataset", get_dataset)
+            if way == "A":
+                monkeypatch.setattr(torch.cuda, "is_available", lambda: False)
+                model_cls = RefCTANtgb
+            else:
+                monkeypatch.setattr(tl, "LastNeighborLoader", LastNeighborLoader)
+                model_cls = CTAN_tgb
+            if way == "C":
+                monkeypatch.setattr(tl, "tgb_train", TL.tgb_train)
+                monkeypatch.setattr(tl, "tgb_test", TL.tgb_test)
+            with pyg_shim.stable_sort(), ref_loops.legacy_torch_load(), fixed_randint(st["neg"]):
+                ts, vl, tr, epoch, _, history = tl.tgb_link_prediction_single(model_cls, conf_for(tmp))
+            results[way] = (ts, vl, tr, epoch, history)
+    monkeypatch.undo()
+    a = results["A"]
+    for way in "BC":
+        b = results[way]
+        assert b[3] == a[3], (way, "best epoch", b[3], a[3])
+        for i, name in enumerate(("test", "val", "train")):
+            assert abs(b[i]["mrr"] - a[i]["mrr"]) <= 1e-2, (way, name, b[i]["mrr"], a[i]["mrr"])
+        for ha, hb in zip(a[4], b[4]):
+            assert abs(hb["val"]["mrr"] - ha["val"]["mrr"]) <= 2e-2
+            assert abs(hb["train"]["loss"] - ha["train"]["loss"]) <= 2e-3 * abs(ha["train"]["loss"])
