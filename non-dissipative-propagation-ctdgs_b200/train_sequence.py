@@ -30,17 +30,31 @@ def _order(meta_loader):
     return batches
 
 
-def _uniform(data, loaders):
+def _uniform(model, data, loaders):
+    """L-1 if every sequence has the same number of events, one event per loader batch, and ONE node-feature table
+    (the dataset shares `x` between its sequences, datasets/label_prediction_sequence.py:33-52; after the driver's
+    per-sequence `.to(device)` they are equal copies, which is checked once per data list), else 0."""
     L1 = int(data[0].src.numel())
-    x0 = getattr(data[0], "x", None)
     for d in data:
-        if int(d.src.numel()) != L1 or getattr(d, "x", None) is not x0 and (
-                x0 is None or getattr(d, "x", None) is None or d.x.data_ptr() != x0.data_ptr()):
+        if int(d.src.numel()) != L1:
             return 0
     for ld in (loaders.values() if isinstance(loaders, dict) else loaders):
         if getattr(ld, "batch_size", 1) != 1:
             return 0
-    return L1
+    cache = model.__dict__.setdefault("_ctan_seq_x_ok", {})
+    key = (id(data), len(data))
+    if key not in cache:
+        x0 = getattr(data[0], "x", None)
+        ok = True
+        for d in data[1:]:
+            x = getattr(d, "x", None)
+            if x is x0:
+                continue
+            if x is None or x0 is None or x.shape != x0.shape or (x.data_ptr() != x0.data_ptr() and not torch.equal(x, x0)):
+                ok = False
+                break
+        cache[key] = ok
+    return L1 if cache[key] else 0
 
 
 def _stacked(model, data, dev):
@@ -56,10 +70,12 @@ def _stacked(model, data, dev):
 def _engine(model, neighbor_loader, optimizer, criterion, data, L1, n_seq_max, dev):
     cache = model.__dict__.setdefault("_ctan_engines", {})
     O = model.readout.lin_final.weight.size(0)
-    key = ("seq", id(neighbor_loader), L1, type(criterion).__name__, data[0].x.data_ptr() if getattr(data[0], "x", None) is not None else 0)
+    x0 = getattr(data[0], "x", None)
+    key = ("seq", id(neighbor_loader), L1, type(criterion).__name__, tuple(x0.shape) if x0 is not None else None)
     ent = cache.get(key)
-    if ent is not None and ent["cap"] < n_seq_max:
-        ent = None
+    if ent is not None and (ent["cap"] < n_seq_max or (x0 is not None and ent["x"] is not x0
+                                                       and not torch.equal(ent["x"], x0.to(ent["x"].device)))):
+        ent = None                                            # larger pass, or another node-feature table: rebuild
     if ent is None:
         n_ev = n_seq_max * L1
         Fe = data[0].msg.size(1)
@@ -74,7 +90,7 @@ def _engine(model, neighbor_loader, optimizer, criterion, data, L1, n_seq_max, d
         model.memory.memory.copy_(keep[0]); model.memory.last_update.copy_(keep[1])
         neighbor_loader.e_id.copy_(keep[2]); neighbor_loader.neighbors.copy_(keep[3]); neighbor_loader._deg.copy_(keep[4])
         neighbor_loader.cur_e_id = keep[5]
-        ent = {"eng": eng, "st": st, "cap": n_seq_max}
+        ent = {"eng": eng, "st": st, "cap": n_seq_max, "x": x0}
         cache[key] = ent
     eng = ent["eng"]
     if optimizer is not None:
@@ -146,7 +162,7 @@ def train(train_data, model, optimizer, train_meta_loader, train_loaders, criter
     model.reset_memory()
     neighbor_loader.reset_state()
     batches = _order(train_meta_loader)
-    L1 = _uniform(train_data, train_loaders)
+    L1 = _uniform(model, train_data, train_loaders)
     ok = (L1 >= 1 and getattr(model, "predict_dst", False) and type(criterion).__name__ in LOSS_MODES
           and LOSS_MODES[type(criterion).__name__] != 1)
     if not ok:
@@ -179,7 +195,7 @@ def eval(eval_data, model, meta_loader, eval_loaders, criterion, neighbor_loader
     model.eval()
     batches = _order(meta_loader)
     order = [i for b in batches for i in b]
-    L1 = _uniform(eval_data, eval_loaders)
+    L1 = _uniform(model, eval_data, eval_loaders)
     ok = (L1 >= 1 and getattr(model, "predict_dst", False) and type(criterion).__name__ in LOSS_MODES
           and LOSS_MODES[type(criterion).__name__] != 1)
     if ok:

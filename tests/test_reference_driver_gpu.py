@@ -162,3 +162,84 @@ def test_reference_tgb_driver_three_ways(small_stream, monkeypatch):
         for ha, hb in zip(a[4], b[4]):
             assert abs(hb["val"]["mrr"] - ha["val"]["mrr"]) <= 2e-2
             assert abs(hb["train"]["loss"] - ha["train"]["loss"]) <= 2e-3 * abs(ha["train"]["loss"])
+
+
+class _FakeSequenceDataset:
+    """datasets/label_prediction_sequence.py in miniature: `num_seq` path graphs of `seq_len` nodes, one shared x table,
+    label = parity of the sequence index, first message / first node feature carry the signal."""
+
+    def __init__(self, TD, num_seq=40, seq_len=7, feat_dim=1, seed=9):
+        rng = np.random.default_rng(seed)
+        x = rng.uniform(-1.0, 1.0, size=(seq_len * num_seq, feat_dim))
+        x[::seq_len] = np.array([(i % 2) * 2 - 1 for i in range(num_seq)], dtype=np.float64).reshape(-1, 1)
+        x = torch.from_numpy(x.reshape(1, seq_len * num_seq, -1)).float()
+        self.data, first = [], 0
+        for i in range(num_seq):
+            msg = rng.uniform(-1.0, 1.0, size=(seq_len - 1, feat_dim))
+            msg[0] = (i % 2) * 2 - 1
+            self.data.append(TD(src=torch.arange(first, first + seq_len - 1), dst=torch.arange(first + 1, first + seq_len),
+                                t=torch.arange(seq_len - 1), x=x, msg=torch.from_numpy(msg).float(),
+                                y=torch.tensor([float(i % 2)])))
+            first += seq_len
+        self.num_nodes = seq_len * num_seq
+
+    def train_val_test_split(self, val_ratio, test_ratio):
+        a = int(len(self.data) * (1 - val_ratio - test_ratio))
+        b = int(len(self.data) * val_ratio) + a
+        return self.data[:a], self.data[a:b], self.data[b:]
+
+
+def test_reference_sequence_driver_three_ways(monkeypatch):
+    """And for `run_sequence.py`'s driver, `train_sequence.sequence_prediction_single` (train_sequence.py:138-311):
+    shuffled meta-batches of sequences, SequencePredictor head, train / eval / eval per epoch, final three passes."""
+    from oracle import pyg_shim, ref_loops
+    if not ref_loops.available():
+        pytest.skip("reference loop files not present")
+    R = ref_loops.load()
+    import ctan_b200  # noqa: F401
+    from ctan_b200 import train_sequence as TS
+    from ctan_b200.models import CTAN, LastNeighborLoader
+    ts_mod = R.train_sequence
+    L = 7
+
+    def get_dataset(root, name, seed):
+        ds = _FakeSequenceDataset(R.TemporalData, num_seq=40, seq_len=L)
+        return ds, ds.num_nodes, 1, 1, 1, 0, None
+
+    def conf_for(tmp):
+        return {"wandb": False, "seed": 5, "exp_seed": 9, "data_dir": tmp, "data_name": "labelsequence", "split": (0.15, 0.15),
+                "batch": 8, "sampler": {"size": 5}, "model": "CTAN", "regression": False, "metric": "accuracy",
+                "optim_params": {"lr": 3e-3, "wd": 1e-5}, "lr_scheduler": False, "ckpt_path": tmp, "conf_id": 0,
+                "overwrite_ckpt": True, "epochs": 3, "debug": False, "verbose": False, "reset_memory_eval": False,
+                "patience": 10, "log": True,
+                "model_params": dict(num_nodes=40 * L, edge_dim=1, memory_dim=26, time_dim=1, node_dim=1, num_iters=3,
+                                     epsilon=0.5, gamma=0.1, readout_hidden=13, readout_out=1, mean_delta_t=1.67,
+                                     std_delta_t=1.49, init_time=0, final_act="tanh", predict_dst=True)}
+    results = {}
+    for way in "ABC":
+        with tempfile.TemporaryDirectory() as tmp:
+            monkeypatch.undo()
+            monkeypatch.setattr(ts_mod, "get_dataset", get_dataset)
+            if way == "A":
+                monkeypatch.setattr(torch.cuda, "is_available", lambda: False)
+                model_cls = R.ns.CTAN
+            else:
+                monkeypatch.setattr(ts_mod, "LastNeighborLoader", LastNeighborLoader)
+                model_cls = CTAN
+            if way == "C":
+                monkeypatch.setattr(ts_mod, "train", TS.train)
+                monkeypatch.setattr(ts_mod, "eval", TS.eval)
+            with pyg_shim.stable_sort(), ref_loops.legacy_torch_load():
+                ts, vl, tr, epoch, _, history = ts_mod.sequence_prediction_single(model_cls, conf_for(tmp))
+            results[way] = (ts, vl, tr, epoch, history)
+    monkeypatch.undo()
+    a = results["A"]
+    for way in "BC":
+        b = results[way]
+        assert b[3] == a[3], (way, "best epoch", b[3], a[3])
+        for i, name in enumerate(("test", "val", "train")):
+            for strat in a[i]:
+                assert abs(float(b[i][strat]["loss"]) - float(a[i][strat]["loss"])) <= 5e-3, (way, name)
+                assert abs(float(b[i][strat]["accuracy"]) - float(a[i][strat]["accuracy"])) <= 0.101, (way, name)
+        for ha, hb in zip(a[4], b[4]):
+            assert abs(hb["val"]["loss"] - ha["val"]["loss"]) <= 5e-3
