@@ -41,8 +41,9 @@ def test_sequence_loops_match_the_reference_run(use_engine):
     g = _gold()
     mm, loader, helper = _model(g)
     data = _data(g, TL.TemporalData, DEV)
-    if not use_engine:
-        data[3].x = data[3].x.clone()                        # a private x tensor: the engine declines, the module path runs
+    if not use_engine:                                       # a sequence with its OWN node-feature table (differing only at a
+        data[3].x = data[3].x.clone()                        # node it never touches): the engine declines, the module path runs
+        data[3].x[0, -1, 0] += 1.0
     n, mb = g["n_seq"], g["meta_batch"]
     meta = [torch.arange(i, i + mb) for i in range(0, n, mb)]
     loaders = [TL.TemporalDataLoader(d, batch_size=1) for d in data]
