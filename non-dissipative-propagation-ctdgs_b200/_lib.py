@@ -81,6 +81,7 @@ SIGNATURES.update({
     "ctan_adam_step": [P, P, P, P, I, F, F, F, F, F, L, P, P],
     "ctan_loss_generic": [P, I, I, I, P, F, P, P, P, I, P],
     "ctan_eid_mod": [P, I, P, I, P],
+    "ctan_zero_arena": [P, L, I, P, P, P, P, P, P, P, P, P, P, I],
     "ctan_record_rows": [P, I, P, I, P],
     # sym.cu (the host-side ctan_sym_* / ctan_ipc_* setup calls take no stream: bound in sym.py)
     "ctan_xchg_push": [P, I, I, I, I, P, I, I, I, ctypes.c_size_t, P, P],

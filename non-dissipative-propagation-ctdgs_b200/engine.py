@@ -191,6 +191,7 @@ class StepEngine:
         o_dZ = o_dA + pad(D * D)
         self._o_ws = o_dZ                                      # [0, _o_ws): parameter gradients + dA; beyond: per-step scratch
         self._accumulate = False
+        self._arena = (o_dZ, o_DQ, o_DX)
         o_DQ = o_dZ + pad(N * D)
         o_DX = o_DQ + pad(N * 4 * D)
         self.zero_buf = torch.zeros(o_DX + K * N * D, device=self.dev)
@@ -507,11 +508,6 @@ class StepEngine:
             else:
                 call("ctan_antisym_prep", W, float(m.gnn.aconv.gamma), D, ptr(w["A"]))
             w["H"].zero_()
-            if train:
-                if self._accumulate:                         # keep flat_g and dA (they accumulate over several steps)
-                    self.zero_buf[self._o_ws:].zero_()
-                else:
-                    self.zero_buf.zero_()
         # Programmatic dependent launch (csrc/common.cuh) shortens the single-chain no-grad step (80 -> 75 us) but
         # LENGTHENS the training step (118 -> 122..127 us, more the further into the DAG it is enabled): dependents
         # scheduled early hold SM slots that the step's parallel branches need.  So: inference on, training off.
@@ -536,6 +532,9 @@ class StepEngine:
         eps = float(m.gnn.aconv.epsilon)
         if not prep_done:
             self._prep(train)
+        if train:
+            with self._fork(2):                              # the accumulation arena, cleared by the batch's TRUE node count
+                self._zero_arena(f)
         def insert():
             call("ctan_nbr_insert", ptr(ld.neighbors), ptr(ld.e_id), ptr(ld._deg), ptr(f["b_src"]), ptr(f["b_dst"]),
                  B, 0, cur1, S, ptr(w["ins_ws"]))
@@ -628,7 +627,7 @@ class StepEngine:
         for k in range(K - 1, -1, -1):
             if k != K - 1:
                 self._join(0)                                # the previous iteration's dW contraction reads DQKVA
-                w["DQKVA"].zero_()
+                self._zero_arena(f, only_dq=True)
             call("ctan_edge_bwd", ptr(w["QKVA"][k]), ptr(w["EP"]), ptr(f["rowptr"]), ptr(f["esrc"]), N, Nd, D, ptr(g),
                  ptr(w["TH"][k]), ptr(w["ALPHA"][k]), eps, ptr(w["DQKVA"]), ptr(w["dEP"]), int(k != K - 1),
                  ptr(w["DS"]))
@@ -660,6 +659,26 @@ class StepEngine:
         if not self._accumulate:
             self._adam()
         _lib.lib().ctan_set_pdl(1, None)
+
+    def _zero_arena(self, f, only_dq: bool = False):
+        """Clear what the backward accumulates into: parameter gradients + dA (unless accumulating over steps) and the
+        first N rows of dZ, DQKVA and dX_k -- N read on the device, not the workspace bound."""
+        import ctypes
+        N, D, K = self.n_cap, self.D, self.K
+        o_dZ, o_DQ, o_DX = self._arena
+        zb = self.zero_buf.data_ptr()
+        if only_dq:
+            segs = [(zb + 4 * o_DQ, 4 * D)]
+            base, head = None, 0
+        else:
+            segs = [(zb + 4 * o_dZ, D), (zb + 4 * o_DQ, 4 * D)] + [(zb + 4 * (o_DX + k * N * D), D) for k in range(K)]
+            base, head = (None, 0) if self._accumulate else (zb, o_dZ)
+        if len(segs) > 8:                                    # more than 6 iterations: plain memset of the tail
+            self.zero_buf[o_DX:].zero_()
+            segs = segs[:2]
+        rows = (ctypes.c_int * 8)(*([r for _, r in segs] + [0] * (8 - len(segs))))
+        ptrs = [p for p, _ in segs] + [None] * (8 - len(segs))
+        call("ctan_zero_arena", base, head, len(segs), *ptrs, ctypes.cast(rows, ctypes.c_void_p), ptr(f["Nd"]), N)
 
     def _adam(self):
         call("ctan_adam_step", ptr(self.flat_p), ptr(self.flat_g), ptr(self.adam_m), ptr(self.adam_v),

@@ -34,6 +34,7 @@ REF = {
     "ctan_adam_step": "torch.optim.Adam.step -- train_link.py:281",
     "ctan_loss_generic": "criterion(pos_out, batch.y): CrossEntropyLoss / MSELoss / L1Loss (train_link.py:329,706-709) and BCEWithLogitsLoss on labels (train_sequence.py:57), with its gradient",
     "ctan_eid_mod": "e_id = e_id % data.msg.shape[0] -- train_sequence.py:41, 87",
+    "ctan_zero_arena": "optimizer.zero_grad() + the zero-initialised buffers autograd accumulates into -- train_link.py:240, 279",
     "ctan_record_rows": "y_pred_confidence_list.append(...) -- per-batch scores kept for the end-of-pass metrics, train_link.py:383-395",
     "ctan_neg_sample": "NegativeSampler.sample -- negative_sampler.py:27-40",
     "ctan_sym_alloc": "(symmetric peer-memory block of the sharded evaluation; host-side, no reference counterpart)",
