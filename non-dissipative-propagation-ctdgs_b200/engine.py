@@ -191,10 +191,10 @@ class StepEngine:
         o_dZ = o_dA + pad(D * D)
         self._o_ws = o_dZ                                      # [0, _o_ws): parameter gradients + dA; beyond: per-step scratch
         self._accumulate = False
-        self._arena = (o_dZ, o_DQ, o_DX)
         o_DQ = o_dZ + pad(N * D)
         o_DX = o_DQ + pad(N * 4 * D)
         self.zero_buf = torch.zeros(o_DX + K * N * D, device=self.dev)
+        self._arena = (o_dZ, o_DQ, o_DX)
         self.flat_g = self.zero_buf[:n]
         self._dA = self.zero_buf[o_dA:o_dA + D * D].view(D, D)
         self._dZ = self.zero_buf[o_dZ:o_dZ + N * D].view(N, D)

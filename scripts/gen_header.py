@@ -99,6 +99,8 @@ for f in ("loader.cu", "edge.cu", "dense.cu", "step.cu", "tc_gemm.cu", "stats.cu
     out.append(f"/* ---------------------------------------------------------------- {f} */")
     for m in re.finditer(r'((?:^//[^\n]*\n)*)extern "C" int (\w+)\(([^{]*?)\)\s*\{', src, re.M):
         comment, name, args = m.group(1), m.group(2), " ".join(m.group(3).split())
+        if name == "ctan_tc_trace_read":          # exists only in -DCTAN_TC_TRACE profiling builds
+            continue
         names.append(name)
         out.append(f"/* replaces: {REF.get(name, '(internal helper)')} */")
         if comment.strip():
