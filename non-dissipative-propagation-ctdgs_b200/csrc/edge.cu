@@ -549,25 +549,50 @@ __global__ void enc_prep_kernel(const float* __restrict__ mem, int D, const floa
                                 const int64_t* __restrict__ n_id, int N_host, const int* __restrict__ N_dev,
                                 const float* __restrict__ Wenc, float* __restrict__ zmain, float* __restrict__ tail) {
     ctan_pdl_begin();
+    // the node-feature columns of enc_x.weight ([D, D+Fn], column D+f of row d) are strided by D+Fn floats: staged
+    // once per CTA as Wt[f][d] so that the per-row tail is a coalesced multiply-add (was 32 sectors per warp load)
+    extern __shared__ float Wt[];
+    const int ldw = D + Fn;
+    for (int i = threadIdx.x; i < Fn * D; i += blockDim.x) {
+        const int f = i / D, d = i - f * D;
+        Wt[i] = __ldg(Wenc + (size_t)d * ldw + D + f);
+    }
+    __syncthreads();
     const int N = N_dev ? *N_dev : N_host;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    const int ldw = D + Fn;
+    const bool vec = (D & 3) == 0 && ((((uintptr_t)mem | (uintptr_t)zmain | (uintptr_t)tail) & 15) == 0);
     for (int r = warp; r < N; r += nw) {
         const int64_t g = n_id[r];
-        for (int d = lane; d < D; d += 32) {
-            zmain[(size_t)r * D + d] = __ldg(mem + (size_t)g * D + d);
-            float t = 0.f;
-            for (int f = 0; f < Fn; ++f) t = fmaf(__ldg(xfeat + (size_t)g * Fn + f), __ldg(Wenc + (size_t)d * ldw + D + f), t);
-            tail[(size_t)r * D + d] = t;
+        if (vec) {
+            for (int d4 = lane; d4 < (D >> 2); d4 += 32) {
+                const float4 m = __ldg(reinterpret_cast<const float4*>(mem + (size_t)g * D) + d4);
+                reinterpret_cast<float4*>(zmain + (size_t)r * D)[d4] = m;
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int f = 0; f < Fn; ++f) {
+                    const float x = __ldg(xfeat + (size_t)g * Fn + f);
+                    const float4 w4 = *reinterpret_cast<const float4*>(Wt + f * D + 4 * d4);
+                    t.x = fmaf(x, w4.x, t.x); t.y = fmaf(x, w4.y, t.y); t.z = fmaf(x, w4.z, t.z); t.w = fmaf(x, w4.w, t.w);
+                }
+                reinterpret_cast<float4*>(tail + (size_t)r * D)[d4] = t;
+            }
+        } else {
+            for (int d = lane; d < D; d += 32) {
+                zmain[(size_t)r * D + d] = __ldg(mem + (size_t)g * D + d);
+                float t = 0.f;
+                for (int f = 0; f < Fn; ++f) t = fmaf(__ldg(xfeat + (size_t)g * Fn + f), Wt[f * D + d], t);
+                tail[(size_t)r * D + d] = t;
+            }
         }
     }
 }
 extern "C" int ctan_enc_prep(const float* mem, int D, const float* xfeat, int Fn, const int64_t* n_id, int N,
                              const int* N_dev, const float* Wenc, float* zmain, float* tail, cudaStream_t stream) {
     if (N <= 0) return 0;
-    CTAN_LAUNCH((enc_prep_kernel), ctan_grid((long long)N * 32, 256), 256, 0, stream, mem, D, xfeat, Fn, n_id, N, N_dev, Wenc,
-                                                                           zmain, tail);
+    const size_t smem = (size_t)(Fn > 0 ? Fn : 1) * D * sizeof(float);
+    if (smem > 48 * 1024) return CTAN_ERR_UNSUPPORTED;
+    CTAN_LAUNCH((enc_prep_kernel), ctan_grid((long long)N * 32, 256, 4), 256, smem, stream, mem, D, xfeat, Fn, n_id, N, N_dev,
+                Wenc, zmain, tail);
     CTAN_CHECK_LAUNCH();
     return 0;
 }

@@ -394,15 +394,20 @@ class TGBEvalEngine:
         B, D = self.B, self.D
         mem, lu = m.memory.memory, m.memory.last_update
         rows = self._rows(xpar)
-        call("ctan_accum_col", ptr(rows), B, self.row, 0, ptr(w["acc"]))
+        cur = torch.cuda.current_stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):                   # the metric accumulation only feeds the final MRR: beside the
+            call("ctan_accum_col", ptr(rows), B, self.row, 0, ptr(w["acc"]))          # memory write-back, not before it
         emb = ptr(rows) + 4 * (1 + self.L)
         if dry:      # warm-up: same kernels, but the state update goes to scratch tables
             sm, sl, sn, se, sd = self._scratch
             call("ctan_mem_update", ptr(sm), ptr(sl), D, ptr(sl), ptr(sl), ptr(sl), 1, emb, emb + 4 * D, self.row,
                  None, None)
+            cur.wait_stream(self._side)
             return
         call("ctan_mem_update", ptr(mem), ptr(lu), D, ptr(f["b_src"]), ptr(f["b_dst"]), ptr(f["b_t"]), B, emb,
              emb + 4 * D, self.row, None, None)
+        cur.wait_stream(self._side)
 
     def warmup(self):
         """One eager dry batch: loads every kernel and initialises the communicator before graph capture.
