@@ -281,3 +281,27 @@ def _dump(obj):
     buf = io.BytesIO()
     torch.save(obj, buf)
     return buf.getvalue()
+
+
+def test_compute_stats_reference_signature(small_stream):
+    """utils.compute_stats(data, split, init_time, sequence_prediction) (the caller at main.py:302 /
+    main_tgb_ctan.py:270), imported unmodified, against ctan_b200.stats.compute_stats_from_data on the same objects."""
+    from ctan_b200.stats import compute_stats_from_data
+    RL, R = _ref()
+    st, n = small_stream, 1500
+    d = R.TemporalData(src=st["src"][:n], dst=st["dst"][:n], t=st["t"][:n], msg=st["msg"][:n])
+    ref = R.utils.compute_stats(d, (0.15, 0.15), 0)
+    mine = compute_stats_from_data(d, (0.15, 0.15), 0, device=DEV)
+    assert abs(mine[0] - float(ref[0])) <= 1e-9 * abs(float(ref[0])) and abs(mine[1] - float(ref[1])) <= 1e-9 * float(ref[1])
+
+    class Seqs:                                              # the sequence case: a dataset object whose split returns lists
+        def __init__(self):
+            self.data = [R.TemporalData(src=torch.arange(i * 7, i * 7 + 6), dst=torch.arange(i * 7 + 1, i * 7 + 7),
+                                        t=torch.arange(6)) for i in range(20)]
+
+        def train_val_test_split(self, val_ratio, test_ratio):
+            a = int(len(self.data) * (1 - val_ratio - test_ratio))
+            return self.data[:a], self.data[a:a + 3], self.data[a + 3:]
+    ref = R.utils.compute_stats(Seqs(), (0.15, 0.15), 0, sequence_prediction=True)
+    mine = compute_stats_from_data(Seqs(), (0.15, 0.15), 0, sequence_prediction=True, device=DEV)
+    assert abs(mine[0] - float(ref[0])) <= 1e-12 + 1e-9 * abs(float(ref[0])) and abs(mine[1] - float(ref[1])) <= 1e-9 * float(ref[1])
