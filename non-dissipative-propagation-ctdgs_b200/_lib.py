@@ -103,6 +103,9 @@ SIGNATURES.update({
     "ctan_gemm_tc": [P, I, P, I, P, P, I, P, P, P, P, I, P, I, P, I],
     "ctan_enc_prep": [P, I, P, I, P, I, P, P, P, P],
     "ctan_head_gather": [P, I, P, P, P, I, P, P, P],
+    "ctan_fuse_enc_prep": [P, P, P, P, P, P, P, P, P, P, I, I, I, P, P],
+    "ctan_enc_prep_ext": [P, I, P, I, P, I, P, I, P],
+    "ctan_enc_qkva_tc": [P, I, P, I, P, P, I, P, P, P, I],
     "ctan_head_pack": [P, I, P, I, P, P, P, I, I, P, P, P],
     "ctan_set_pdl": [I],
     "ctan_delta_t_stats_ws_bytes": [L, P],

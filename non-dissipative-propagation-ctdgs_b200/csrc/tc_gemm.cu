@@ -145,7 +145,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-struct Bias4 { const float* p[4]; int D; int vec; const float* res; int ldr; int cvec; };   // + optional residual res[m][n]; cvec: C rows 16-byte aligned
+struct Bias4 { const float* p[4]; int D; int vec; const float* res; int ldr; int cvec;   // + optional residual res[m][n]; cvec: C rows 16-byte aligned
+               float* C2; int split; int ldc2; };   // columns >= split go to C2[m][n - split] (split % BN == 0: uniform per tile)
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -416,22 +417,25 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         o[i].x += r4.x; o[i].y += r4.y; o[i].z += r4.z; o[i].w += r4.w;
                     }
                 }
-                float* outb = C + (size_t)(m0 + q * 32 + sub_r) * ldc + n;
+                float* outb = (bias.C2 && n0 >= bias.split)
+                                  ? bias.C2 + (size_t)(m0 + q * 32 + sub_r) * bias.ldc2 + (n - bias.split)
+                                  : C + (size_t)(m0 + q * 32 + sub_r) * ldc + n;
                 const int rows_left = M - (m0 + q * 32 + sub_r);        // row i is valid iff 4*i < rows_left
+                const int ldo = (bias.C2 && n0 >= bias.split) ? bias.ldc2 : ldc;
                 if (n < N) {
                     if (emode == 0) {                                   // plain 16-byte stores (full 128-byte lines per row)
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            if (4 * i < rows_left) *reinterpret_cast<float4*>(outb + (size_t)(4 * i) * ldc) = o[i];
+                            if (4 * i < rows_left) *reinterpret_cast<float4*>(outb + (size_t)(4 * i) * ldo) = o[i];
                     } else if (emode == 2) {                            // split-K: one 16-byte red per vector
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            if (4 * i < rows_left) atomicAdd(reinterpret_cast<float4*>(outb + (size_t)(4 * i) * ldc), o[i]);
+                            if (4 * i < rows_left) atomicAdd(reinterpret_cast<float4*>(outb + (size_t)(4 * i) * ldo), o[i]);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
                             if (4 * i < rows_left) {
-                                float* out = outb + (size_t)(4 * i) * ldc;
+                                float* out = outb + (size_t)(4 * i) * ldo;
                                 if (emode == 1) { out[0] = o[i].x; out[1] = o[i].y; out[2] = o[i].z; out[3] = o[i].w; }
                                 else { atomicAdd(out, o[i].x); atomicAdd(out + 1, o[i].y); atomicAdd(out + 2, o[i].z); atomicAdd(out + 3, o[i].w); }
                             }
@@ -583,7 +587,7 @@ extern "C" int ctan_qkva_fwd_tc(const float* X, int N, const int* N_dev, int D, 
         attr_set = true;
     }
     const uintptr_t ball = (uintptr_t)bq | (uintptr_t)bk | (uintptr_t)bv | (uintptr_t)b | (uintptr_t)QKVA;
-    tc::Bias4 bias{{bq, bk, bv, b}, D, (ball & 15) == 0 ? 1 : 0, nullptr, 0, ((uintptr_t)QKVA & 15) == 0 ? 1 : 0};
+    tc::Bias4 bias{{bq, bk, bv, b}, D, (ball & 15) == 0 ? 1 : 0, nullptr, 0, ((uintptr_t)QKVA & 15) == 0 ? 1 : 0, nullptr, 0, 0};
     dim3 grid((4 * D) / tc::BN, tc::bounded_rows(N, N_dev, (4 * D) / tc::BN, m_typ));
     tc::qkva_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, bias, QKVA, 4 * D, N, N_dev, 4 * D, D,
                                                               mode);
@@ -609,7 +613,7 @@ extern "C" int ctan_dx_tc(const float* DQKVA, const float* G, int N, const int* 
     if (rc) return rc;
     cudaError_t e = cudaFuncSetAttribute(tc::qkva_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    tc::Bias4 epi{{nullptr, nullptr, nullptr, nullptr}, D, 1, G, D, 1};       // (every base was checked 16-byte aligned above)
+    tc::Bias4 epi{{nullptr, nullptr, nullptr, nullptr}, D, 1, G, D, 1, nullptr, 0, 0};       // (every base was checked 16-byte aligned above)
     // K = 4D is long and there are few row tiles: split K when the caller provides a zeroed dXin (n_split > 1)
     const int n_kb = (4 * D) / tc::BKF;
     int splits = n_split < 1 ? 1 : n_split;
@@ -691,9 +695,112 @@ extern "C" int ctan_gemm_tc(const float* A, int M, const int* M_dev, int K, cons
     if (e != cudaSuccess) return (int)e;
     const uintptr_t ball = (uintptr_t)b0 | (uintptr_t)b1 | (uintptr_t)b2 | (uintptr_t)b3 | (uintptr_t)res |
                            (uintptr_t)(ldr * 4);
-    tc::Bias4 epi{{b0, b1, b2, b3}, seg, (ball & 15) == 0 ? 1 : 0, res, ldr, 1};   // (C was checked 16-byte aligned above, Nout % 128 == 0)
+    tc::Bias4 epi{{b0, b1, b2, b3}, seg, (ball & 15) == 0 ? 1 : 0, res, ldr, 1, nullptr, 0, 0};   // (C was checked 16-byte aligned above, Nout % 128 == 0)
     dim3 grid(Nout / tc::BN, tc::bounded_rows(M, M_dev, Nout / tc::BN, m_typ));
     tc::qkva_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, epi, C, Nout, M, M_dev, Nout, K, mode);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ enc_x folded into the projection
+// With ONE anti-symmetric iteration the first thing the step does is two chained linear maps of the gathered rows:
+//   X0 = z0 Wenc^T + benc ;  [q|k|v|x.A^T] = X0 Wcat^T + bcat     (models/gnn_layers.py:96, PyG App. A.5)
+// Both are linear in z0, so with frozen weights (evaluation: tgb_test is @torch.no_grad) they are ONE contraction
+//   [X0 | QKVA] = z0 [Wenc ; Wcat Wenc]^T + [benc ; Wcat benc + bcat]
+// against a [5D, Kx] panel formed once per run.  z0 = [memory row | node features | 0-pad] with Kx = D+Fn rounded up to
+// 32 (the node features become ordinary K columns: no residual pass).  One launch and one dependent stage fewer per batch.
+__global__ void fuse_enc_kernel(const float* __restrict__ Wq, const float* __restrict__ Wk, const float* __restrict__ Wv,
+                                const float* __restrict__ A, const float* __restrict__ bq, const float* __restrict__ bk,
+                                const float* __restrict__ bv, const float* __restrict__ b, const float* __restrict__ Wenc,
+                                const float* __restrict__ benc, int D, int Fn, int Kx, float* __restrict__ Wce,
+                                float* __restrict__ bce) {
+    const int ldw = D + Fn;
+    const long long n = 5LL * D * Kx;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n + 5LL * D; i += (long long)gridDim.x * blockDim.x) {
+        const bool is_bias = i >= n;
+        const int r = is_bias ? (int)(i - n) : (int)(i / Kx), c = is_bias ? 0 : (int)(i - (long long)r * Kx);
+        float v;
+        if (r < D) {                                          // the enc_x block itself (zero padded to Kx)
+            v = is_bias ? benc[r] : (c < ldw ? Wenc[(size_t)r * ldw + c] : 0.f);
+        } else {                                              // row r-D of Wcat = [Wq;Wk;Wv;A] times enc_x
+            const int rr = r - D, seg = rr / D, ro = rr - seg * D;
+            const float* W = seg == 0 ? Wq : (seg == 1 ? Wk : (seg == 2 ? Wv : A));
+            const float* bb = seg == 0 ? bq : (seg == 1 ? bk : (seg == 2 ? bv : b));
+            double acc = 0.0;                                 // fp64 accumulation: the panel is formed once per run
+            if (is_bias) {
+                for (int d = 0; d < D; ++d) acc += (double)W[(size_t)ro * D + d] * (double)benc[d];
+                acc += (double)bb[ro];
+            } else if (c < ldw) {
+                for (int d = 0; d < D; ++d) acc += (double)W[(size_t)ro * D + d] * (double)Wenc[(size_t)d * ldw + c];
+            }
+            v = (float)acc;
+        }
+        if (is_bias) bce[r] = v; else Wce[i] = v;
+    }
+}
+// Wce [5D, Kx], bce [5D]; A = W - W^T - gamma I (from ctan_wcat_prep / ctan_antisym_prep).
+extern "C" int ctan_fuse_enc_prep(const float* Wq, const float* Wk, const float* Wv, const float* A, const float* bq,
+                                  const float* bk, const float* bv, const float* b, const float* Wenc, const float* benc,
+                                  int D, int Fn, int Kx, float* Wce, float* bce, cudaStream_t stream) {
+    if (D <= 0 || Fn < 0 || Kx < D + Fn || Kx % 32 != 0) return CTAN_ERR_BAD_ARG;
+    fuse_enc_kernel<<<ctan_grid(5LL * D * Kx, 256), 256, 0, stream>>>(Wq, Wk, Wv, A, bq, bk, bv, b, Wenc, benc, D, Fn, Kx, Wce, bce);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+// zext[r] = [ mem[n_id[r]] (D) | xfeat[n_id[r]] (Fn) | 0 ... ] with row pitch Kx (a dense TMA operand); one warp per row.
+__global__ void enc_prep_ext_kernel(const float* __restrict__ mem, int D, const float* __restrict__ xfeat, int Fn,
+                                    const int64_t* __restrict__ n_id, int N_host, const int* __restrict__ N_dev, int Kx,
+                                    float* __restrict__ zext) {
+    ctan_pdl_begin();
+    const int N = N_dev ? *N_dev : N_host;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const bool vec = (D & 3) == 0 && (Kx & 3) == 0 && ((((uintptr_t)mem | (uintptr_t)zext) & 15) == 0);
+    for (int r = warp; r < N; r += nw) {
+        const int64_t g = n_id[r];
+        float* out = zext + (size_t)r * Kx;
+        if (vec) {
+            for (int d4 = lane; d4 < (D >> 2); d4 += 32)
+                reinterpret_cast<float4*>(out)[d4] = __ldg(reinterpret_cast<const float4*>(mem + (size_t)g * D) + d4);
+        } else {
+            for (int d = lane; d < D; d += 32) out[d] = __ldg(mem + (size_t)g * D + d);
+        }
+        for (int c = D + lane; c < Kx; c += 32) out[c] = c < D + Fn ? __ldg(xfeat + (size_t)g * Fn + (c - D)) : 0.f;
+    }
+}
+extern "C" int ctan_enc_prep_ext(const float* mem, int D, const float* xfeat, int Fn, const int64_t* n_id, int N,
+                                 const int* N_dev, int Kx, float* zext, cudaStream_t stream) {
+    if (N <= 0) return 0;
+    if (Kx < D + Fn) return CTAN_ERR_BAD_ARG;
+    CTAN_LAUNCH((enc_prep_ext_kernel), ctan_grid((long long)N * 32, 256, 4), 256, 0, stream, mem, D, xfeat, Fn, n_id, N, N_dev,
+                Kx, zext);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
+// [X0 | QKVA] = zext Wce^T + bce on tcgen05: columns [0,D) -> X0 [N,D], columns [D,5D) -> QKVA [N,4D].
+// Wce_hi/Wce_lo: the split panel of ctan_fuse_enc_prep's Wce (ctan_pack_split), or a BF16 panel in mode 2.
+extern "C" int ctan_enc_qkva_tc(const float* zext, int N, const int* N_dev, int Kx, const float* Wce_hi, const float* Wce_lo,
+                                int D, const float* bce, float* X0, float* QKVA, int mode, cudaStream_t stream) {
+    if (N <= 0) return 0;
+    const int m_typ = mode >> 8;
+    mode &= 0xFF;
+    const bool bf = mode == 2;
+    if (Kx % (bf ? 2 * tc::BKF : tc::BKF) != 0 || D % tc::BN != 0 ||
+        (((uintptr_t)zext | (uintptr_t)Wce_hi | (bf ? 0 : (uintptr_t)Wce_lo) | (uintptr_t)X0 | (uintptr_t)QKVA | (uintptr_t)bce) & 15))
+        return CTAN_ERR_UNSUPPORTED;
+    CUtensorMap tmA, tmBhi, tmBlo;
+    int rc = tc::make_map(&tmA, zext, N, Kx);
+    if (!rc) rc = bf ? tc::make_map_bf16(&tmBhi, Wce_hi, 5 * D, Kx) : tc::make_map(&tmBhi, Wce_hi, 5 * D, Kx);
+    if (!rc) rc = bf ? tc::make_map_bf16(&tmBlo, Wce_hi, 5 * D, Kx) : tc::make_map(&tmBlo, Wce_lo, 5 * D, Kx);
+    if (rc) return rc;
+    cudaError_t e = cudaFuncSetAttribute(tc::qkva_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    // one bias segment spanning all 5D columns; columns >= D are redirected to QKVA (row pitch 4D)
+    tc::Bias4 epi{{bce, nullptr, nullptr, nullptr}, 5 * D, 1, nullptr, 0, 1, QKVA, D, 4 * D};
+    dim3 grid((5 * D) / tc::BN, tc::bounded_rows(N, N_dev, (5 * D) / tc::BN, m_typ));
+    tc::qkva_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, epi, X0, D, N, N_dev, 5 * D, Kx, mode);
     CTAN_CHECK_LAUNCH();
     return 0;
 }

@@ -165,6 +165,16 @@ class TGBEvalEngine:
             w["Wep_bf"] = torch.zeros((D, self.Kep), **bf16)
             w["Aep"] = torch.zeros((self.e_cap + 128, self.Kep), **f32)
             w["Wep_hi"], w["Wep_lo"] = torch.zeros((D, self.Kep), **f32), torch.zeros((D, self.Kep), **f32)
+        # num_iters = 1 with frozen weights: enc_x and the projection are one contraction against [Wenc; Wcat Wenc]
+        # (csrc/tc_gemm.cu::ctan_enc_qkva_tc) -- one tcgen05 launch and one dependent stage fewer per batch
+        self.fuse_enc = (self.use_tc_enc and K == 1 and _os.environ.get("CTAN_EVAL_FUSE_ENC", "1") == "1")
+        if self.fuse_enc:
+            kq = 64 if self.tc_mode == 2 else 32
+            self.Kx = ((D + self.Fn + kq - 1) // kq) * kq
+            w["zext"] = torch.zeros((N + 128, self.Kx), **f32)
+            w["Wce"], w["bce"] = torch.zeros((5 * D, self.Kx), **f32), torch.zeros(5 * D, **f32)
+            w["Wce_hi"], w["Wce_lo"] = torch.zeros((5 * D, self.Kx), **f32), torch.zeros((5 * D, self.Kx), **f32)
+            w["Wce_bf"] = torch.zeros((5 * D, self.Kx), **bf16)
         if self.use_tc_enc:
             w["zmain"], w["ztail"] = torch.zeros((N, D), **f32), torch.zeros((N, D), **f32)
             w["Wenc_hi"], w["Wenc_lo"] = torch.zeros((D, D), **f32), torch.zeros((D, D), **f32)
@@ -279,7 +289,11 @@ class TGBEvalEngine:
                 else:
                     call("ctan_eproj_fwd", ptr(self.msg), Fe, ptr(f["eid"]), ptr(w["rel"]), ptr(g.time_enc.lin.weight),
                          ptr(g.time_enc.lin.bias), T, ptr(ph.lin_edge.weight), E, Ed, D, ptr(w["EP"]))
-            if self.use_tc_enc:          # gather -> dense rows; enc_x on the tensor cores; node-feature columns as residual
+            if self.fuse_enc:            # gather -> [mem | x | 0] rows; enc_x AND q/k/v/x.A^T in one tcgen05 contraction
+                call("ctan_enc_prep_ext", ptr(mem), D, xf, Fn, ptr(f["n_id"]), N, Nd, self.Kx, ptr(w["zext"]))
+                call("ctan_enc_qkva_tc", ptr(w["zext"]), N, Nd, self.Kx, *self._panel("Wce"), D, ptr(w["bce"]),
+                     ptr(w["X"][0]), ptr(w["QKVA"]), self.tc_mode | self._n_hint)
+            elif self.use_tc_enc:        # gather -> dense rows; enc_x on the tensor cores; node-feature columns as residual
                 call("ctan_enc_prep", ptr(mem), D, xf, Fn, ptr(f["n_id"]), N, Nd, ptr(g.enc_x.weight), ptr(w["zmain"]),
                      ptr(w["ztail"]))
                 call("ctan_gemm_tc", ptr(w["zmain"]), N, Nd, D, *self._panel("Wenc"), D,
@@ -290,7 +304,9 @@ class TGBEvalEngine:
             torch.cuda.current_stream().wait_stream(self._side)
             for k in range(K):
                 xi, xo = w["X"][k & 1], w["X"][(k + 1) & 1]
-                if self.use_tc:
+                if self.fuse_enc and k == 0:
+                    pass                                                 # QKVA of the only iteration came with X0
+                elif self.use_tc:
                     call("ctan_qkva_fwd_tc", ptr(xi), N, Nd, D, *self._panel("Wcat"),
                          ptr(ph.lin_query.bias), ptr(ph.lin_key.bias), ptr(ph.lin_value.bias), ptr(a.bias),
                          ptr(w["QKVA"]), self.tc_mode | self._n_hint)
@@ -347,6 +363,13 @@ class TGBEvalEngine:
             if self.use_tc_ep:
                 call("ctan_pack_split_pad", ptr(ph.lin_edge.weight), D, self.Fe + self.T, self.Fe + self.T, self.Kep,
                      ptr(w["Wep_hi"]), ptr(w["Wep_lo"]))
+            if self.fuse_enc:            # [Wenc; Wcat Wenc] and its bias, then the hi/lo (or BF16) panel of it
+                call("ctan_fuse_enc_prep", ptr(ph.lin_query.weight), ptr(ph.lin_key.weight), ptr(ph.lin_value.weight),
+                     ptr(w["A"]), ptr(ph.lin_query.bias), ptr(ph.lin_key.bias), ptr(ph.lin_value.bias), ptr(a.bias),
+                     ptr(g.enc_x.weight), ptr(g.enc_x.bias), D, Fn, self.Kx, ptr(w["Wce"]), ptr(w["bce"]))
+                call("ctan_pack_split", ptr(w["Wce"]), 5 * D, self.Kx, self.Kx, ptr(w["Wce_hi"]), ptr(w["Wce_lo"]))
+                if self.tc_mode == 2:
+                    call("ctan_pack_bf16", ptr(w["Wce"]), 5 * D, self.Kx, self.Kx, self.Kx, w["Wce_bf"].data_ptr())
             if self.tc_mode == 2:                    # BF16 panels of the same weights (A = W - W^T - gamma I from above)
                 bp = w["Wcat_bf"].data_ptr()
                 for i, src in enumerate((ph.lin_query.weight, ph.lin_key.weight, ph.lin_value.weight, w["A"])):

@@ -58,6 +58,9 @@ REF = {
     "ctan_pack_bf16": "(BF16 weight panel for the 1e-2 tensor-core path; no reference counterpart)",
     "ctan_gemm_tc": "torch.nn.Linear on tcgen05 tensor cores (enc_x: models/gnn_layers.py:96; readout lin_src/lin_dst: models/predictors.py:16-17)",
     "ctan_enc_prep": "SimpleMemory.forward gather + node-feature columns of enc_x -- models/memory_layers.py:155-156, models/gnn_layers.py:96",
+    "ctan_fuse_enc_prep": "enc_x folded into the q/k/v/x.A^T projection for frozen weights: [Wenc; Wcat Wenc] -- models/gnn_layers.py:96 + PyG App. A.5",
+    "ctan_enc_prep_ext": "SimpleMemory.forward gather + cat(z, x[n_id]) as a dense padded operand -- models/memory_layers.py:155-156, models/ctdg_models.py:444-453",
+    "ctan_enc_qkva_tc": "enc_x and lin_query/lin_key/lin_value/x @ A^T in ONE tcgen05 contraction (evaluation, num_iters = 1) -- models/gnn_layers.py:96, PyG App. A.5",
     "ctan_head_gather": "TGBLinkPredictor.forward on pre-projected node rows -- models/predictors.py:16-19",
     "ctan_head_pack": "TGBLinkPredictor.forward on pre-projected rows + per-query reciprocal rank (TGB/tgb/linkproppred/evaluate.py:109-120) + the packed row every rank exchanges",
     "ctan_delta_t_stats_ws_bytes": "(workspace size of ctan_delta_t_stats; host-side query)",
