@@ -350,6 +350,16 @@ class StepEngine:
         self.use_tc_dx = (self.use_tc and D % 128 == 0          # dX contraction on tcgen05 needs 128-wide output tiles
                           and os.environ.get("CTAN_TC_DX", "1") == "1")
         w["WcatT_hi"], w["WcatT_lo"] = torch.zeros((D, 4 * D), **f32), torch.zeros((D, 4 * D), **f32)
+        # no-grad steps with ONE anti-symmetric iteration: enc_x folded into the projection (frozen weights inside a
+        # run(train=False) call): one tcgen05 contraction of [memory row | node features | 0] against [Wenc; Wcat Wenc]
+        self.fuse_enc = (self.use_tc and D % 128 == 0 and K == 1 and _lib.TC_MODE != 2 and not self.seq_mod
+                         and os.environ.get("CTAN_INFER_FUSE_ENC", "1") == "1")
+        if self.fuse_enc:
+            self.Kx = ((D + self.Fn + 31) // 32) * 32
+            w["zext"] = torch.zeros((N + 128, self.Kx), **f32)
+            w["Wce"], w["bce"] = torch.zeros((5 * D, self.Kx), **f32), torch.zeros(5 * D, **f32)
+            w["Wce_hi"], w["Wce_lo"] = torch.zeros((5 * D, self.Kx), **f32), torch.zeros((5 * D, self.Kx), **f32)
+            self._fuse_ver = None
         w["QKVA"] = torch.zeros((K, N, 4 * D), **f32)
         w["TH"] = torch.zeros((K, N, D), **f32)
         w["ALPHA"] = torch.zeros((K, E), **f32)
@@ -554,14 +564,22 @@ class StepEngine:
         if train:
             with self._fork(1):                              # side 1: saved copy of the gathered input rows
                 call("ctan_gather_rows2", ptr(mem), D, xf, Fn, ptr(f["n_id"]), N, Nd, ptr(w["z0"]))
-        call("ctan_enc_fwd", ptr(mem), D, xf, Fn, ptr(f["n_id"]), None, N, Nd, Wenc, benc, ptr(w["X"][0]))
+        fused = self.fuse_enc and not train
+        if fused:                # X0 and QKVA of the only iteration in one contraction (panel formed by _prep_infer_weights)
+            call("ctan_enc_prep_ext", ptr(mem), D, xf, Fn, ptr(f["n_id"]), N, Nd, self.Kx, ptr(w["zext"]))
+            call("ctan_enc_qkva_tc", ptr(w["zext"]), N, Nd, self.Kx, ptr(w["Wce_hi"]), ptr(w["Wce_lo"]), D, ptr(w["bce"]),
+                 ptr(w["X"][0]), ptr(w["QKVA"][0]), _lib.TC_MODE | self._row_hint)
+        else:
+            call("ctan_enc_fwd", ptr(mem), D, xf, Fn, ptr(f["n_id"]), None, N, Nd, Wenc, benc, ptr(w["X"][0]))
         self._join(0)
         self._join(2)
         for k in range(K):
             xi = w["X"][k] if train else w["X"][k & 1]
             xo = w["X"][k + 1] if train else w["X"][(k + 1) & 1]
             qk = w["QKVA"][k] if train else w["QKVA"][0]
-            if self.use_tc:      # tcgen05 + TMA projection
+            if fused:
+                pass             # (came with X0)
+            elif self.use_tc:    # tcgen05 + TMA projection
                 call("ctan_qkva_fwd_tc", ptr(xi), N, Nd, D, ptr(w["Wcat_hi"]), ptr(w["Wcat_lo"]), bq, bk, bv, b,
                      ptr(qk), _lib.TC_MODE | self._row_hint)
             else:
@@ -680,6 +698,23 @@ class StepEngine:
         ptrs = [p for p, _ in segs] + [None] * (8 - len(segs))
         call("ctan_zero_arena", base, head, len(segs), *ptrs, ctypes.cast(rows, ctypes.c_void_p), ptr(f["Nd"]), N)
 
+    def _prep_infer_weights(self):
+        """[Wenc; Wcat Wenc] and its bias for the folded no-grad step; re-formed when the weights changed since the last
+        no-grad run (torch tensor versions + _lib.WEIGHTS_EPOCH for the engine's own raw-pointer Adam)."""
+        if not self.fuse_enc:
+            return
+        ver = (_lib.WEIGHTS_EPOCH,) + tuple((p.data_ptr(), p._version) for p in self._plist)
+        if ver == self._fuse_ver:
+            return
+        w, m, D = self.w, self.model, self.D
+        (Wenc, benc, Wq, bq, Wk, bk, Wv, bv, We, W, b) = (ptr(t) for t in self.p[:11])
+        with torch.cuda.device(self.dev):
+            call("ctan_antisym_prep", W, float(m.gnn.aconv.gamma), D, ptr(w["A"]))
+            call("ctan_fuse_enc_prep", Wq, Wk, Wv, ptr(w["A"]), bq, bk, bv, b, Wenc, benc, D, self.Fn, self.Kx,
+                 ptr(w["Wce"]), ptr(w["bce"]))
+            call("ctan_pack_split", ptr(w["Wce"]), 5 * D, self.Kx, self.Kx, ptr(w["Wce_hi"]), ptr(w["Wce_lo"]))
+        self._fuse_ver = ver
+
     def _adam(self):
         call("ctan_adam_step", ptr(self.flat_p), ptr(self.flat_g), ptr(self.adam_m), ptr(self.adam_v),
              self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 0, ptr(self.w["counters"]),
@@ -785,11 +820,13 @@ class StepEngine:
             self._launch(True)
             if base:
                 self.w["counters"][0] = base
+            self._prep_infer_weights()
             self._launch(False)
         torch.cuda.synchronize(self.dev)
         self.flat_p.copy_(keep)
         self.reset(reset_optimizer=True)
         self.w["loss_hist"].zero_()
+        self._fuse_ver = None                                # (the panel above came from the throw-away step's weights)
         if not self.seq_mod:
             self.capture_all()
 
@@ -815,6 +852,8 @@ class StepEngine:
         """The replay sequence of n_steps steps as a list of callables (one per step; the first also issues the first
         front-end).  Training steps prefetch the next step's front-end beside their backward, no-grad steps beside their
         forward, except the last of the sequence: the state after the sequence is exactly that of n_steps self-contained steps."""
+        if not train:
+            self._prep_infer_weights()       # (the folded no-grad step reads a weight panel formed outside the graph)
         if self.host_staged:
             return [lambda: self._run_staged(train) for _ in range(n_steps)]
         if not self.use_graph:

@@ -61,26 +61,40 @@ def test_engine_training_matches_oracle(small_stream, tgb, K, final_act, use_gra
         assert d <= 5e-4 * float(po[k].abs().max()) + 1e-6, (k, d)
 
 
-def test_engine_inference_matches_oracle(small_stream):
+@pytest.mark.parametrize("D,n_train", [(64, 0), (128, 0), (128, 3)])
+def test_engine_inference_matches_oracle(small_stream, D, n_train):
+    """No-grad steps (train_link.py:361-405).  D=128, K=1 takes the folded enc_x + projection contraction
+    (csrc/tc_gemm.cu::ctan_enc_qkva_tc) whose weight panel is formed outside the graph: with n_train > 0 the panel must
+    follow the optimizer steps taken in between."""
     from oracle import ctan_oracle as O
     st = small_stream
     B, S, steps = 200, 10, 8
-    om, mm, ld, eng = _setup(st, True, 1, 64, 16, 64, None, S, B, True)
+    om, mm, ld, eng = _setup(st, True, 1, D, 16, 64, None, S, B, True)
+    assert eng.fuse_enc == (D == 128)
     lo_ref = O.TorchNeighborLoader(st["num_nodes"], S)
     h = torch.zeros(st["num_nodes"], dtype=torch.long)
     crit = torch.nn.BCEWithLogitsLoss()
+    opt = torch.optim.Adam(om.parameters(), lr=1e-3)
     ref = []
-    for it in range(steps):
+    if n_train:
+        eng.run(1, train=False)                      # forms the panel once with the initial weights ...
+        eng.reset()
+        for it in range(n_train):                    # ... which these steps must invalidate
+            O.train_step_ref(om, lo_ref, h, opt, st, it * B, (it + 1) * B, st["neg"][it * B:(it + 1) * B])
+        eng.run(n_train, train=True)
+    for it in range(n_train, n_train + steps):
         po, no = O.infer_step_ref(om, lo_ref, h, st, it * B, (it + 1) * B, st["neg"][it * B:(it + 1) * B])
         ref.append(float(crit(po, torch.ones_like(po)) + crit(no, torch.zeros_like(no))))
     eng.run(steps, train=False)
     torch.cuda.synchronize()
     eng.check()
-    mine = eng.losses(steps).cpu().tolist()
+    mine = eng.losses(n_train + steps).cpu().tolist()[n_train:]
     for a, b in zip(mine, ref):
         assert abs(a - b) <= 2e-4 * abs(b) + 1e-6, (mine, ref)
     assert torch.equal(ld.e_id.cpu(), lo_ref.e_id)
     assert torch.equal(mm.memory.last_update.cpu(), om.memory.last_update)
+    mo = om.memory.memory
+    assert float((mm.memory.memory.cpu() - mo).abs().max()) <= 5e-4 * float(mo.abs().max())
 
 
 def test_engine_then_dropin_loop_share_state(small_stream):
