@@ -37,6 +37,7 @@ SIGNATURES = {
     # dense.cu
     "ctan_enc_fwd": [P, I, P, I, P, P, I, P, P, P, P],
     "ctan_eproj_fwd": [P, I, P, P, P, P, I, P, I, P, I, P],
+    "ctan_eproj_fwd_rows": [P, I, P, P, P, P, I, P, I, P, I, P],
     "ctan_qkva_fwd": [P, I, P, I, P, P, P, P, P, P, P, P, P],
     "ctan_readout_fwd": [P, I, P, P, P, I, P, I, I, P, P, P, P, P, P, P, P, I],
     "ctan_readout_bwd": [P, P, P, I, P, P, P, I, P, I, I, P, P, P, P, P, P, P, P, P, P, P, I],
@@ -104,6 +105,7 @@ SIGNATURES.update({
     "ctan_enc_prep": [P, I, P, I, P, I, P, P, P, P],
     "ctan_head_gather": [P, I, P, P, P, I, P, P, P],
     "ctan_fuse_enc_prep": [P, P, P, P, P, P, P, P, P, P, I, I, I, P, P],
+    "ctan_fuse_enc_prep_split": [P, P, P, P, F, P, P, P, P, P, P, I, I, I, P, P, P],
     "ctan_enc_prep_ext": [P, I, P, I, P, I, P, I, P],
     "ctan_enc_qkva_tc": [P, I, P, I, P, P, I, P, P, P, I],
     "ctan_head_pack": [P, I, P, I, P, P, P, I, I, P, P, P],
@@ -173,6 +175,7 @@ N_LAUNCHES = 0
 # Optional timeline probing (scripts/timeline_step.py): PROBE = (ts_tensor, names_list) -> after every call made
 # on the stream that was current when probing was switched on, a probe kernel stores %globaltimer.
 PROBE = None
+PROBE_SIDE = False
 
 
 def call(name: str, *args):
@@ -188,9 +191,13 @@ def call(name: str, *args):
         rc = fn(*args, stream_ptr())
         if rc != 0:
             raise CtanLibraryError(f"{name} failed with code {rc}")
-        if torch.cuda.current_stream().cuda_stream == main:
+        cur = torch.cuda.current_stream().cuda_stream
+        if cur == main:
             lib().ctan_probe(ts.data_ptr(), len(names), stream_ptr())
             names.append(name)
+        elif PROBE_SIDE and len(names) < ts.numel():         # side-stream calls too (scripts/timeline_step.py ALL=1)
+            lib().ctan_probe(ts.data_ptr(), len(names), stream_ptr())
+            names.append(f"{name} [side {cur & 0xFFFF:04x}]")
         return
     if TRACE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -42,6 +42,127 @@ extern "C" int ctan_eproj_fwd(const float* msg, int Fe, const int64_t* eidx, con
     return launch(A, B, epi, E, E_dev, D, Fe + T, nullptr, 1, stream);
 }
 
+// ---- the same projection for a SMALL edge set (a training batch: ~1e3 edges, K = Fe+T ~ 190): latency, not throughput.
+// The tiled GEMM above walks K in six dependent gather rounds (19 us at E = 1.1 k); here every global load of a CTA is
+// in flight at once: the WHOLE weight [D, K] (cp.async, L2-resident, shared by all CTAs) and the 16 gathered attribute
+// rows land in shared memory behind one wait, then 4 warps x (4 rows x D/32 columns per lane) finish in ~2 us.
+// Shared layout: row stride S floats with S/4 odd, so the 128-bit reads of 8 consecutive lanes (rows l*S) hit all 32 banks.
+namespace eproj_rows {
+constexpr int TE = 16, THREADS = 128;
+__device__ __forceinline__ void cp16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory"); }
+
+template <int NC>   // D = 32 * NC
+__global__ void __launch_bounds__(THREADS)
+kernel(const float* __restrict__ msg, int Fe, const int64_t* __restrict__ eidx, const float* __restrict__ rel,
+       const float* __restrict__ tw, const float* __restrict__ tb, int T, const float* __restrict__ We, int E_host,
+       const int* __restrict__ E_dev, float* __restrict__ EP, int S, int vec_msg) {
+    ctan_pdl_begin();
+    extern __shared__ __align__(16) float sm[];
+    constexpr int D = 32 * NC;
+    const int E = E_dev ? *E_dev : E_host;
+    if ((long long)blockIdx.x * TE >= E) return;              // (the grid is sized by a bound)
+    const int K = Fe + T, K4 = K >> 2;
+    float* Ws = sm;                                           // [D][S]
+    float* At = sm + (size_t)D * S;                           // [TE][S]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < D * K4; i += THREADS) {             // the weight, once per CTA
+        const int d = i / K4, k4 = i - d * K4;
+        cp16(Ws + (size_t)d * S + 4 * k4, We + (size_t)d * K + 4 * k4);
+    }
+    for (int g = blockIdx.x; (long long)g * TE < E; g += gridDim.x) {
+        const int e0 = g * TE;
+        if (g != (int)blockIdx.x) __syncthreads();            // the previous group's rows are still being read
+        if (vec_msg) {
+            const int F4 = Fe >> 2;
+            for (int i = tid; i < TE * F4; i += THREADS) {
+                const int r = i / F4, c4 = i - r * F4, e = e0 + r;
+                if (e < E) {
+                    const int64_t row = eidx ? __ldg(eidx + e) : (int64_t)e;
+                    cp16(At + (size_t)r * S + 4 * c4, msg + (size_t)row * Fe + 4 * c4);
+                }
+            }
+        } else {
+            for (int i = tid; i < TE * Fe; i += THREADS) {
+                const int r = i / Fe, c = i - r * Fe, e = e0 + r;
+                if (e < E) {
+                    const int64_t row = eidx ? __ldg(eidx + e) : (int64_t)e;
+                    At[(size_t)r * S + c] = __ldg(msg + (size_t)row * Fe + c);
+                }
+            }
+        }
+        for (int i = tid; i < TE * T; i += THREADS) {         // cos(w * rel + b)   (TGB/modules/time_enc.py:23-24)
+            const int r = i / T, j = i - r * T, e = e0 + r;
+            if (e < E) At[(size_t)r * S + Fe + j] = cosf(fmaf(__ldg(rel + e), __ldg(tw + j), __ldg(tb + j)));
+        }
+        cp_wait_all();
+        __syncthreads();
+        float acc[4][NC];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int j = 0; j < NC; ++j) acc[r][j] = 0.f;
+        const float* a0 = At + (size_t)(4 * warp) * S;
+        const float* w0 = Ws + (size_t)lane * S;
+#pragma unroll 2
+        for (int k4 = 0; k4 < K4; ++k4) {
+            float4 a[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) a[r] = *reinterpret_cast<const float4*>(a0 + (size_t)r * S + 4 * k4);
+#pragma unroll
+            for (int j = 0; j < NC; ++j) {
+                const float4 b = *reinterpret_cast<const float4*>(w0 + (size_t)(32 * j) * S + 4 * k4);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {                  // k ascending, like the tiled kernel's accumulation order
+                    acc[r][j] = fmaf(a[r].x, b.x, acc[r][j]);
+                    acc[r][j] = fmaf(a[r].y, b.y, acc[r][j]);
+                    acc[r][j] = fmaf(a[r].z, b.z, acc[r][j]);
+                    acc[r][j] = fmaf(a[r].w, b.w, acc[r][j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int e = e0 + 4 * warp + r;
+            if (e < E) {
+#pragma unroll
+                for (int j = 0; j < NC; ++j) EP[(size_t)e * D + lane + 32 * j] = acc[r][j];
+            }
+        }
+    }
+}
+}  // namespace eproj_rows
+
+// Same result as ctan_eproj_fwd (same k-ascending fp32 accumulation), for edge sets of a few thousand rows at most.
+// Requirements: D in {32,64,128,256}, (Fe+T) % 4 == 0, We 16-byte aligned, D*(K+4)*4 + 16*(K+4)*4 bytes of shared memory
+// available; otherwise CTAN_ERR_UNSUPPORTED (the caller keeps ctan_eproj_fwd).
+extern "C" int ctan_eproj_fwd_rows(const float* msg, int Fe, const int64_t* eidx, const float* rel, const float* tw,
+                                   const float* tb, int T, const float* We, int E, const int* E_dev, int D, float* EP,
+                                   cudaStream_t stream) {
+    if (E <= 0) return 0;
+    const int K = Fe + T;
+    if (K <= 0 || (K & 3) || !aligned16(We) || (D != 32 && D != 64 && D != 128 && D != 256)) return CTAN_ERR_UNSUPPORTED;
+    const int S = ((K >> 2) & 1) ? K : K + 4;                 // S/4 odd
+    const size_t smem = ((size_t)D + eproj_rows::TE) * S * sizeof(float);
+    if (smem > 220 * 1024) return CTAN_ERR_UNSUPPORTED;
+    const int vec_msg = (Fe > 0 && (Fe & 3) == 0 && aligned16(msg)) ? 1 : 0;
+    long long groups = ((long long)E + eproj_rows::TE - 1) / eproj_rows::TE;
+    const int grid = (int)(groups < 2LL * CTAN_SM_COUNT ? groups : 2LL * CTAN_SM_COUNT);
+#define CTAN_EPROJ_ROWS(NC)                                                                                               \
+    {                                                                                                                     \
+        cudaError_t e = cudaFuncSetAttribute(eproj_rows::kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return (int)e;                                                                              \
+        CTAN_LAUNCH((eproj_rows::kernel<NC>), grid, eproj_rows::THREADS, smem, stream, msg, Fe, eidx, rel, tw, tb, T, We, \
+                    E, E_dev, EP, S, vec_msg);                                                                            \
+    }
+    if (D == 32) CTAN_EPROJ_ROWS(1) else if (D == 64) CTAN_EPROJ_ROWS(2) else if (D == 128) CTAN_EPROJ_ROWS(4) else CTAN_EPROJ_ROWS(8)
+#undef CTAN_EPROJ_ROWS
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
 // QKVA[N,4D] = X [Wq;Wk;Wv;A]^T + [bq;bk;bv;b]
 extern "C" int ctan_qkva_fwd(const float* X, int N, const int* N_dev, int D, const float* Wq, const float* Wk,
                              const float* Wv, const float* A_, const float* bq, const float* bk, const float* bv,

@@ -748,6 +748,117 @@ extern "C" int ctan_fuse_enc_prep(const float* Wq, const float* Wk, const float*
     return 0;
 }
 
+// The same panel formed EVERY training step (the weights move with each optimizer step): one kernel, tiled through
+// shared memory, fp32 accumulation, A = W - W^T - gamma I taken on the fly, hi/lo split (3xTF32 operands) written directly.
+//   rows [0,D)   : Wenc zero-padded to Kx                       bias benc
+//   rows [D,5D)  : [Wq;Wk;Wv;A] Wenc                            bias [Wq;Wk;Wv;A] benc + [bq;bk;bv;b]
+// The bias is column Kx of the extended product.  grid = (Kx/32 + 1, 5D/32), 256 threads, 4 outputs per thread;
+// D % 32 == 0, D <= 256 (each thread stages D/8 elements of either tile from registers).
+__global__ void __launch_bounds__(256)
+fuse_enc_split_kernel(const float* __restrict__ Wq, const float* __restrict__ Wk, const float* __restrict__ Wv,
+                      const float* __restrict__ W, float gamma, const float* __restrict__ bq,
+                      const float* __restrict__ bk, const float* __restrict__ bv, const float* __restrict__ b,
+                      const float* __restrict__ Wenc, const float* __restrict__ benc, int D, int Fn, int Kx,
+                      float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ bce) {
+    ctan_pdl_begin();
+    extern __shared__ float fsm[];
+    const int ldw = D + Fn;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;                       // output column; c == Kx is the bias
+    const int r0 = blockIdx.y * 32;
+    auto put = [&](int r, float v) {
+        if (c < Kx) {
+            const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+            hi[(size_t)r * Kx + c] = h;
+            lo[(size_t)r * Kx + c] = v - h;
+        } else if (c == Kx) {
+            bce[r] = v;
+        }
+    };
+    if (r0 < D) {                                             // the enc_x block itself
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = r0 + ty + 8 * j;
+            put(r, c < ldw ? Wenc[(size_t)r * ldw + c] : (c == Kx ? benc[r] : 0.f));
+        }
+        return;
+    }
+    const int seg = (r0 - D) / D, ro0 = (r0 - D) - seg * D;   // (D % 32 == 0: a tile never straddles two segments)
+    const float* Wl = seg == 0 ? Wq : (seg == 1 ? Wk : (seg == 2 ? Wv : W));
+    const float* bb = seg == 0 ? bq : (seg == 1 ? bk : (seg == 2 ? bv : b));
+    // the whole K extent of both operand tiles at once (every global load of the CTA in flight together: the kernel
+    // sits on the step's critical path, and it is latency, not bandwidth, that it costs)
+    const int SA = D + 4;                                     // 16-byte aligned rows: the k loop reads them as float4
+    float* As = fsm;                                          // [32][D + 4]   rows of [Wq;Wk;Wv;A]   (warp-uniform reads)
+    float* Bs = fsm + 32 * SA;                                // [D][33]       columns of [Wenc | benc]
+    const int nq = D >> 5;                                    // <= 8
+    float va[4][8], vb[4][8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (q < nq) {
+                va[j][q] = Wl[(size_t)(ro0 + ty + 8 * j) * D + tx + 32 * q];       // row ty+8j, k = tx+32q
+                const int dk = ty + 8 * (j * nq + q);                               // k = dk, column tx
+                vb[j][q] = c < ldw ? Wenc[(size_t)dk * ldw + c] : (c == Kx ? benc[dk] : 0.f);
+            }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (q < nq) {
+                As[(ty + 8 * j) * SA + tx + 32 * q] = va[j][q];
+                Bs[(ty + 8 * (j * nq + q)) * 33 + tx] = vb[j][q];
+            }
+    if (seg == 3) {                                           // A = W - W^T - gamma I: the transposed half, read coalesced
+        __syncthreads();                                      // (row = lane, k = ty + 8u) and folded in through shared memory
+        for (int u0 = 0; u0 < (D >> 3); u0 += 8) {
+            float vt[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) vt[u] = (u0 + u) < (D >> 3) ? W[(size_t)(ty + 8 * (u0 + u)) * D + ro0 + tx] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int d = ty + 8 * (u0 + u);
+                if (d < D) As[tx * SA + d] = As[tx * SA + d] - vt[u] - ((ro0 + tx) == d ? gamma : 0.f);
+            }
+        }
+    }
+    __syncthreads();
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < D; k += 4) {
+        const float b0 = Bs[(k + 0) * 33 + tx], b1 = Bs[(k + 1) * 33 + tx], b2 = Bs[(k + 2) * 33 + tx], b3 = Bs[(k + 3) * 33 + tx];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 a = *reinterpret_cast<const float4*>(As + (ty + 8 * j) * SA + k);
+            acc[j] = fmaf(a.x, b0, acc[j]);
+            acc[j] = fmaf(a.y, b1, acc[j]);
+            acc[j] = fmaf(a.z, b2, acc[j]);
+            acc[j] = fmaf(a.w, b3, acc[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ro = ro0 + ty + 8 * j;
+        put(r0 + ty + 8 * j, c == Kx ? acc[j] + bb[ro] : acc[j]);
+    }
+}
+// Wce_hi / Wce_lo [5D, Kx], bce [5D] from the raw weights; D % 32 == 0, D <= 256, Kx % 32 == 0, Kx >= D + Fn.
+extern "C" int ctan_fuse_enc_prep_split(const float* Wq, const float* Wk, const float* Wv, const float* W, float gamma,
+                                        const float* bq, const float* bk, const float* bv, const float* b,
+                                        const float* Wenc, const float* benc, int D, int Fn, int Kx, float* Wce_hi,
+                                        float* Wce_lo, float* bce, cudaStream_t stream) {
+    if (D <= 0 || D % 32 != 0 || D > 256 || Fn < 0 || Kx < D + Fn || Kx % 32 != 0) return CTAN_ERR_BAD_ARG;
+    const size_t smem = (size_t)(32 * (D + 4) + D * 33) * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(fuse_enc_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    CTAN_LAUNCH((fuse_enc_split_kernel), dim3(Kx / 32 + 1, 5 * D / 32), 256, smem, stream, Wq, Wk, Wv, W, gamma, bq, bk, bv, b,
+                Wenc, benc, D, Fn, Kx, Wce_hi, Wce_lo, bce);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
 // zext[r] = [ mem[n_id[r]] (D) | xfeat[n_id[r]] (Fn) | 0 ... ] with row pitch Kx (a dense TMA operand); one warp per row.
 __global__ void enc_prep_ext_kernel(const float* __restrict__ mem, int D, const float* __restrict__ xfeat, int Fn,
                                     const int64_t* __restrict__ n_id, int N_host, const int* __restrict__ N_dev, int Kx,

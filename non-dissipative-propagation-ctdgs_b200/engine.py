@@ -345,6 +345,10 @@ class StepEngine:
         self.use_tc = _lib.use_tensor_cores(D)
         # expected row count of the node-side contractions, packed into the `mode` argument of the tcgen05 entry points:
         # their CTAs need a whole SM each, so the persistent grid is sized by the typical N, not by the workspace bound
+        # a batch's edge set is small (~1e3 rows): the all-loads-in-flight variant of the edge projection (csrc/dense.cu)
+        small = (self.e_typ <= 8192 and (self.Fe + self.T) % 4 == 0 and D in (32, 64, 128, 256)
+                 and (D + 16) * (self.Fe + self.T + 4) * 4 <= 220 * 1024 and os.environ.get("CTAN_EPROJ_ROWS", "1") == "1")
+        self._eproj_fn = "ctan_eproj_fwd_rows" if small else "ctan_eproj_fwd"
         self._row_hint = (self.n_typ << 8) if os.environ.get("CTAN_TC_ROW_HINT", "1") == "1" else 0
         w["Wcat_hi"], w["Wcat_lo"] = torch.zeros((4 * D, D), **f32), torch.zeros((4 * D, D), **f32)
         self.use_tc_dx = (self.use_tc and D % 128 == 0          # dX contraction on tcgen05 needs 128-wide output tiles
@@ -354,7 +358,11 @@ class StepEngine:
         # run(train=False) call): one tcgen05 contraction of [memory row | node features | 0] against [Wenc; Wcat Wenc]
         self.fuse_enc = (self.use_tc and D % 128 == 0 and K == 1 and _lib.TC_MODE != 2 and not self.seq_mod
                          and os.environ.get("CTAN_INFER_FUSE_ENC", "1") == "1")
-        if self.fuse_enc:
+        # training steps (any num_iters: the first iteration): the same fold, the panel re-formed every step by ONE small
+        # kernel on a side stream (ctan_fuse_enc_prep_split) -- one dependent stage fewer on the forward critical path
+        self.fuse_train = (self.use_tc and D % 128 == 0 and _lib.TC_MODE != 2 and not self.seq_mod
+                           and os.environ.get("CTAN_TRAIN_FUSE_ENC", "1") == "1")
+        if self.fuse_enc or self.fuse_train:
             self.Kx = ((D + self.Fn + 31) // 32) * 32
             w["zext"] = torch.zeros((N + 128, self.Kx), **f32)
             w["Wce"], w["bce"] = torch.zeros((5 * D, self.Kx), **f32), torch.zeros(5 * D, **f32)
@@ -510,6 +518,11 @@ class StepEngine:
         w, m = self.w, self.model
         D = self.D
         Wq, Wk, Wv, W = (ptr(self.p[i]) for i in (2, 4, 6, 9))
+        if train and self.fuse_train:                        # side 3: [Wenc; Wcat Wenc] of THIS step's weights (joined just
+            with self._fork(3):                              # before the forward contraction; the rest of the prep later)
+                Wenc, benc, bq, bk, bv, b = (ptr(self.p[i]) for i in (0, 1, 3, 5, 7, 10))
+                call("ctan_fuse_enc_prep_split", Wq, Wk, Wv, W, float(m.gnn.aconv.gamma), bq, bk, bv, b, Wenc, benc, D,
+                     self.Fn, self.Kx, ptr(w["Wce_hi"]), ptr(w["Wce_lo"]), ptr(w["bce"]))
         with self._fork(2):
             if self.use_tc:      # A = W - W^T - gamma I, packed with q/k/v weights and split for 3xTF32
                 call("ctan_wcat_prep", Wq, Wk, Wv, W, float(m.gnn.aconv.gamma), D, ptr(w["Wcat_hi"]),
@@ -559,31 +572,38 @@ class StepEngine:
             if early or self.seq_mod:                        # delta-t of THIS step (the front-end left it out)
                 call("ctan_edge_rel", ptr(lu), ptr(f["n_id"]), ptr(f["esrc"]), ptr(self.t_tab), ptr(f["eid"]), E, Ed,
                      float(m.gnn.mean_delta_t), float(m.gnn.std_delta_t), ptr(f["rel"]))
-            call("ctan_eproj_fwd", ptr(self.msg), Fe, ptr(f["eid"]), ptr(f["rel"]), tw, tb, T, We, E, Ed, D,
+            call(self._eproj_fn, ptr(self.msg), Fe, ptr(f["eid"]), ptr(f["rel"]), tw, tb, T, We, E, Ed, D,
                  ptr(w["EP"]))
         if train:
             with self._fork(1):                              # side 1: saved copy of the gathered input rows
                 call("ctan_gather_rows2", ptr(mem), D, xf, Fn, ptr(f["n_id"]), N, Nd, ptr(w["z0"]))
-        fused = self.fuse_enc and not train
-        if fused:                # X0 and QKVA of the only iteration in one contraction (panel formed by _prep_infer_weights)
+        fused = self.fuse_train if train else self.fuse_enc
+        if fused:                # X0 and QKVA of the first iteration in one contraction (panel: _prep / _prep_infer_weights)
             call("ctan_enc_prep_ext", ptr(mem), D, xf, Fn, ptr(f["n_id"]), N, Nd, self.Kx, ptr(w["zext"]))
+            if train:
+                self._join(3)
             call("ctan_enc_qkva_tc", ptr(w["zext"]), N, Nd, self.Kx, ptr(w["Wce_hi"]), ptr(w["Wce_lo"]), D, ptr(w["bce"]),
                  ptr(w["X"][0]), ptr(w["QKVA"][0]), _lib.TC_MODE | self._row_hint)
         else:
             call("ctan_enc_fwd", ptr(mem), D, xf, Fn, ptr(f["n_id"]), None, N, Nd, Wenc, benc, ptr(w["X"][0]))
-        self._join(0)
-        self._join(2)
+        late_join = fused and train      # side 2 (arena clear, Wcat panels, H) is first needed AFTER the first projection
+        if not late_join:
+            self._join(2)
         for k in range(K):
             xi = w["X"][k] if train else w["X"][k & 1]
             xo = w["X"][k + 1] if train else w["X"][(k + 1) & 1]
             qk = w["QKVA"][k] if train else w["QKVA"][0]
-            if fused:
+            if fused and k == 0:
                 pass             # (came with X0)
             elif self.use_tc:    # tcgen05 + TMA projection
                 call("ctan_qkva_fwd_tc", ptr(xi), N, Nd, D, ptr(w["Wcat_hi"]), ptr(w["Wcat_lo"]), bq, bk, bv, b,
                      ptr(qk), _lib.TC_MODE | self._row_hint)
             else:
                 call("ctan_qkva_fwd", ptr(xi), N, Nd, D, Wq, Wk, Wv, ptr(w["A"]), bq, bk, bv, b, ptr(qk))
+            if k == 0:
+                self._join(0)                                # edge projections (side 0) are first read by the edge kernel
+                if late_join:
+                    self._join(2)
             last = k == K - 1
             ef = (ptr(qk), ptr(w["EP"]), ptr(f["rowptr"]), ptr(f["esrc"]), N, Nd, D, ptr(xi), eps, ptr(xo),
                   ptr(w["TH"][k]) if train else None, ptr(w["ALPHA"][k]) if train else None,
@@ -852,7 +872,9 @@ class StepEngine:
         """The replay sequence of n_steps steps as a list of callables (one per step; the first also issues the first
         front-end).  Training steps prefetch the next step's front-end beside their backward, no-grad steps beside their
         forward, except the last of the sequence: the state after the sequence is exactly that of n_steps self-contained steps."""
-        if not train:
+        if train:
+            self._fuse_ver = None            # (training steps re-form the shared panel buffers and move the weights)
+        else:
             self._prep_infer_weights()       # (the folded no-grad step reads a weight panel formed outside the graph)
         if self.host_staged:
             return [lambda: self._run_staged(train) for _ in range(n_steps)]

@@ -23,6 +23,7 @@ REF = {
     "ctan_csr_from_sorted": "(no reference counterpart: CSR pointer of a destination-sorted edge_index)",
     "ctan_enc_fwd": "CTANEmbedding.enc_x on gathered memory rows -- models/gnn_layers.py:96",
     "ctan_eproj_fwd": "edge_attr=[msg|TimeEncoder(rel)] -> TransformerConv.lin_edge -- models/gnn_layers.py:97, TGB/modules/time_enc.py:23-24",
+    "ctan_eproj_fwd_rows": "the same projection for a small edge set (a training batch): every load of a CTA in flight at once -- models/gnn_layers.py:97, TGB/modules/time_enc.py:23-24",
     "ctan_qkva_fwd": "TransformerConv lin_query/lin_key/lin_value + x @ A^T + bias -- PyG 2.3.1 (SURVEY.md App. A.5)",
     "ctan_readout_fwd": "LinkPredictor / TGBLinkPredictor / SequencePredictor.forward -- models/predictors.py:16-19,31-34,45-48",
     "ctan_readout_bwd": "gradient of the above (autograd in the reference)",
@@ -59,6 +60,7 @@ REF = {
     "ctan_gemm_tc": "torch.nn.Linear on tcgen05 tensor cores (enc_x: models/gnn_layers.py:96; readout lin_src/lin_dst: models/predictors.py:16-17)",
     "ctan_enc_prep": "SimpleMemory.forward gather + node-feature columns of enc_x -- models/memory_layers.py:155-156, models/gnn_layers.py:96",
     "ctan_fuse_enc_prep": "enc_x folded into the q/k/v/x.A^T projection for frozen weights: [Wenc; Wcat Wenc] -- models/gnn_layers.py:96 + PyG App. A.5",
+    "ctan_fuse_enc_prep_split": "the same panel formed every training step from the raw weights (A = W - W^T - gamma I on the fly, hi/lo split written directly) -- models/gnn_layers.py:86, 96 + PyG App. A.5",
     "ctan_enc_prep_ext": "SimpleMemory.forward gather + cat(z, x[n_id]) as a dense padded operand -- models/memory_layers.py:155-156, models/ctdg_models.py:444-453",
     "ctan_enc_qkva_tc": "enc_x and lin_query/lin_key/lin_value/x @ A^T in ONE tcgen05 contraction (evaluation, num_iters = 1) -- models/gnn_layers.py:96, PyG App. A.5",
     "ctan_head_gather": "TGBLinkPredictor.forward on pre-projected node rows -- models/predictors.py:16-19",

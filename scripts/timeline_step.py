@@ -12,6 +12,10 @@ st, mean, std = bench.make_workload(800 * 200)
 eng = bench.build_engine(st, int(os.environ.get("ITERS", "1")), mean, std, dev)
 eng.run(300, train=True)
 torch.cuda.synchronize()
+if os.environ.get("PREFETCHED", "0") == "1":
+    with torch.cuda.device(dev):
+        eng._frontend(0)
+    torch.cuda.synchronize()
 train = os.environ.get("INFER", "0") != "1"
 ts = torch.zeros(256, dtype=torch.int64, device=dev)
 names = []
@@ -20,7 +24,14 @@ with torch.cuda.graph(g):
     _lib.lib().ctan_probe(ts.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
     names.append("start")
     _lib.PROBE = (ts, names, torch.cuda.current_stream().cuda_stream)
-    eng._launch(train)
+    _lib.PROBE_SIDE = os.environ.get("ALL", "0") == "1"      # also probe the side-stream calls (order = issue order)
+    if os.environ.get("PREFETCHED", "0") == "1":             # the step as run(n) replays it: front-end done beforehand
+        try:
+            eng._step(train, 0, False)
+        finally:
+            _lib.lib().ctan_set_pdl(1, None)
+    else:
+        eng._launch(train)
     _lib.PROBE = None
 R = 100
 acc = torch.zeros(len(names), dtype=torch.float64)

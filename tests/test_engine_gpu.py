@@ -110,14 +110,24 @@ def test_engine_then_dropin_loop_share_state(small_stream):
     assert int(eid.max()) < 300 and ld.cur_e_id == 300
 
 
-@pytest.mark.parametrize("K", [1, 3])
-def test_bench_configuration_matches_oracle(K):
+@pytest.mark.parametrize("K,fold", [(1, True), (3, True), (1, False)])
+def test_bench_configuration_matches_oracle(K, fold, monkeypatch):
     """The exact workload bench.py times (BASELINE configs[1]: wiki-shaped stream, 9 227 nodes, 172-d messages,
     batch 200, CTAN D=128 T=16 S=5 H=64, tcgen05 projections): 30 warm-up + 12 compared training steps
-    (loss, parameters, memory, neighbour tables) against the oracle on the same events."""
+    (loss, parameters, memory, neighbour tables) against the oracle on the same events.
+
+    fold=False (CTAN_TRAIN_FUSE_ENC=0) keeps the reference's operation order (enc_x, then the projections): parameters
+    stay within 2e-3 of the oracle's after 42 Adam steps.  The default folds enc_x into the first projection
+    ([Wenc; Wcat Wenc] re-formed every step): every step's outputs and gradients agree with the two-step order to
+    ~2e-6 (test_folded_training_step_gradients_match_two_step below; the bar is 1e-4), but Adam normalises each
+    element by its own gradient history, so elements whose gradients are 100x below the tensor's scale turn that
+    rounding-level difference into a visible fraction of lr per step: the 42-step PARAMETER bound is 2e-2 there, the
+    loss / memory / neighbour-table bounds are the same."""
     import bench
     from oracle import ctan_oracle as O
     dev = torch.device("cuda:0")
+    monkeypatch.setenv("CTAN_TRAIN_FUSE_ENC", "1" if fold else "0")
+    p_tol = 2e-2 if fold else 2e-3
     steps, B, S = 42, bench.WIKI["B"], bench.WIKI["S"]
     st, mean, std = bench.make_workload((steps + 8) * B)
     eng = bench.build_engine(st, K, mean, std, dev)
@@ -143,7 +153,49 @@ def test_bench_configuration_matches_oracle(K):
     for k, p in mm.named_parameters():
         if "lin_skip" not in k:
             d = float((p.detach().cpu() - po[k].detach()).abs().max())
-            assert d <= 2e-3 * float(po[k].abs().max()) + 1e-6, (k, d)
+            assert d <= p_tol * float(po[k].abs().max()) + 1e-6, (k, d)
+    assert eng.fuse_train == fold
+
+
+def test_folded_training_step_gradients_match_two_step():
+    """One training step from the SAME state (bench workload after 40 optimizer steps, lr = 0 for the probed step) with
+    the two-step forward (enc_x, then q/k/v/x.A^T) and with the folded forward: loss and every parameter gradient agree
+    to 1e-5 of the tensor's largest gradient (measured: 1-3e-6; a re-run of the same path differs by 1-7e-7 from the
+    float-atomic accumulation order alone)."""
+    import bench
+    dev = torch.device("cuda:0")
+    steps = 40
+    st, mean, std = bench.make_workload((steps + 8) * 200)
+    eng = bench.build_engine(st, 1, mean, std, dev)
+    m, ld = eng.model, eng.loader
+    eng.run(steps, train=True)
+    eng.set_hyper(lr=0.0)
+    torch.cuda.synchronize()
+    state = (m.memory.memory, m.memory.last_update, ld.e_id, ld.neighbors, ld._deg, eng.w["counters"])
+    keep = [t.clone() for t in state]
+
+    def one(fold):
+        for t, v in zip(state, keep):
+            t.copy_(v)
+        eng.fuse_train = fold
+        eng._graphs.clear()
+        eng.run(1, train=True)
+        torch.cuda.synchronize()
+        return eng.flat_g.clone(), float(eng.losses(1)[0])
+
+    g0, l0 = one(False)
+    g1, l1 = one(True)
+    assert abs(l0 - l1) <= 1e-5 * abs(l0), (l0, l1)
+    off = 0
+    names = {id(p): n for n, p in m.named_parameters()}
+    for p in eng._plist:
+        n = p.numel()
+        a, b = g0[off:off + n], g1[off:off + n]
+        off += n
+        s = float(a.abs().max())
+        if s < 1e-8:
+            continue                                   # lin_key.bias: the softmax is shift-invariant, its true gradient is 0
+        assert float((a - b).abs().max()) <= 1e-5 * s, (names.get(id(p)), float((a - b).abs().max()) / s)
 
 
 def test_host_staged_matches_device_resident(small_stream):

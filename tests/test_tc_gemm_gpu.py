@@ -140,3 +140,61 @@ def test_bf16_mode_matches_fp64_at_1e2(M, K, Nout):
     assert bool((C[M:] == 7.0).all())                       # rows past the true M untouched
     exact = A[:M].to(torch.bfloat16).double() @ Wb.double().t() + b.double() + res[:M].double()
     assert float((C[:M].double() - exact).abs().max() / ref.abs().max()) < 1e-5     # = bf16 inputs, fp32 accumulate
+
+
+@pytest.mark.parametrize("N,D,Fn", [(640, 128, 1), (300, 128, 0), (1000, 256, 5), (100, 96, 3), (100, 32, 0)])
+def test_folded_enc_projection_matches_fp64(N, D, Fn):
+    """enc_x folded into the projection (csrc/tc_gemm.cu): the per-step panel kernel ctan_fuse_enc_prep_split against
+    the once-per-run pair (ctan_fuse_enc_prep + ctan_pack_split) and fp64, then [X0 | QKVA] = zext Wce^T + bce on
+    tcgen05 against the two chained fp64 maps X0 = z Wenc^T + benc, QKVA = X0 Wcat^T + bcat
+    (models/gnn_layers.py:96 + PyG TransformerConv / AntiSymmetricConv projections, App. A.5)."""
+    from ctan_b200._lib import call, ptr
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(N + D + Fn)
+    rnd = lambda *s: torch.randn(*s, generator=g)
+    Ws = [(rnd(D, D) / D ** 0.5).to(dev) for _ in range(4)]                     # Wq, Wk, Wv, W
+    bs = [rnd(D).to(dev) for _ in range(4)]
+    Wenc, benc = (rnd(D, D + Fn) / D ** 0.5).to(dev), rnd(D).to(dev)
+    gamma = 0.1
+    Kx = ((D + Fn + 31) // 32) * 32
+    A = (Ws[3] - Ws[3].t() - gamma * torch.eye(D, device=dev)).contiguous()
+    Wce, bce = torch.empty(5 * D, Kx, device=dev), torch.empty(5 * D, device=dev)
+    hi1, lo1 = torch.empty_like(Wce), torch.empty_like(Wce)
+    call("ctan_fuse_enc_prep", ptr(Ws[0]), ptr(Ws[1]), ptr(Ws[2]), ptr(A), ptr(bs[0]), ptr(bs[1]), ptr(bs[2]), ptr(bs[3]),
+         ptr(Wenc), ptr(benc), D, Fn, Kx, ptr(Wce), ptr(bce))
+    call("ctan_pack_split", ptr(Wce), 5 * D, Kx, Kx, ptr(hi1), ptr(lo1))
+    hi2, lo2 = torch.full_like(Wce, float("nan")), torch.full_like(Wce, float("nan"))
+    bce2 = torch.full_like(bce, float("nan"))
+    call("ctan_fuse_enc_prep_split", ptr(Ws[0]), ptr(Ws[1]), ptr(Ws[2]), ptr(Ws[3]), gamma, ptr(bs[0]), ptr(bs[1]),
+         ptr(bs[2]), ptr(bs[3]), ptr(Wenc), ptr(benc), D, Fn, Kx, ptr(hi2), ptr(lo2), ptr(bce2))
+    torch.cuda.synchronize()
+    Wcat = torch.cat([Ws[0], Ws[1], Ws[2], A]).double()
+    Wce_ref = torch.zeros(5 * D, Kx, dtype=torch.float64, device=dev)
+    Wce_ref[:D, :D + Fn] = Wenc.double()
+    Wce_ref[D:, :D + Fn] = Wcat @ Wenc.double()
+    bce_ref = torch.cat([benc.double(), Wcat @ benc.double() + torch.cat(bs).double()])
+    s = float(Wce_ref.abs().max())
+    assert float(((hi1 + lo1).double() - Wce_ref).abs().max()) < 1e-6 * s
+    assert not torch.isnan(hi2).any() and not torch.isnan(lo2).any() and not torch.isnan(bce2).any()
+    assert float(((hi2 + lo2).double() - Wce_ref).abs().max()) < 2e-6 * s          # fp32 accumulation
+    assert torch.equal(hi2[:D] + lo2[:D], Wce[:D])                                 # the enc_x block is a copy
+    assert float((bce2.double() - bce_ref).abs().max()) < 2e-6 * float(bce_ref.abs().max())
+    if D % 128:
+        return                                       # (the panel kernel is general in D % 32; the contraction needs 128-wide tiles)
+    # the contraction itself, device-sized row count, rows beyond N untouched
+    mem, xfeat = rnd(2000, D).to(dev), (rnd(2000, Fn).to(dev) if Fn else None)
+    n_id = torch.randperm(2000, generator=g)[:N].sort().values.to(dev)
+    Nd = torch.tensor([N], dtype=torch.int32, device=dev)
+    cap = N + 200
+    zext = torch.zeros(cap + 128, Kx, device=dev)
+    call("ctan_enc_prep_ext", ptr(mem), D, ptr(xfeat) if Fn else None, Fn, ptr(n_id), cap, ptr(Nd), Kx, ptr(zext))
+    X0 = torch.full((cap, D), 7.0, device=dev)
+    Q = torch.full((cap, 4 * D), 7.0, device=dev)
+    call("ctan_enc_qkva_tc", ptr(zext), cap, ptr(Nd), Kx, ptr(hi2), ptr(lo2), D, ptr(bce2), ptr(X0), ptr(Q), 0 | (N << 8))
+    torch.cuda.synchronize()
+    z = torch.cat([mem[n_id], xfeat[n_id]], 1).double() if Fn else mem[n_id].double()
+    X0_ref = z @ Wenc.double().t() + benc.double()
+    Q_ref = X0_ref @ Wcat.t() + torch.cat(bs).double()
+    assert float((X0[:N].double() - X0_ref).abs().max()) < 5e-6 * float(X0_ref.abs().max())
+    assert float((Q[:N].double() - Q_ref).abs().max()) < 1e-5 * float(Q_ref.abs().max())
+    assert bool((X0[N:] == 7.0).all()) and bool((Q[N:] == 7.0).all())
