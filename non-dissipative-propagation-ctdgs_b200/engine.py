@@ -513,8 +513,11 @@ class StepEngine:
         finally:
             _lib.lib().ctan_set_pdl(1, None)               # the launch-mode switch is thread-local host state: never leak it
 
-    def _prep(self, train: bool):
-        """Side branch with no dependence on the batch (weight-only operands, memsets) + the launch mode of the step."""
+    def _prep(self, train: bool, defer: bool = False):
+        """Side branch with no dependence on the batch (weight-only operands, memsets) + the launch mode of the step.
+        defer (folded training step whose front-end is already done): only the panel of the forward contraction is issued
+        now; everything the forward does not need at once (_prep_rest) is issued by _step once the gather is under way,
+        so that it does not compete with the two kernels the step's critical path starts with."""
         w, m = self.w, self.model
         D = self.D
         Wq, Wk, Wv, W = (ptr(self.p[i]) for i in (2, 4, 6, 9))
@@ -523,6 +526,17 @@ class StepEngine:
                 Wenc, benc, bq, bk, bv, b = (ptr(self.p[i]) for i in (0, 1, 3, 5, 7, 10))
                 call("ctan_fuse_enc_prep_split", Wq, Wk, Wv, W, float(m.gnn.aconv.gamma), bq, bk, bv, b, Wenc, benc, D,
                      self.Fn, self.Kx, ptr(w["Wce_hi"]), ptr(w["Wce_lo"]), ptr(w["bce"]))
+        if not defer:
+            self._prep_rest(train)
+        # Programmatic dependent launch (csrc/common.cuh) shortens the single-chain no-grad step (80 -> 75 us) but
+        # LENGTHENS the training step (118 -> 122..127 us, more the further into the DAG it is enabled): dependents
+        # scheduled early hold SM slots that the step's parallel branches need.  So: inference on, training off.
+        _lib.lib().ctan_set_pdl(0 if train else 1, None)
+
+    def _prep_rest(self, train: bool):
+        w, m = self.w, self.model
+        D = self.D
+        Wq, Wk, Wv, W = (ptr(self.p[i]) for i in (2, 4, 6, 9))
         with self._fork(2):
             if self.use_tc:      # A = W - W^T - gamma I, packed with q/k/v weights and split for 3xTF32
                 call("ctan_wcat_prep", Wq, Wk, Wv, W, float(m.gnn.aconv.gamma), D, ptr(w["Wcat_hi"]),
@@ -531,10 +545,6 @@ class StepEngine:
             else:
                 call("ctan_antisym_prep", W, float(m.gnn.aconv.gamma), D, ptr(w["A"]))
             w["H"].zero_()
-        # Programmatic dependent launch (csrc/common.cuh) shortens the single-chain no-grad step (80 -> 75 us) but
-        # LENGTHENS the training step (118 -> 122..127 us, more the further into the DAG it is enabled): dependents
-        # scheduled early hold SM slots that the step's parallel branches need.  So: inference on, training off.
-        _lib.lib().ctan_set_pdl(0 if train else 1, None)
 
     def _step(self, train: bool, par: int, prefetch: bool, prep_done: bool = False, early: bool = False):
         """Issue one step whose front-end is already in buffer set `par`.  Work that is off the critical path (edge
@@ -553,11 +563,19 @@ class StepEngine:
         cur1 = ptr(w["counters"]) + 8                       # &counters[1]: current batch start
         xf = ptr(self.x) if Fn else None
         eps = float(m.gnn.aconv.epsilon)
+        defer = (not prep_done) and train and self.fuse_train and os.environ.get("CTAN_DEFER_PREP", "1") == "1"
         if not prep_done:
-            self._prep(train)
-        if train:
-            with self._fork(2):                              # the accumulation arena, cleared by the batch's TRUE node count
+            self._prep(train, defer)
+
+        def backward_prep():                                 # the accumulation arena, cleared by the batch's TRUE node count,
+            if defer:                                        # the saved copy of the gathered rows, and the deferred prep
+                self._prep_rest(train)
+            with self._fork(2):
                 self._zero_arena(f)
+            with self._fork(1):                              # side 1: saved copy of the gathered input rows
+                call("ctan_gather_rows2", ptr(mem), D, xf, Fn, ptr(f["n_id"]), N, Nd, ptr(w["z0"]))
+        if train and not defer:
+            backward_prep()
         def insert():
             call("ctan_nbr_insert", ptr(ld.neighbors), ptr(ld.e_id), ptr(ld._deg), ptr(f["b_src"]), ptr(f["b_dst"]),
                  B, 0, cur1, S, ptr(w["ins_ws"]))
@@ -574,12 +592,11 @@ class StepEngine:
                      float(m.gnn.mean_delta_t), float(m.gnn.std_delta_t), ptr(f["rel"]))
             call(self._eproj_fn, ptr(self.msg), Fe, ptr(f["eid"]), ptr(f["rel"]), tw, tb, T, We, E, Ed, D,
                  ptr(w["EP"]))
-        if train:
-            with self._fork(1):                              # side 1: saved copy of the gathered input rows
-                call("ctan_gather_rows2", ptr(mem), D, xf, Fn, ptr(f["n_id"]), N, Nd, ptr(w["z0"]))
         fused = self.fuse_train if train else self.fuse_enc
         if fused:                # X0 and QKVA of the first iteration in one contraction (panel: _prep / _prep_infer_weights)
             call("ctan_enc_prep_ext", ptr(mem), D, xf, Fn, ptr(f["n_id"]), N, Nd, self.Kx, ptr(w["zext"]))
+            if defer:
+                backward_prep()                              # (forked behind the gather: runs beside the contraction)
             if train:
                 self._join(3)
             call("ctan_enc_qkva_tc", ptr(w["zext"]), N, Nd, self.Kx, ptr(w["Wce_hi"]), ptr(w["Wce_lo"]), D, ptr(w["bce"]),
@@ -593,6 +610,8 @@ class StepEngine:
             xi = w["X"][k] if train else w["X"][k & 1]
             xo = w["X"][k + 1] if train else w["X"][(k + 1) & 1]
             qk = w["QKVA"][k] if train else w["QKVA"][0]
+            if late_join and k == 1:
+                self._join(2)    # (the Wcat panels)
             if fused and k == 0:
                 pass             # (came with X0)
             elif self.use_tc:    # tcgen05 + TMA projection
@@ -602,8 +621,6 @@ class StepEngine:
                 call("ctan_qkva_fwd", ptr(xi), N, Nd, D, Wq, Wk, Wv, ptr(w["A"]), bq, bk, bv, b, ptr(qk))
             if k == 0:
                 self._join(0)                                # edge projections (side 0) are first read by the edge kernel
-                if late_join:
-                    self._join(2)
             last = k == K - 1
             ef = (ptr(qk), ptr(w["EP"]), ptr(f["rowptr"]), ptr(f["esrc"]), N, Nd, D, ptr(xi), eps, ptr(xo),
                   ptr(w["TH"][k]) if train else None, ptr(w["ALPHA"][k]) if train else None,
@@ -615,6 +632,8 @@ class StepEngine:
                 self._join(0)
             else:
                 call("ctan_edge_fwd", *ef, None, 0, 0)
+        if late_join and K == 1:
+            self._join(2)        # (H cleared for the readout; the arena and the Wcat^T panels for the backward)
         xk = w["X"][K] if train else w["X"][K & 1]
         z = w["Z"] if self.final_tanh else xk
         self._z = z
