@@ -33,6 +33,7 @@ SIGNATURES = {
     "ctan_edge_bwd": [P, P, P, P, I, P, I, P, P, P, F, P, P, I, P],
     "ctan_tanh_bwd": [P, P, I, P, I, P],
     "ctan_tenc_bwd": [P, P, P, P, I, P, I, P, P],
+    "ctan_tenc_bwd_fused": [P, P, I, I, I, P, P, P, I, P, P, P],
     "ctan_csr_from_sorted": [P, I, I, P, P],
     # dense.cu
     "ctan_enc_fwd": [P, I, P, I, P, P, I, P, P, P, P],
@@ -43,6 +44,7 @@ SIGNATURES = {
     "ctan_readout_bwd": [P, P, P, I, P, P, P, I, P, I, I, P, P, P, P, P, P, P, P, P, P, P, I],
     "ctan_head_loss": [P, I, I, P, P, I, P, P, P, P, I, P],
     "ctan_qkva_bwd": [P, P, P, I, P, I, P, P, P, P, P, P, P, P, P, P, P, P, P, I],
+    "ctan_qkva_wgrad": [P, P, I, P, I, P, P, P, P, P, P, P, P, I],
     "ctan_enc_bwd": [P, P, I, P, I, I, P, P, I],
     "ctan_eproj_bwd": [P, P, I, P, P, P, P, I, P, I, P, I, P, P, I],
 }

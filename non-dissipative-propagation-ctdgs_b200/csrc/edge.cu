@@ -525,6 +525,84 @@ extern "C" int ctan_tenc_bwd(const float* dTenc, const float* rel, const float* 
     return 0;
 }
 
+// The same gradients straight from dEP (no dTenc round trip): dTenc[e,tau] = sum_d dEP[e,d] We[d, Fe+tau] is formed in
+// registers, one warp per edge (the time columns of We staged once per CTA as Wt[tau][d]), and reduced like above.
+// For batch-sized edge sets this replaces a [E,D]x[D,T] contraction launch plus ctan_tenc_bwd by one short kernel.
+__global__ void __launch_bounds__(256)
+tenc_bwd_fused_kernel(const float* __restrict__ dEP, const float* __restrict__ We, int Fe, int T, int D,
+                      const float* __restrict__ rel, const float* __restrict__ tw, const float* __restrict__ tb,
+                      int E_host, const int* __restrict__ E_dev, float* __restrict__ dtw, float* __restrict__ dtb) {
+    ctan_pdl_begin();
+    extern __shared__ float tsm[];
+    float* Wt = tsm;                                          // [T][D]
+    float* red = tsm + (size_t)T * D;                         // [8 warps][2][T]
+    const int E = E_dev ? *E_dev : E_host;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * 8 + warp, nw = gridDim.x * 8;
+    if (blockIdx.x * 8 >= E) return;
+    const int K = Fe + T;
+    for (int i = threadIdx.x; i < T * D; i += 256) {          // coalesced along tau within a weight row
+        const int d = i / T, tau = i - d * T;
+        Wt[(size_t)tau * D + d] = We[(size_t)d * K + Fe + tau];
+    }
+    for (int i = threadIdx.x; i < 16 * T; i += 256) red[i] = 0.f;
+    __syncthreads();
+    const int nq = D >> 5;                                    // D % 32 == 0, D <= 256
+    for (int t0 = 0; t0 < T; t0 += 32) {                      // lane <-> time channel t0 + lane
+        const int tau = t0 + lane;
+        const float w = tau < T ? tw[tau] : 0.f, b = tau < T ? tb[tau] : 0.f;
+        float sw = 0.f, sb = 0.f;
+        for (int e = gw; e < E; e += nw) {
+            float x[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) x[q] = q < nq ? dEP[(size_t)e * D + lane + 32 * q] : 0.f;
+            const float r = rel[e];
+            float mine = 0.f;
+            const int tn = min(32, T - t0);
+            for (int j = 0; j < tn; ++j) {
+                const float* wr = Wt + (size_t)(t0 + j) * D + lane;
+                float p = 0.f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (q < nq) p = fmaf(x[q], wr[32 * q], p);
+                p = warp_sum(p);
+                if (j == lane) mine = p;
+            }
+            if (tau < T) {
+                const float g = -sinf(fmaf(r, w, b)) * mine;
+                sw = fmaf(g, r, sw);
+                sb += g;
+            }
+        }
+        if (tau < T) { red[(warp * 2 + 0) * T + tau] = sw; red[(warp * 2 + 1) * T + tau] = sb; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * T; i += 256) {
+        const int which = i / T, tau = i - which * T;
+        float v = 0.f;
+        for (int wv = 0; wv < 8; ++wv) v += red[(wv * 2 + which) * T + tau];
+        atomicAdd((which ? dtb : dtw) + tau, v);
+    }
+}
+// Requirements: D % 32 == 0, D <= 256, (T*D + 16*T) floats of shared memory (<= 96 KB); else CTAN_ERR_UNSUPPORTED
+// (the caller keeps ctan_eproj_bwd(.., dTenc) + ctan_tenc_bwd).
+extern "C" int ctan_tenc_bwd_fused(const float* dEP, const float* We, int Fe, int T, int D, const float* rel,
+                                   const float* tw, const float* tb, int E, const int* E_dev, float* dtw, float* dtb,
+                                   cudaStream_t stream) {
+    if (E <= 0 || T <= 0) return 0;
+    const size_t smem = ((size_t)T * D + 16 * (size_t)T) * sizeof(float);
+    if (D % 32 != 0 || D > 256 || smem > 96 * 1024) return CTAN_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(tenc_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    int grid = ctan_div_up(E, 16);                            // ~2 edges per warp at the bound
+    if (grid > 2 * CTAN_SM_COUNT) grid = 2 * CTAN_SM_COUNT;
+    CTAN_LAUNCH((tenc_bwd_fused_kernel), grid, 256, smem, stream, dEP, We, Fe, T, D, rel, tw, tb, E, E_dev, dtw, dtb);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
 // rowptr from a destination-sorted edge list that did not come from our loader.  flag[0] |= 1 if unsorted.
 __global__ void csr_from_sorted_kernel(const int64_t* __restrict__ edst, int E, int N, int32_t* __restrict__ rowptr,
                                        int* __restrict__ flag) {

@@ -207,8 +207,15 @@ struct EpiAtomic {                 // split-K accumulate: C[m][n] += acc (+ res[
 struct EpiAtomicSeg4 {             // rows split into 4 segments of D rows, each with its own output / bias-grad
     static constexpr bool HAS_ROWSUM = true;
     float* C[4]; float* rs[4]; int D; int ldc;
+    int antisym = 0;               // 1: segment 3 is the gradient of A = W - W^T - gamma I, accumulated straight into dW
     __device__ __forceinline__ void operator()(int m, int n, float v, bool) const {
-        atomicAdd(sel4(C, m / D) + (size_t)(m % D) * ldc + n, v);
+        const int seg = m / D, r = m - seg * D;
+        if (antisym && seg == 3) {                            // dW += dA - dA^T   (ldc == D)
+            atomicAdd(C[3] + (size_t)r * ldc + n, v);
+            atomicAdd(C[3] + (size_t)n * ldc + r, -v);
+        } else {
+            atomicAdd(sel4(C, seg) + (size_t)r * ldc + n, v);
+        }
     }
     __device__ __forceinline__ void rowsum(int m, float v) const {
         float* r = sel4(rs, m / D);

@@ -349,6 +349,11 @@ class StepEngine:
         small = (self.e_typ <= 8192 and (self.Fe + self.T) % 4 == 0 and D in (32, 64, 128, 256)
                  and (D + 16) * (self.Fe + self.T + 4) * 4 <= 220 * 1024 and os.environ.get("CTAN_EPROJ_ROWS", "1") == "1")
         self._eproj_fn = "ctan_eproj_fwd_rows" if small else "ctan_eproj_fwd"
+        # batch-sized backward side branches: W's gradient accumulated straight through A = W - W^T - gamma I (not in
+        # gradient-accumulation mode, where dW is only formed at the end), time-encoder gradients straight from dEP
+        self._wgrad_direct = (not self.seq_mod) and os.environ.get("CTAN_WGRAD_DIRECT", "1") == "1"
+        self._tenc_fused = (self.e_typ <= 16384 and D % 32 == 0 and D <= 256 and (self.T * D + 16 * self.T) * 4 <= 96 * 1024
+                            and os.environ.get("CTAN_TENC_FUSED", "1") == "1")
         self._row_hint = (self.n_typ << 8) if os.environ.get("CTAN_TC_ROW_HINT", "1") == "1" else 0
         w["Wcat_hi"], w["Wcat_lo"] = torch.zeros((4 * D, D), **f32), torch.zeros((4 * D, D), **f32)
         self.use_tc_dx = (self.use_tc and D % 128 == 0          # dX contraction on tcgen05 needs 128-wide output tiles
@@ -470,6 +475,14 @@ class StepEngine:
         self._side[i].wait_stream(torch.cuda.current_stream())
         return torch.cuda.stream(self._side[i])
 
+    def _fork_from(self, i, ev):
+        """Side stream i continues from the recorded point `ev` of the main stream (not from its tail): what the main
+        stream issued after `ev` is a sibling of the side branch, created -- and so launched -- before it."""
+        if not self.parallel:
+            return contextlib.nullcontext()
+        self._side[i].wait_event(ev)
+        return torch.cuda.stream(self._side[i])
+
     def _join(self, i):
         if self.parallel:
             torch.cuda.current_stream().wait_stream(self._side[i])
@@ -574,6 +587,8 @@ class StepEngine:
                 self._zero_arena(f)
             with self._fork(1):                              # side 1: saved copy of the gathered input rows
                 call("ctan_gather_rows2", ptr(mem), D, xf, Fn, ptr(f["n_id"]), N, Nd, ptr(w["z0"]))
+                self._z0_ready = torch.cuda.Event()
+                self._z0_ready.record(torch.cuda.current_stream())
         if train and not defer:
             backward_prep()
         def insert():
@@ -689,32 +704,55 @@ class StepEngine:
                  ptr(w["TH"][k]), ptr(w["ALPHA"][k]), eps, ptr(w["DQKVA"]), ptr(w["dEP"]), int(k != K - 1),
                  ptr(w["DS"]))
             qb = (ptr(w["DQKVA"]), ptr(w["X"][k]), ptr(g), N, Nd, D, Wq, Wk, Wv, ptr(w["A"]))
-            with self._fork(0):                              # side 0: weight gradients of this iteration
-                call("ctan_qkva_bwd", *qb, None, gWq, gWk, gWv, ptr(w["dA"]), gbq, gbk, gbv, gb, self.n_typ)
-                if k == 0:
-                    call("ctan_antisym_bwd", ptr(w["dA"]), D, gW)
+            gn = self._DX[k]
+            # dX is the critical path and its tcgen05 CTAs need a whole SM each: it is issued BEFORE the weight-gradient
+            # branches that depend on the same edge_bwd, so that their many small CTAs do not take the SMs first
+            dx_first = self.use_tc_dx and self.parallel and os.environ.get("CTAN_DX_FIRST", "1") == "1"
+            def dx():
+                if self.use_tc_dx:   # dX = G + DQKVA Wcat on tcgen05 (plain stores)
+                    call("ctan_dx_tc", ptr(w["DQKVA"]), ptr(g), N, Nd, D, ptr(w["WcatT_hi"]), ptr(w["WcatT_lo"]), ptr(gn),
+                         _lib.TC_MODE | self._row_hint,
+                         int(os.environ.get("CTAN_DX_SPLIT", "4")) if self.n_typ <= 4096 else 1)
+                    # (kernel body at N=640: 18 / 12 / 9 us with 1 / 2 / 4 splits, scripts/micro_tc3.py)
+                else:
+                    call("ctan_qkva_bwd", *qb, ptr(gn), None, None, None, None, None, None, None, None, self.n_typ)
+            if dx_first:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())
+                dx()
+                fork = lambda i: self._fork_from(i, ev)
+            else:
+                fork = self._fork
+            with fork(0):                                    # side 0: weight gradients of this iteration
+                if self._wgrad_direct:                       # (dA - dA^T accumulated straight into dW)
+                    call("ctan_qkva_wgrad", ptr(w["DQKVA"]), ptr(w["X"][k]), N, Nd, D, gWq, gWk, gWv, gW, gbq, gbk, gbv,
+                         gb, self.n_typ)
+                else:
+                    call("ctan_qkva_bwd", *qb, None, gWq, gWk, gWv, ptr(w["dA"]), gbq, gbk, gbv, gb, self.n_typ)
+                    if k == 0:
+                        call("ctan_antisym_bwd", ptr(w["dA"]), D, gW)
             if k == 0:
                 ep = (ptr(w["dEP"]), ptr(self.msg), Fe, ptr(f["eid"]), ptr(f["rel"]), tw, tb, T, We, E, Ed, D)
-                with self._fork(3):                          # side 3: lin_edge weight gradient
+                with fork(3):                                # side 3: lin_edge weight gradient
                     call("ctan_eproj_bwd", *ep, gWe, None, self.e_typ)
-                with self._fork(2):                          # side 2 (readout gradients long done): time-encoder gradients
-                    call("ctan_eproj_bwd", *ep, None, ptr(w["dTenc"]), self.e_typ)
-                    call("ctan_tenc_bwd", ptr(w["dTenc"]), ptr(f["rel"]), tw, tb, E, Ed, T, gtw, gtb)
-            gn = self._DX[k]
-            if self.use_tc_dx:   # dX = G + DQKVA Wcat on tcgen05 (plain stores)
-                call("ctan_dx_tc", ptr(w["DQKVA"]), ptr(g), N, Nd, D, ptr(w["WcatT_hi"]), ptr(w["WcatT_lo"]), ptr(gn),
-                     _lib.TC_MODE | self._row_hint, int(os.environ.get("CTAN_DX_SPLIT", "4")) if self.n_typ <= 4096 else 1)
-                # (kernel body at N=640: 18 / 12 / 9 us with 1 / 2 / 4 splits, scripts/micro_tc3.py)
-            else:
-                call("ctan_qkva_bwd", *qb, ptr(gn), None, None, None, None, None, None, None, None, self.n_typ)
+                with fork(2):                                # side 2 (readout gradients long done): time-encoder gradients
+                    if self._tenc_fused:
+                        call("ctan_tenc_bwd_fused", ptr(w["dEP"]), We, Fe, T, D, ptr(f["rel"]), tw, tb, E, Ed, gtw, gtb)
+                    else:
+                        call("ctan_eproj_bwd", *ep, None, ptr(w["dTenc"]), self.e_typ)
+                        call("ctan_tenc_bwd", ptr(w["dTenc"]), ptr(f["rel"]), tw, tb, E, Ed, T, gtw, gtb)
+            if not dx_first:
+                dx()
             g = gn
-        self._join(1)                                        # z0 is complete (and the state write-back done)
+        if self.parallel:                                    # z0 is complete (side 1 itself -- state write-back, the next
+            torch.cuda.current_stream().wait_event(self._z0_ready)    # step's front-end -- is only joined at the end)
         call("ctan_enc_bwd", ptr(g), ptr(w["z0"]), N, Nd, D, Fn, gWenc, gbenc, self.n_typ)
         self._join(0)
         self._join(2)
         self._join(3)
         if not self._accumulate:
             self._adam()
+        self._join(1)
         _lib.lib().ctan_set_pdl(1, None)
 
     def _zero_arena(self, f, only_dq: bool = False):

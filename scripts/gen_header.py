@@ -20,6 +20,7 @@ REF = {
     "ctan_edge_bwd": "gradient of the above (autograd in the reference)",
     "ctan_tanh_bwd": "gradient of final_act=tanh -- models/ctdg_models.py:457-458",
     "ctan_tenc_bwd": "gradient of TimeEncoder -- TGB/modules/time_enc.py:23-24",
+    "ctan_tenc_bwd_fused": "TimeEncoder parameter gradients straight from the lin_edge output gradient (one kernel for batch-sized edge sets) -- autograd of TGB/modules/time_enc.py:23-24 + models/gnn_layers.py:97 (train_link.py:279)",
     "ctan_csr_from_sorted": "(no reference counterpart: CSR pointer of a destination-sorted edge_index)",
     "ctan_enc_fwd": "CTANEmbedding.enc_x on gathered memory rows -- models/gnn_layers.py:96",
     "ctan_eproj_fwd": "edge_attr=[msg|TimeEncoder(rel)] -> TransformerConv.lin_edge -- models/gnn_layers.py:97, TGB/modules/time_enc.py:23-24",
@@ -28,6 +29,7 @@ REF = {
     "ctan_readout_fwd": "LinkPredictor / TGBLinkPredictor / SequencePredictor.forward -- models/predictors.py:16-19,31-34,45-48",
     "ctan_readout_bwd": "gradient of the above (autograd in the reference)",
     "ctan_qkva_bwd": "gradient of the projections (autograd in the reference)",
+    "ctan_qkva_wgrad": "weight / bias gradients of the q,k,v projections and of W through A = W - W^T - gamma I, accumulated straight into dW -- autograd of PyG TransformerConv / AntiSymmetricConv (train_link.py:279)",
     "ctan_enc_bwd": "gradient of enc_x (autograd in the reference)",
     "ctan_eproj_bwd": "gradient of lin_edge and of the time encoding input (autograd in the reference)",
     "ctan_stage_batch": "batch slicing, cat(src,src)/cat(dst,neg), seed cat -- train_link.py:239-256",

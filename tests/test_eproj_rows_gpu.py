@@ -54,3 +54,68 @@ def test_eproj_rows_rejects_unsupported_shapes():
         call("ctan_eproj_fwd_rows", ptr(z), 4, None, ptr(z), ptr(z), ptr(z), 4, ptr(z), 8, None, 74, ptr(z))
     with pytest.raises(CtanLibraryError):                      # Fe + T = 7
         call("ctan_eproj_fwd_rows", ptr(z), 4, None, ptr(z), ptr(z), ptr(z), 3, ptr(z), 8, None, 64, ptr(z))
+
+
+@pytest.mark.parametrize("E,Fe,T,D,e_true", [(1106, 172, 16, 128, None), (3000, 8, 100, 64, 777), (40, 4, 4, 32, None),
+                                              (64, 8, 8, 128, 0)])
+def test_tenc_bwd_fused_matches_two_kernel_path_and_fp64(E, Fe, T, D, e_true):
+    """Time-encoder gradients straight from dEP (ctan_tenc_bwd_fused) against ctan_eproj_bwd(.., dTenc) +
+    ctan_tenc_bwd and against fp64 autograd of cos(w * rel + b) -> lin_edge (TGB/modules/time_enc.py:23-24)."""
+    from ctan_b200._lib import call, ptr
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(E + T + D)
+    dEP = torch.randn(E, D, generator=g).to(dev)
+    We = (torch.randn(D, Fe + T, generator=g) / (Fe + T) ** 0.5).to(dev)
+    rel = (torch.rand(E, generator=g) * 20.0).to(dev)
+    tw, tb = torch.randn(T, generator=g).to(dev), torch.randn(T, generator=g).to(dev)
+    msg = torch.randn(E, Fe, generator=g).to(dev)
+    Ed = None if e_true is None else torch.tensor([e_true], dtype=torch.int32, device=dev)
+    n = E if e_true is None else e_true
+    a_w, a_b = torch.zeros(T, device=dev), torch.zeros(T, device=dev)
+    b_w, b_b = torch.zeros(T, device=dev), torch.zeros(T, device=dev)
+    dT = torch.zeros(E, T, device=dev)
+    edp = ptr(Ed) if Ed is not None else None
+    call("ctan_eproj_bwd", ptr(dEP), ptr(msg), Fe, None, ptr(rel), ptr(tw), ptr(tb), T, ptr(We), E, edp, D, None, ptr(dT), 0)
+    call("ctan_tenc_bwd", ptr(dT), ptr(rel), ptr(tw), ptr(tb), E, edp, T, ptr(a_w), ptr(a_b))
+    call("ctan_tenc_bwd_fused", ptr(dEP), ptr(We), Fe, T, D, ptr(rel), ptr(tw), ptr(tb), E, edp, ptr(b_w), ptr(b_b))
+    torch.cuda.synchronize()
+    if n == 0:
+        assert float(b_w.abs().max()) == 0.0 and float(b_b.abs().max()) == 0.0
+        return
+    w64, b64 = tw.double().requires_grad_(), tb.double().requires_grad_()
+    tenc = torch.cos(rel[:n, None].double() * w64 + b64)
+    (tenc @ We[:, Fe:].double().t() * dEP[:n].double()).sum().backward()
+    for got, ref in ((a_w, w64.grad), (b_w, w64.grad), (a_b, b64.grad), (b_b, b64.grad)):
+        assert float((got.double() - ref).abs().max()) <= 2e-5 * float(ref.abs().max()) + 1e-6, (got, ref)
+
+
+@pytest.mark.parametrize("N,D,n_true", [(640, 128, None), (3600, 128, 611), (200, 32, None)])
+def test_qkva_wgrad_matches_bwd_plus_antisym(N, D, n_true):
+    """ctan_qkva_wgrad (dA - dA^T accumulated straight into dW) against ctan_qkva_bwd + ctan_antisym_bwd and fp64."""
+    from ctan_b200._lib import call, ptr
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(N + D)
+    DQ = torch.randn(N, 4 * D, generator=g).to(dev)
+    X = torch.randn(N, D, generator=g).to(dev)
+    Nd = None if n_true is None else torch.tensor([n_true], dtype=torch.int32, device=dev)
+    n = N if n_true is None else n_true
+    ndp = ptr(Nd) if Nd is not None else None
+    A = [torch.zeros(D, D, device=dev) for _ in range(4)] + [torch.zeros(D, device=dev) for _ in range(4)]
+    B = [torch.zeros(D, D, device=dev) for _ in range(4)] + [torch.zeros(D, device=dev) for _ in range(4)]
+    dW_a = torch.zeros(D, D, device=dev)
+    z = torch.zeros(D, D, device=dev)
+    call("ctan_qkva_bwd", ptr(DQ), ptr(X), None, N, ndp, D, ptr(z), ptr(z), ptr(z), ptr(z), None, *(ptr(t) for t in A),
+         min(N, 900))
+    call("ctan_antisym_bwd", ptr(A[3]), D, ptr(dW_a))
+    call("ctan_qkva_wgrad", ptr(DQ), ptr(X), N, ndp, D, *(ptr(t) for t in B), min(N, 900))
+    torch.cuda.synchronize()
+    ref = DQ[:n].double().t() @ X[:n].double()                    # [4D, D]
+    refs = [ref[i * D:(i + 1) * D] for i in range(3)] + [ref[3 * D:] - ref[3 * D:].t()]
+    for i in range(4):
+        got_a = dW_a if i == 3 else A[i]
+        s = float(refs[i].abs().max())
+        assert float((got_a.double() - refs[i]).abs().max()) <= 1e-5 * s
+        assert float((B[i].double() - refs[i]).abs().max()) <= 1e-5 * s
+        bref = DQ[:n, i * D:(i + 1) * D].double().sum(0)
+        assert float((B[4 + i].double() - bref).abs().max()) <= 1e-5 * float(bref.abs().max())
+        assert float((A[4 + i] - B[4 + i]).abs().max()) <= 1e-5 * float(bref.abs().max())
