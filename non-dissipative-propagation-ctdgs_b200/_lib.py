@@ -43,6 +43,7 @@ SIGNATURES = {
     "ctan_readout_fwd": [P, I, P, P, P, I, P, I, I, P, P, P, P, P, P, P, P, I],
     "ctan_readout_bwd": [P, P, P, I, P, P, P, I, P, I, I, P, P, P, P, P, P, P, P, P, P, P, I],
     "ctan_head_loss": [P, I, I, P, P, I, P, P, P, P, I, P],
+    "ctan_readout_link_fused": [P, I, P, P, P, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, I, P],
     "ctan_qkva_bwd": [P, P, P, I, P, I, P, P, P, P, P, P, P, P, P, P, P, P, P, I],
     "ctan_qkva_wgrad": [P, P, I, P, I, P, P, P, P, P, P, P, P, I],
     "ctan_enc_bwd": [P, P, I, P, I, I, P, P, I],

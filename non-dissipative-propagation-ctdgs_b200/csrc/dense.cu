@@ -285,6 +285,150 @@ extern "C" int ctan_head_loss(const float* H, int P, int Hd, const float* Wfin, 
     return 0;
 }
 
+// ---- the whole binary link readout of a training batch in ONE launch (models/predictors.py:16-19 / 31-34 +
+// train_link.py:269-270 + their gradients): hidden layer, head, BCE loss, dOUT, dHid and the scatter of dZ.
+// P is a few hundred pairs and the three kernels it replaces (hidden contraction, head + loss, dHid -> dZ contraction)
+// are each pure launch + gather latency on the step's critical path.  A CTA scores PT = 256/Hd pairs: both weight
+// matrices ([Hd, D] each, L2-resident, shared by all CTAs) and the gathered embedding rows land in shared memory behind
+// one wait (cp.async); thread (pair, h) forms H[pair][h]; the pair's threads reduce the head; thread (pair, side, d)
+// forms dZ row elements from dHid (kept in shared memory) and adds them atomically (a node is scored by several pairs).
+// H (pre-activation, biases included) and dHid are also written out for the weight-gradient kernels.
+namespace link_fused {
+constexpr int THREADS = 256;
+__device__ __forceinline__ void cp16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__global__ void __launch_bounds__(THREADS)
+kernel(const float* __restrict__ Z, int D, const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+       const int64_t* __restrict__ map, int P, int n_pos, int Hd, const float* __restrict__ Wsrc,
+       const float* __restrict__ bsrc, const float* __restrict__ Wdst, const float* __restrict__ bdst,
+       const float* __restrict__ Wfin, const float* __restrict__ bfin, float* __restrict__ H, float* __restrict__ OUT,
+       float* __restrict__ dOUT, float* __restrict__ dHid, float* __restrict__ dZ, float* __restrict__ loss_hist,
+       int hist_cap, const int64_t* __restrict__ counters, int S) {
+    ctan_pdl_begin();
+    extern __shared__ __align__(16) float lsm[];
+    const int PT = THREADS / Hd;
+    float* Ws = lsm;                                          // [Hd][S]
+    float* Wd = Ws + (size_t)Hd * S;                          // [Hd][S]
+    float* zs = Wd + (size_t)Hd * S;                          // [PT][2][D]   (src row | dst row)
+    float* dh = zs + (size_t)PT * 2 * D;                      // [PT][Hd]
+    float* red = dh + (size_t)PT * Hd;                        // [8] per-warp partial heads
+    __shared__ int64_t rows[16];                              // [PT][2] resolved local rows
+    __shared__ float s_loss;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int p0 = blockIdx.x * PT;
+    const int D4 = D >> 2;
+    if (tid == 0) s_loss = 0.f;
+    for (int i = tid; i < Hd * D4; i += THREADS) {            // the weights: no dependence, issued first
+        const int h = i / D4, c = i - h * D4;
+        cp16(Ws + (size_t)h * S + 4 * c, Wsrc + (size_t)h * D + 4 * c);
+        cp16(Wd + (size_t)h * S + 4 * c, Wdst + (size_t)h * D + 4 * c);
+    }
+    for (int i = tid; i < PT * 2 * D4; i += THREADS) {        // the two embedding rows of every pair
+        const int pr = i / D4, c = i - pr * D4;               // pr = pair-in-CTA * 2 + side
+        const int p = p0 + (pr >> 1);
+        if (p < P) {
+            int64_t r = (pr & 1) ? dst[p] : src[p];
+            if (map) r = map[r];
+            if (c == 0) rows[pr] = r;
+            cp16(zs + (size_t)pr * D + 4 * c, Z + (size_t)r * D + 4 * c);
+        }
+    }
+    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // hidden layer: thread (pp, h)
+    const int pp = tid / Hd, h = tid - pp * Hd;
+    const int p = p0 + pp;
+    const bool live = p < P;
+    float acc = 0.f;
+    if (live) {
+        acc = __ldg(bsrc + h) + __ldg(bdst + h);
+        const float4* ws = reinterpret_cast<const float4*>(Ws + (size_t)h * S);
+        const float4* wd = reinterpret_cast<const float4*>(Wd + (size_t)h * S);
+        const float4* a = reinterpret_cast<const float4*>(zs + (size_t)(2 * pp) * D);
+        const float4* b = reinterpret_cast<const float4*>(zs + (size_t)(2 * pp + 1) * D);
+#pragma unroll 4
+        for (int c = 0; c < D4; ++c) {
+            const float4 x = a[c], w = ws[c], y = b[c], v = wd[c];
+            acc = fmaf(x.x, w.x, acc); acc = fmaf(x.y, w.y, acc); acc = fmaf(x.z, w.z, acc); acc = fmaf(x.w, w.w, acc);
+            acc = fmaf(y.x, v.x, acc); acc = fmaf(y.y, v.y, acc); acc = fmaf(y.z, v.z, acc); acc = fmaf(y.w, v.w, acc);
+        }
+        H[(size_t)p * Hd + h] = acc;
+    }
+    const float wf = __ldg(Wfin + h);
+    float part = live ? fmaxf(acc, 0.f) * wf : 0.f;
+    part = warp_sum(part);                                    // Hd >= 32: a warp never straddles two pairs
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    const int wpp = Hd >> 5;                                  // warps per pair
+    float x = __ldg(bfin);
+    for (int i = 0; i < wpp; ++i) x += red[pp * wpp + i];
+    float dx = 0.f;
+    if (live) {
+        const int n_neg = P - n_pos;
+        float my;
+        if (p < n_pos) {
+            my = (fmaxf(-x, 0.f) + log1pf(expf(-fabsf(x)))) / (float)n_pos;
+            dx = -1.f / (1.f + expf(x)) / (float)n_pos;
+        } else {
+            my = (fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)))) / (float)n_neg;
+            dx = 1.f / (1.f + expf(-x)) / (float)n_neg;
+        }
+        if (h == 0) {
+            OUT[p] = x;
+            if (dOUT) dOUT[p] = dx;
+            atomicAdd(&s_loss, my);
+        }
+        const float g = acc > 0.f ? dx * wf : 0.f;
+        dh[pp * Hd + h] = g;
+        if (dHid) dHid[(size_t)p * Hd + h] = g;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        long long slot = counters ? (long long)counters[3] - 1 : 0;
+        if (slot < 0) slot = 0;
+        atomicAdd(loss_hist + (slot % hist_cap), s_loss);
+    }
+    if (!dZ) return;
+    // dZ[row(src)] += dHid Wsrc ; dZ[row(dst)] += dHid Wdst : thread (pair, side, d)
+    for (int i = tid; i < PT * 2 * D; i += THREADS) {
+        const int pr = i / D, d = i - pr * D;
+        const int q = pr >> 1;
+        if (p0 + q >= P) continue;
+        const float* W = (pr & 1) ? Wd : Ws;
+        const float* g = dh + (size_t)q * Hd;
+        float v = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < Hd; ++k) v = fmaf(g[k], W[(size_t)k * S + d], v);
+        atomicAdd(dZ + (size_t)rows[pr] * D + d, v);
+    }
+}
+}  // namespace link_fused
+
+// Requirements: O == 1 (the caller's head), Hd in {32,64,128,256}, D % 4 == 0, Z / Wsrc / Wdst 16-byte aligned rows,
+// (2 Hd (D+4) + (256/Hd)(2D + Hd) + 8) floats of shared memory <= 200 KB; else CTAN_ERR_UNSUPPORTED (the caller keeps
+// ctan_readout_fwd + ctan_head_loss + ctan_readout_bwd).  dOUT / dHid / dZ may be NULL (no-grad step: scores + loss).
+// loss_hist slot as in ctan_head_loss.  dZ is ACCUMULATED (zero it first).
+extern "C" int ctan_readout_link_fused(const float* Z, int D, const int64_t* src, const int64_t* dst, const int64_t* map,
+                                       int P, int n_pos, int Hd, const float* Wsrc, const float* bsrc, const float* Wdst,
+                                       const float* bdst, const float* Wfin, const float* bfin, float* H, float* OUT,
+                                       float* dOUT, float* dHid, float* dZ, float* loss_hist, int hist_cap,
+                                       const int64_t* counters, cudaStream_t stream) {
+    if (P <= 0 || n_pos <= 0 || n_pos >= P || hist_cap <= 0) return CTAN_ERR_BAD_ARG;
+    if ((Hd != 32 && Hd != 64 && Hd != 128 && Hd != 256) || (D & 3) || !v4(Z, D) || !v4(Wsrc, D) || !v4(Wdst, D))
+        return CTAN_ERR_UNSUPPORTED;
+    const int S = ((D >> 2) & 1) ? D : D + 4;                 // S/4 odd: conflict-free 128-bit reads of 8 consecutive rows
+    const int PT = link_fused::THREADS / Hd;
+    const size_t smem = ((size_t)2 * Hd * S + (size_t)PT * (2 * D + Hd) + 8) * sizeof(float);
+    if (smem > 200 * 1024) return CTAN_ERR_UNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(link_fused::kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    CTAN_LAUNCH((link_fused::kernel), ctan_div_up(P, PT), link_fused::THREADS, smem, stream, Z, D, src, dst, map, P, n_pos, Hd,
+                Wsrc, bsrc, Wdst, bdst, Wfin, bfin, H, OUT, dOUT, dHid, dZ, loss_hist, hist_cap, counters, S);
+    CTAN_CHECK_LAUNCH();
+    return 0;
+}
+
 struct BRowCat2 {                  // b(k,n) = n<D ? W1[k*ld+n] : W2[k*ld+n-D]   (vector along n)
     static constexpr bool K_CONTIG = false;
     const float* p1; const float* p2; int D; int ld; bool vec;

@@ -349,6 +349,11 @@ class StepEngine:
         small = (self.e_typ <= 8192 and (self.Fe + self.T) % 4 == 0 and D in (32, 64, 128, 256)
                  and (D + 16) * (self.Fe + self.T + 4) * 4 <= 220 * 1024 and os.environ.get("CTAN_EPROJ_ROWS", "1") == "1")
         self._eproj_fn = "ctan_eproj_fwd_rows" if small else "ctan_eproj_fwd"
+        # the binary link readout (hidden + head + loss + gradients wrt the embeddings) as one launch
+        pt = 256 // self.Hd if self.Hd in (32, 64, 128, 256) else 0
+        self._link_fused = (not self.labelled and self.O == 1 and pt > 0 and D % 4 == 0 and self.n_neg >= 1
+                            and (2 * self.Hd * (D + 4) + pt * (2 * D + self.Hd) + 8) * 4 <= 200 * 1024
+                            and os.environ.get("CTAN_LINK_FUSED", "1") == "1")
         # batch-sized backward side branches: W's gradient accumulated straight through A = W - W^T - gamma I (not in
         # gradient-accumulation mode, where dW is only formed at the end), time-encoder gradients straight from dEP
         self._wgrad_direct = (not self.seq_mod) and os.environ.get("CTAN_WGRAD_DIRECT", "1") == "1"
@@ -393,6 +398,9 @@ class StepEngine:
         w["dA"] = self._dA
         self.w = w
         self.prefetch = (not self.host_staged) and not self.seq_mod and os.environ.get("CTAN_TRAIN_PREFETCH", "1") == "1"
+        # training steps too issue the neighbour insert and the next step's front-end (minus delta-t) at their first
+        # instant, beside the forward: the state write-back + front-end branch had become as long as the backward chain
+        self.early_train = os.environ.get("CTAN_TRAIN_EARLY", "1") == "1"
 
     # ------------------------------------------------------------------ state
     def reset(self, reset_optimizer: bool = False):
@@ -652,7 +660,13 @@ class StepEngine:
         xk = w["X"][K] if train else w["X"][K & 1]
         z = w["Z"] if self.final_tanh else xk
         self._z = z
-        if not self.labelled:
+        if self._link_fused:
+            # hidden layer + head + BCE loss + dOUT + dHid + the dZ scatter in ONE launch (csrc/dense.cu::link_fused)
+            call("ctan_readout_link_fused", ptr(z), D, ptr(f["pair_src"]), ptr(f["pair_dst"]), ptr(assoc), P, B, Hd,
+                 Wsrc, bsrc, Wdst, bdst, Wfin, bfin, ptr(w["H"]), ptr(w["OUT"]), ptr(w["dOUT"]) if train else None,
+                 ptr(w["dHid"]) if train else None, ptr(w["dZ"]) if train else None, ptr(w["loss_hist"]), self.hist_cap,
+                 ptr(f["ctr"]))
+        elif not self.labelled:
             call("ctan_readout_fwd", ptr(z), D, ptr(f["pair_src"]), ptr(f["pair_dst"]), ptr(assoc), P, None, Hd, O,
                  Wsrc, bsrc, Wdst, bdst, Wfin, bfin, ptr(w["H"]), None, 1)
             # head + BCE loss + dOUT + dHid in one launch (the loss slot was cleared by the stage kernel)
@@ -682,14 +696,15 @@ class StepEngine:
             return
         with self._fork(1):                                  # side 1 (after the z0 gather): state write-back ...
             state_update()
-            if prefetch:                                     # ... then the NEXT step's front-end, beside this backward
-                self._frontend(par ^ 1)
+            if prefetch and not early:                       # ... then the NEXT step's front-end, beside this backward
+                self._frontend(par ^ 1)                      # (early: it already ran beside the forward, without delta-t)
         (gWenc, gbenc, gWq, gbq, gWk, gbk, gWv, gbv, gWe, gW, gb, gtw, gtb, gWsrc, gbsrc, gWdst, gbdst, gWfin,
          gbfin) = (ptr(t) for t in self.g)
         rb_args = (ptr(w["dOUT"]), ptr(w["H"]), ptr(z), D, ptr(f["pair_src"]), ptr(f["pair_dst"]), ptr(assoc), P,
                    None, Hd, O, Wsrc, Wdst, Wfin, ptr(w["dHid"]))
         ready = 0 if self.labelled else 1                    # (the fused binary head already produced dHid)
-        call("ctan_readout_bwd", *rb_args, ptr(w["dZ"]), None, None, None, None, None, None, ready)
+        if not self._link_fused:                             # (else dZ came with the forward launch)
+            call("ctan_readout_bwd", *rb_args, ptr(w["dZ"]), None, None, None, None, None, None, ready)
         with self._fork(2):                                  # side 2: readout weight gradients
             call("ctan_readout_bwd", *rb_args, None, gWsrc, gbsrc, gWdst, gbdst, gWfin, gbfin, 1)
         g = w["dZ"]
@@ -919,16 +934,18 @@ class StepEngine:
                 elif not self.prefetch:
                     self._graph(tr)
                 else:
-                    self._graph_frontend(0, with_rel=tr)
+                    early = (not tr) or self.early_train
+                    self._graph_frontend(0, with_rel=not early)
                     for par in (0, 1):
                         for pf in (True, False):
-                            self._graph(tr, par, pf, inline=False, early=not tr)
+                            self._graph(tr, par, pf, inline=False, early=early)
         torch.cuda.synchronize(self.dev)
 
     def plan(self, n_steps: int, train: bool = True):
         """The replay sequence of n_steps steps as a list of callables (one per step; the first also issues the first
-        front-end).  Training steps prefetch the next step's front-end beside their backward, no-grad steps beside their
-        forward, except the last of the sequence: the state after the sequence is exactly that of n_steps self-contained steps."""
+        front-end).  Every step but the last of the sequence issues the next step's front-end beside its forward
+        (CTAN_TRAIN_EARLY=0: training steps beside their backward): the state after the sequence is exactly that of
+        n_steps self-contained steps."""
         if train:
             self._fuse_ver = None            # (training steps re-form the shared panel buffers and move the weights)
         else:
@@ -941,10 +958,11 @@ class StepEngine:
             g = self._graph(train)
             return [g.replay for _ in range(n_steps)]
         seq, par = [], 0
+        early = (not train) or self.early_train
         for j in range(n_steps):
-            g = self._graph(train, par, j < n_steps - 1, inline=False, early=not train)
+            g = self._graph(train, par, j < n_steps - 1, inline=False, early=early)
             if j == 0:
-                fe = self._graph_frontend(0, with_rel=train)
+                fe = self._graph_frontend(0, with_rel=not early)
                 seq.append(lambda fe=fe, g=g: (fe.replay(), g.replay()))
             else:
                 seq.append(g.replay)

@@ -53,6 +53,7 @@ REF = {
     "ctan_accum_col": "mean of the per-query metric -- train_link.py:201",
     "ctan_nbr_fill_rel": "LastNeighborLoader.__call__ edge list + CTANEmbedding delta-t -- TGB/modules/neighbor_loader.py:28-39, models/gnn_layers.py:94-95",
     "ctan_head_loss": "predictor head + BCEWithLogitsLoss + their gradients -- models/predictors.py:18-19, train_link.py:269-270,279",
+    "ctan_readout_link_fused": "LinkPredictor / TGBLinkPredictor forward, BCE-with-logits loss and their gradients wrt the embeddings in one launch -- models/predictors.py:16-19, 31-34, train_link.py:269-270, 279",
     "ctan_probe": "(profiling aid, no reference counterpart)",
     "ctan_wcat_prep": "AntiSymmetricConv W - W^T - gamma*I, packed with the q/k/v weights and split for 3xTF32 -- PyG 2.3.1",
     "ctan_pack_split": "(weight packing + TF32 split for the tensor-core path; no reference counterpart)",

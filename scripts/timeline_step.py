@@ -14,7 +14,7 @@ eng.run(300, train=True)
 torch.cuda.synchronize()
 if os.environ.get("PREFETCHED", "0") == "1":
     with torch.cuda.device(dev):
-        eng._frontend(0)
+        eng._frontend(0, with_rel=os.environ.get("EARLY", "0") != "1")
     torch.cuda.synchronize()
 train = os.environ.get("INFER", "0") != "1"
 ts = torch.zeros(256, dtype=torch.int64, device=dev)
@@ -27,7 +27,7 @@ with torch.cuda.graph(g):
     _lib.PROBE_SIDE = os.environ.get("ALL", "0") == "1"      # also probe the side-stream calls (order = issue order)
     if os.environ.get("PREFETCHED", "0") == "1":             # the step as run(n) replays it: front-end done beforehand
         try:
-            eng._step(train, 0, False)
+            eng._step(train, 0, os.environ.get("PF", "0") == "1", early=os.environ.get("EARLY", "0") == "1")
         finally:
             _lib.lib().ctan_set_pdl(1, None)
     else:

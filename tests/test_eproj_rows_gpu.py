@@ -119,3 +119,63 @@ def test_qkva_wgrad_matches_bwd_plus_antisym(N, D, n_true):
         bref = DQ[:n, i * D:(i + 1) * D].double().sum(0)
         assert float((B[4 + i].double() - bref).abs().max()) <= 1e-5 * float(bref.abs().max())
         assert float((A[4 + i] - B[4 + i]).abs().max()) <= 1e-5 * float(bref.abs().max())
+
+
+@pytest.mark.parametrize("P,n_pos,D,Hd,N", [(400, 200, 128, 64, 640), (401, 200, 128, 64, 300), (30, 10, 32, 32, 50),
+                                            (66, 33, 128, 128, 100), (10, 5, 64, 256, 20)])
+def test_readout_link_fused_matches_three_kernel_path_and_autograd(P, n_pos, D, Hd, N):
+    """ctan_readout_link_fused against ctan_readout_fwd + ctan_head_loss + ctan_readout_bwd and against fp64 autograd of
+    LinkPredictor (models/predictors.py:16-19) + BCEWithLogitsLoss on positives / negatives (train_link.py:269-270)."""
+    from ctan_b200._lib import call, ptr
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(P + D + Hd)
+    rnd = lambda *s: torch.randn(*s, generator=g)
+    Z = rnd(N, D).to(dev)
+    n_glob = 3 * N
+    perm = torch.randperm(n_glob, generator=g)[:N]
+    amap = torch.full((n_glob,), -1, dtype=torch.long)
+    amap[perm] = torch.arange(N)
+    src = perm[torch.randint(0, N, (P,), generator=g)].to(dev)
+    dst = perm[torch.randint(0, N, (P,), generator=g)].to(dev)
+    amap = amap.to(dev)
+    Wsrc, Wdst = (rnd(Hd, D) / D ** 0.5).to(dev), (rnd(Hd, D) / D ** 0.5).to(dev)
+    bsrc, bdst = rnd(Hd).to(dev), rnd(Hd).to(dev)
+    Wfin, bfin = (rnd(1, Hd) / Hd ** 0.5).to(dev), rnd(1).to(dev)
+    ctr = torch.tensor([0, 0, 0, 1], dtype=torch.long, device=dev)
+
+    def bufs():
+        return dict(H=torch.zeros(P, Hd, device=dev), OUT=torch.zeros(P, device=dev), dOUT=torch.zeros(P, device=dev),
+                    dHid=torch.zeros(P, Hd, device=dev), dZ=torch.zeros(N, D, device=dev), loss=torch.zeros(4, device=dev))
+    a, b = bufs(), bufs()
+    call("ctan_readout_fwd", ptr(Z), D, ptr(src), ptr(dst), ptr(amap), P, None, Hd, 1, ptr(Wsrc), ptr(bsrc), ptr(Wdst),
+         ptr(bdst), ptr(Wfin), ptr(bfin), ptr(a["H"]), None, 1)
+    call("ctan_head_loss", ptr(a["H"]), P, Hd, ptr(Wfin), ptr(bfin), n_pos, ptr(a["OUT"]), ptr(a["dOUT"]), ptr(a["dHid"]),
+         ptr(a["loss"]), 4, ptr(ctr))
+    call("ctan_readout_bwd", ptr(a["dOUT"]), ptr(a["H"]), ptr(Z), D, ptr(src), ptr(dst), ptr(amap), P, None, Hd, 1,
+         ptr(Wsrc), ptr(Wdst), ptr(Wfin), ptr(a["dHid"]), ptr(a["dZ"]), None, None, None, None, None, None, 1)
+    call("ctan_readout_link_fused", ptr(Z), D, ptr(src), ptr(dst), ptr(amap), P, n_pos, Hd, ptr(Wsrc), ptr(bsrc),
+         ptr(Wdst), ptr(bdst), ptr(Wfin), ptr(bfin), ptr(b["H"]), ptr(b["OUT"]), ptr(b["dOUT"]), ptr(b["dHid"]),
+         ptr(b["dZ"]), ptr(b["loss"]), 4, ptr(ctr))
+    # no-grad form: scores + loss only
+    c = bufs()
+    call("ctan_readout_link_fused", ptr(Z), D, ptr(src), ptr(dst), ptr(amap), P, n_pos, Hd, ptr(Wsrc), ptr(bsrc),
+         ptr(Wdst), ptr(bdst), ptr(Wfin), ptr(bfin), ptr(c["H"]), ptr(c["OUT"]), None, None, None, ptr(c["loss"]), 4,
+         ptr(ctr))
+    torch.cuda.synchronize()
+    z64 = Z.double().requires_grad_()
+    rs, rd = amap[src], amap[dst]
+    h = z64[rs] @ Wsrc.double().t() + bsrc.double() + z64[rd] @ Wdst.double().t() + bdst.double()
+    out = (h.relu() @ Wfin.double().t() + bfin.double()).squeeze(-1)
+    bce = torch.nn.BCEWithLogitsLoss()
+    loss = bce(out[:n_pos], torch.ones(n_pos, dtype=torch.float64, device=dev)) + \
+        bce(out[n_pos:], torch.zeros(P - n_pos, dtype=torch.float64, device=dev))
+    loss.backward()
+    for d in (a, b):
+        assert float((d["OUT"].double() - out.detach()).abs().max()) <= 2e-5 * float(out.abs().max()) + 1e-6
+        assert abs(float(d["loss"][0]) - float(loss)) <= 1e-5 * abs(float(loss))
+        assert float((d["dZ"].double() - z64.grad).abs().max()) <= 2e-5 * float(z64.grad.abs().max()) + 1e-9
+    assert float((a["H"] - b["H"]).abs().max()) <= 1e-5 * float(a["H"].abs().max())
+    assert float((a["dHid"] - b["dHid"]).abs().max()) <= 1e-5 * float(a["dHid"].abs().max()) + 1e-9
+    assert float((a["dOUT"] - b["dOUT"]).abs().max()) <= 1e-6
+    assert float((c["OUT"] - b["OUT"]).abs().max()) == 0.0 and abs(float(c["loss"][0] - b["loss"][0])) <= 1e-6
+    assert float(c["dZ"].abs().max()) == 0.0
