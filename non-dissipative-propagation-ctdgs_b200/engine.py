@@ -552,7 +552,7 @@ class StepEngine:
         # Programmatic dependent launch (csrc/common.cuh) shortens the single-chain no-grad step (80 -> 75 us) but
         # LENGTHENS the training step (118 -> 122..127 us, more the further into the DAG it is enabled): dependents
         # scheduled early hold SM slots that the step's parallel branches need.  So: inference on, training off.
-        _lib.lib().ctan_set_pdl(0 if train else 1, None)
+        _lib.lib().ctan_set_pdl(0 if (train and os.environ.get("CTAN_TRAIN_PDL", "0") != "1") else 1, None)
 
     def _prep_rest(self, train: bool):
         w, m = self.w, self.model
