@@ -594,6 +594,13 @@ def main():
         "ctan_readout_bwd": eng.P * (4 * D + 3 * Hd + 2) * 4 + 4 * Hd * D * 4,
         "ctan_enc_fwd": N_last * (2 * D + 1) * 4 + D * (D + 1) * 4,
         "ctan_enc_bwd": N_last * (2 * D + 1) * 4 + D * (D + 1) * 4,
+        # folded enc_x + projection: gathered rows [N, Kx] + hi/lo panel [5D, Kx] in, X0 [N, D] + QKVA [N, 4D] out
+        "ctan_enc_qkva_tc": N_last * getattr(eng, "Kx", D + 1) * 4 + 2 * 5 * D * getattr(eng, "Kx", D + 1) * 4
+                            + N_last * 5 * D * 4,
+        "ctan_enc_prep_ext": N_last * (D + eng.Fn) * 4 + N_last * 8 + N_last * getattr(eng, "Kx", D + 1) * 4,
+        # one-launch link readout: two embedding rows per pair + both weights in; H, dHid, OUT, dOUT out; dZ atomics
+        "ctan_readout_link_fused": eng.P * (2 * D * 4 + 16) + 2 * Hd * D * 4 + eng.P * (2 * Hd + 2) * 4
+                                   + eng.P * 2 * D * 4,
     }.get(top_name)
     roof = {"bound": "hbm", "kernel": top_name, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
             "traffic": None, "peak_source": peak_src, "ms_per_launch": top_us * 1e-3,
@@ -604,18 +611,20 @@ def main():
         ach = alg_bytes / (top_us * 1e-6) / 1e9
         roof.update(achieved=ach, frac=ach / peak, algorithmic_bytes=alg_bytes)
     # a tcgen05 contraction is bounded by the tensor pipe, not HBM: report useful flops against the measured dense peak
-    tc_flops = {"ctan_dx_tc": 2.0 * N_last * 4 * D * D, "ctan_qkva_fwd_tc": 2.0 * N_last * D * 4 * D}.get(top_name)
+    tc_flops = {"ctan_dx_tc": 2.0 * N_last * 4 * D * D, "ctan_qkva_fwd_tc": 2.0 * N_last * D * 4 * D,
+                "ctan_enc_qkva_tc": 2.0 * N_last * (D + eng.Fn) * 5 * D}.get(top_name)
+    # roofline.traffic = DRAM bytes of ONE launch of this kernel at this shape from the committed `ncu --set full`
+    # capture of the round (DRAM counters need the profiler: they are not measured in this run, and the field says
+    # where they come from): profiles/r02_traffic.json, keyed by C-ABI entry point (+ the two older tcgen05 keys)
+    tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if K == 1 and os.path.exists(tp):
+        tj = json.load(open(tp))
+        tr = tj.get(top_name + "@wiki") or tj.get({"ctan_dx_tc": "qkva_tc_kernel@wiki_dx",
+                                                   "ctan_qkva_fwd_tc": "qkva_tc_kernel@wiki_qkva"}.get(top_name, ""))
+        if tr:
+            roof["traffic"] = tr["traffic_bytes"]
+            roof["traffic_source"] = tr.get("source", "ncu --set full capture under profiles/")
     if tc_flops:
-        # roofline.traffic = DRAM bytes of ONE launch of this kernel at this shape from the committed `ncu --set full`
-        # capture of the round (profiles/r02_ncu_tc_wiki.txt; DRAM counters need the profiler: they are not measured
-        # in this run, and the field says where they come from)
-        tkey = {"ctan_dx_tc": "qkva_tc_kernel@wiki_dx", "ctan_qkva_fwd_tc": "qkva_tc_kernel@wiki_qkva"}[top_name]
-        tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
-        if K == 1 and os.path.exists(tp):
-            tr = json.load(open(tp)).get(tkey)
-            if tr:
-                roof["traffic"] = tr["traffic_bytes"]
-                roof["traffic_source"] = tr.get("source", "ncu --set full capture under profiles/")
         tpeak, tsrc = load_tensor_peak()
         ach = tc_flops / (top_us * 1e-6) / 1e12
         roof.update(bound="tensor", unit="TFLOP/s", achieved=ach, peak=tpeak, frac=ach / tpeak, peak_source=tsrc,
