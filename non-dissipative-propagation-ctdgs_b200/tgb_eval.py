@@ -94,9 +94,10 @@ class TGBEvalEngine:
         self._alloc()
         self._graph = None
         import os
-        # prefetching the next batch's front-end beside the scoring pays on one GPU (153 -> 138 us per batch); with the
-        # batch sharded the scoring graph is short and the contention eats the gain (2 GPUs: 133 us inline vs 138 us)
-        self.prefetch = os.environ.get("CTAN_EVAL_PREFETCH", "1" if world == 1 else "0") == "1"
+        # prefetching the next batch's front-end beside the scoring pays while the rank's shard is large enough for the
+        # scoring chain to cover it: 125 -> 115 us per batch on one GPU, 111.8 -> 104.2 at 2 ranks, 102.4 -> 99.2 at 4;
+        # at 8 ranks (25 queries = 550 seeds per rank) it is neutral to slightly negative (91.8 vs 92.8): inline there
+        self.prefetch = os.environ.get("CTAN_EVAL_PREFETCH", "1" if (world == 1 or self.n_seeds >= 1000) else "0") == "1"
         self._side = torch.cuda.Stream(device=dev)
         self._side2 = torch.cuda.Stream(device=dev)
         # the per-batch exchange: "peer" = our kernels store the packed rows into every peer's symmetric buffer over
