@@ -81,6 +81,18 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
         ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(crd_inner), "r"(crd_outer)
         : "memory");
 }
+// Same load, delivered to the same shared-memory offset of every CTA of the cluster named in cta_mask, each of whose
+// mbarrier (same offset) receives the complete_tx.
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int crd_inner,
+                                               int crd_outer, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "h"(cta_mask), "r"(crd_inner), "r"(crd_outer)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // K-major operand tile, 128-byte swizzle: rows 128 B apart, 8-row groups 1024 B apart (SBO), version 1.
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
@@ -117,6 +129,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {        // lo
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
+}
+// the same arrival delivered to the mbarrier at this offset in every CTA of cta_mask (a stage whose B half was multicast
+// by the peer is free only when BOTH CTAs' MMAs have read it)
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
@@ -167,15 +185,24 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 //         tiles; the transform warps convert the fp32 activation tile to a BF16 tile in the canonical K-major 128-byte-
 //         swizzled layout (what TMA would have produced) and the MMA (kind::f16) reads both operands from shared memory;
 //         tmBhi is then the tensor map of a BF16 weight panel, tmBlo is unused.
-__global__ void __launch_bounds__(THREADS, 1)
-qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
-               const __grid_constant__ CUtensorMap tmBlo, Bias4 bias, float* __restrict__ C, int ldc, int M_host,
-               const int* __restrict__ M_dev, int N, int K, int mode) {
+// PAIR (mode 0 only): the kernel runs as clusters of two CTAs that share a column tile and take adjacent row tiles.  The
+// weight tiles of a k-block are the same for both, so each CTA fetches HALF of them (rank 0: B_hi, rank 1: B_lo) and
+// multicasts it into both CTAs' stage: 32 KB instead of 48 KB of L2 reads per CTA per k-block -- at evaluation shapes
+// (all SMs busy) the ring is bound by exactly that traffic.  A stage is released by BOTH CTAs' MMAs (multicast commit,
+// empty[s] counts two arrivals); the two CTAs walk the same number of (tile, k-block) steps -- the second one takes a
+// dummy tile (rows >= M: nothing stored) when the row-tile count is odd.
+template <bool PAIR>
+__device__ __forceinline__ void tc_body(const CUtensorMap* tmA, const CUtensorMap* tmBhi, const CUtensorMap* tmBlo,
+                                        const Bias4& bias, float* __restrict__ C, int ldc, int M_host,
+                                        const int* __restrict__ M_dev, int N, int K, int mode) {
     ctan_pdl_begin();
     extern __shared__ uint8_t smem_raw[];
     const int M = M_dev ? *M_dev : M_host;
     const int n0 = blockIdx.x * BN;
-    if ((int)blockIdx.y * BM >= M) return;                            // uniform, before any allocation
+    uint32_t crank = 0;
+    if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const int y_lead = PAIR ? (int)(blockIdx.y & ~1u) : (int)blockIdx.y;   // first row tile of the cluster
+    if (y_lead * BM >= M) return;                                     // uniform over the cluster, before any allocation
     if (threadIdx.x == 0) TC_TRACE(0);
     // 1024-byte alignment as an OFFSET from the __shared__ array (not an integer round trip of the pointer): the
     // compiler keeps the shared address space, so the staging / transform accesses compile to LDS/STS, not generic LD/ST
@@ -190,7 +217,7 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
 
     if (t == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&raw[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&raw[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], PAIR ? 2 : 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&done[b], 1); mbar_init(&accfree[b], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -201,6 +228,7 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (PAIR) cluster_sync_all();                                     // the peer's barriers exist before anything targets them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_holder;
     if (threadIdx.x == 0) TC_TRACE(1);
@@ -218,21 +246,29 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ------------------------------------------------ TMA producer
         if (lane == 0) {
             int it = 0;                                                 // k-blocks issued so far (all tiles)
-            for (int m0 = blockIdx.y * BM; m0 < M; m0 += gridDim.y * BM)
+            for (int mL = y_lead * BM; mL < M; mL += gridDim.y * BM)
             for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                const int m0 = mL + (int)crank * BM;
                 const int s = it % nst;
                 if (it >= nst) mbar_wait(&empty[s], ((it / nst) - 1) & 1);
                 if (bf) {
                     mbar_expect_tx(&raw[s], 3 * TILE_BYTES);
-                    tma_load_2d(stage_ptr(s, 0), &tmA, &raw[s], (kb0 + kb) * bke, m0);
-                    tma_load_2d(stage_ptr(s, 1), &tmA, &raw[s], (kb0 + kb) * bke + BKF, m0);
-                    tma_load_2d(stage_ptr(s, 3), &tmBhi, &raw[s], (kb0 + kb) * bke, n0);
+                    tma_load_2d(stage_ptr(s, 0), tmA, &raw[s], (kb0 + kb) * bke, m0);
+                    tma_load_2d(stage_ptr(s, 1), tmA, &raw[s], (kb0 + kb) * bke + BKF, m0);
+                    tma_load_2d(stage_ptr(s, 3), tmBhi, &raw[s], (kb0 + kb) * bke, n0);
+                    continue;
+                }
+                if (PAIR) {                                             // own A tile + one half of B for both CTAs
+                    mbar_expect_tx(&raw[s], 3 * TILE_BYTES);
+                    tma_load_2d(stage_ptr(s, 0), tmA, &raw[s], (kb0 + kb) * BKF, m0);
+                    if (crank == 0) tma_load_2d_mc(stage_ptr(s, 1), tmBhi, &raw[s], (kb0 + kb) * BKF, n0, (uint16_t)3);
+                    else            tma_load_2d_mc(stage_ptr(s, 2), tmBlo, &raw[s], (kb0 + kb) * BKF, n0, (uint16_t)3);
                     continue;
                 }
                 mbar_expect_tx(&raw[s], (mode == 0 ? 3 : 2) * TILE_BYTES);
-                tma_load_2d(stage_ptr(s, 0), &tmA, &raw[s], (kb0 + kb) * BKF, m0);
-                tma_load_2d(stage_ptr(s, 1), &tmBhi, &raw[s], (kb0 + kb) * BKF, n0);
-                if (mode == 0) tma_load_2d(stage_ptr(s, 2), &tmBlo, &raw[s], (kb0 + kb) * BKF, n0);
+                tma_load_2d(stage_ptr(s, 0), tmA, &raw[s], (kb0 + kb) * BKF, m0);
+                tma_load_2d(stage_ptr(s, 1), tmBhi, &raw[s], (kb0 + kb) * BKF, n0);
+                if (mode == 0) tma_load_2d(stage_ptr(s, 2), tmBlo, &raw[s], (kb0 + kb) * BKF, n0);
                 if (it == 0) TC_TRACE(2);
             }
         }
@@ -241,7 +277,7 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             const uint32_t idesc = instr_desc_tf32();
             int it = 0, tile = 0;
-            for (int m0 = blockIdx.y * BM; m0 < M; m0 += gridDim.y * BM, ++tile) {
+            for (int mL = y_lead * BM; mL < M; mL += gridDim.y * BM, ++tile) {
                 const int buf = tile & 1;
                 if (tile >= 2) {                                        // the epilogue has drained this accumulator
                     mbar_wait(&accfree[buf], ((tile >> 1) - 1) & 1);
@@ -276,7 +312,8 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             mma_tf32_ta(acc, a_hi + k * 8, smem_desc_sw128(b_hi + off), idesc, (kb | k) ? 1u : 0u);
                         }
                     }
-                    mma_commit(&empty[s]);                              // arrives when these MMAs have read stage s
+                    if (PAIR) mma_commit_mc(&empty[s], (uint16_t)3);   // ... in both CTAs: the peer's next multicast lands here too
+                    else mma_commit(&empty[s]);                         // arrives when these MMAs have read stage s
                 }
                 mma_commit(&done[buf]);                                 // this tile's accumulator is complete
                 TC_TRACE(5);
@@ -291,7 +328,7 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int r = q * 32 + lane;                                    // tile row = TMEM lane
         const uint32_t tlane = (uint32_t)(q * 32) << 16;
         int it = 0;
-        for (int m0 = blockIdx.y * BM; m0 < M; m0 += gridDim.y * BM)
+        for (int mL = y_lead * BM; mL < M; mL += gridDim.y * BM)
         for (int kb = 0; kb < n_kb; ++kb, ++it) {
             if (it % TGROUPS != grp) continue;
             const int s = it % nst;
@@ -341,7 +378,8 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool first = blockIdx.z == 0;                             // bias / residual are added by one split only
         const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
         int tile = 0;
-        for (int m0 = blockIdx.y * BM; m0 < M; m0 += gridDim.y * BM, ++tile) {
+        for (int mL = y_lead * BM; mL < M; mL += gridDim.y * BM, ++tile) {
+            const int m0 = mL + (int)crank * BM;                        // (PAIR, odd tile count: may lie past M -- nothing is stored)
             const int buf = tile & 1;
             // bias of this thread's 4 columns in each 32-column chunk: requested while the MMAs of the tile still run
             float4 bvs[BN / 32];
@@ -451,9 +489,24 @@ qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (PAIR) cluster_sync_all();             // no CTA leaves while its peer may still signal its barriers
     if (threadIdx.x == 0) TC_TRACE(8);
     if (warp == 1)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+qkva_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+               const __grid_constant__ CUtensorMap tmBlo, Bias4 bias, float* __restrict__ C, int ldc, int M_host,
+               const int* __restrict__ M_dev, int N, int K, int mode) {
+    tc_body<false>(&tmA, &tmBhi, &tmBlo, bias, C, ldc, M_host, M_dev, N, K, mode);
+}
+// clusters of two CTAs along y (launched with cudaLaunchAttributeClusterDimension {1,2,1}; gridDim.y even); mode 0 only
+__global__ void __launch_bounds__(THREADS, 1)
+qkva_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                    const __grid_constant__ CUtensorMap tmBlo, Bias4 bias, float* __restrict__ C, int ldc, int M_host,
+                    const int* __restrict__ M_dev, int N, int K, int mode) {
+    tc_body<true>(&tmA, &tmBhi, &tmBlo, bias, C, ldc, M_host, M_dev, N, K, mode);
 }
 
 // NOTE: the tcgen05 kernel is launched the plain way (no programmatic dependent launch): one of its CTAs owns a whole
@@ -516,6 +569,34 @@ static int bounded_rows(int M_max, const int* M_dev, int gx, int m_typ = 0) {
     return gy;
 }
 
+// Launch of the contraction kernel.  pair: clusters of two CTAs along y sharing the weight tiles by TMA multicast
+// (`mode` bit 6 of the entry points below, 3xTF32 only); gridDim.y is made even for it.
+static inline bool want_pair(int mode) { return (mode & 0x40) && (mode & 0x3F) == 0; }
+static int launch(dim3 grid, bool pair, cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmBhi,
+                  const CUtensorMap& tmBlo, const Bias4& epi, float* C, int ldc, int M, const int* M_dev, int N, int K,
+                  int mode) {
+    if (!pair) {
+        qkva_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, epi, C, ldc, M, M_dev, N, K, mode);
+        return 0;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(qkva_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    if (grid.y & 1)                                                    // even: up if that still fits one wave, else down
+        grid.y += ((grid.x * (grid.y + 1) * grid.z <= (unsigned)CTAN_SM_COUNT || grid.y == 1) ? 1 : -1);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 2; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, qkva_tc_pair_kernel, tmA, tmBhi, tmBlo, epi, C, ldc, M, M_dev, N, K, mode);
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
 }  // namespace tc
 
 // Wcat_hi/Wcat_lo [4D, D]: TF32 split of the stacked weights [Wq; Wk; Wv; A], A = W - W^T - gamma I.
@@ -569,7 +650,8 @@ extern "C" int ctan_qkva_fwd_tc(const float* X, int N, const int* N_dev, int D, 
                                 const float* b, float* QKVA, int mode, cudaStream_t stream) {
     if (N <= 0) return 0;
     const int m_typ = mode >> 8;              // bits 8+: expected row count (0 = unknown), sizes the persistent grid only
-    mode &= 0xFF;
+    const bool pair = tc::want_pair(mode & 0xFF);
+    mode &= 0x3F;
     const bool bf = mode == 2;                // Wcat_hi is then a BF16 [4D, D] panel (ctan_pack_bf16), Wcat_lo unused
     if (D % (bf ? 2 * tc::BKF : tc::BKF) != 0 || ((4 * D) % tc::BN) != 0 ||
         (((uintptr_t)X | (uintptr_t)Wcat_hi | (bf ? 0 : (uintptr_t)Wcat_lo)) & 15))
@@ -589,8 +671,8 @@ extern "C" int ctan_qkva_fwd_tc(const float* X, int N, const int* N_dev, int D, 
     const uintptr_t ball = (uintptr_t)bq | (uintptr_t)bk | (uintptr_t)bv | (uintptr_t)b | (uintptr_t)QKVA;
     tc::Bias4 bias{{bq, bk, bv, b}, D, (ball & 15) == 0 ? 1 : 0, nullptr, 0, ((uintptr_t)QKVA & 15) == 0 ? 1 : 0, nullptr, 0, 0};
     dim3 grid((4 * D) / tc::BN, tc::bounded_rows(N, N_dev, (4 * D) / tc::BN, m_typ));
-    tc::qkva_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, bias, QKVA, 4 * D, N, N_dev, 4 * D, D,
-                                                              mode);
+    { const int lrc = tc::launch(grid, pair, stream, tmA, tmBhi, tmBlo, bias, QKVA, 4 * D, N, N_dev, 4 * D, D,
+                                                              mode); if (lrc) return lrc; }
     CTAN_CHECK_LAUNCH();
     return 0;
 }
@@ -603,7 +685,8 @@ extern "C" int ctan_dx_tc(const float* DQKVA, const float* G, int N, const int* 
                           const float* WcatT_lo, float* dXin, int mode, int n_split, cudaStream_t stream) {
     if (N <= 0) return 0;
     const int m_typ = mode >> 8;              // (see ctan_qkva_fwd_tc)
-    mode &= 0xFF;
+    const bool pair = tc::want_pair(mode & 0xFF);
+    mode &= 0x3F;
     if (D % tc::BN != 0 || (((uintptr_t)DQKVA | (uintptr_t)WcatT_hi | (uintptr_t)WcatT_lo | (uintptr_t)G | (uintptr_t)dXin) & 15))
         return CTAN_ERR_UNSUPPORTED;
     CUtensorMap tmA, tmBhi, tmBlo;
@@ -619,7 +702,7 @@ extern "C" int ctan_dx_tc(const float* DQKVA, const float* G, int N, const int* 
     int splits = n_split < 1 ? 1 : n_split;
     while (splits > 1 && (n_kb % splits != 0)) --splits;
     dim3 grid(D / tc::BN, tc::bounded_rows(N, N_dev, (D / tc::BN) * splits, m_typ), splits);
-    tc::qkva_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, epi, dXin, D, N, N_dev, D, 4 * D, mode);
+    { const int lrc = tc::launch(grid, pair, stream, tmA, tmBhi, tmBlo, epi, dXin, D, N, N_dev, D, 4 * D, mode); if (lrc) return lrc; }
     CTAN_CHECK_LAUNCH();
     return 0;
 }
@@ -681,7 +764,8 @@ extern "C" int ctan_gemm_tc(const float* A, int M, const int* M_dev, int K, cons
                             const float* res, int ldr, float* C, int mode, cudaStream_t stream) {
     if (M <= 0) return 0;
     const int m_typ = mode >> 8;              // (see ctan_qkva_fwd_tc)
-    mode &= 0xFF;
+    const bool pair = tc::want_pair(mode & 0xFF);
+    mode &= 0x3F;
     const bool bf = mode == 2;                // Bhi is then a BF16 [Nout, K] panel (ctan_pack_bf16), Blo unused
     if (K % (bf ? 2 * tc::BKF : tc::BKF) != 0 || Nout % tc::BN != 0 || seg <= 0 || seg % 16 != 0 ||
         (((uintptr_t)A | (uintptr_t)Bhi | (bf ? 0 : (uintptr_t)Blo) | (uintptr_t)C) & 15))
@@ -697,7 +781,7 @@ extern "C" int ctan_gemm_tc(const float* A, int M, const int* M_dev, int K, cons
                            (uintptr_t)(ldr * 4);
     tc::Bias4 epi{{b0, b1, b2, b3}, seg, (ball & 15) == 0 ? 1 : 0, res, ldr, 1, nullptr, 0, 0};   // (C was checked 16-byte aligned above, Nout % 128 == 0)
     dim3 grid(Nout / tc::BN, tc::bounded_rows(M, M_dev, Nout / tc::BN, m_typ));
-    tc::qkva_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, epi, C, Nout, M, M_dev, Nout, K, mode);
+    { const int lrc = tc::launch(grid, pair, stream, tmA, tmBhi, tmBlo, epi, C, Nout, M, M_dev, Nout, K, mode); if (lrc) return lrc; }
     CTAN_CHECK_LAUNCH();
     return 0;
 }
@@ -896,7 +980,8 @@ extern "C" int ctan_enc_qkva_tc(const float* zext, int N, const int* N_dev, int 
                                 int D, const float* bce, float* X0, float* QKVA, int mode, cudaStream_t stream) {
     if (N <= 0) return 0;
     const int m_typ = mode >> 8;
-    mode &= 0xFF;
+    const bool pair = tc::want_pair(mode & 0xFF);
+    mode &= 0x3F;
     const bool bf = mode == 2;
     if (Kx % (bf ? 2 * tc::BKF : tc::BKF) != 0 || D % tc::BN != 0 ||
         (((uintptr_t)zext | (uintptr_t)Wce_hi | (bf ? 0 : (uintptr_t)Wce_lo) | (uintptr_t)X0 | (uintptr_t)QKVA | (uintptr_t)bce) & 15))
@@ -911,7 +996,7 @@ extern "C" int ctan_enc_qkva_tc(const float* zext, int N, const int* N_dev, int 
     // one bias segment spanning all 5D columns; columns >= D are redirected to QKVA (row pitch 4D)
     tc::Bias4 epi{{bce, nullptr, nullptr, nullptr}, 5 * D, 1, nullptr, 0, 1, QKVA, D, 4 * D};
     dim3 grid((5 * D) / tc::BN, tc::bounded_rows(N, N_dev, (5 * D) / tc::BN, m_typ));
-    tc::qkva_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmA, tmBhi, tmBlo, epi, X0, D, N, N_dev, 5 * D, Kx, mode);
+    { const int lrc = tc::launch(grid, pair, stream, tmA, tmBhi, tmBlo, epi, X0, D, N, N_dev, 5 * D, Kx, mode); if (lrc) return lrc; }
     CTAN_CHECK_LAUNCH();
     return 0;
 }

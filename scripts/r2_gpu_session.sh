@@ -15,6 +15,8 @@ for k in ("other_configs", "torch_gpu_baseline", "speedup_vs_torch_gpu", "drop_i
     if k in d: print(k, "=", d.get(k))
 PY
 }
+timeout 300 python __graft_entry__.py smoke > $O/r2_smoke.log 2>&1
+echo "== smoke rc=$?"; tail -2 $O/r2_smoke.log
 for ab in "$@"; do
   env $ab timeout 300 python bench.py --steps 100 --warmup 10 --no-baselines > $O/r2_bench_ab.json 2> $O/r2_bench_ab.err
   echo "== A/B bench with $ab rc=$?"; show $O/r2_bench_ab.json

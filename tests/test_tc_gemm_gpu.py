@@ -198,3 +198,61 @@ def test_folded_enc_projection_matches_fp64(N, D, Fn):
     assert float((X0[:N].double() - X0_ref).abs().max()) < 5e-6 * float(X0_ref.abs().max())
     assert float((Q[:N].double() - Q_ref).abs().max()) < 1e-5 * float(Q_ref.abs().max())
     assert bool((X0[N:] == 7.0).all()) and bool((Q[N:] == 7.0).all())
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("N,D,n_true", [(700, 128, None), (5000, 256, None), (129, 128, None), (300, 128, None),
+                                        (40000, 256, None), (3000, 128, 1300), (128, 128, None)])
+def test_tc_pair_multicast_is_bit_identical(N, D, n_true):
+    """The two-CTA-cluster form of the tcgen05 kernel (weight tiles fetched once per pair and TMA-multicast, `mode` bit 6)
+    issues exactly the same MMAs per tile as the single-CTA form: outputs must be BIT-identical -- odd row-tile counts
+    (the second CTA of the last pair takes a dummy tile), device-sized row counts and the folded enc_x + projection form
+    (column redirect) included."""
+    from ctan_b200._lib import call, ptr
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(N + D)
+    X = torch.randn(N, D, generator=g).to(dev)
+    Ws = [(torch.randn(D, D, generator=g) / D ** 0.5).to(dev) for _ in range(4)]
+    bs = [torch.randn(D, generator=g).to(dev) for _ in range(4)]
+    hi, lo, A = torch.empty(4 * D, D, device=dev), torch.empty(4 * D, D, device=dev), torch.empty(D, D, device=dev)
+    call("ctan_wcat_prep", ptr(Ws[0]), ptr(Ws[1]), ptr(Ws[2]), ptr(Ws[3]), 0.1, D, ptr(hi), ptr(lo), ptr(A), None, None)
+    Nd = None if n_true is None else torch.tensor([n_true], dtype=torch.int32, device=dev)
+    n = N if n_true is None else n_true
+    outs = []
+    for mode in (0, 0x40):
+        out = torch.full((N, 4 * D), 5.0, device=dev)
+        call("ctan_qkva_fwd_tc", ptr(X), N, ptr(Nd) if Nd is not None else None, D, ptr(hi), ptr(lo), ptr(bs[0]), ptr(bs[1]),
+             ptr(bs[2]), ptr(bs[3]), ptr(out), mode | ((n << 8) if n_true else 0))
+        outs.append(out)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    assert bool((outs[1][n:] == 5.0).all())
+    ref = X[:n].double() @ torch.cat([Ws[0], Ws[1], Ws[2], A]).double().t() + torch.cat(bs).double()
+    assert float((outs[1][:n].double() - ref).abs().max()) < 5e-6 * float(ref.abs().max())
+    # generic contraction with a residual + the folded form with the column redirect
+    R = torch.randn(N, 4 * D, generator=g).to(dev)
+    o2 = []
+    for mode in (0, 0x40):
+        out = torch.full((N, 4 * D), 5.0, device=dev)
+        call("ctan_gemm_tc", ptr(X), N, ptr(Nd) if Nd is not None else None, D, ptr(hi), ptr(lo), 4 * D, ptr(bs[0]), ptr(bs[1]),
+             ptr(bs[2]), ptr(bs[3]), D, ptr(R), 4 * D, ptr(out), mode)
+        o2.append(out)
+    torch.cuda.synchronize()
+    assert torch.equal(o2[0], o2[1])
+    if D % 128 == 0:
+        Fn = 3
+        Kx = ((D + Fn + 31) // 32) * 32
+        Wenc, benc = (torch.randn(D, D + Fn, generator=g) / D ** 0.5).to(dev), torch.randn(D, generator=g).to(dev)
+        ph, pl, bce = torch.empty(5 * D, Kx, device=dev), torch.empty(5 * D, Kx, device=dev), torch.empty(5 * D, device=dev)
+        call("ctan_fuse_enc_prep_split", ptr(Ws[0]), ptr(Ws[1]), ptr(Ws[2]), ptr(Ws[3]), 0.1, ptr(bs[0]), ptr(bs[1]), ptr(bs[2]),
+             ptr(bs[3]), ptr(Wenc), ptr(benc), D, Fn, Kx, ptr(ph), ptr(pl), ptr(bce))
+        zext = torch.zeros(N + 128, Kx, device=dev)
+        zext[:N, :D + Fn] = torch.randn(N, D + Fn, generator=g).to(dev)
+        o3 = []
+        for mode in (0, 0x40):
+            X0, Q = torch.full((N, D), 5.0, device=dev), torch.full((N, 4 * D), 5.0, device=dev)
+            call("ctan_enc_qkva_tc", ptr(zext), N, ptr(Nd) if Nd is not None else None, Kx, ptr(ph), ptr(pl), D, ptr(bce), ptr(X0),
+                 ptr(Q), mode)
+            o3.append((X0, Q))
+        torch.cuda.synchronize()
+        assert torch.equal(o3[0][0], o3[1][0]) and torch.equal(o3[0][1], o3[1][1])
