@@ -643,8 +643,9 @@ extern "C" int ctan_wcat_prep(const float* Wq, const float* Wk, const float* Wv,
 // QKVA[N,4D] = X Wcat^T + [bq;bk;bv;b] on tcgen05 (3xTF32).  Requirements: D % 32 == 0, X has at least
 // ceil(N/128)*128 addressable rows or N rows (TMA zero-fills out-of-bounds rows), 16-byte aligned bases.
 // Returns CTAN_ERR_UNSUPPORTED when the shape does not qualify (the caller then uses ctan_qkva_fwd).
-// mode: bits 0-7 = precision (0 3xTF32, 1 TF32, 2 BF16); bits 8+ = optional estimate of the true row count when N is only
-// a workspace bound (sizes the persistent grid; 0 = unknown).
+// mode: bits 0-5 = precision (0 3xTF32, 1 TF32, 2 BF16); bit 6 = run as two-CTA clusters that share the weight tiles by TMA
+// multicast (3xTF32 only; same results bit for bit); bits 8+ = optional estimate of the true row count when N is only a
+// workspace bound (sizes the persistent grid; 0 = unknown).
 extern "C" int ctan_qkva_fwd_tc(const float* X, int N, const int* N_dev, int D, const float* Wcat_hi,
                                 const float* Wcat_lo, const float* bq, const float* bk, const float* bv,
                                 const float* b, float* QKVA, int mode, cudaStream_t stream) {
