@@ -301,13 +301,15 @@ def run_e2e(st, K, mean, std, dev, n_steps, warmup):
     ids_pin = torch.cat([st["src"][:nb * B].view(nb, B), st["dst"][:nb * B].view(nb, B), st["t"][:nb * B].view(nb, B),
                          st["neg"][:nb * B].view(nb, B)], 1).contiguous().pin_memory()   # the loader's packed batches
 
+    msg_rows = pin["msg"][:nb * B].view(nb, B, -1)           # (views made once: the loop below is host-bound)
+    loss_dst = [loss_host[0:1], loss_host[1:2]]
+    loss_src = [eng.w["loss_hist"][i:i + 1] for i in range(min(eng.hist_cap, warmup + n_steps + 1))]
+
     def issue(it):
         nonlocal h2d
-        lo, hi = it * B, (it + 1) * B
-        h2d = eng.push_packed(ids_pin[it], pin["msg"][lo:hi])
+        h2d = eng.push_packed(ids_pin[it], msg_rows[it])
         eng.run(1, train=True)
-        slot = it % eng.hist_cap
-        loss_host[it & 1:(it & 1) + 1].copy_(eng.w["loss_hist"][slot:slot + 1], non_blocking=True)
+        loss_dst[it & 1].copy_(loss_src[it % len(loss_src)] if len(loss_src) == eng.hist_cap else loss_src[it], non_blocking=True)
         done[it & 1].record()
 
     def collect(it):                                         # host read of step `it`'s loss (blocks until it is there)

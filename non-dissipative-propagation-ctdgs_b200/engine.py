@@ -111,6 +111,7 @@ class StepEngine:
             self._copy_stream = torch.cuda.Stream(device=dev)
             self._copied = [torch.cuda.Event(), torch.cuda.Event()]      # staging set filled
             self._consumed = [None, None]                                 # step that read the staging set is done
+            self._consumed_evs = [torch.cuda.Event(), torch.cuda.Event()]
             self._push_par = self._run_par = 0
             self.t_tab = torch.zeros(self.n_events, dtype=torch.long, device=dev)
             self.msg = torch.zeros((self.n_events, self.Fe), device=dev)
@@ -153,9 +154,14 @@ class StepEngine:
         self.n_cap = min(self.num_nodes, self.n_seeds * (self.S + 1) ** self.K)
         c_cap = min(self.num_nodes, self.n_seeds * (self.S + 1) ** (self.K - 1))
         self.e_cap = max(c_cap * self.S, 1)
-        # typical sizes (only used to size split-K grids): a third of the bound, at least the seed count
-        self.n_typ = max(min(self.n_cap, self.n_seeds), self.n_cap // 4)
-        self.e_typ = max(min(self.e_cap, 2 * self.n_seeds), self.e_cap // 4)
+        # typical sizes (they size split-K grids and pick the batch-sized kernel variants; correctness never depends on
+        # them): a quarter of the bound, but between 1x and 2x the seed count for nodes and 2x..4x for edges -- multi-hop
+        # neighbourhoods overlap heavily (wiki, 600 seeds: N = 640 / 816 / 844 and E = 1.3 k / 2.8 k / 3.0 k at 1 / 3 / 5
+        # hops against bounds of 3 600 / 9 227 nodes and 3 k / 46 k edges).  An OVER-estimate is what hurts: the K split
+        # of the weight-gradient contractions becomes too coarse (lin_edge gradient at 3 hops: 60 us, 30 CTAs x 38 gather
+        # rounds, with the old e_cap/4 guess).  retune() replaces the guesses by observed sizes.
+        self.n_typ = min(self.n_cap, max(self.n_seeds, min(self.n_cap // 4, 2 * self.n_seeds)))
+        self.e_typ = min(self.e_cap, max(2 * self.n_seeds, min(self.e_cap // 4, 4 * self.n_seeds)))
         self._flatten_params()
         self._alloc()
         self._graphs = {}
@@ -163,6 +169,39 @@ class StepEngine:
         # both have CTAs pending, the block scheduler serves the critical path first
         self._main = torch.cuda.Stream(device=dev, priority=-1)
         self._side = [torch.cuda.Stream(device=dev, priority=0) for _ in range(4)]
+
+    def _derive_choices(self):
+        """Kernel variants and grid hints that follow from the typical sizes n_typ / e_typ."""
+        D = self.D
+        # a batch's edge set is small (~1e3 rows): the all-loads-in-flight variant of the edge projection (csrc/dense.cu)
+        small = (self.e_typ <= 8192 and (self.Fe + self.T) % 4 == 0 and D in (32, 64, 128, 256)
+                 and (D + 16) * (self.Fe + self.T + 4) * 4 <= 220 * 1024 and os.environ.get("CTAN_EPROJ_ROWS", "1") == "1")
+        self._eproj_fn = "ctan_eproj_fwd_rows" if small else "ctan_eproj_fwd"
+        # the binary link readout (hidden + head + loss + gradients wrt the embeddings) as one launch
+        pt = 256 // self.Hd if self.Hd in (32, 64, 128, 256) else 0
+        self._link_fused = (not self.labelled and self.O == 1 and pt > 0 and D % 4 == 0 and self.n_neg >= 1
+                            and (2 * self.Hd * (D + 4) + pt * (2 * D + self.Hd) + 8) * 4 <= 200 * 1024
+                            and os.environ.get("CTAN_LINK_FUSED", "1") == "1")
+        # batch-sized backward side branches: W's gradient accumulated straight through A = W - W^T - gamma I (not in
+        # gradient-accumulation mode, where dW is only formed at the end), time-encoder gradients straight from dEP
+        self._wgrad_direct = (not self.seq_mod) and os.environ.get("CTAN_WGRAD_DIRECT", "1") == "1"
+        self._tenc_fused = (self.e_typ <= 16384 and D % 32 == 0 and D <= 256 and (self.T * D + 16 * self.T) * 4 <= 96 * 1024
+                            and os.environ.get("CTAN_TENC_FUSED", "1") == "1")
+        # expected row count of the node-side contractions, packed into the `mode` argument of the tcgen05 entry points:
+        # their CTAs need a whole SM each, so the persistent grid is sized by the typical N, not by the workspace bound
+        self._row_hint = (self.n_typ << 8) if os.environ.get("CTAN_TC_ROW_HINT", "1") == "1" else 0
+
+    def retune(self, n_nodes: int = 0, n_edges: int = 0):
+        """Replace the typical-size guesses by observed sizes (default: the last batch's, read from the device -- one
+        synchronisation) with 25 % head-room, re-derive the kernel choices and drop the captured graphs (they are
+        re-captured on the next run).  Results never depend on the hints; call it once the stream is in its steady state
+        if the subgraph sizes are far from 1-2x the seed count."""
+        if n_nodes <= 0 or n_edges <= 0:
+            n_nodes, n_edges = (int(v) for v in self.w["counts"][:2].tolist())
+        self.n_typ = min(self.n_cap, max(64, n_nodes + n_nodes // 4))
+        self.e_typ = min(self.e_cap, max(64, n_edges + n_edges // 4))
+        self._derive_choices()
+        self._graphs = {}
 
     # ------------------------------------------------------------------ parameters in one flat buffer
     def _flatten_params(self):
@@ -343,23 +382,7 @@ class StepEngine:
         self.hub_cap = min(N, 16384)                      # rows of degree > 8 go to the block-cooperative kernel
         w["A"] = torch.zeros((D, D), **f32)
         self.use_tc = _lib.use_tensor_cores(D)
-        # expected row count of the node-side contractions, packed into the `mode` argument of the tcgen05 entry points:
-        # their CTAs need a whole SM each, so the persistent grid is sized by the typical N, not by the workspace bound
-        # a batch's edge set is small (~1e3 rows): the all-loads-in-flight variant of the edge projection (csrc/dense.cu)
-        small = (self.e_typ <= 8192 and (self.Fe + self.T) % 4 == 0 and D in (32, 64, 128, 256)
-                 and (D + 16) * (self.Fe + self.T + 4) * 4 <= 220 * 1024 and os.environ.get("CTAN_EPROJ_ROWS", "1") == "1")
-        self._eproj_fn = "ctan_eproj_fwd_rows" if small else "ctan_eproj_fwd"
-        # the binary link readout (hidden + head + loss + gradients wrt the embeddings) as one launch
-        pt = 256 // self.Hd if self.Hd in (32, 64, 128, 256) else 0
-        self._link_fused = (not self.labelled and self.O == 1 and pt > 0 and D % 4 == 0 and self.n_neg >= 1
-                            and (2 * self.Hd * (D + 4) + pt * (2 * D + self.Hd) + 8) * 4 <= 200 * 1024
-                            and os.environ.get("CTAN_LINK_FUSED", "1") == "1")
-        # batch-sized backward side branches: W's gradient accumulated straight through A = W - W^T - gamma I (not in
-        # gradient-accumulation mode, where dW is only formed at the end), time-encoder gradients straight from dEP
-        self._wgrad_direct = (not self.seq_mod) and os.environ.get("CTAN_WGRAD_DIRECT", "1") == "1"
-        self._tenc_fused = (self.e_typ <= 16384 and D % 32 == 0 and D <= 256 and (self.T * D + 16 * self.T) * 4 <= 96 * 1024
-                            and os.environ.get("CTAN_TENC_FUSED", "1") == "1")
-        self._row_hint = (self.n_typ << 8) if os.environ.get("CTAN_TC_ROW_HINT", "1") == "1" else 0
+        self._derive_choices()
         w["Wcat_hi"], w["Wcat_lo"] = torch.zeros((4 * D, D), **f32), torch.zeros((4 * D, D), **f32)
         self.use_tc_dx = (self.use_tc and D % 128 == 0          # dX contraction on tcgen05 needs 128-wide output tiles
                           and os.environ.get("CTAN_TC_DX", "1") == "1")
@@ -980,7 +1003,7 @@ class StepEngine:
             self._prep(train)
             self._frontend(par)
             self._step(train, par, False, prep_done=True)
-        ev = torch.cuda.Event()
+        ev = self._consumed_evs[par]                         # (re-recorded every second step; waits snapshot it)
         ev.record(cur)
         self._consumed[par] = ev
         self._run_par = par ^ 1
@@ -992,8 +1015,16 @@ class StepEngine:
         if train:
             _lib.WEIGHTS_EPOCH += 1                          # (see _lib.WEIGHTS_EPOCH)
         with torch.cuda.device(self.dev):
-            for fn in self.plan(n_steps, train):
-                fn()
+            if self.host_staged:                             # (per-batch calls: keep the host path short)
+                if train:
+                    self._fuse_ver = None
+                else:
+                    self._prep_infer_weights()
+                for _ in range(n_steps):
+                    self._run_staged(train)
+            else:
+                for fn in self.plan(n_steps, train):
+                    fn()
         self.loader.cur_e_id += n_steps * self.B
         if train:
             self._opt_steps += n_steps

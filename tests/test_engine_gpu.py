@@ -277,3 +277,24 @@ def test_mixed_train_infer_calls_match_oracle(small_stream):
     assert eng.cursor == it * B and ld.cur_e_id == it * B
     assert torch.equal(ld.e_id.cpu(), lo_ref.e_id)
     assert torch.equal(mm.memory.last_update.cpu(), om.memory.last_update)
+
+
+def test_retune_changes_hints_not_results(small_stream):
+    """StepEngine.retune() replaces the typical-size guesses (split-K grids, batch-sized kernel variants) by observed
+    sizes and re-captures the graphs: the trajectory is the same with and without it."""
+    st = small_stream
+    runs = []
+    for tune in (False, True):
+        om, mm, ld, eng = _setup(st, False, 2, 32, 8, 32, "tanh", 5, 100, True)
+        eng.run(4, train=True)
+        if tune:
+            before = (eng.n_typ, eng.e_typ)
+            eng.retune()
+            n, e = (int(v) for v in eng.w["counts"][:2].tolist())
+            assert eng.n_typ == min(eng.n_cap, max(64, n + n // 4)) and eng.e_typ == min(eng.e_cap, max(64, e + e // 4))
+            assert (eng.n_typ, eng.e_typ) != before and not eng._graphs
+        eng.run(6, train=True)
+        torch.cuda.synchronize()
+        eng.check()
+        runs.append(eng.losses(10).cpu())
+    assert float((runs[0] - runs[1]).abs().max()) <= 1e-5 * float(runs[0].abs().max())
