@@ -231,13 +231,18 @@ class StepEngine:
         self._o_ws = o_dZ                                      # [0, _o_ws): parameter gradients + dA; beyond: per-step scratch
         self._accumulate = False
         o_DQ = o_dZ + pad(N * D)
-        o_DX = o_DQ + pad(N * 4 * D)
+        # one DQKVA buffer PER anti-symmetric iteration: the backward of iteration k-1 does not wait for iteration k's
+        # weight-gradient contraction (a side branch that reads DQKVA) nor re-clear the buffer on the critical path
+        self.nDQ = K if os.environ.get("CTAN_DQ_MULTI", "1") == "1" else 1
+        o_DX = o_DQ + self.nDQ * pad(N * 4 * D)
         self.zero_buf = torch.zeros(o_DX + K * N * D, device=self.dev)
         self._arena = (o_dZ, o_DQ, o_DX)
         self.flat_g = self.zero_buf[:n]
         self._dA = self.zero_buf[o_dA:o_dA + D * D].view(D, D)
         self._dZ = self.zero_buf[o_dZ:o_dZ + N * D].view(N, D)
-        self._DQKVA = self.zero_buf[o_DQ:o_DQ + N * 4 * D].view(N, 4 * D)
+        self._dq_stride = pad(N * 4 * D)
+        self._DQKVA = [self.zero_buf[o_DQ + i * self._dq_stride:o_DQ + i * self._dq_stride + N * 4 * D].view(N, 4 * D)
+                       for i in range(self.nDQ)]
         self._DX = self.zero_buf[o_DX:o_DX + K * N * D].view(K, N, D)      # dL/dx_k, accumulated by split-K
         self.adam_m = torch.zeros(n, device=self.dev)
         self.adam_v = torch.zeros(n, device=self.dev)
@@ -735,20 +740,21 @@ class StepEngine:
             call("ctan_tanh_bwd", ptr(w["dZ"]), ptr(z), N, Nd, D, ptr(w["gA"]))
             g = w["gA"]
         for k in range(K - 1, -1, -1):
-            if k != K - 1:
+            if k != K - 1 and self.nDQ == 1:
                 self._join(0)                                # the previous iteration's dW contraction reads DQKVA
                 self._zero_arena(f, only_dq=True)
+            dq = w["DQKVA"][k if self.nDQ > 1 else 0]
             call("ctan_edge_bwd", ptr(w["QKVA"][k]), ptr(w["EP"]), ptr(f["rowptr"]), ptr(f["esrc"]), N, Nd, D, ptr(g),
-                 ptr(w["TH"][k]), ptr(w["ALPHA"][k]), eps, ptr(w["DQKVA"]), ptr(w["dEP"]), int(k != K - 1),
+                 ptr(w["TH"][k]), ptr(w["ALPHA"][k]), eps, ptr(dq), ptr(w["dEP"]), int(k != K - 1),
                  ptr(w["DS"]))
-            qb = (ptr(w["DQKVA"]), ptr(w["X"][k]), ptr(g), N, Nd, D, Wq, Wk, Wv, ptr(w["A"]))
+            qb = (ptr(dq), ptr(w["X"][k]), ptr(g), N, Nd, D, Wq, Wk, Wv, ptr(w["A"]))
             gn = self._DX[k]
             # dX is the critical path and its tcgen05 CTAs need a whole SM each: it is issued BEFORE the weight-gradient
             # branches that depend on the same edge_bwd, so that their many small CTAs do not take the SMs first
             dx_first = self.use_tc_dx and self.parallel and os.environ.get("CTAN_DX_FIRST", "1") == "1"
             def dx():
                 if self.use_tc_dx:   # dX = G + DQKVA Wcat on tcgen05 (plain stores)
-                    call("ctan_dx_tc", ptr(w["DQKVA"]), ptr(g), N, Nd, D, ptr(w["WcatT_hi"]), ptr(w["WcatT_lo"]), ptr(gn),
+                    call("ctan_dx_tc", ptr(dq), ptr(g), N, Nd, D, ptr(w["WcatT_hi"]), ptr(w["WcatT_lo"]), ptr(gn),
                          _lib.TC_MODE | self._row_hint,
                          int(os.environ.get("CTAN_DX_SPLIT", "4")) if self.n_typ <= 4096 else 1)
                     # (kernel body at N=640: 18 / 12 / 9 us with 1 / 2 / 4 splits, scripts/micro_tc3.py)
@@ -763,7 +769,7 @@ class StepEngine:
                 fork = self._fork
             with fork(0):                                    # side 0: weight gradients of this iteration
                 if self._wgrad_direct:                       # (dA - dA^T accumulated straight into dW)
-                    call("ctan_qkva_wgrad", ptr(w["DQKVA"]), ptr(w["X"][k]), N, Nd, D, gWq, gWk, gWv, gW, gbq, gbk, gbv,
+                    call("ctan_qkva_wgrad", ptr(dq), ptr(w["X"][k]), N, Nd, D, gWq, gWk, gWv, gW, gbq, gbk, gbv,
                          gb, self.n_typ)
                 else:
                     call("ctan_qkva_bwd", *qb, None, gWq, gWk, gWv, ptr(w["dA"]), gbq, gbk, gbv, gb, self.n_typ)
@@ -804,14 +810,15 @@ class StepEngine:
             segs = [(zb + 4 * o_DQ, 4 * D)]
             base, head = None, 0
         else:
-            segs = [(zb + 4 * o_dZ, D), (zb + 4 * o_DQ, 4 * D)] + [(zb + 4 * (o_DX + k * N * D), D) for k in range(K)]
+            segs = ([(zb + 4 * o_dZ, D)] + [(zb + 4 * (o_DQ + i * self._dq_stride), 4 * D) for i in range(self.nDQ)]
+                    + [(zb + 4 * (o_DX + k * N * D), D) for k in range(K)])
             base, head = (None, 0) if self._accumulate else (zb, o_dZ)
-        if len(segs) > 8:                                    # more than 6 iterations: plain memset of the tail
-            self.zero_buf[o_DX:].zero_()
-            segs = segs[:2]
-        rows = (ctypes.c_int * 8)(*([r for _, r in segs] + [0] * (8 - len(segs))))
-        ptrs = [p for p, _ in segs] + [None] * (8 - len(segs))
-        call("ctan_zero_arena", base, head, len(segs), *ptrs, ctypes.cast(rows, ctypes.c_void_p), ptr(f["Nd"]), N)
+        for c0 in range(0, len(segs), 8):                    # (the kernel takes up to 8 segments per launch)
+            part = segs[c0:c0 + 8]
+            rows = (ctypes.c_int * 8)(*([r for _, r in part] + [0] * (8 - len(part))))
+            ptrs = [p for p, _ in part] + [None] * (8 - len(part))
+            call("ctan_zero_arena", base if c0 == 0 else None, head if c0 == 0 else 0, len(part), *ptrs,
+                 ctypes.cast(rows, ctypes.c_void_p), ptr(f["Nd"]), N)
 
     def _prep_infer_weights(self):
         """[Wenc; Wcat Wenc] and its bias for the folded no-grad step; re-formed when the weights changed since the last
