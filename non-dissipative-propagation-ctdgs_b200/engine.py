@@ -688,6 +688,19 @@ class StepEngine:
         xk = w["X"][K] if train else w["X"][K & 1]
         z = w["Z"] if self.final_tanh else xk
         self._z = z
+
+        def state_update():
+            # ground-truth state update (train_link.py:276-277)
+            call("ctan_mem_update", ptr(mem), ptr(lu), D, ptr(f["b_src"]), ptr(f["b_dst"]), ptr(f["b_t"]), B, None,
+                 None, 0, ptr(z), ptr(assoc))
+            if not early:
+                insert()
+        # no-grad step: the memory write-back and the readout both only READ z -- side by side (the next step's gather,
+        # the first reader of the memory, is in the next graph)
+        mem_side = (not train) and early and self.parallel and os.environ.get("CTAN_INFER_MEM_SIDE", "1") == "1"
+        if mem_side:
+            with self._fork(2):
+                state_update()
         if self._link_fused:
             # hidden layer + head + BCE loss + dOUT + dHid + the dZ scatter in ONE launch (csrc/dense.cu::link_fused)
             call("ctan_readout_link_fused", ptr(z), D, ptr(f["pair_src"]), ptr(f["pair_dst"]), ptr(assoc), P, B, Hd,
@@ -710,14 +723,11 @@ class StepEngine:
         if w["out_hist"] is not None:
             call("ctan_record_rows", ptr(w["OUT"]), P * O, ptr(w["out_hist"]), self.out_cap, ptr(f["ctr"]))
 
-        def state_update():
-            # ground-truth state update (train_link.py:276-277)
-            call("ctan_mem_update", ptr(mem), ptr(lu), D, ptr(f["b_src"]), ptr(f["b_dst"]), ptr(f["b_t"]), B, None,
-                 None, 0, ptr(z), ptr(assoc))
-            if not early:
-                insert()
         if not train:
-            state_update()
+            if mem_side:
+                self._join(2)
+            else:
+                state_update()
             if early:
                 self._join(1)
             _lib.lib().ctan_set_pdl(1, None)
