@@ -392,9 +392,9 @@ class StepEngine:
         self.use_tc_dx = (self.use_tc and D % 128 == 0          # dX contraction on tcgen05 needs 128-wide output tiles
                           and os.environ.get("CTAN_TC_DX", "1") == "1")
         w["WcatT_hi"], w["WcatT_lo"] = torch.zeros((D, 4 * D), **f32), torch.zeros((D, 4 * D), **f32)
-        # no-grad steps with ONE anti-symmetric iteration: enc_x folded into the projection (frozen weights inside a
-        # run(train=False) call): one tcgen05 contraction of [memory row | node features | 0] against [Wenc; Wcat Wenc]
-        self.fuse_enc = (self.use_tc and D % 128 == 0 and K == 1 and _lib.TC_MODE != 2 and not self.seq_mod
+        # no-grad steps: enc_x folded into the first iteration's projection (frozen weights inside a run(train=False)
+        # call): one tcgen05 contraction of [memory row | node features | 0] against [Wenc; Wcat Wenc]
+        self.fuse_enc = (self.use_tc and D % 128 == 0 and _lib.TC_MODE != 2 and not self.seq_mod
                          and os.environ.get("CTAN_INFER_FUSE_ENC", "1") == "1")
         # training steps (any num_iters: the first iteration): the same fold, the panel re-formed every step by ONE small
         # kernel on a side stream (ctan_fuse_enc_prep_split) -- one dependent stage fewer on the forward critical path

@@ -61,15 +61,15 @@ def test_engine_training_matches_oracle(small_stream, tgb, K, final_act, use_gra
         assert d <= 5e-4 * float(po[k].abs().max()) + 1e-6, (k, d)
 
 
-@pytest.mark.parametrize("D,n_train", [(64, 0), (128, 0), (128, 3)])
-def test_engine_inference_matches_oracle(small_stream, D, n_train):
+@pytest.mark.parametrize("D,n_train,K", [(64, 0, 1), (128, 0, 1), (128, 3, 1), (128, 0, 2), (128, 2, 3)])
+def test_engine_inference_matches_oracle(small_stream, D, n_train, K):
     """No-grad steps (train_link.py:361-405).  D=128, K=1 takes the folded enc_x + projection contraction
     (csrc/tc_gemm.cu::ctan_enc_qkva_tc) whose weight panel is formed outside the graph: with n_train > 0 the panel must
     follow the optimizer steps taken in between."""
     from oracle import ctan_oracle as O
     st = small_stream
     B, S, steps = 200, 10, 8
-    om, mm, ld, eng = _setup(st, True, 1, D, 16, 64, None, S, B, True)
+    om, mm, ld, eng = _setup(st, True, K, D, 16, 64, None, S, B, True)
     assert eng.fuse_enc == (D == 128)
     lo_ref = O.TorchNeighborLoader(st["num_nodes"], S)
     h = torch.zeros(st["num_nodes"], dtype=torch.long)
