@@ -94,10 +94,16 @@ class TGBEvalEngine:
         self._alloc()
         self._graph = None
         import os
-        # prefetching the next batch's front-end beside the scoring pays while the rank's shard is large enough for the
-        # scoring chain to cover it: 125 -> 115 us per batch on one GPU, 111.8 -> 104.2 at 2 ranks, 102.4 -> 99.2 at 4;
-        # at 8 ranks (25 queries = 550 seeds per rank) it is neutral to slightly negative (91.8 vs 92.8): inline there
-        self.prefetch = os.environ.get("CTAN_EVAL_PREFETCH", "1" if (world == 1 or self.n_seeds >= 1000) else "0") == "1"
+        # The next batch's front-end (stage, K-hop lookup, fill) only needs this batch's neighbour insert, so it is issued
+        # ahead, into the other buffer set.  One rank ("1"): beside the scoring (125 -> 115 us per batch).  Sharded ("2"):
+        # forked AFTER the scoring chain, beside the exchange -- push -> wait -> update is mostly waiting on NVLink, while
+        # beside the scoring its many small CTAs keep the tcgen05 CTAs (a whole SM each) off the SMs: per batch at
+        # 2 ranks 111.8 inline / 104.6 beside the scoring / 101.3 us beside the exchange; at 8 ranks 91.8 / 92.8 / 81.8 us.
+        pf = os.environ.get("CTAN_EVAL_PREFETCH", "1" if world == 1 else "2")
+        self.prefetch = pf in ("1", "2")
+        # "2": the next front-end is forked AFTER the scoring chain, beside the exchange (push -> wait -> update is mostly
+        # waiting on NVLink), instead of beside the scoring, whose tcgen05 CTAs it would keep off the SMs
+        self.prefetch_late = pf == "2"
         self._side = torch.cuda.Stream(device=dev)
         self._side2 = torch.cuda.Stream(device=dev)
         # the per-batch exchange: "peer" = our kernels store the packed rows into every peer's symmetric buffer over
@@ -106,6 +112,9 @@ class TGBEvalEngine:
         if exchange == "auto":
             exchange = _os.environ.get("CTAN_EVAL_EXCHANGE", "peer")
         self.exchange = exchange if world > 1 else "none"
+        if self.exchange == "nccl" and "CTAN_EVAL_PREFETCH" not in _os.environ:
+            # (two graphs around a host-issued collective: no place beside the exchange; beside the scoring only for big shards)
+            self.prefetch, self.prefetch_late = self.n_seeds >= 1000, False
         self.sym = None
         if self.exchange == "peer":
             from .sym import SymmetricExchange
@@ -250,13 +259,26 @@ class TGBEvalEngine:
         """Score the batch whose front-end is in buffer set `par`; beside it (side branch): its neighbour insert and,
         if `prefetch`, the front-end of the NEXT batch into the other buffer set."""
         cur = torch.cuda.current_stream()
+        late = prefetch and self.prefetch_late and self.exchange != "nccl"
         self._side2.wait_stream(cur)
         with torch.cuda.stream(self._side2):
             self._insert(par, dry)            # reads counters[1] of this batch: before the next stage overwrites it
-            if prefetch:
+            if prefetch and not late:
                 self._frontend(par ^ 1)
         self._forward(par)
-        cur.wait_stream(self._side2)
+        if late:                              # same stream as the insert: ordered behind it; joined by _join_late()
+            self._side2.wait_stream(cur)
+            with torch.cuda.stream(self._side2):
+                self._frontend(par ^ 1)
+            self._late_pending = True
+        else:
+            cur.wait_stream(self._side2)
+
+    def _join_late(self):
+        """End of a batch whose next front-end was forked beside the exchange (prefetch_late)."""
+        if getattr(self, "_late_pending", False):
+            torch.cuda.current_stream().wait_stream(self._side2)
+            self._late_pending = False
 
     def _panel(self, name: str):
         """(B_hi, B_lo) pointers of a weight panel for the current precision mode (BF16: one panel, no lo part)."""
@@ -493,6 +515,7 @@ class TGBEvalEngine:
                     self._exchange_peer(xpar)
                 if one:
                     self._update(par, False, xpar)
+                    self._join_late()
             if not one:
                 gb = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gb):
@@ -537,6 +560,7 @@ class TGBEvalEngine:
                     self._batch(par, self.prefetch and j < n_batches - 1)
                     xpar = self._exchange()
                     self._update(par, False, xpar)
+                    self._join_late()
                     if self.prefetch:
                         par ^= 1
         self.loader.cur_e_id += n_batches * self.B
